@@ -1,0 +1,19 @@
+"""eventpretrain_b200 — B200-native (sm_100a) input hot path of BIT-Vision/EventPretrain.
+
+Raw events -> dense tensors -> diff-map target -> mask / patchify / visible-token gather, as
+hand-written CUDA kernels behind a C ABI (include/eventpretrain_b200.h), with drop-in Python
+functions that keep the reference's call signatures.  No CPU fallback.
+"""
+from . import config  # noqa: F401
+from ._lib import LIB_PATH, NativeLibraryMissing, load as load_library  # noqa: F401
+from .augmentation import events_reshape, get_random_index, reshape_scale  # noqa: F401
+from .dataset_utils import (events_to_EvRep, events_to_image_ecdp, events_to_image_mem,  # noqa: F401
+                            events_to_voxel_grid, remove_hot_pixel_mem)
+from .events import (BadEventsError, RaggedEvents, bin_events, bin_events_aos, evrep, from_soa,  # noqa: F401
+                     mem_hotpixel, normalise, pack_events)
+from .masking import (block_mask_expand, convvit_keep_masks, gather_tokens, len_keep_of,  # noqa: F401
+                      mask_from_noise, patch_density, random_masking, swin_apply_mask, unshuffle_tokens)
+from .reshape import (diffmap_frames, frame2emb, patchify_gather, reconstruct_loss, target_normpix,  # noqa: F401
+                      target_patch_loss)
+
+__version__ = "0.1.0"

@@ -1,0 +1,96 @@
+"""ctypes binding of the C ABI declared in include/eventpretrain_b200.h.
+
+There is NO CPU fallback: if the CUDA library has not been built, or no CUDA device is present,
+every operator raises.  (The CPU oracle under oracle/ is test infrastructure and is never
+imported from this package.)
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeventpretrain_b200.so")
+
+EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64 = range(1, 9)
+EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
+EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
+
+c_void_p, c_int, c_int64, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                         ctypes.c_size_t, ctypes.c_float, ctypes.c_double)
+
+
+class EventsSoa(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("y", c_void_p), ("t", c_void_p), ("p", c_void_p),
+                ("xy_dtype", c_int), ("t_dtype", c_int), ("p_dtype", c_int), ("batch", c_int),
+                ("t_div", c_double), ("offsets", c_void_p), ("offsets_host", c_void_p)]
+
+
+class EventsAos(ctypes.Structure):
+    _fields_ = [("events", c_void_p), ("dtype", c_int), ("n", c_int64)]
+
+
+class BinParams(ctypes.Structure):
+    _fields_ = [("height", c_int), ("width", c_int), ("num_bins", c_int), ("count_channels", c_int),
+                ("scale_x", c_double), ("scale_y", c_double), ("time_f32", c_int), ("flags", c_int)]
+
+
+P = ctypes.POINTER
+# name -> (restype, argtypes); must list every symbol the header declares (tests check this)
+SIGNATURES = {
+    "ep_abi_version": (c_int, []),
+    "ep_status_string": (ctypes.c_char_p, [c_int]),
+    "ep_bin_events_workspace_bytes": (c_size_t, [P(BinParams), c_int, P(c_size_t)]),
+    "ep_bin_events": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_size_t, c_void_p]),
+    "ep_bin_events_aos": (c_int, [c_void_p, P(EventsAos), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    "ep_normalise_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ep_normalise": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
+    "ep_mem_hotpixel_workspace_bytes": (c_size_t, [c_int]),
+    "ep_mem_hotpixel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_size_t]),
+    "ep_evrep_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
+    "ep_evrep": (c_int, [c_void_p, P(EventsSoa), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ep_diffmap_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),
+    "ep_patchify_normpix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ep_target_patch_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                     c_void_p]),
+    "ep_mask_from_noise": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ep_patch_density": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ep_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ep_patchify_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
+    "ep_block_mask_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ep_swin_apply_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    "ep_unshuffle_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load the C-ABI library; fail loudly (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -m eventpretrain_b200.build` "
+            "(nvcc, sm_100a).  eventpretrain_b200 has no CPU / PyTorch fallback by design.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here == header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().ep_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")

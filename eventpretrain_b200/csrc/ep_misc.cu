@@ -1,0 +1,191 @@
+// Per-sample normalisers, hot-pixel filter, frame-side diff-map target, ABI housekeeping (sm_100a).
+#include <math.h>
+
+#include "ep_common.cuh"
+
+namespace ep {
+namespace {
+
+constexpr int kStatBlocks = 64;   // partial-sum blocks per sample (fixed => deterministic reduction order)
+
+// order-preserving float <-> uint key, so a plain unsigned atomicMax orders all finite floats
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---- normalisers   dataset/pretrain/pr_n_imagenet_dataset.py:142-143, ft_n_caltech101_dataset.py:93-98
+__global__ void __launch_bounds__(256) k_plane_max(const float* __restrict__ img, int64_t HW, uint32_t* __restrict__ keys) {
+    const int plane = blockIdx.y;
+    const float* p = img + (int64_t)plane * HW;
+    float m = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, p[i]);
+    m = warp_reduce(m, [](float a, float b) { return fmaxf(a, b); });
+    if ((threadIdx.x & 31) == 0) atomicMax(keys + plane, f2key(m));
+}
+
+__global__ void __launch_bounds__(256) k_normalise_apply(float* __restrict__ img, int C, int64_t HW, int mode,
+                                                         const uint32_t* __restrict__ keys) {
+    const int plane = blockIdx.y;           // b * C + c
+    const int b = plane / C, c = plane % C;
+    float* p = img + (int64_t)plane * HW;
+    if (mode == EP_NORM_COUNT) {
+        const float den = key2f(keys[plane]) + 1.0f;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
+            p[i] = __fmul_rn(__fsub_rn(__fdiv_rn(p[i], den), 0.5f), 2.0f);
+    } else {
+        if (c == 1) return;   // [0::2] only
+        const float mx = fmaxf(key2f(keys[b * C + 0]), key2f(keys[b * C + 2]));
+        const float factor = (mode == EP_NORM_MEM_GUARD && mx == 0.0f) ? (float)(1.0 / 0.001) : __fdiv_rn(1.0f, mx);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
+            p[i] = __fmul_rn(p[i], factor);
+    }
+}
+
+// ---- remove_hot_pixel_mem   dataset/dataset_utils/events_to_image.py:65-75
+__global__ void __launch_bounds__(256) k_hot_stats(const float* __restrict__ hist, int64_t HW, float divide_by,
+                                                   double* __restrict__ partial) {
+    __shared__ double s_sum[8], s_sq[8];
+    const int b = blockIdx.y;
+    const float* c0 = hist + (int64_t)b * 3 * HW;
+    const float* c2 = c0 + 2 * HW;
+    double s = 0.0, q = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * HW; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = i < HW ? c0[i] : c2[i - HW];
+        if (divide_by != 1.0f) v = __fdiv_rn(v, divide_by);
+        s += (double)v;
+        q += (double)v * (double)v;
+    }
+    s = warp_reduce(s, [](double a, double c) { return a + c; });
+    q = warp_reduce(q, [](double a, double c) { return a + c; });
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = s; s_sq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int w = 0; w < 8; ++w) { ts += s_sum[w]; tq += s_sq[w]; }
+        partial[((int64_t)b * kStatBlocks + blockIdx.x) * 2] = ts;
+        partial[((int64_t)b * kStatBlocks + blockIdx.x) * 2 + 1] = tq;
+    }
+}
+
+__global__ void k_hot_threshold(const double* __restrict__ partial, int B, int64_t HW, float num_stds,
+                                float* __restrict__ thr) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < kStatBlocks; ++i) { s += partial[((int64_t)b * kStatBlocks + i) * 2]; q += partial[((int64_t)b * kStatBlocks + i) * 2 + 1]; }
+    const double m = (double)(2 * HW);
+    const double mean = s / m;
+    double var = (q - m * mean * mean) / (m - 1.0);
+    if (var < 0.0) var = 0.0;
+    thr[b] = __fadd_rn((float)mean, __fmul_rn(num_stds, (float)sqrt(var)));   // :69 in fp32
+}
+
+__global__ void __launch_bounds__(256) k_hot_apply(float* __restrict__ hist, int64_t HW, float divide_by,
+                                                   const float* __restrict__ thr) {
+    const int b = blockIdx.y;
+    float* c0 = hist + (int64_t)b * 3 * HW;
+    const float t = thr[b];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        float a = c0[i], m = c0[HW + i], c = c0[2 * HW + i];
+        if (divide_by != 1.0f) { a = __fdiv_rn(a, divide_by); m = __fdiv_rn(m, divide_by); c = __fdiv_rn(c, divide_by); }
+        if (a > t || c > t) { a = 0.0f; c = 0.0f; }   // :70-73
+        c0[i] = a; c0[HW + i] = m; c0[2 * HW + i] = c;
+    }
+}
+
+// ---- frame-side difference map (self-defined formula; sign flip = view_augment.py:60-63)
+__global__ void __launch_bounds__(256) k_diffmap(const float* __restrict__ f0, const float* __restrict__ f1,
+                                                 float* __restrict__ out, int64_t n, int64_t per_sample, int mode,
+                                                 float eps, const uint8_t* __restrict__ negate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = ld_stream(f0 + i), b = ld_stream(f1 + i);
+        float d = mode == 1 ? __fsub_rn(logf(b + eps), logf(a + eps)) : __fsub_rn(b, a);
+        if (negate && negate[i / per_sample]) d = -d;
+        st_stream(out + i, d);
+    }
+}
+
+}  // namespace
+}  // namespace ep
+
+extern "C" {
+
+int ep_abi_version(void) { return EP_ABI_VERSION; }
+
+const char* ep_status_string(int status) {
+    switch (status) {
+        case EP_OK: return "ok";
+        case EP_EINVAL: return "invalid argument";
+        case EP_EWORKSPACE: return "workspace too small";
+        case EP_EUNSUPPORTED: return "unsupported shape";
+        case EP_EALIGN: return "misaligned pointer";
+        default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
+    }
+}
+
+size_t ep_normalise_workspace_bytes(int batch, int channels) {
+    return batch > 0 && channels > 0 ? ep::align_up(sizeof(uint32_t) * (size_t)batch * channels, 256) : 0;
+}
+
+int ep_normalise(void* stream, float* img, int batch, int channels, int height, int width, int mode, void* workspace,
+                 size_t workspace_bytes) {
+    if (!img || batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || !workspace) return EP_EINVAL;
+    if (mode != EP_NORM_COUNT && mode != EP_NORM_MEM && mode != EP_NORM_MEM_GUARD) return EP_EINVAL;
+    if (mode != EP_NORM_COUNT && channels != 3) return EP_EINVAL;
+    if (workspace_bytes < ep_normalise_workspace_bytes(batch, channels)) return EP_EWORKSPACE;
+    if ((int64_t)batch * channels > 65535) return EP_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* keys = static_cast<uint32_t*>(workspace);
+    cudaError_t ce = cudaMemsetAsync(keys, 0, sizeof(uint32_t) * (size_t)batch * channels, st);
+    if (ce != cudaSuccess) return (int)ce;
+    const int64_t HW = (int64_t)height * width;
+    unsigned bx = (unsigned)ep::ceil_div64(HW, 256 * 8);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, (unsigned)(batch * channels));
+    ep::k_plane_max<<<grid, 256, 0, st>>>(img, HW, keys);
+    EP_LAUNCH_CHECK();
+    ep::k_normalise_apply<<<grid, 256, 0, st>>>(img, channels, HW, mode, keys);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+size_t ep_mem_hotpixel_workspace_bytes(int batch) {
+    return batch > 0 ? ep::align_up(sizeof(double) * (size_t)batch * (2 * ep::kStatBlocks + 1), 256) : 0;
+}
+
+int ep_mem_hotpixel(void* stream, float* hist, int batch, int height, int width, float divide_by, float num_stds,
+                    void* workspace, size_t workspace_bytes) {
+    if (!hist || batch <= 0 || height <= 0 || width <= 0 || !workspace || !(divide_by != 0.0f)) return EP_EINVAL;
+    if (workspace_bytes < ep_mem_hotpixel_workspace_bytes(batch)) return EP_EWORKSPACE;
+    if (batch > 65535) return EP_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* partial = static_cast<double*>(workspace);
+    float* thr = reinterpret_cast<float*>(partial + (size_t)batch * 2 * ep::kStatBlocks);
+    const int64_t HW = (int64_t)height * width;
+    dim3 g1(ep::kStatBlocks, (unsigned)batch);
+    ep::k_hot_stats<<<g1, 256, 0, st>>>(hist, HW, divide_by, partial);
+    EP_LAUNCH_CHECK();
+    ep::k_hot_threshold<<<(batch + 127) / 128, 128, 0, st>>>(partial, batch, HW, num_stds, thr);
+    EP_LAUNCH_CHECK();
+    ep::k_hot_apply<<<g1, 256, 0, st>>>(hist, HW, divide_by, thr);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_diffmap_frames(void* stream, const float* f0, const float* f1, float* out, int64_t n, int64_t per_sample,
+                      int mode, float eps, const uint8_t* negate) {
+    if (!f0 || !f1 || !out || n <= 0 || per_sample <= 0 || (mode != 0 && mode != 1)) return EP_EINVAL;
+    int64_t blocks = ep::ceil_div64(n, 256 * 4);
+    if (blocks > ep::kNumSMs * 16) blocks = ep::kNumSMs * 16;
+    ep::k_diffmap<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f0, f1, out, n, per_sample, mode, eps, negate);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,436 @@
+// Stage 3 — masking, patchify, visible-token gather; and the patchified diff-map target (sm_100a).
+//
+// Every kernel here is a permutation / small reduction over fp32 tensors: HBM-bound, no dense
+// contraction, so no tensor cores.  Rows are moved with 16-byte vector accesses by one warp per
+// row; outputs that are consumed once downstream are written with streaming stores.
+#include "ep_common.cuh"
+
+namespace ep {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// random_masking core   model/backbone/vit.py:91-105
+// One CTA per sample.  rank_i = #{ j : n_j < n_i or (n_j == n_i and j < i) }  (stable ascending
+// argsort); ids_restore[i] = rank_i; ids_keep[rank_i] = i when rank_i < len_keep; mask = rank >= keep.
+// The all-pairs count reads noise from shared memory as warp-wide broadcasts: L^2 = 38k compares
+// for L = 196, far cheaper than two device-wide sorts plus four gather launches.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_mask_from_noise(const float* __restrict__ noise, int L, int len_keep,
+                                  int64_t* __restrict__ ids_keep, float* __restrict__ mask,
+                                  int64_t* __restrict__ ids_restore) {
+    extern __shared__ float s_noise[];
+    const int b = blockIdx.x;
+    const float* n = noise + (int64_t)b * L;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s_noise[i] = n[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float v = s_noise[i];
+        int rank = 0;
+        for (int j = 0; j < L; ++j) {
+            const float w = s_noise[j];
+            rank += (w < v) || (w == v && j < i);
+        }
+        ids_restore[(int64_t)b * L + i] = rank;
+        mask[(int64_t)b * L + i] = rank >= len_keep ? 1.0f : 0.0f;
+        if (rank < len_keep) ids_keep[(int64_t)b * len_keep + rank] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// density noise   model/backbone/vit.py:80-83
+// One thread per patch.  fp32 accumulation in the reference's order: channels in order, then the
+// p x p window row-major into a zero-initialised accumulator, then one division by p*p.
+// ---------------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(128) k_patch_density(const float* __restrict__ x, int B, int C, int H, int W,
+                                                       int p, float sign, float* __restrict__ out) {
+    const int gh = H / p, gw = W / p, L = gh * gw;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * L) return;
+    const int b = (int)(idx / L), l = (int)(idx % L);
+    const int py = l / gw, px = l % gw;
+    const int64_t HW = (int64_t)H * W;
+    const float* base = x + (int64_t)b * C * HW + (int64_t)(py * p) * W + px * p;
+    float acc = 0.0f;
+    for (int r = 0; r < p; ++r) {
+        const float* row = base + (int64_t)r * W;
+        if (VEC4) {
+            for (int q = 0; q < p; q += 4) {
+                float4 s = __ldg(reinterpret_cast<const float4*>(row + q));
+                for (int c = 1; c < C; ++c) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c * HW + q));
+                    s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y);
+                    s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
+                }
+                acc = __fadd_rn(acc, fabsf(s.x)); acc = __fadd_rn(acc, fabsf(s.y));
+                acc = __fadd_rn(acc, fabsf(s.z)); acc = __fadd_rn(acc, fabsf(s.w));
+            }
+        } else {
+            for (int q = 0; q < p; ++q) {
+                float s = __ldg(row + q);
+                for (int c = 1; c < C; ++c) s = __fadd_rn(s, __ldg(row + c * HW + q));
+                acc = __fadd_rn(acc, fabsf(s));
+            }
+        }
+    }
+    out[idx] = sign * __fdiv_rn(acc, (float)(p * p));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row movers: one warp per destination row of D floats (D % 4 == 0), 16-byte accesses
+// ---------------------------------------------------------------------------------------------------
+// visible-token gather   model/backbone/vit.py:113-115
+__global__ void __launch_bounds__(256) k_gather_tokens(const float* __restrict__ tokens,
+                                                       const float* __restrict__ pos,
+                                                       const int64_t* __restrict__ ids, int64_t rows, int L,
+                                                       int K, int D, float* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = row / K;
+    int64_t src = ids[row];
+    if (src < 0 || src >= L) src = 0;   // torch.gather raises; ids come from ep_mask_from_noise
+    const float4* s = reinterpret_cast<const float4*>(tokens + (b * L + src) * D);
+    const float4* pp = pos ? reinterpret_cast<const float4*>(pos + src * D) : nullptr;
+    float4* o = reinterpret_cast<float4*>(out + row * D);
+    for (int i = lane; i < D / 4; i += 32) {
+        float4 v = ld_stream(s + i);
+        if (pp) {
+            const float4 q = __ldg(pp + i);
+            v.x = __fadd_rn(v.x, q.x); v.y = __fadd_rn(v.y, q.y); v.z = __fadd_rn(v.z, q.z); v.w = __fadd_rn(v.w, q.w);
+        }
+        o[i] = v;
+    }
+}
+
+// decoder un-shuffle   model/pretrain/pr_rec_decoder.py:56-62
+__global__ void __launch_bounds__(256) k_unshuffle_tokens(const float* __restrict__ emb,
+                                                          const float* __restrict__ mask_token,
+                                                          const float* __restrict__ pos,
+                                                          const int64_t* __restrict__ ids_restore, int64_t rows,
+                                                          int L, int K, int D, float* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = row / L, l = row % L;
+    const int64_t src = ids_restore[row];
+    const float4* s = (src >= 0 && src < K) ? reinterpret_cast<const float4*>(emb + (b * K + src) * D)
+                                            : reinterpret_cast<const float4*>(mask_token);
+    const float4* pp = pos ? reinterpret_cast<const float4*>(pos + l * D) : nullptr;
+    float4* o = reinterpret_cast<float4*>(out + row * D);
+    for (int i = lane; i < D / 4; i += 32) {
+        float4 v = __ldg(s + i);
+        if (pp) {
+            const float4 q = __ldg(pp + i);
+            v.x = __fadd_rn(v.x, q.x); v.y = __fadd_rn(v.y, q.y); v.z = __fadd_rn(v.z, q.z); v.w = __fadd_rn(v.w, q.w);
+        }
+        o[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// patchify (+ gather)   utils/reshape.py:15-22 / Conv2d(k=s=p) operand order
+// One CTA (128 threads) per destination patch; threads walk the destination row so stores are
+// fully coalesced; sources are p-float row segments of one 16x16xC box (L1-resident).
+// ---------------------------------------------------------------------------------------------------
+template <int ORDER, bool VEC4>
+__global__ void __launch_bounds__(128) k_patchify_gather(const float* __restrict__ x,
+                                                         const int64_t* __restrict__ ids, int C, int H, int W,
+                                                         int p, int K, float* __restrict__ out) {
+    const int gw = W / p, L = (H / p) * gw;
+    const int64_t row = blockIdx.x;            // b * K + k
+    const int64_t b = row / K;
+    int64_t l = ids ? ids[row] : row % K;
+    if (l < 0 || l >= L) l = 0;
+    const int py = (int)(l / gw), px = (int)(l % gw);
+    const int64_t HW = (int64_t)H * W;
+    const float* base = x + b * C * HW + (int64_t)(py * p) * W + px * p;
+    const int n = C * p * p;
+    float* o = out + row * n;
+    if (ORDER == EP_ORDER_CPQ) {
+        if (VEC4) {
+            for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+                const int e = i * 4, c = e / (p * p), r = (e / p) % p, q = e % p;
+                st_stream(reinterpret_cast<float4*>(o) + i,
+                          __ldg(reinterpret_cast<const float4*>(base + c * HW + (int64_t)r * W + q)));
+            }
+        } else {
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                const int c = e / (p * p), r = (e / p) % p, q = e % p;
+                st_stream(o + e, __ldg(base + c * HW + (int64_t)r * W + q));
+            }
+        }
+    } else {   // (ph, pw, c)
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int c = e % C, q = (e / C) % p, r = e / (C * p);
+            st_stream(o + e, __ldg(base + c * HW + (int64_t)r * W + q));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// target patchify + norm_pix (+ fused per-patch MSE)   model/pretrain/pr_hub_model.py:125-139
+// One warp per patch: the patch is staged in this warp's slice of shared memory in (ph,pw,c)
+// order, mean and unbiased variance are two shuffle reductions, then either the normalised patch is
+// written (coalesced) or it is compared with `pred` and only the per-patch loss is written.
+// ---------------------------------------------------------------------------------------------------
+template <bool LOSS>
+__global__ void __launch_bounds__(256) k_patch_target(const float* __restrict__ frame,
+                                                      const float* __restrict__ pred, int64_t patches, int C,
+                                                      int H, int W, int p, int norm_pix, float eps,
+                                                      float* __restrict__ out) {
+    extern __shared__ float s_patch[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= patches) return;
+    const int gw = W / p, L = (H / p) * gw;
+    const int64_t b = row / L;
+    const int l = (int)(row % L);
+    const int py = l / gw, px = l % gw;
+    const int64_t HW = (int64_t)H * W;
+    const float* base = frame + b * C * HW + (int64_t)(py * p) * W + px * p;
+    const int n = C * p * p;
+    float* sp = s_patch + (int64_t)warp * n;
+    float sum = 0.f;
+    for (int e = lane; e < n; e += 32) {
+        const int c = e % C, q = (e / C) % p, r = e / (C * p);
+        const float v = ld_stream(base + c * HW + (int64_t)r * W + q);
+        sp[e] = v;
+        sum += v;
+    }
+    float mean = 0.f, sd = 1.f;
+    if (norm_pix) {
+        sum = warp_reduce(sum, [](float a, float c) { return a + c; });
+        mean = sum / (float)n;
+        float ss = 0.f;
+        __syncwarp();
+        for (int e = lane; e < n; e += 32) { const float d = sp[e] - mean; ss += d * d; }
+        ss = warp_reduce(ss, [](float a, float c) { return a + c; });
+        const float var = ss / (float)(n - 1);          // torch.var default: unbiased
+        sd = sqrtf(var + eps);                          // (var + 1e-6) ** .5
+    }
+    __syncwarp();
+    if (LOSS) {
+        const float* pr = pred + row * n;
+        float acc = 0.f;
+        for (int e = lane; e < n; e += 32) {
+            const float t = norm_pix ? (sp[e] - mean) / sd : sp[e];
+            const float d = ld_stream(pr + e) - t;
+            acc += d * d;
+        }
+        acc = warp_reduce(acc, [](float a, float c) { return a + c; });
+        if (lane == 0) out[row] = acc / (float)n;
+    } else {
+        float* o = out + row * n;
+        for (int e = lane; e < n; e += 32) st_stream(o + e, norm_pix ? (sp[e] - mean) / sd : sp[e]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ConvViT block masks   model/backbone/convvit.py:129-130,142-143
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_block_mask_expand(const float* __restrict__ mask, int64_t total, int grid,
+                                                           int rep, int invert, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int side = grid * rep;
+    const int X = (int)(i % side), Y = (int)((i / side) % side);
+    const int64_t b = i / ((int64_t)side * side);
+    const float m = __ldg(mask + b * grid * grid + (Y / rep) * grid + X / rep);
+    out[i] = invert ? 1.0f - m : m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Swin apply_mask   model/backbone/swin.py:154-179
+// Kernel 1 (one CTA): expand mask row 0 to the token grid, block-wide exclusive scan of the
+// visibility bits (warp-shuffle scans + one shared-memory pass), write vis_mask, coords, n_vis.
+// Kernel 2: one warp per (b, visible token) row copy.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_swin_scan(const float* __restrict__ mask_row, int Mh, int Mw, int rep,
+                                                    int n_vis_max, int64_t* __restrict__ coords,
+                                                    uint8_t* __restrict__ vis_mask, int* __restrict__ n_vis_out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base, s_total;
+    const int Wt = Mw * rep, N = Mh * rep * Wt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < N; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        int vis = 0, h = 0, w = 0;
+        if (i < N) {
+            h = i / Wt; w = i % Wt;
+            vis = (__ldg(mask_row + (h / rep) * Mw + w / rep) == 0.0f);   // mask.bool(): nonzero = removed
+            vis_mask[i] = (uint8_t)vis;
+        }
+        const int incl = warp_incl_scan(vis, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_warp[lane];               // blockDim.x == 1024: all 32 entries are live
+            const int s = warp_incl_scan(v, lane);
+            s_warp[lane] = s - v;                     // exclusive offset of each warp
+            if (lane == 31) s_total = s;
+        }
+        __syncthreads();
+        const int pos = s_base + s_warp[warp] + incl - vis;
+        if (vis && pos < n_vis_max) { coords[2 * (int64_t)pos] = h; coords[2 * (int64_t)pos + 1] = w; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_vis_out = s_base;
+}
+
+__global__ void __launch_bounds__(256) k_swin_gather(const float* __restrict__ x, const int64_t* __restrict__ coords,
+                                                     const int* __restrict__ n_vis, int B, int N, int Wt, int C,
+                                                     int n_vis_max, float* __restrict__ x_vis) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = min(*n_vis, n_vis_max);
+    if (row >= (int64_t)B * nv) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = row / nv, j = row % nv;
+    const int64_t src = coords[2 * j] * Wt + coords[2 * j + 1];
+    const float4* s = reinterpret_cast<const float4*>(x + (b * N + src) * C);
+    float4* o = reinterpret_cast<float4*>(x_vis + (b * nv + j) * C);
+    for (int i = lane; i < C / 4; i += 32) o[i] = ld_stream(s + i);
+}
+
+}  // namespace
+}  // namespace ep
+
+extern "C" {
+
+int ep_mask_from_noise(void* stream, const float* noise, int batch, int L, int len_keep, int64_t* ids_keep,
+                       float* mask, int64_t* ids_restore) {
+    if (!noise || !mask || !ids_restore || batch <= 0 || L <= 0 || len_keep < 0 || len_keep > L) return EP_EINVAL;
+    if (len_keep > 0 && !ids_keep) return EP_EINVAL;
+    if (L > 4096) return EP_EUNSUPPORTED;
+    int threads = (L + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    ep::k_mask_from_noise<<<batch, threads, L * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        noise, L, len_keep, ids_keep, mask, ids_restore);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_patch_density(void* stream, const float* x, int batch, int channels, int height, int width, int patch,
+                     float sign, float* out) {
+    if (!x || !out || batch <= 0 || channels <= 0 || patch <= 0 || height < patch || width < patch) return EP_EINVAL;
+    const int64_t total = (int64_t)batch * (height / patch) * (width / patch);
+    const unsigned blocks = (unsigned)ep::ceil_div64(total, 128);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (patch % 4 == 0) && (width % 4 == 0) && ep::aligned16(x);
+    if (vec) ep::k_patch_density<true><<<blocks, 128, 0, st>>>(x, batch, channels, height, width, patch, sign, out);
+    else ep::k_patch_density<false><<<blocks, 128, 0, st>>>(x, batch, channels, height, width, patch, sign, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_gather_tokens(void* stream, const float* tokens, const float* pos_embed, const int64_t* ids_keep, int batch,
+                     int L, int K, int D, float* out) {
+    if (!tokens || !ids_keep || !out || batch <= 0 || L <= 0 || K <= 0 || D <= 0) return EP_EINVAL;
+    if (D % 4) return EP_EUNSUPPORTED;
+    if (!ep::aligned16(tokens) || !ep::aligned16(out) || (pos_embed && !ep::aligned16(pos_embed))) return EP_EALIGN;
+    const int64_t rows = (int64_t)batch * K;
+    ep::k_gather_tokens<<<(unsigned)ep::ceil_div64(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        tokens, pos_embed, ids_keep, rows, L, K, D, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask_token, const float* pos_embed,
+                        const int64_t* ids_restore, int batch, int L, int K, int D, float* out) {
+    if (!emb || !mask_token || !ids_restore || !out || batch <= 0 || L <= 0 || K < 0 || K > L || D <= 0) return EP_EINVAL;
+    if (D % 4) return EP_EUNSUPPORTED;
+    if (!ep::aligned16(emb) || !ep::aligned16(out) || !ep::aligned16(mask_token) ||
+        (pos_embed && !ep::aligned16(pos_embed)))
+        return EP_EALIGN;
+    const int64_t rows = (int64_t)batch * L;
+    ep::k_unshuffle_tokens<<<(unsigned)ep::ceil_div64(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        emb, mask_token, pos_embed, ids_restore, rows, L, K, D, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_patchify_gather(void* stream, const float* x, const int64_t* ids_keep, int batch, int channels, int height,
+                       int width, int patch, int K, int order, float* out) {
+    if (!x || !out || batch <= 0 || channels <= 0 || patch <= 0 || height < patch || width < patch || K <= 0)
+        return EP_EINVAL;
+    if (order != EP_ORDER_CPQ && order != EP_ORDER_PQC) return EP_EINVAL;
+    if (height % patch || width % patch) return EP_EUNSUPPORTED;
+    if (!ids_keep && K != (height / patch) * (width / patch)) return EP_EINVAL;
+    const int64_t rows = (int64_t)batch * K;
+    if (rows > 0x7fffffffLL) return EP_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (patch % 4 == 0) && (width % 4 == 0) && ep::aligned16(x) && ep::aligned16(out);
+    if (order == EP_ORDER_CPQ) {
+        if (vec) ep::k_patchify_gather<EP_ORDER_CPQ, true><<<(unsigned)rows, 128, 0, st>>>(x, ids_keep, channels, height, width, patch, K, out);
+        else ep::k_patchify_gather<EP_ORDER_CPQ, false><<<(unsigned)rows, 128, 0, st>>>(x, ids_keep, channels, height, width, patch, K, out);
+    } else {
+        ep::k_patchify_gather<EP_ORDER_PQC, false><<<(unsigned)rows, 128, 0, st>>>(x, ids_keep, channels, height, width, patch, K, out);
+    }
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+static int launch_patch_target(void* stream, bool loss, const float* frame, const float* pred, int batch,
+                               int channels, int height, int width, int patch, int norm_pix, float eps, float* out) {
+    if (!frame || !out || (loss && !pred) || batch <= 0 || channels <= 0 || patch <= 0) return EP_EINVAL;
+    if (height < patch || width < patch || height % patch || width % patch) return EP_EUNSUPPORTED;
+    const int n = channels * patch * patch;
+    if (n < 2 || n > 6144) return EP_EUNSUPPORTED;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * n * sizeof(float);
+    const int64_t patches = (int64_t)batch * (height / patch) * (width / patch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = (unsigned)ep::ceil_div64(patches, warps);
+    if (loss) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(ep::k_patch_target<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ep::k_patch_target<true><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, out);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(ep::k_patch_target<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ep::k_patch_target<false><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, out);
+    }
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_patchify_normpix(void* stream, const float* frame, int batch, int channels, int height, int width, int patch,
+                        int norm_pix, float eps, float* out) {
+    return launch_patch_target(stream, false, frame, nullptr, batch, channels, height, width, patch, norm_pix, eps, out);
+}
+
+int ep_target_patch_loss(void* stream, const float* frame, const float* pred, int batch, int channels, int height,
+                         int width, int patch, int norm_pix, float eps, float* patch_loss) {
+    return launch_patch_target(stream, true, frame, pred, batch, channels, height, width, patch, norm_pix, eps, patch_loss);
+}
+
+int ep_block_mask_expand(void* stream, const float* mask, int batch, int grid, int rep, int invert, float* out) {
+    if (!mask || !out || batch <= 0 || grid <= 0 || rep <= 0) return EP_EINVAL;
+    const int64_t total = (int64_t)batch * grid * rep * grid * rep;
+    ep::k_block_mask_expand<<<(unsigned)ep::ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask, total, grid, rep, invert, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_swin_apply_mask(void* stream, const float* x, const float* mask_row, int batch, int Mh, int Mw, int rep, int C,
+                       int n_vis_max, float* x_vis, int64_t* coords, uint8_t* vis_mask, int* n_vis_out) {
+    if (!x || !mask_row || !x_vis || !coords || !vis_mask || !n_vis_out) return EP_EINVAL;
+    if (batch <= 0 || Mh <= 0 || Mw <= 0 || rep <= 0 || C <= 0 || n_vis_max < 0) return EP_EINVAL;
+    if (C % 4) return EP_EUNSUPPORTED;
+    if (!ep::aligned16(x) || !ep::aligned16(x_vis)) return EP_EALIGN;
+    const int Wt = Mw * rep, N = Mh * rep * Wt;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ep::k_swin_scan<<<1, 1024, 0, st>>>(mask_row, Mh, Mw, rep, n_vis_max, coords, vis_mask, n_vis_out);
+    EP_LAUNCH_CHECK();
+    if (n_vis_max > 0) {
+        const int64_t rows = (int64_t)batch * n_vis_max;
+        ep::k_swin_gather<<<(unsigned)ep::ceil_div64(rows, 8), 256, 0, st>>>(x, coords, n_vis_out, batch, N, Wt, C, n_vis_max, x_vis);
+        EP_LAUNCH_CHECK();
+    }
+    return EP_OK;
+}
+
+}  // extern "C"

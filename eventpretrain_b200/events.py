@@ -1,0 +1,259 @@
+"""Ragged event batches on the device and the batched stage-1 operators.
+
+The reference bins one sample at a time on the CPU inside Dataset.__getitem__.  The
+fast path here keeps raw events as a ragged structure-of-arrays batch (x,y u16 | t i64/f64 | p u8 +
+offsets), built once by the collate step in pinned memory, and bins the whole batch on the GPU.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._runtime import lib, ptr, require_cuda, stream_ptr, workspace
+
+_NP_TAG = {np.dtype(np.uint8): _lib.EP_U8, np.dtype(np.int8): _lib.EP_I8, np.dtype(np.uint16): _lib.EP_U16,
+           np.dtype(np.int16): _lib.EP_I16, np.dtype(np.int32): _lib.EP_I32, np.dtype(np.int64): _lib.EP_I64,
+           np.dtype(np.float32): _lib.EP_F32, np.dtype(np.float64): _lib.EP_F64}
+_TORCH_TAG = {torch.uint8: _lib.EP_U8, torch.int8: _lib.EP_I8, torch.uint16: _lib.EP_U16, torch.int16: _lib.EP_I16,
+              torch.int32: _lib.EP_I32, torch.int64: _lib.EP_I64, torch.float32: _lib.EP_F32,
+              torch.float64: _lib.EP_F64}
+
+
+@dataclass
+class RaggedEvents:
+    """Structure-of-arrays batch of event streams; sample b owns [offsets[b], offsets[b+1])."""
+    x: torch.Tensor
+    y: torch.Tensor
+    t: torch.Tensor
+    p: torch.Tensor
+    offsets: torch.Tensor          # int64 (B+1), same device as the data
+    offsets_host: np.ndarray       # int64 (B+1)
+    t_div: float = 1.0             # timestamp value = t / t_div (int64 microseconds, t_div=1e6 -> seconds)
+
+    @property
+    def batch(self):
+        return int(self.offsets_host.shape[0] - 1)
+
+    @property
+    def num_events(self):
+        return int(self.offsets_host[-1] - self.offsets_host[0])
+
+    @property
+    def device(self):
+        return self.x.device
+
+    def nbytes(self):
+        return sum(int(a.numel()) * a.element_size() for a in (self.x, self.y, self.t, self.p, self.offsets))
+
+    def to(self, device, non_blocking=True):
+        mv = lambda a: a.to(device, non_blocking=non_blocking)
+        return RaggedEvents(mv(self.x), mv(self.y), mv(self.t), mv(self.p), mv(self.offsets), self.offsets_host,
+                            self.t_div)
+
+    def pin_memory(self):
+        pm = lambda a: a.pin_memory()
+        return RaggedEvents(pm(self.x), pm(self.y), pm(self.t), pm(self.p), pm(self.offsets), self.offsets_host,
+                            self.t_div)
+
+    def shard(self, rank, world_size):
+        """Samples [rank*B/G, (rank+1)*B/G): DistributedSampler-style contiguous split (main_pretrain.py:218-220).
+        Slices are views; offsets keep their absolute values (ep_events_soa allows offsets[0] > 0)."""
+        B = self.batch
+        lo, hi = (B * rank) // world_size, (B * (rank + 1)) // world_size
+        return RaggedEvents(self.x, self.y, self.t, self.p, self.offsets[lo:hi + 1], self.offsets_host[lo:hi + 1],
+                            self.t_div)
+
+    def _desc(self):
+        d = _lib.EventsSoa()
+        d.x, d.y, d.t, d.p = ptr(self.x), ptr(self.y), ptr(self.t), ptr(self.p)
+        if self.x.dtype != self.y.dtype:
+            raise TypeError("x and y must share a dtype")
+        d.xy_dtype = _TORCH_TAG[self.x.dtype]
+        d.t_dtype = _TORCH_TAG[self.t.dtype]
+        d.p_dtype = _TORCH_TAG[self.p.dtype]
+        d.batch = self.batch
+        d.t_div = float(self.t_div)
+        d.offsets = ptr(self.offsets)
+        self._off_host = np.ascontiguousarray(self.offsets_host, np.int64)
+        d.offsets_host = self._off_host.ctypes.data
+        return d
+
+
+def pack_events(samples, t_div=1.0, canonical=True, pin=True):
+    """Collate per-sample (N,4) x,y,t,p arrays (the reference's event format) into a host-side ragged SoA batch.
+
+    canonical=True stores x,y as uint16 and p as uint8 (requires integer coordinates in [0, 65535] and
+    p in {0,1}); timestamps keep their dtype (float64, or int64 ticks with `t_div`).  canonical=False
+    keeps float coordinates (events with sub-pixel jitter from erase_and_add_events).
+    """
+    counts = np.array([len(s) for s in samples], np.int64)
+    offsets = np.zeros(len(samples) + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    ev = np.concatenate([np.asarray(s) for s in samples], axis=0) if len(samples) else np.zeros((0, 4))
+    if canonical:
+        x = ev[:, 0].astype(np.uint16)
+        y = ev[:, 1].astype(np.uint16)
+        if not (np.array_equal(x, ev[:, 0]) and np.array_equal(y, ev[:, 1])):
+            raise ValueError("canonical packing needs integer coordinates in [0, 65535]")
+        if not np.isin(ev[:, 3], (0, 1)).all():
+            raise ValueError("canonical packing needs polarity in {0, 1}")
+        p = ev[:, 3].astype(np.uint8)
+    else:
+        x = np.ascontiguousarray(ev[:, 0])
+        y = np.ascontiguousarray(ev[:, 1])
+        p = np.ascontiguousarray(ev[:, 3])
+    t = np.ascontiguousarray(ev[:, 2])
+    return from_soa(x, y, t, p, offsets, t_div=t_div, pin=pin)
+
+
+def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
+    """Wrap host SoA numpy arrays (any dtype tag of ep_dtype) as a host-resident RaggedEvents."""
+    off = np.ascontiguousarray(offsets, np.int64)
+    tens = [torch.from_numpy(np.ascontiguousarray(a)) for a in (x, y, t, p)]
+    tens.append(torch.from_numpy(off.copy()))
+    if pin and torch.cuda.is_available():
+        tens = [a.pin_memory() for a in tens]
+    return RaggedEvents(*tens, offsets_host=off, t_div=t_div)
+
+
+def _bin_params(size, num_bins, count_channels, scale, time_f32):
+    prm = _lib.BinParams()
+    prm.height, prm.width = int(size[0]), int(size[1])
+    prm.num_bins, prm.count_channels = int(num_bins), int(count_channels)
+    prm.scale_x, prm.scale_y = float(scale[0]), float(scale[1])
+    prm.time_f32 = int(bool(time_f32))
+    prm.flags = 0
+    return prm
+
+
+class BadEventsError(IndexError):
+    """Out-of-range coordinates / unsupported polarity (the reference raises IndexError / RuntimeError)."""
+
+
+def _raise_bad(bad):
+    v = int(bad.item())
+    if v & 0x80000000:
+        raise OverflowError("voxel accumulator headroom exceeded (>= 2^18 net same-polarity events on one pixel "
+                            "within one temporal interval)")
+    if v:
+        raise BadEventsError(f"{v} event(s) index outside the grid or carry a polarity outside {{-1,0,1}}")
+
+
+def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_sum=False, time_f32=False,
+               check=False, out=None):
+    """Batched events -> tensors: voxel grid (B,num_bins,H,W), optional voxel.sum(0) plane (B,1,H,W) and/or
+    polarity count frame (B,count_channels,H,W); one C-ABI call (ep_bin_events).
+
+    Returns a dict with the keys that were requested: 'voxel', 'voxel_sum', 'count'.
+    check=True synchronises and raises for events the reference would have raised on.
+    """
+    require_cuda(ev.x)
+    dev = ev.device
+    B, (H, W) = ev.batch, size
+    prm = _bin_params(size, num_bins, count_channels, scale, time_f32)
+    out = {} if out is None else out
+    if num_bins and "voxel" not in out:
+        out["voxel"] = torch.empty((B, num_bins, H, W), dtype=torch.float32, device=dev)
+    if voxel_sum and "voxel_sum" not in out:
+        out["voxel_sum"] = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    if count_channels and "count" not in out:
+        out["count"] = torch.empty((B, count_channels, H, W), dtype=torch.float32, device=dev)
+    L = lib()
+    nbytes = L.ep_bin_events_workspace_bytes(ctypes.byref(prm), B, None)
+    ws = workspace(nbytes, dev, "bin")
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    desc = ev._desc()
+    with torch.cuda.device(dev):
+        rc = L.ep_bin_events(stream_ptr(dev), ctypes.byref(desc), ctypes.byref(prm), ptr(out.get("voxel")),
+                             ptr(out.get("voxel_sum")) if voxel_sum else 0, ptr(out.get("count")), ws.data_ptr(),
+                             ws.numel(), ptr(bad))
+    _lib.check(rc, "ep_bin_events")
+    if check:
+        _raise_bad(bad)
+    return out
+
+
+def bin_events_aos(events, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_sum=False, check=True):
+    """Single (N,4) x,y,t,p CUDA tensor, fp64 or fp32 (fp32 => the reference's fp32 time arithmetic)."""
+    require_cuda(events)
+    if events.dim() != 2 or events.shape[1] != 4:
+        raise AssertionError("events must be (N, 4)")   # events_to_voxel_grid.py:9
+    if events.shape[0] == 0:
+        raise IndexError("index 0 is out of bounds for dimension 0 with size 0")   # events[0, 2] in the reference
+    events = events.contiguous()
+    dev = events.device
+    H, W = size
+    prm = _bin_params(size, num_bins, count_channels, scale, events.dtype == torch.float32)
+    d = _lib.EventsAos()
+    d.events, d.dtype, d.n = events.data_ptr(), _TORCH_TAG[events.dtype], events.shape[0]
+    out = {}
+    if num_bins:
+        out["voxel"] = torch.empty((num_bins, H, W), dtype=torch.float32, device=dev)
+    if voxel_sum:
+        out["voxel_sum"] = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+    if count_channels:
+        out["count"] = torch.empty((count_channels, H, W), dtype=torch.float32, device=dev)
+    L = lib()
+    nbytes = L.ep_bin_events_workspace_bytes(ctypes.byref(prm), 1, None)
+    ws = workspace(nbytes, dev, "bin")
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    with torch.cuda.device(dev):
+        rc = L.ep_bin_events_aos(stream_ptr(dev), ctypes.byref(d), ctypes.byref(prm), ptr(out.get("voxel")),
+                                 ptr(out.get("voxel_sum")), ptr(out.get("count")), ws.data_ptr(), ws.numel(), ptr(bad))
+    _lib.check(rc, "ep_bin_events_aos")
+    if check:
+        _raise_bad(bad)
+    return out
+
+
+def normalise(img, mode):
+    """In-place per-sample normaliser on (B,C,H,W) or (C,H,W): mode 'count' | 'mem' | 'mem_guard'."""
+    require_cuda(img)
+    code = {"count": _lib.EP_NORM_COUNT, "mem": _lib.EP_NORM_MEM, "mem_guard": _lib.EP_NORM_MEM_GUARD}[mode]
+    v = img if img.dim() == 4 else img.unsqueeze(0)
+    if not v.is_contiguous() or v.dtype != torch.float32:
+        raise ValueError("normalise works in place on a contiguous float32 tensor")
+    B, C, H, W = v.shape
+    L = lib()
+    ws = workspace(L.ep_normalise_workspace_bytes(B, C), v.device, "norm")
+    with torch.cuda.device(v.device):
+        rc = L.ep_normalise(stream_ptr(v.device), v.data_ptr(), B, C, H, W, code, ws.data_ptr(), ws.numel())
+    _lib.check(rc, "ep_normalise")
+    return img
+
+
+def mem_hotpixel(hist, num_stds=10.0, divide_by=1.0):
+    """In-place remove_hot_pixel_mem on (B,3,H,W) or (3,H,W), optionally fusing the callers' `/ 255`."""
+    require_cuda(hist)
+    v = hist if hist.dim() == 4 else hist.unsqueeze(0)
+    if not v.is_contiguous() or v.dtype != torch.float32 or v.shape[1] != 3:
+        raise ValueError("mem_hotpixel works in place on a contiguous float32 (B,3,H,W) tensor")
+    B, _, H, W = v.shape
+    L = lib()
+    ws = workspace(L.ep_mem_hotpixel_workspace_bytes(B), v.device, "hot")
+    with torch.cuda.device(v.device):
+        rc = L.ep_mem_hotpixel(stream_ptr(v.device), v.data_ptr(), B, H, W, float(divide_by), float(num_stds),
+                               ws.data_ptr(), ws.numel())
+    _lib.check(rc, "ep_mem_hotpixel")
+    return hist
+
+
+def evrep(ev, size, check=False):
+    """Batched EvRep: (B,3,H,W) float64 = [E_C, E_I, E_T] (events_to_image.py:77-125)."""
+    require_cuda(ev.x)
+    dev = ev.device
+    H, W = size
+    B = ev.batch
+    out = torch.empty((B, 3, H, W), dtype=torch.float64, device=dev)
+    L = lib()
+    ws = workspace(L.ep_evrep_workspace_bytes(B, H, W, ev.num_events), dev, "evrep")
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    desc = ev._desc()
+    with torch.cuda.device(dev):
+        rc = L.ep_evrep(stream_ptr(dev), ctypes.byref(desc), H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), ptr(bad))
+    _lib.check(rc, "ep_evrep")
+    if check:
+        _raise_bad(bad)
+    return out

@@ -1,0 +1,232 @@
+/*
+ * eventpretrain_b200.h — C ABI of the B200-native EventPretrain input hot path.
+ *
+ * The reference (BIT-Vision/EventPretrain) is pure Python: it has no plugin / operator / FFI layer
+ * (SURVEY.md F3).  Its boundary for this path is a set of Python call signatures; this header is
+ * the C ABI underneath the drop-in Python functions in eventpretrain_b200/ that keep those
+ * signatures.  Every entry point cites the reference function (file:line relative to the
+ * EventPretrain root) whose computation it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, POD structs only; no torch / C++ types.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous,
+ *     never synchronise the device, never allocate; the caller owns every buffer.  All data
+ *     pointers are DEVICE pointers on the current device unless the name ends in `_host`.
+ *   - Outputs are fully overwritten.  Scratch is passed explicitly; query its size with the
+ *     matching *_workspace_bytes().
+ *   - Return: EP_OK (0); a negative EP_E* code for argument errors; a positive cudaError_t value
+ *     if a launch failed.  ep_status_string() renders either.
+ *   - Thread-safe and re-entrant (no global state); one process per GPU.
+ *   - Out-of-range events are never clamped or silently dropped (the reference raises IndexError /
+ *     RuntimeError for them): kernels skip them and add to the optional device counter
+ *     `bad_count`, which the Python shim turns into IndexError when checking is enabled.
+ */
+#ifndef EVENTPRETRAIN_B200_H
+#define EVENTPRETRAIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EP_API __attribute__((visibility("default")))
+#else
+#define EP_API
+#endif
+
+#define EP_OK 0
+#define EP_EINVAL (-1)       /* bad argument (null pointer, non-positive size, unsupported dtype tag) */
+#define EP_EWORKSPACE (-2)   /* workspace smaller than *_workspace_bytes() minimum */
+#define EP_EUNSUPPORTED (-3) /* shape outside what the kernels were built for */
+#define EP_EALIGN (-4)       /* pointer not aligned as documented */
+
+/* dtype tags for ragged event buffers */
+enum ep_dtype {
+    EP_U8 = 1, EP_I8 = 2, EP_U16 = 3, EP_I16 = 4, EP_I32 = 5, EP_I64 = 6, EP_F32 = 7, EP_F64 = 8
+};
+
+EP_API int ep_abi_version(void);
+EP_API const char* ep_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 — raw events -> dense tensors
+ * ------------------------------------------------------------------------------------------- */
+
+/* Ragged structure-of-arrays batch of event streams.  Sample b owns events
+ * [offsets[b], offsets[b+1]).  The canonical (fast, vectorised) layout is x,y = EP_U16,
+ * t = EP_I64 or EP_F64, p = EP_U8 with 16-byte aligned base pointers; any other combination of
+ * the tags above takes a scalar-load kernel.  Timestamp value used by the arithmetic is
+ * (double)t / t_div when t_div != 1 (e.g. int64 microseconds with t_div = 1e6 reproduce the
+ * reference's `t / 1e6` seconds, dataset/pretrain/pr_n_imagenet_dataset.py:52-54), else (double)t.
+ * Polarity: 1 = positive; 0 or -1 = negative (events_to_voxel_grid.py:35-36, events_to_image.py:13-16).
+ */
+typedef struct ep_events_soa {
+    const void* x;
+    const void* y;
+    const void* t;
+    const void* p;
+    int xy_dtype;                /* EP_U16 | EP_I16 | EP_I32 | EP_F32 | EP_F64 (fractional coords truncate toward 0) */
+    int t_dtype;                 /* EP_I64 | EP_F64 | EP_F32 */
+    int p_dtype;                 /* EP_U8 | EP_I8 | EP_F32 | EP_F64 */
+    int batch;                   /* B */
+    double t_div;
+    const int64_t* offsets;      /* device, B+1 entries, offsets[0] may be > 0 */
+    const int64_t* offsets_host; /* host copy of the same B+1 entries (required: sizes the launches) */
+} ep_events_soa;
+
+/* Array-of-structures single sample: the reference's own (N,4) x,y,t,p array
+ * (events_to_voxel_grid.py:8, events_to_image.py:10), fp64 or fp32, resident on the device. */
+typedef struct ep_events_aos {
+    const void* events;          /* (n,4) row-major */
+    int dtype;                   /* EP_F64 | EP_F32 (fp32 input => the reference's fp32 time arithmetic) */
+    int64_t n;
+} ep_events_aos;
+
+typedef struct ep_bin_params {
+    int height, width;           /* output grid (size[0], size[1] of the reference calls) */
+    int num_bins;                /* voxel bins (args.num_bins); 0 = no voxel grid */
+    int count_channels;          /* 0 = none, 2 = events_to_image_ecdp [pos,neg], 3 = events_to_image_mem [pos,0,neg] */
+    double scale_x, scale_y;     /* events_reshape fused (dataset/augmentation/events_augment.py:22-26):
+                                    x*scale_x, y*scale_y in fp64, then truncation; 1.0 = none */
+    int time_f32;                /* 1 = do the time arithmetic in fp32 (what torch does for float32 event arrays) */
+    int flags;                   /* reserved, 0 */
+} ep_bin_params;
+
+/* Scratch for ep_bin_events*: per-sample accumulator slots.  Returns the recommended size (enough
+ * slots to keep one group of samples L2-resident); any size >= the minimum (one slot + per-sample
+ * metadata), returned through *min_bytes when non-NULL, works. */
+EP_API size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch, size_t* min_bytes);
+
+/* Replaces, for a whole ragged batch in one call:
+ *   events_to_voxel_grid(args, events, size)   dataset/dataset_utils/events_to_voxel_grid.py:4-61
+ *   events_to_image_ecdp / events_to_image_mem dataset/dataset_utils/events_to_image.py:6-62
+ *   events_reshape (fused scale)               dataset/augmentation/events_augment.py:22-26
+ *   voxel.sum(dim=0)[None] (event-side diff proxy) dataset/pretrain/pr_ef_imagenet_dataset.py:192-193
+ * out_voxel (B,num_bins,H,W) f32; out_voxel_sum (B,1,H,W) f32 or NULL; out_count (B,count_channels,H,W)
+ * f32 (exact integers) or NULL.  Voxel weights are accumulated in 64-bit fixed point (Q24), so the
+ * result is independent of event order and bit-reproducible run to run. */
+EP_API int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* prm,
+                  float* out_voxel, float* out_voxel_sum, float* out_count,
+                  void* workspace, size_t workspace_bytes, unsigned int* bad_count);
+
+/* Same, for one (N,4) array exactly as the reference functions receive it. */
+EP_API int ep_bin_events_aos(void* stream, const ep_events_aos* ev, const ep_bin_params* prm,
+                      float* out_voxel, float* out_voxel_sum, float* out_count,
+                      void* workspace, size_t workspace_bytes, unsigned int* bad_count);
+
+/* Per-sample normalisers applied by the datasets right after binning, in place on (B,C,H,W) f32:
+ *   EP_NORM_COUNT: x/(amax_hw(x)+1) then (x-0.5)*2    dataset/pretrain/pr_n_imagenet_dataset.py:142-143
+ *   EP_NORM_MEM:   channels 0,2 *= 1/max(ch0,ch2)     dataset/finetune_cls/ft_n_caltech101_dataset.py:96-98
+ *   EP_NORM_MEM_GUARD: same, factor 1/0.001 when max == 0   dataset/finetune_flow/ft_mvsec_dataset.py:244-249
+ * workspace: ep_normalise_workspace_bytes(). */
+#define EP_NORM_COUNT 1
+#define EP_NORM_MEM 2
+#define EP_NORM_MEM_GUARD 3
+EP_API size_t ep_normalise_workspace_bytes(int batch, int channels);
+EP_API int ep_normalise(void* stream, float* img, int batch, int channels, int height, int width, int mode,
+                 void* workspace, size_t workspace_bytes);
+
+/* remove_hot_pixel_mem(hist, num_stds)   dataset/dataset_utils/events_to_image.py:65-75
+ * In place on (B,3,H,W) f32: threshold = mean + num_stds*std (unbiased) over channels 0,2 jointly;
+ * pixels where either exceeds it get both zeroed.  Optional `scale` multiplies the frame first
+ * (the callers' `/ 255`, ft_n_caltech101_dataset.py:75, passed as 255 -> divide; 1 = none).  workspace: ep_mem_hotpixel_workspace_bytes(). */
+EP_API size_t ep_mem_hotpixel_workspace_bytes(int batch);
+EP_API int ep_mem_hotpixel(void* stream, float* hist, int batch, int height, int width, float divide_by,
+                    float num_stds, void* workspace, size_t workspace_bytes);
+
+/* events_to_EvRep(xs, ys, ts, ps, resolution=(W,H))   dataset/dataset_utils/events_to_image.py:77-125
+ * out (B,3,H,W) f64 = [E_C, E_I, E_T] like the reference (callers cast to f32).  Bit-exact: events are
+ * counting-sorted by pixel in the reference's lexsort order and each pixel's deltas are accumulated
+ * sequentially with numpy's add.at rounding. */
+EP_API size_t ep_evrep_workspace_bytes(int batch, int height, int width, int64_t n_total);
+EP_API int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, double* out,
+             void* workspace, size_t workspace_bytes, unsigned int* bad_count);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 — difference-map target
+ * ------------------------------------------------------------------------------------------- */
+
+/* Frame-side target T = g(f1) - g(f0), g = identity (mode 0) or log(.+eps) (mode 1), negated when
+ * negate[b] != 0 (time reversal flips the sign: dataset/augmentation/view_augment.py:60-63,86-87).
+ * The reference loads pre-computed sub_frame files (dataset/pretrain/pr_ef_imagenet_dataset.py:167-173)
+ * and ships no generator, so this formula is the build's own (DESIGN.md "parity unpinned" list).
+ * f0,f1,out: (B,1,H,W) f32 — n = B*H*W elements, per_sample = H*W; negate: B bytes or NULL. */
+EP_API int ep_diffmap_frames(void* stream, const float* f0, const float* f1, float* out, int64_t n,
+                      int64_t per_sample, int mode, float eps, const uint8_t* negate);
+
+/* Target half of PrHubModel.reconstruct_loss   model/pretrain/pr_hub_model.py:125-131
+ * + frame2emb                                   utils/reshape.py:15-22
+ * frame (B,C,H,W) f32 -> out (B,(H/p)*(W/p), p*p*C) f32 in (ph,pw,c) element order; when norm_pix != 0
+ * each patch is normalised (x-mean)/sqrt(var_unbiased + eps). */
+EP_API int ep_patchify_normpix(void* stream, const float* frame, int batch, int channels, int height,
+                        int width, int patch, int norm_pix, float eps, float* out);
+
+/* Loss tail   model/pretrain/pr_hub_model.py:133-139
+ * fused with the target build: per-patch mean((pred - target)^2) -> patch_loss (B,L) f32.  The final
+ * (mask*loss).sum()/mask.sum() is two tiny reductions left to the caller. */
+EP_API int ep_target_patch_loss(void* stream, const float* frame, const float* pred, int batch, int channels,
+                         int height, int width, int patch, int norm_pix, float eps, float* patch_loss);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 — masking, patchify, visible-token gather
+ * ------------------------------------------------------------------------------------------- */
+
+/* random_masking(x) with the noise supplied by the caller
+ *   model/backbone/vit.py:66-105 (= convvit.py:85-124, swin.py:113-152)
+ * noise (B,L) f32 -> ids_keep (B,len_keep) i64, mask (B,L) f32 (1 = removed), ids_restore (B,L) i64.
+ * Ranks are those of a stable ascending argsort.  L <= 1024. */
+EP_API int ep_mask_from_noise(void* stream, const float* noise, int batch, int L, int len_keep,
+                       int64_t* ids_keep, float* mask, int64_t* ids_restore);
+
+/* density noise   model/backbone/vit.py:80-83, swin.py:127-130
+ * x (B,C,H,W) f32 -> out (B,(H/p)*(W/p)) f32 = sign * AvgPool2d(p,p)(abs(sum_c x)); sign = +1 "density",
+ * -1 "anti-density".  Accumulation order matches the reference's CPU ops (bit-exact). */
+EP_API int ep_patch_density(void* stream, const float* x, int batch, int channels, int height, int width,
+                     int patch, float sign, float* out);
+
+/* visible-token gather   model/backbone/vit.py:113-115, convvit.py:137-139,149-151,157-159
+ * out[b,k,:] = tokens[b, ids_keep[b,k], :] + pos_embed[ids_keep[b,k], :]   (pos_embed may be NULL).
+ * tokens (B,L,D) f32, pos_embed (L,D) f32, ids_keep (B,K) i64, out (B,K,D) f32.  D % 4 == 0. */
+EP_API int ep_gather_tokens(void* stream, const float* tokens, const float* pos_embed, const int64_t* ids_keep,
+                     int batch, int L, int K, int D, float* out);
+
+/* patchify + gather on the raw input, so PatchEmbed runs on visible patches only (the per-patch ops
+ * of vit.py:110-115 commute with the gather).  x (B,C,H,W) f32 -> out (B,K,C*p*p) f32.
+ * order 0: (c,ph,pw) = Conv2d(k=s=p) weight order (model/sub_module/vit_block.py:44-68);
+ * order 1: (ph,pw,c) = frame2emb order (utils/reshape.py:19).  ids_keep NULL = all patches in order. */
+#define EP_ORDER_CPQ 0
+#define EP_ORDER_PQC 1
+EP_API int ep_patchify_gather(void* stream, const float* x, const int64_t* ids_keep, int batch, int channels,
+                       int height, int width, int patch, int K, int order, float* out);
+
+/* ConvViT block masks   model/backbone/convvit.py:129-130,142-143 (+ the `1 - mask` of :133,146)
+ * mask (B,grid*grid) f32 -> out (B,1,grid*rep,grid*rep) f32, each cell repeated rep x rep;
+ * invert != 0 writes 1 - mask (what ConvBlock receives, model/sub_module/conv_block.py:41-44). */
+EP_API int ep_block_mask_expand(void* stream, const float* mask, int batch, int grid, int rep, int invert,
+                         float* out);
+
+/* Swin apply_mask   model/backbone/swin.py:154-179
+ * Uses mask row 0 only (batch-shared, :158).  mask_row (Mh*Mw) f32 (nonzero = removed);
+ * x (B,N,C) f32 with N = (Mh*r)*(Mw*r).  Writes vis_mask (N) u8, coords (n_vis,2) i64 (h,w),
+ * x_vis (B,n_vis,C) f32 in row-major token order, and *n_vis_out (device int).  n_vis is data
+ * dependent; the caller sizes x_vis/coords for n_vis_max = number of zeros in the mask row times r*r
+ * (known on the host from len_keep) and passes it.  C % 4 == 0. */
+EP_API int ep_swin_apply_mask(void* stream, const float* x, const float* mask_row, int batch, int Mh, int Mw,
+                       int rep, int C, int n_vis_max, float* x_vis, int64_t* coords, uint8_t* vis_mask,
+                       int* n_vis_out);
+
+/* decoder un-shuffle   model/pretrain/pr_rec_decoder.py:56-62
+ * out[b,l,:] = (ids_restore[b,l] < K ? emb[b, ids_restore[b,l], :] : mask_token[:]) + pos_embed[l,:]. */
+EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask_token, const float* pos_embed,
+                        const int64_t* ids_restore, int batch, int L, int K, int D, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVENTPRETRAIN_B200_H */
