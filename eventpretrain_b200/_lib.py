@@ -18,6 +18,9 @@ c_void_p, c_int, c_int64, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes
                                                          ctypes.c_size_t, ctypes.c_float, ctypes.c_double)
 
 
+P = ctypes.POINTER
+
+
 class EventsSoa(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("y", c_void_p), ("t", c_void_p), ("p", c_void_p),
                 ("xy_dtype", c_int), ("t_dtype", c_int), ("p_dtype", c_int), ("batch", c_int),
@@ -28,16 +31,22 @@ class EventsAos(ctypes.Structure):
     _fields_ = [("events", c_void_p), ("dtype", c_int), ("n", c_int64)]
 
 
+class ProfileStats(ctypes.Structure):
+    _fields_ = [("ms", c_double * 3), ("launches", c_int * 3)]
+
+
 class BinParams(ctypes.Structure):
     _fields_ = [("height", c_int), ("width", c_int), ("num_bins", c_int), ("count_channels", c_int),
                 ("scale_x", c_double), ("scale_y", c_double), ("time_f32", c_int), ("flags", c_int)]
 
 
-P = ctypes.POINTER
 # name -> (restype, argtypes); must list every symbol the header declares (tests check this)
 SIGNATURES = {
     "ep_abi_version": (c_int, []),
     "ep_status_string": (ctypes.c_char_p, [c_int]),
+    "ep_launch_count": (ctypes.c_ulonglong, []),
+    "ep_profile_enable": (c_int, [c_int]),
+    "ep_profile_read": (c_int, [P(ProfileStats)]),
     "ep_bin_events_workspace_bytes": (c_size_t, [P(BinParams), c_int, P(c_size_t)]),
     "ep_bin_events": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),

@@ -233,6 +233,12 @@ __global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------
+// publish "sample has p == 0 events" (selects the neg class of the count frame, events_to_image.py:13-16);
+// the flag is read through L2 so that one RED per sample, not per thread, is the steady state
+__device__ __forceinline__ void publish_zero_flag(const BinArgs& a, int b) {
+    if (!(__ldcg(&a.meta[b].flags) & kFlagZeroPol)) atomicOr(&a.meta[b].flags, kFlagZeroPol);
+}
+
 template <class Loader>
 __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
     typedef typename Loader::time_t_ TT;
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
         const int64_t i = i0 + j;
         if (i < a.begin || i >= a.end) continue;
         if (i >= b_end) {
+            if (zero_b >= 0) { publish_zero_flag(a, zero_b); zero_b = -1; }
             do { ++b; b_end = off_at(a, b + 1); } while (i >= b_end);
             t0 = (TT)a.meta[b].t0;
             dT = (TT)a.meta[b].dT;
@@ -295,9 +302,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
             }
         }
     }
-    // publish "sample has p == 0 events" (selects the neg class of the count frame); the flag is read
-    // through L2 so that one RED per sample, not per thread, is the steady state
-    if (zero_b >= 0 && !(__ldcg(&a.meta[zero_b].flags) & kFlagZeroPol)) atomicOr(&a.meta[zero_b].flags, kFlagZeroPol);
+    if (zero_b >= 0) publish_zero_flag(a, zero_b);
 }
 
 // ---- finalize: packed accumulators -> fp32 outputs, slots re-zeroed ---------------------------------
@@ -432,7 +437,9 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
     a.n_total = off_host ? off_host[B] : single_n;
     a.vox_acc = nullptr; a.cnt_acc = nullptr;
 
+    profile_begin(st, kProfOther);
     k_sample_meta<Loader><<<(B + 127) / 128, 128, 0, st>>>(ld, a, B);
+    profile_end(st);
     EP_LAUNCH_CHECK();
     cudaError_t ce = cudaMemsetAsync(slots, 0, (size_t)G * L.slot_bytes, st);
     if (ce != cudaSuccess) return (int)ce;
@@ -450,10 +457,13 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
             const int64_t nthreads = ceil_div64(a.end - a.start4, kEvPerThread);
             const int64_t nblocks = ceil_div64(nthreads, kThreads);
             if (nblocks > 0x7fffffffLL) return EP_EUNSUPPORTED;
+            profile_begin(st, kProfScatter);
             k_scatter<Loader><<<(unsigned)nblocks, kThreads, 0, st>>>(ld, a);
+            profile_end(st);
             EP_LAUNCH_CHECK();
         }
         if (p->num_bins > 0) {
+            profile_begin(st, kProfFinalize);
             if (HW % 2 == 0) {
                 dim3 grid((unsigned)ceil_div64(HW / 2, 256), (unsigned)(g1 - g0));
                 k_finalize_voxel<2><<<grid, 256, 0, st>>>(a, out_voxel, out_sum);
@@ -461,11 +471,14 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
                 dim3 grid((unsigned)ceil_div64(HW, 256), (unsigned)(g1 - g0));
                 k_finalize_voxel<1><<<grid, 256, 0, st>>>(a, out_voxel, out_sum);
             }
+            profile_end(st);
             EP_LAUNCH_CHECK();
         }
         if (p->count_channels > 0) {
             dim3 grid((unsigned)ceil_div64(HW, 256), (unsigned)(g1 - g0));
+            profile_begin(st, kProfFinalize);
             k_finalize_count<<<grid, 256, 0, st>>>(a, out_count);
+            profile_end(st);
             EP_LAUNCH_CHECK();
         }
     }

@@ -9,11 +9,22 @@ namespace ep {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// Every kernel launch of the library goes through EP_LAUNCH_CHECK(): it counts the launch (bench.py's
+// gpu_launches) and surfaces launch errors as the entry point's return value.
+extern unsigned long long g_launch_count;
+
 #define EP_LAUNCH_CHECK()                                   \
     do {                                                    \
         cudaError_t _e = cudaGetLastError();                \
         if (_e != cudaSuccess) return (int)_e;              \
+        __atomic_fetch_add(&ep::g_launch_count, 1ull, __ATOMIC_RELAXED); \
     } while (0)
+
+// Optional per-kernel timing (ep_profile_*): CUDA events recorded on the launching stream around a launch.
+enum ProfileKind { kProfScatter = 0, kProfFinalize = 1, kProfOther = 2, kProfKinds = 3 };
+bool profile_enabled();
+void profile_begin(cudaStream_t st, int kind);
+void profile_end(cudaStream_t st);
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -3,7 +3,44 @@
 
 #include "ep_common.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace ep {
+
+unsigned long long g_launch_count = 0;
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; int kind; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+bool g_prof_on = false;
+cudaEvent_t g_prof_open = nullptr;
+int g_prof_open_kind = 0;
+}  // namespace
+
+bool profile_enabled() { return g_prof_on; }
+
+void profile_begin(cudaStream_t st, int kind) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventCreate(&g_prof_open);
+    cudaEventRecord(g_prof_open, st);
+    g_prof_open_kind = kind;
+}
+
+void profile_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_open) return;
+    ProfRec r;
+    r.a = g_prof_open; r.kind = g_prof_open_kind;
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+    g_prof_open = nullptr;
+}
+
 namespace {
 
 constexpr int kStatBlocks = 64;   // partial-sum blocks per sample (fixed => deterministic reduction order)
@@ -116,6 +153,33 @@ __global__ void __launch_bounds__(256) k_diffmap(const float* __restrict__ f0, c
 extern "C" {
 
 int ep_abi_version(void) { return EP_ABI_VERSION; }
+
+unsigned long long ep_launch_count(void) { return __atomic_load_n(&ep::g_launch_count, __ATOMIC_RELAXED); }
+
+int ep_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(ep::g_prof_mu);
+    for (auto& r : ep::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ep::g_prof.clear();
+    ep::g_prof_on = on != 0;
+    return EP_OK;
+}
+
+int ep_profile_read(ep_profile_stats* out) {
+    if (!out) return EP_EINVAL;
+    std::lock_guard<std::mutex> lk(ep::g_prof_mu);
+    for (int k = 0; k < 3; ++k) { out->ms[k] = 0.0; out->launches[k] = 0; }
+    for (auto& r : ep::g_prof) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) return (int)e;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        out->ms[r.kind] += ms;
+        out->launches[r.kind] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    ep::g_prof.clear();
+    return EP_OK;
+}
 
 const char* ep_status_string(int status) {
     switch (status) {

@@ -54,6 +54,18 @@ enum ep_dtype {
 EP_API int ep_abi_version(void);
 EP_API const char* ep_status_string(int status);
 
+/* Instrumentation (bench.py): kernels launched by this library since load, and optional per-kernel
+ * device timing of the binning path (CUDA events recorded on the launching stream around each launch;
+ * kind 0 = scatter, 1 = finalize, 2 = other).  ep_profile_read synchronises on the recorded events,
+ * sums them and clears the log.  Profiling state is process-global and off by default. */
+typedef struct ep_profile_stats {
+    double ms[3];
+    int launches[3];
+} ep_profile_stats;
+EP_API unsigned long long ep_launch_count(void);
+EP_API int ep_profile_enable(int on);
+EP_API int ep_profile_read(ep_profile_stats* out);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 1 — raw events -> dense tensors
  * ------------------------------------------------------------------------------------------- */

@@ -45,31 +45,41 @@
         T deltaT = last - first;                                          /* :22 */             \
         if (deltaT == 0) deltaT = (T)1.0;                                 /* :24-25 */          \
         const T scale = (T)(num_bins - 1);                                                      \
-        for (int pass = 0; pass < 2; ++pass) {                                                  \
-            for (int64_t i = 0; i < n; ++i) {                                                   \
-                const T* e = ev + i * 4;                                                        \
-                const int64_t xs = (int64_t)e[0], ys = (int64_t)e[1];     /* :32-33 trunc */    \
-                const T ts = scale * (e[2] - first) / deltaT;             /* :34 */             \
-                float ps = (float)e[3];                                   /* :35 */             \
-                if (ps == 0.0f) ps = -1.0f;                               /* :36 */             \
-                const T tis = FLOOR(ts);                                  /* :38 */             \
-                const float dts = (float)(ts - tis);                      /* :40-42 .float() */ \
-                int64_t idx;                                                                    \
-                float val;                                                                      \
-                if (pass == 0) {                                                                \
-                    if (!(tis < (T)num_bins && tis >= 0)) continue;       /* :44-45 */          \
-                    val = ps * (1.0f - dts);                              /* :41 */             \
-                    idx = xs + ys * W + (int64_t)tis * plane;             /* :47-48 */          \
-                } else {                                                                        \
-                    if (!((tis + 1) < (T)num_bins && tis >= 0)) continue; /* :51-52 */          \
-                    val = ps * dts;                                       /* :42 */             \
-                    idx = xs + ys * W + ((int64_t)tis + 1) * plane;       /* :55-56 */          \
-                }                                                                               \
-                if (idx < 0 || idx >= total) return EP_ORACLE_EINDEX;     /* index_add_ raises */\
-                out[idx] += val;                                          /* fp32, in order */  \
-            }                                                                                   \
+        /* the reference materialises these per-event vectors too (:32-42) */                   \
+        int64_t* il = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);                            \
+        float* vl = (float*)malloc(sizeof(float) * (size_t)n);                                  \
+        float* vr = (float*)malloc(sizeof(float) * (size_t)n);                                  \
+        unsigned char* ok = (unsigned char*)malloc((size_t)n);                                  \
+        if (!il || !vl || !vr || !ok) { free(il); free(vl); free(vr); free(ok); return EP_ORACLE_EINVAL; } \
+        for (int64_t i = 0; i < n; ++i) {                                                       \
+            const T* e = ev + i * 4;                                                            \
+            const int64_t xs = (int64_t)e[0], ys = (int64_t)e[1];         /* :32-33 trunc */    \
+            const T ts = scale * (e[2] - first) / deltaT;                 /* :34 */             \
+            float ps = (float)e[3];                                       /* :35 */             \
+            if (ps == 0.0f) ps = -1.0f;                                   /* :36 */             \
+            const T tis = FLOOR(ts);                                      /* :38 */             \
+            const float dts = (float)(ts - tis);                          /* :40-42 .float() */ \
+            vl[i] = ps * (1.0f - dts);                                    /* :41 */             \
+            vr[i] = ps * dts;                                             /* :42 */             \
+            const int in_left = (tis < (T)num_bins) && (tis >= 0);        /* :44-45 */          \
+            const int in_right = ((tis + 1) < (T)num_bins) && (tis >= 0); /* :51-52 */          \
+            ok[i] = (unsigned char)(in_left | (in_right << 1));                                 \
+            il[i] = in_left ? xs + ys * W + (int64_t)tis * plane : 0;     /* :47-48 */          \
         }                                                                                       \
-        return 0;                                                                               \
+        int rc = 0;                                                                             \
+        for (int64_t i = 0; i < n && rc == 0; ++i) {      /* first index_add_, event order */   \
+            if (!(ok[i] & 1)) continue;                                                         \
+            if (il[i] < 0 || il[i] >= total) rc = EP_ORACLE_EINDEX;       /* index_add_ raises */\
+            else out[il[i]] += vl[i];                                     /* fp32, in order */  \
+        }                                                                                       \
+        for (int64_t i = 0; i < n && rc == 0; ++i) {      /* second index_add_ */               \
+            if (!(ok[i] & 2)) continue;                                                         \
+            const int64_t idx = il[i] + plane;                            /* :55-56 */          \
+            if (idx < 0 || idx >= total) rc = EP_ORACLE_EINDEX;                                 \
+            else out[idx] += vr[i];                                                             \
+        }                                                                                       \
+        free(il); free(vl); free(vr); free(ok);                                                 \
+        return rc;                                                                              \
     }
 
 VOXEL_IMPL(oracle_voxel_grid_f64, double, floor)

@@ -84,6 +84,8 @@ def test_patchify_gather_commutes_with_patch_embed(ep):
     """Gathering raw patches in Conv2d operand order then applying the conv weight as a matmul equals
     PatchEmbed's conv on the full image followed by the token gather (vit.py:110-115)."""
     torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     x = torch.randn(3, 5, 224, 224, device="cuda")
     conv = torch.nn.Conv2d(5, 32, 16, 16).cuda()
     ik, _, _ = ep.mask_from_noise(torch.rand(3, 196, device="cuda"), 49)
@@ -93,7 +95,7 @@ def test_patchify_gather_commutes_with_patch_embed(ep):
         full = conv(x).flatten(2).permute(0, 2, 1)
         ref = torch.gather(full, 1, ik[..., None].repeat(1, 1, 32))
         got = patches @ conv.weight.reshape(32, -1).T + conv.bias
-    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4)
+    assert torch.allclose(got, ref, atol=1e-3, rtol=1e-3)
     unf = torch.nn.functional.unfold(x, 16, stride=16).permute(0, 2, 1)      # (B, L, C*p*p) in (c,ph,pw) order
     assert torch.equal(patches, torch.gather(unf, 1, ik[..., None].repeat(1, 1, unf.shape[-1])))
 
