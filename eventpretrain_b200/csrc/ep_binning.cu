@@ -306,6 +306,11 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
 }
 
 // ---- finalize: packed accumulators -> fp32 outputs, slots re-zeroed ---------------------------------
+// Bins are processed in register-resident chunks of kFinChunk planes so that all accumulator loads of a
+// chunk are in flight together (the first version issued one dependent L2 round trip per bin and was
+// latency-bound: profiles/r01_binning_v1_ncu.txt).
+constexpr int kFinChunk = 8;
+
 template <int VEC>
 __global__ void __launch_bounds__(256) k_finalize_voxel(BinArgs a, float* __restrict__ out_voxel,
                                                         float* __restrict__ out_sum) {
@@ -318,40 +323,52 @@ __global__ void __launch_bounds__(256) k_finalize_voxel(BinArgs a, float* __rest
     const int64_t pix = idx * VEC;
     const bool last_used = (a.meta[b].flags & kFlagLastPlane) != 0;
     const int B = a.num_bins;
+    const int n_planes = last_used ? B : B - 1;        // plane B-1 is untouched unless flagged
     long long a_prev[VEC];
     float sum[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { a_prev[v] = 0; sum[v] = 0.f; }
     unsigned long long* acc = a.vox_acc + (int64_t)slot * B * HW + pix;
     float* o = out_voxel + (int64_t)b * B * HW + pix;
-    for (int k = 0; k < B; ++k) {
-        unsigned long long w[VEC];
-        if (k < B - 1 || last_used) {
-            if (VEC == 2) {
-                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(acc + (int64_t)k * HW);
-                w[0] = q.x; w[VEC - 1] = q.y;
-                *reinterpret_cast<ulonglong2*>(acc + (int64_t)k * HW) = make_ulonglong2(0ull, 0ull);
+    for (int k0 = 0; k0 < B; k0 += kFinChunk) {
+        unsigned long long w[kFinChunk][VEC];
+#pragma unroll
+        for (int j = 0; j < kFinChunk; ++j) {
+            const int k = k0 + j;
+            if (k < n_planes) {
+                if (VEC == 2) {
+                    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(acc + (int64_t)k * HW);
+                    w[j][0] = q.x; w[j][VEC - 1] = q.y;
+                } else {
+                    w[j][0] = acc[(int64_t)k * HW];
+                }
             } else {
-                w[0] = acc[(int64_t)k * HW];
-                acc[(int64_t)k * HW] = 0ull;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) w[j][v] = 0ull;
             }
-        } else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) w[v] = 0ull;
         }
-        float r[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const long long A = ((long long)(w[v] << (64 - kABits))) >> (64 - kABits);
-            const long long C = ((long long)(w[v] - (unsigned long long)A)) >> kABits;
-            if ((C >= (1ll << 18) || C < -(1ll << 18)) && a.bad_count) atomicOr(a.bad_count, 0x80000000u);
-            const long long val = C * (1ll << kQ) - A + a_prev[v];
-            a_prev[v] = A;
-            r[v] = __ll2float_rn(val) * (1.0f / 16777216.0f);
-            sum[v] += r[v];    // voxel.sum(dim=0): sequential fp32 over bins
+        for (int j = 0; j < kFinChunk; ++j) {
+            const int k = k0 + j;
+            if (k >= B) break;
+            if (k < n_planes) {
+                if (VEC == 2) *reinterpret_cast<ulonglong2*>(acc + (int64_t)k * HW) = make_ulonglong2(0ull, 0ull);
+                else acc[(int64_t)k * HW] = 0ull;
+            }
+            float r[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const long long A = ((long long)(w[j][v] << (64 - kABits))) >> (64 - kABits);
+                const long long C = ((long long)(w[j][v] - (unsigned long long)A)) >> kABits;
+                if ((C >= (1ll << 18) || C < -(1ll << 18)) && a.bad_count) atomicOr(a.bad_count, 0x80000000u);
+                const long long val = C * (1ll << kQ) - A + a_prev[v];
+                a_prev[v] = A;
+                r[v] = __ll2float_rn(val) * (1.0f / 16777216.0f);
+                sum[v] += r[v];    // voxel.sum(dim=0): sequential fp32 over bins
+            }
+            if (VEC == 2) st_stream(reinterpret_cast<float2*>(o + (int64_t)k * HW), make_float2(r[0], r[VEC - 1]));
+            else st_stream(o + (int64_t)k * HW, r[0]);
         }
-        if (VEC == 2) st_stream(reinterpret_cast<float2*>(o + (int64_t)k * HW), make_float2(r[0], r[VEC - 1]));
-        else st_stream(o + (int64_t)k * HW, r[0]);
     }
     if (out_sum) {
         float* s = out_sum + (int64_t)b * HW + pix;
