@@ -215,7 +215,7 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
 
     def step():
-        ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out)
+        ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method)
         if world > 1:
             # the path's only collective: a small all-reduce of batch statistics (events binned, samples), issued
             # on a side stream so it never gates the binning kernels
@@ -279,9 +279,10 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_per_step(), "peak_source": peak_src,
                 "frac_of_8TBs_spec": achieved / 8000.0,
-                "kernels": {"k_scatter_ms_per_step": scatter_ms, "k_finalize_voxel_ms_per_step": finalize_ms,
-                            "scatter_launches_per_step": prof.launches[0] // args.steps,
-                            "scatter_Gevents_per_s": n_events / (scatter_ms * 1e-3) / 1e9},
+                "kernels": {"pass1_ms_per_step (k_route | k_scatter)": scatter_ms,
+                            "pass2_ms_per_step (k_sweep | k_finalize_voxel)": finalize_ms,
+                            "pass1_launches_per_step": prof.launches[0] // args.steps,
+                            "pass1_Gevents_per_s": n_events / (scatter_ms * 1e-3) / 1e9},
                 "algorithmic_bytes_per_step": alg}
 
     # ---- skewed distribution (contention evidence): same sizes, 70 % of events on 64 segments + hot pixels -----
@@ -313,7 +314,7 @@ def run_ours(args):
 
     def e2e_step():
         d = host.to(dev, non_blocking=True)
-        o = ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=out)
+        o = ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method)
         return o["voxel_sum"].sum(dim=(1, 2, 3)).cpu()       # (B,) fp32: sum of polarities per sample
 
     for _ in range(2):
@@ -360,7 +361,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": "SoA x,y u16 | t i64 us | p u8 (13 B/event)",
                            "cache": "inputs (3.3 GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
-                           "parallelism": f"shard-by-sample x{world}, no data-path collective"},
+                           "parallelism": f"shard-by-sample x{world}, no data-path collective", "method": args.method},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -374,6 +375,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="auto", choices=["auto", "global", "banded"], help="binning kernel family")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libeventpretrain_b200.so")
 EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64 = range(1, 9)
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
+EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_BANDED = 1, 2
 
 c_void_p, c_int, c_int64, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                          ctypes.c_size_t, ctypes.c_float, ctypes.c_double)
@@ -48,6 +49,7 @@ SIGNATURES = {
     "ep_profile_enable": (c_int, [c_int]),
     "ep_profile_read": (c_int, [P(ProfileStats)]),
     "ep_bin_events_workspace_bytes": (c_size_t, [P(BinParams), c_int, P(c_size_t)]),
+    "ep_bin_events_workspace_bytes_for": (c_size_t, [P(EventsSoa), P(BinParams)]),
     "ep_bin_events": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "ep_bin_events_aos": (c_int, [c_void_p, P(EventsAos), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,

@@ -24,213 +24,16 @@
 //     temporal interval of ONE sample.  The finalize kernel reports cells with |C| >= 2^18 through
 //     bad_count (bit 31), which is a sound detector for samples of fewer than 786432 events; see
 //     DESIGN.md "limits" for larger samples.
-#include <math.h>
-#include <stdlib.h>
-
-#include "ep_common.cuh"
+#include "ep_binning_common.cuh"
 
 namespace ep {
+
+// banded shared-memory sweep (ep_binning_banded.cu); returns EP_EUNSUPPORTED when the shape does not qualify
+int run_banded_canon(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                     float* out_count, void* ws, size_t ws_bytes, unsigned int* bad);
+size_t banded_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
+
 namespace {
-
-constexpr int kQ = 24;                       // fractional bits of the temporal weight
-constexpr int kABits = 44;                   // low field of the packed accumulator
-constexpr int kThreads = 256;
-constexpr int kEvPerThread = 4;
-constexpr uint32_t kFlagLastPlane = 1u;      // an event landed in interval num_bins-1 with d > 0
-constexpr uint32_t kFlagZeroPol = 2u;        // the sample has p == 0 events (count-frame neg class)
-
-struct __align__(16) SampleMeta {
-    double t0;        // first row's timestamp (events_to_voxel_grid.py:19)
-    double dT;        // last - first, 1.0 when zero (:22-25)
-    uint32_t flags;
-    uint32_t pad[3];
-};
-
-struct BinArgs {
-    const int64_t* offsets;   // device B+1, or nullptr for the single-sample AoS entry
-    int64_t single_n;
-    int64_t begin, end;       // event range of this group
-    int64_t n_total;          // events allocated in the arrays (vector loads stay below it)
-    int64_t start4;           // begin rounded down to a multiple of kEvPerThread
-    int g0, g1;               // samples [g0, g1) of this group
-    int H, W, num_bins, count_channels;
-    double sx, sy;
-    int scaled;
-    SampleMeta* meta;
-    unsigned long long* vox_acc;   // [slot][num_bins][HW]
-    uint32_t* cnt_acc;             // [slot][3][HW]  classes: p==1, p==0, p==-1
-    unsigned int* bad_count;
-};
-
-__device__ __forceinline__ int64_t off_at(const BinArgs& a, int b) {
-    return a.offsets ? a.offsets[b] : (b == 0 ? 0 : a.single_n);
-}
-
-// polarity classes: 0 -> p == 1, 1 -> p == 0, 2 -> p == -1, 3 -> anything else (unsupported)
-__device__ __forceinline__ int pol_class_i(int p) { return p == 1 ? 0 : (p == 0 ? 1 : (p == -1 ? 2 : 3)); }
-__device__ __forceinline__ int pol_class_d(double p) { return p == 1.0 ? 0 : (p == 0.0 ? 1 : (p == -1.0 ? 2 : 3)); }
-
-// ---- loaders: produce (xi, yi, t, class) for kEvPerThread consecutive events --------------------
-template <typename TT>
-struct Ev {
-    int64_t x[kEvPerThread], y[kEvPerThread];
-    TT t[kEvPerThread];
-    int cls[kEvPerThread];
-};
-
-// canonical SoA: x,y u16; t i64 or f64; p u8.  i0 is a multiple of 4 and bases are 16B aligned.
-template <bool T_IS_I64>
-struct SoaCanonLoader {
-    const uint16_t* x;
-    const uint16_t* y;
-    const void* t;
-    const uint8_t* p;
-    double t_div;
-    typedef double time_t_;
-    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
-        (void)hi;
-        uint2 xv, yv;
-        uint32_t pv;
-        double tv[4];
-        if (i0 + 4 <= a.n_total) {
-            xv = ld_stream(reinterpret_cast<const uint2*>(x + i0));
-            yv = ld_stream(reinterpret_cast<const uint2*>(y + i0));
-            pv = ld_stream(reinterpret_cast<const uint32_t*>(p + i0));
-            if (T_IS_I64) {
-                const longlong2 a0 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(t) + i0));
-                const longlong2 a1 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(t) + i0 + 2));
-                tv[0] = (double)a0.x; tv[1] = (double)a0.y; tv[2] = (double)a1.x; tv[3] = (double)a1.y;
-            } else {
-                const double2 a0 = ld_stream(reinterpret_cast<const double2*>(static_cast<const double*>(t) + i0));
-                const double2 a1 = ld_stream(reinterpret_cast<const double2*>(static_cast<const double*>(t) + i0 + 2));
-                tv[0] = a0.x; tv[1] = a0.y; tv[2] = a1.x; tv[3] = a1.y;
-            }
-        } else {   // last, partial quad of the arrays: scalar loads, nothing read past the end
-            uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0};
-            pv = 0;
-            for (int j = 0; j < 4; ++j) {
-                tv[j] = 0.0;
-                if (i0 + j < a.n_total) {
-                    xs_[j] = x[i0 + j]; ys_[j] = y[i0 + j];
-                    pv |= (uint32_t)p[i0 + j] << (8 * j);
-                    tv[j] = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i0 + j] : static_cast<const double*>(t)[i0 + j];
-                }
-            }
-            xv = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
-            yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
-        }
-        const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
-        const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (a.scaled) {
-                e.x[j] = __double2ll_rz(__dmul_rn((double)xs[j], a.sx));
-                e.y[j] = __double2ll_rz(__dmul_rn((double)ys[j], a.sy));
-            } else {
-                e.x[j] = xs[j];
-                e.y[j] = ys[j];
-            }
-            e.t[j] = (t_div != 1.0) ? tv[j] / t_div : tv[j];
-            e.cls[j] = pol_class_i((int)((pv >> (8 * j)) & 0xffu));
-        }
-    }
-    __device__ __forceinline__ double time_at(int64_t i) const {
-        double v = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
-        return (t_div != 1.0) ? v / t_div : v;
-    }
-};
-
-// any tagged SoA layout, scalar loads.  TT = float reproduces torch's fp32 time arithmetic.
-template <typename TT>
-struct SoaGenericLoader {
-    const void* x;
-    const void* y;
-    const void* t;
-    const void* p;
-    int xy_dtype, t_dtype, p_dtype;
-    double t_div;
-    typedef TT time_t_;
-    __device__ __forceinline__ TT time_at(int64_t i) const {
-        if (sizeof(TT) == 4) {
-            float v = (t_dtype == EP_F32) ? static_cast<const float*>(t)[i] : (float)load_as_double(t, t_dtype, i);
-            return (TT)((t_div != 1.0) ? v / (float)t_div : v);
-        }
-        double v = load_as_double(t, t_dtype, i);
-        return (TT)((t_div != 1.0) ? v / t_div : v);
-    }
-    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<TT>& e) const {
-#pragma unroll
-        for (int j = 0; j < kEvPerThread; ++j) {
-            const int64_t i = i0 + j;
-            if (i >= hi || i < a.begin) { e.cls[j] = 3; e.x[j] = 0; e.y[j] = 0; e.t[j] = 0; continue; }
-            double xd = load_as_double(x, xy_dtype, i), yd = load_as_double(y, xy_dtype, i);
-            if (a.scaled) {
-                if (xy_dtype == EP_F32) {   // numpy keeps fp32 arrays in fp32 under `*= python_float`
-                    xd = (double)__fmul_rn((float)xd, (float)a.sx);
-                    yd = (double)__fmul_rn((float)yd, (float)a.sy);
-                } else {
-                    xd = __dmul_rn(xd, a.sx);
-                    yd = __dmul_rn(yd, a.sy);
-                }
-            }
-            e.x[j] = __double2ll_rz(xd);
-            e.y[j] = __double2ll_rz(yd);
-            e.t[j] = time_at(i);
-            e.cls[j] = pol_class_d(load_as_double(p, p_dtype, i));
-        }
-    }
-};
-
-// the reference's own (N,4) x,y,t,p rows
-template <typename ET>   // ET = double | float (element type AND time arithmetic type)
-struct AosLoader {
-    const ET* ev;
-    typedef ET time_t_;
-    __device__ __forceinline__ ET time_at(int64_t i) const { return ev[i * 4 + 2]; }
-    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const {
-#pragma unroll
-        for (int j = 0; j < kEvPerThread; ++j) {
-            const int64_t i = i0 + j;
-            if (i >= hi || i < a.begin) { e.cls[j] = 3; e.x[j] = 0; e.y[j] = 0; e.t[j] = 0; continue; }
-            ET xv, yv, tv, pv;
-            if (sizeof(ET) == 8) {
-                const double2 q0 = ld_stream(reinterpret_cast<const double2*>(ev + i * 4));
-                const double2 q1 = ld_stream(reinterpret_cast<const double2*>(ev + i * 4 + 2));
-                xv = (ET)q0.x; yv = (ET)q0.y; tv = (ET)q1.x; pv = (ET)q1.y;
-            } else {
-                const float4 q = ld_stream(reinterpret_cast<const float4*>(ev + i * 4));
-                xv = (ET)q.x; yv = (ET)q.y; tv = (ET)q.z; pv = (ET)q.w;
-            }
-            if (a.scaled) {
-                if (sizeof(ET) == 8) { xv = (ET)__dmul_rn((double)xv, a.sx); yv = (ET)__dmul_rn((double)yv, a.sy); }
-                else { xv = (ET)__fmul_rn((float)xv, (float)a.sx); yv = (ET)__fmul_rn((float)yv, (float)a.sy); }
-            }
-            e.x[j] = (sizeof(ET) == 8) ? __double2ll_rz((double)xv) : __float2ll_rz((float)xv);
-            e.y[j] = (sizeof(ET) == 8) ? __double2ll_rz((double)yv) : __float2ll_rz((float)yv);
-            e.t[j] = tv;
-            e.cls[j] = pol_class_d((double)pv);
-        }
-    }
-};
-
-// ---- per-sample metadata: first/last timestamps ---------------------------------------------------
-template <class Loader>
-__global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    typedef typename Loader::time_t_ TT;
-    const int64_t lo = off_at(a, b), hi = off_at(a, b + 1);
-    SampleMeta m;
-    m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.pad[0] = m.pad[1] = m.pad[2] = 0;
-    if (hi > lo) {
-        const TT first = ld.time_at(lo), last = ld.time_at(hi - 1);
-        TT d = last - first;
-        if (d == (TT)0) d = (TT)1;
-        m.t0 = (double)first;
-        m.dT = (double)d;
-    }
-    a.meta[b] = m;
-}
 
 // ---- scatter ----------------------------------------------------------------------------------------
 // publish "sample has p == 0 events" (selects the neg class of the count frame, events_to_image.py:13-16);
@@ -240,10 +43,12 @@ __device__ __forceinline__ void publish_zero_flag(const BinArgs& a, int b) {
 }
 
 template <class Loader>
-__global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
+__device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a, int64_t first_tile, int64_t tile_stride) {
     typedef typename Loader::time_t_ TT;
-    const int64_t i0 = a.start4 + ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kEvPerThread;
-    if (i0 >= a.end) return;
+  // persistent stride loop over 1024-event tiles
+  for (int64_t tile = first_tile; tile < a.n_tiles; tile += tile_stride) {
+    const int64_t i0 = a.start4 + (tile * kThreads + threadIdx.x) * kEvPerThread;
+    if (i0 >= a.end) continue;
 
     // sample that owns the first in-range event of this thread: last b with off[b] <= i
     const int64_t ifirst = i0 < a.begin ? a.begin : i0;
@@ -259,8 +64,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
     ld.load(i0, a.end, a, e);
 
     const int64_t HW = (int64_t)a.H * a.W;
-    const TT nbm1 = (TT)(a.num_bins - 1);
-    TT t0 = (TT)a.meta[b].t0, dT = (TT)a.meta[b].dT;
+    SampleMeta m = a.meta[b];
     int zero_b = -1;
 
 #pragma unroll
@@ -270,8 +74,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
         if (i >= b_end) {
             if (zero_b >= 0) { publish_zero_flag(a, zero_b); zero_b = -1; }
             do { ++b; b_end = off_at(a, b + 1); } while (i >= b_end);
-            t0 = (TT)a.meta[b].t0;
-            dT = (TT)a.meta[b].dT;
+            m = a.meta[b];
         }
         const int cls = e.cls[j];
         const int64_t flat = e.x[j] + e.y[j] * (int64_t)a.W;
@@ -285,17 +88,10 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
             if (cls == 1) zero_b = b;
         }
         if (a.num_bins) {
-            // events_to_voxel_grid.py:34-42 in the events' own dtype
-            const TT ts = nbm1 * (e.t[j] - t0) / dT;
-            const TT tis = floor(ts);
-            if (tis >= (TT)0 && tis < (TT)a.num_bins) {
-                int k = (int)tis;
-                const float d = (float)(ts - tis);
-                int r = __float2int_rn(d * 16777216.0f);
-                if (k == a.num_bins - 1) {
-                    if (r == 0 && a.num_bins >= 2) { k -= 1; r = 1 << kQ; }   // weight 1 on the last node
-                    else if (!(__ldcg(&a.meta[b].flags) & kFlagLastPlane)) atomicOr(&a.meta[b].flags, kFlagLastPlane);
-                }
+            int k, r;
+            bool last_plane;
+            if (voxel_weights<Loader, TT>(e, j, m, a.num_bins, k, r, last_plane)) {
+                if (last_plane && !(__ldcg(&a.meta[b].flags) & kFlagLastPlane)) atomicOr(&a.meta[b].flags, kFlagLastPlane);
                 const long long sgn = (cls == 0) ? 1 : -1;
                 const long long delta = sgn * ((1ll << kABits) + (long long)r);
                 atomicAdd(a.vox_acc + ((int64_t)slot * a.num_bins + k) * HW + flat, (unsigned long long)delta);
@@ -303,6 +99,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
         }
     }
     if (zero_b >= 0) publish_zero_flag(a, zero_b);
+  }
 }
 
 // ---- finalize: packed accumulators -> fp32 outputs, slots re-zeroed ---------------------------------
@@ -312,12 +109,11 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
 constexpr int kFinChunk = 8;
 
 template <int VEC>
-__global__ void __launch_bounds__(256) k_finalize_voxel(BinArgs a, float* __restrict__ out_voxel,
-                                                        float* __restrict__ out_sum) {
+__device__ __forceinline__ void finalize_voxel_block(const BinArgs& a, float* __restrict__ out_voxel,
+                                                     float* __restrict__ out_sum, int slot, int64_t blk) {
     const int64_t HW = (int64_t)a.H * a.W;
     const int64_t per = HW / VEC;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = blockIdx.y;
+    const int64_t idx = blk * kThreads + threadIdx.x;
     if (idx >= per) return;
     const int b = a.g0 + slot;
     const int64_t pix = idx * VEC;
@@ -377,10 +173,10 @@ __global__ void __launch_bounds__(256) k_finalize_voxel(BinArgs a, float* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) k_finalize_count(BinArgs a, float* __restrict__ out_count) {
+__device__ __forceinline__ void finalize_count_block(const BinArgs& a, float* __restrict__ out_count, int slot,
+                                                     int64_t blk) {
     const int64_t HW = (int64_t)a.H * a.W;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = blockIdx.y;
+    const int64_t pix = blk * kThreads + threadIdx.x;
     if (pix >= HW) return;
     const int b = a.g0 + slot;
     uint32_t* c = a.cnt_acc + (int64_t)slot * 3 * HW + pix;
@@ -392,6 +188,25 @@ __global__ void __launch_bounds__(256) k_finalize_count(BinArgs a, float* __rest
     st_stream(o, (float)pos);
     if (a.count_channels == 3) { st_stream(o + HW, 0.0f); st_stream(o + 2 * HW, (float)n); }
     else st_stream(o + HW, (float)n);
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------
+// (An experiment that ran the finalize of group g-1 as interleaved CTAs of the scatter launch of group g, with
+// ping-pong accumulator slots, did not help: 3.12 ms vs 3.05 ms per step — both halves are limited by the same L2,
+// see DESIGN.md §3.  The two stay separate launches.)
+template <class Loader>
+__global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
+    scatter_tiles<Loader>(ld, a, blockIdx.x, gridDim.x);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) k_finalize_voxel(BinArgs a, float* __restrict__ out_voxel,
+                                                             float* __restrict__ out_sum) {
+    finalize_voxel_block<VEC>(a, out_voxel, out_sum, blockIdx.y, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kThreads) k_finalize_count(BinArgs a, float* __restrict__ out_count) {
+    finalize_count_block(a, out_count, blockIdx.y, blockIdx.x);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -410,12 +225,17 @@ SlotLayout slot_layout(const ep_bin_params* p, int B) {
 }
 
 size_t l2_group_budget() {
-    // accumulator bytes kept in flight per group; RED throughput on B200 is flat up to ~40 MB of
-    // target footprint and degrades beyond (profiles/r01_scatter_microbench.txt)
+    // accumulator bytes kept in flight per group: 64 MB measured best on B200 (40 -> 78, 64 -> 84, 96 -> 71 Gev/s)
     const char* e = getenv("EP_L2_GROUP_MB");
-    long mb = e ? atol(e) : 40;
+    long mb = e ? atol(e) : 64;
     if (mb < 1) mb = 1;
     return (size_t)mb << 20;
+}
+
+int scatter_ctas_per_sm() {
+    const char* e = getenv("EP_SCATTER_CTAS_PER_SM");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : v;
 }
 
 int check_params(const ep_bin_params* p) {
@@ -450,7 +270,7 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
     a.meta = reinterpret_cast<SampleMeta*>(ws);
     char* slots = static_cast<char*>(ws) + L.meta_bytes;
     a.bad_count = bad;
-    a.begin = a.end = a.start4 = 0; a.g0 = a.g1 = 0;
+    a.begin = a.end = a.start4 = 0; a.g0 = a.g1 = 0; a.n_tiles = 0;
     a.n_total = off_host ? off_host[B] : single_n;
     a.vox_acc = nullptr; a.cnt_acc = nullptr;
 
@@ -471,30 +291,30 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
         a.vox_acc = reinterpret_cast<unsigned long long*>(slots);
         a.cnt_acc = reinterpret_cast<uint32_t*>(slots + (size_t)G * L.vox_bytes);
         if (a.end > a.begin) {
-            const int64_t nthreads = ceil_div64(a.end - a.start4, kEvPerThread);
-            const int64_t nblocks = ceil_div64(nthreads, kThreads);
-            if (nblocks > 0x7fffffffLL) return EP_EUNSUPPORTED;
+            a.n_tiles = ceil_div64(ceil_div64(a.end - a.start4, kEvPerThread), kThreads);
+            const int64_t max_grid = (int64_t)kNumSMs * scatter_ctas_per_sm();
+            const unsigned grid = (unsigned)(a.n_tiles < max_grid ? a.n_tiles : max_grid);
             profile_begin(st, kProfScatter);
-            k_scatter<Loader><<<(unsigned)nblocks, kThreads, 0, st>>>(ld, a);
+            k_scatter<Loader><<<grid, kThreads, 0, st>>>(ld, a);
             profile_end(st);
             EP_LAUNCH_CHECK();
         }
         if (p->num_bins > 0) {
             profile_begin(st, kProfFinalize);
             if (HW % 2 == 0) {
-                dim3 grid((unsigned)ceil_div64(HW / 2, 256), (unsigned)(g1 - g0));
-                k_finalize_voxel<2><<<grid, 256, 0, st>>>(a, out_voxel, out_sum);
+                dim3 grid((unsigned)ceil_div64(HW / 2, kThreads), (unsigned)(g1 - g0));
+                k_finalize_voxel<2><<<grid, kThreads, 0, st>>>(a, out_voxel, out_sum);
             } else {
-                dim3 grid((unsigned)ceil_div64(HW, 256), (unsigned)(g1 - g0));
-                k_finalize_voxel<1><<<grid, 256, 0, st>>>(a, out_voxel, out_sum);
+                dim3 grid((unsigned)ceil_div64(HW, kThreads), (unsigned)(g1 - g0));
+                k_finalize_voxel<1><<<grid, kThreads, 0, st>>>(a, out_voxel, out_sum);
             }
             profile_end(st);
             EP_LAUNCH_CHECK();
         }
         if (p->count_channels > 0) {
-            dim3 grid((unsigned)ceil_div64(HW, 256), (unsigned)(g1 - g0));
+            dim3 grid((unsigned)ceil_div64(HW, kThreads), (unsigned)(g1 - g0));
             profile_begin(st, kProfFinalize);
-            k_finalize_count<<<grid, 256, 0, st>>>(a, out_count);
+            k_finalize_count<<<grid, kThreads, 0, st>>>(a, out_count);
             profile_end(st);
             EP_LAUNCH_CHECK();
         }
@@ -517,6 +337,16 @@ size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch, size_t
     return L.meta_bytes + g * L.slot_bytes;
 }
 
+size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_params* prm) {
+    if (!ev || ep::check_params(prm) != EP_OK || ev->batch <= 0) return 0;
+    size_t need = ep_bin_events_workspace_bytes(prm, ev->batch, nullptr);
+    if (!(prm->flags & EP_BIN_FORCE_GLOBAL) && ev->offsets_host) {
+        const size_t b = ep::banded_workspace_bytes(ev, prm);
+        if (b > need) need = b;
+    }
+    return need;
+}
+
 int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* prm, float* out_voxel,
                   float* out_voxel_sum, float* out_count, void* workspace, size_t workspace_bytes,
                   unsigned int* bad_count) {
@@ -533,6 +363,21 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     const bool canon = ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && !prm->time_f32 &&
                        (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64) && aligned16(ev->x) && aligned16(ev->y) &&
                        aligned16(ev->t) && aligned16(ev->p);
+    if (canon && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
+        // fast path: banded shared-memory sweep.  Falls through to the global-RED path when the shape does not
+        // qualify, the batch is too small to fill the machine, or the caller's workspace is too small for it.
+        const int64_t HWc = (int64_t)prm->height * prm->width;
+        // round 1: the banded sweep is correct but still slower than the global-RED path on B200 (3.8 vs 3.05 ms per
+        // step on the benchmark workload), so it is used only on request
+        const bool worth = (prm->flags & EP_BIN_FORCE_BANDED) != 0;
+        (void)HWc;
+        if (worth) {
+            rc = run_banded_canon(st, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count);
+            if (rc == EP_OK || (rc != EP_EUNSUPPORTED && rc != EP_EWORKSPACE) || (prm->flags & EP_BIN_FORCE_BANDED)) return rc;
+        }
+    } else if (prm->flags & EP_BIN_FORCE_BANDED) {
+        return EP_EUNSUPPORTED;
+    }
     if (canon) {
         if (ev->t_dtype == EP_I64) {
             SoaCanonLoader<true> ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y), ev->t,

@@ -1,0 +1,272 @@
+// Shared pieces of the binning kernels (v1 global-RED path and the banded shared-memory sweep):
+// constants, per-sample metadata, argument block, event loaders.
+#pragma once
+#include <math.h>
+#include <stdlib.h>
+
+#include "ep_common.cuh"
+
+namespace ep {
+namespace {
+
+constexpr int kQ = 24;                       // fractional bits of the temporal weight
+constexpr int kABits = 44;                   // low field of the packed accumulator
+constexpr int kThreads = 256;
+constexpr int kEvPerThread = 4;
+constexpr uint32_t kFlagLastPlane = 1u;      // an event landed in interval num_bins-1 with d > 0
+constexpr uint32_t kFlagZeroPol = 2u;        // the sample has p == 0 events (count-frame neg class)
+
+struct __align__(16) SampleMeta {
+    double t0;        // first row's timestamp (events_to_voxel_grid.py:19)
+    double dT;        // last - first, 1.0 when zero (:22-25)
+    double scale_raw; // (num_bins-1) / (dT * t_div): ts = (t_raw - t0_raw) * scale_raw on the canonical fast path
+    double t0_raw;    // first row's raw stamp (before t_div) when the stamps are fp64
+    int64_t t0_ticks; // first row's raw stamp when the stamps are int64 ticks
+    uint32_t flags;
+    uint32_t pad;
+};
+
+struct BinArgs {
+    const int64_t* offsets;   // device B+1, or nullptr for the single-sample AoS entry
+    int64_t single_n;
+    int64_t begin, end;       // event range of this group
+    int64_t n_total;          // events allocated in the arrays (vector loads stay below it)
+    int64_t start4;           // begin rounded down to a multiple of kEvPerThread
+    int64_t n_tiles;          // 1024-event tiles of the group (k_scatter grid-stride loop)
+    int g0, g1;               // samples [g0, g1) of this group
+    int H, W, num_bins, count_channels;
+    double sx, sy;
+    int scaled;
+    SampleMeta* meta;
+    unsigned long long* vox_acc;   // [slot][num_bins][HW]
+    uint32_t* cnt_acc;             // [slot][3][HW]  classes: p==1, p==0, p==-1
+    unsigned int* bad_count;
+};
+
+__device__ __forceinline__ int64_t off_at(const BinArgs& a, int b) {
+    return a.offsets ? a.offsets[b] : (b == 0 ? 0 : a.single_n);
+}
+
+// polarity classes: 0 -> p == 1, 1 -> p == 0, 2 -> p == -1, 3 -> anything else (unsupported)
+__device__ __forceinline__ int pol_class_i(int p) { return p == 1 ? 0 : (p == 0 ? 1 : (p == -1 ? 2 : 3)); }
+__device__ __forceinline__ int pol_class_d(double p) { return p == 1.0 ? 0 : (p == 0.0 ? 1 : (p == -1.0 ? 2 : 3)); }
+
+// ---- loaders: produce (xi, yi, t, class) for kEvPerThread consecutive events --------------------
+template <typename TT>
+struct Ev {
+    int64_t x[kEvPerThread], y[kEvPerThread];
+    TT t[kEvPerThread];           // timestamp value (raw stamp for the canonical loaders, see kFastTime)
+    int64_t ti[kEvPerThread];     // raw int64 ticks (canonical int64 loader only)
+    int cls[kEvPerThread];
+};
+
+// canonical SoA: x,y u16; t i64 or f64; p u8.  i0 is a multiple of 4 and bases are 16B aligned.
+template <bool T_IS_I64>
+struct SoaCanonLoader {
+    const uint16_t* x;
+    const uint16_t* y;
+    const void* t;
+    const uint8_t* p;
+    double t_div;
+    typedef double time_t_;
+    // Canonical fast path: the per-event time arithmetic is ts = (t_raw - t0_raw) * scale_raw (one exact integer
+    // or fp64 subtraction, one fp64 multiply) instead of the reference's (t/div - t0/div) * (bins-1) / dT with two
+    // fp64 divisions; the two differ by O(1e-13) in ts, far below the 2^-25 weight quantum.
+    static constexpr bool kFastTime = true;
+    static constexpr bool kTicks = T_IS_I64;
+    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        (void)hi;
+        uint2 xv, yv;
+        uint32_t pv;
+        longlong2 a0, a1;     // raw 8-byte stamps (bit patterns)
+        if (i0 + 4 <= a.n_total) {
+            xv = ld_stream(reinterpret_cast<const uint2*>(x + i0));
+            yv = ld_stream(reinterpret_cast<const uint2*>(y + i0));
+            pv = ld_stream(reinterpret_cast<const uint32_t*>(p + i0));
+            a0 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(t) + i0));
+            a1 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(t) + i0 + 2));
+        } else {   // last, partial quad of the arrays: scalar loads, nothing read past the end
+            uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0};
+            long long tv_[4] = {0, 0, 0, 0};
+            pv = 0;
+            for (int j = 0; j < 4; ++j) {
+                if (i0 + j < a.n_total) {
+                    xs_[j] = x[i0 + j]; ys_[j] = y[i0 + j];
+                    pv |= (uint32_t)p[i0 + j] << (8 * j);
+                    tv_[j] = static_cast<const int64_t*>(t)[i0 + j];
+                }
+            }
+            xv = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
+            yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
+            a0 = make_longlong2(tv_[0], tv_[1]); a1 = make_longlong2(tv_[2], tv_[3]);
+        }
+        const long long raw[4] = {a0.x, a0.y, a1.x, a1.y};
+        const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
+        const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (a.scaled) {
+                e.x[j] = __double2ll_rz(__dmul_rn((double)xs[j], a.sx));
+                e.y[j] = __double2ll_rz(__dmul_rn((double)ys[j], a.sy));
+            } else {
+                e.x[j] = xs[j];
+                e.y[j] = ys[j];
+            }
+            e.ti[j] = raw[j];
+            e.t[j] = T_IS_I64 ? 0.0 : __longlong_as_double(raw[j]);
+            e.cls[j] = pol_class_i((int)((pv >> (8 * j)) & 0xffu));
+        }
+    }
+    __device__ __forceinline__ double time_at(int64_t i) const {
+        double v = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
+        return (t_div != 1.0) ? v / t_div : v;
+    }
+    __device__ __forceinline__ double raw_at(int64_t i) const {
+        return T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
+    }
+    __device__ __forceinline__ int64_t ticks_at(int64_t i) const {
+        return T_IS_I64 ? static_cast<const int64_t*>(t)[i] : 0;
+    }
+    __device__ __forceinline__ double div() const { return t_div; }
+};
+
+// any tagged SoA layout, scalar loads.  TT = float reproduces torch's fp32 time arithmetic.
+template <typename TT>
+struct SoaGenericLoader {
+    const void* x;
+    const void* y;
+    const void* t;
+    const void* p;
+    int xy_dtype, t_dtype, p_dtype;
+    double t_div;
+    typedef TT time_t_;
+    static constexpr bool kFastTime = false;
+    static constexpr bool kTicks = false;
+    __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
+    __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
+    __device__ __forceinline__ double div() const { return 1.0; }
+    __device__ __forceinline__ TT time_at(int64_t i) const {
+        if (sizeof(TT) == 4) {
+            float v = (t_dtype == EP_F32) ? static_cast<const float*>(t)[i] : (float)load_as_double(t, t_dtype, i);
+            return (TT)((t_div != 1.0) ? v / (float)t_div : v);
+        }
+        double v = load_as_double(t, t_dtype, i);
+        return (TT)((t_div != 1.0) ? v / t_div : v);
+    }
+    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<TT>& e) const {
+#pragma unroll
+        for (int j = 0; j < kEvPerThread; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= hi || i < a.begin) { e.cls[j] = 3; e.x[j] = 0; e.y[j] = 0; e.t[j] = 0; continue; }
+            double xd = load_as_double(x, xy_dtype, i), yd = load_as_double(y, xy_dtype, i);
+            if (a.scaled) {
+                if (xy_dtype == EP_F32) {   // numpy keeps fp32 arrays in fp32 under `*= python_float`
+                    xd = (double)__fmul_rn((float)xd, (float)a.sx);
+                    yd = (double)__fmul_rn((float)yd, (float)a.sy);
+                } else {
+                    xd = __dmul_rn(xd, a.sx);
+                    yd = __dmul_rn(yd, a.sy);
+                }
+            }
+            e.x[j] = __double2ll_rz(xd);
+            e.y[j] = __double2ll_rz(yd);
+            e.t[j] = time_at(i);
+            e.cls[j] = pol_class_d(load_as_double(p, p_dtype, i));
+        }
+    }
+};
+
+// the reference's own (N,4) x,y,t,p rows
+template <typename ET>   // ET = double | float (element type AND time arithmetic type)
+struct AosLoader {
+    const ET* ev;
+    typedef ET time_t_;
+    static constexpr bool kFastTime = false;
+    static constexpr bool kTicks = false;
+    __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
+    __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
+    __device__ __forceinline__ double div() const { return 1.0; }
+    __device__ __forceinline__ ET time_at(int64_t i) const { return ev[i * 4 + 2]; }
+    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const {
+#pragma unroll
+        for (int j = 0; j < kEvPerThread; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= hi || i < a.begin) { e.cls[j] = 3; e.x[j] = 0; e.y[j] = 0; e.t[j] = 0; continue; }
+            ET xv, yv, tv, pv;
+            if (sizeof(ET) == 8) {
+                const double2 q0 = ld_stream(reinterpret_cast<const double2*>(ev + i * 4));
+                const double2 q1 = ld_stream(reinterpret_cast<const double2*>(ev + i * 4 + 2));
+                xv = (ET)q0.x; yv = (ET)q0.y; tv = (ET)q1.x; pv = (ET)q1.y;
+            } else {
+                const float4 q = ld_stream(reinterpret_cast<const float4*>(ev + i * 4));
+                xv = (ET)q.x; yv = (ET)q.y; tv = (ET)q.z; pv = (ET)q.w;
+            }
+            if (a.scaled) {
+                if (sizeof(ET) == 8) { xv = (ET)__dmul_rn((double)xv, a.sx); yv = (ET)__dmul_rn((double)yv, a.sy); }
+                else { xv = (ET)__fmul_rn((float)xv, (float)a.sx); yv = (ET)__fmul_rn((float)yv, (float)a.sy); }
+            }
+            e.x[j] = (sizeof(ET) == 8) ? __double2ll_rz((double)xv) : __float2ll_rz((float)xv);
+            e.y[j] = (sizeof(ET) == 8) ? __double2ll_rz((double)yv) : __float2ll_rz((float)yv);
+            e.t[j] = tv;
+            e.cls[j] = pol_class_d((double)pv);
+        }
+    }
+};
+
+// ---- temporal-bilinear weights of one event (events_to_voxel_grid.py:34-42, in the events' own dtype) ----
+// Returns false when the event falls outside the bins (:44-45).  k is the interval index the packed
+// weights are filed under and r = rn(d * 2^24) the right-node weight; an event exactly on the last node
+// (ts == num_bins-1, d == 0) is filed under interval num_bins-2 with r = 2^24 so that the last interval
+// plane stays untouched for normal (time-sorted) input; *last_plane reports the rare other case.
+template <typename TT>
+__device__ __forceinline__ bool quantise_ts(TT ts, int num_bins, int& k, int& r, bool& last_plane) {
+    const TT tis = floor(ts);
+    last_plane = false;
+    if (!(tis >= (TT)0 && tis < (TT)num_bins)) return false;
+    k = (int)tis;
+    const float d = (float)(ts - tis);
+    r = __float2int_rn(d * 16777216.0f);
+    if (k == num_bins - 1) {
+        if (r == 0 && num_bins >= 2) { k -= 1; r = 1 << kQ; }
+        else last_plane = true;
+    }
+    return true;
+}
+
+// event j of a loaded quad -> (k, r); Loader::kFastTime selects the multiply form (canonical layout)
+template <class Loader, typename TT>
+__device__ __forceinline__ bool voxel_weights(const Ev<TT>& e, int j, const SampleMeta& m, int num_bins, int& k, int& r,
+                                              bool& last_plane) {
+    if (Loader::kFastTime) {
+        const double dt = Loader::kTicks ? (double)(e.ti[j] - m.t0_ticks) : ((double)e.t[j] - m.t0_raw);
+        return quantise_ts<double>(dt * m.scale_raw, num_bins, k, r, last_plane);
+    }
+    const TT ts = (TT)(num_bins - 1) * (e.t[j] - (TT)m.t0) / (TT)m.dT;
+    return quantise_ts<TT>(ts, num_bins, k, r, last_plane);
+}
+
+// ---- per-sample metadata: first/last timestamps ---------------------------------------------------
+template <class Loader>
+__global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    typedef typename Loader::time_t_ TT;
+    const int64_t lo = off_at(a, b), hi = off_at(a, b + 1);
+    SampleMeta m;
+    m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.pad = 0; m.scale_raw = 0.0; m.t0_raw = 0.0; m.t0_ticks = 0;
+    if (hi > lo) {
+        const TT first = ld.time_at(lo), last = ld.time_at(hi - 1);
+        TT d = last - first;
+        if (d == (TT)0) d = (TT)1;
+        m.t0 = (double)first;
+        m.dT = (double)d;
+        m.t0_raw = ld.raw_at(lo);
+        m.t0_ticks = ld.ticks_at(lo);
+        m.scale_raw = (double)(a.num_bins - 1) / ((double)d * ld.div());
+    }
+    a.meta[b] = m;
+}
+
+
+}  // namespace
+}  // namespace ep

@@ -118,13 +118,16 @@ def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
     return RaggedEvents(*tens, offsets_host=off, t_div=t_div)
 
 
-def _bin_params(size, num_bins, count_channels, scale, time_f32):
+_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "banded": _lib.EP_BIN_FORCE_BANDED}
+
+
+def _bin_params(size, num_bins, count_channels, scale, time_f32, method=None):
     prm = _lib.BinParams()
     prm.height, prm.width = int(size[0]), int(size[1])
     prm.num_bins, prm.count_channels = int(num_bins), int(count_channels)
     prm.scale_x, prm.scale_y = float(scale[0]), float(scale[1])
     prm.time_f32 = int(bool(time_f32))
-    prm.flags = 0
+    prm.flags = _METHOD[method]
     return prm
 
 
@@ -142,17 +145,19 @@ def _raise_bad(bad):
 
 
 def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_sum=False, time_f32=False,
-               check=False, out=None):
+               check=False, out=None, method=None):
     """Batched events -> tensors: voxel grid (B,num_bins,H,W), optional voxel.sum(0) plane (B,1,H,W) and/or
     polarity count frame (B,count_channels,H,W); one C-ABI call (ep_bin_events).
 
     Returns a dict with the keys that were requested: 'voxel', 'voxel_sum', 'count'.
     check=True synchronises and raises for events the reference would have raised on.
+    method: None/"auto" (banded shared-memory sweep when the layout is canonical and the batch fills the GPU,
+    else the global-RED kernels), "global", "banded" — same results bit for bit.
     """
     require_cuda(ev.x)
     dev = ev.device
     B, (H, W) = ev.batch, size
-    prm = _bin_params(size, num_bins, count_channels, scale, time_f32)
+    prm = _bin_params(size, num_bins, count_channels, scale, time_f32, method)
     out = {} if out is None else out
     if num_bins and "voxel" not in out:
         out["voxel"] = torch.empty((B, num_bins, H, W), dtype=torch.float32, device=dev)
@@ -161,10 +166,10 @@ def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_s
     if count_channels and "count" not in out:
         out["count"] = torch.empty((B, count_channels, H, W), dtype=torch.float32, device=dev)
     L = lib()
-    nbytes = L.ep_bin_events_workspace_bytes(ctypes.byref(prm), B, None)
+    desc = ev._desc()
+    nbytes = L.ep_bin_events_workspace_bytes_for(ctypes.byref(desc), ctypes.byref(prm))
     ws = workspace(nbytes, dev, "bin")
     bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
-    desc = ev._desc()
     with torch.cuda.device(dev):
         rc = L.ep_bin_events(stream_ptr(dev), ctypes.byref(desc), ctypes.byref(prm), ptr(out.get("voxel")),
                              ptr(out.get("voxel_sum")) if voxel_sum else 0, ptr(out.get("count")), ws.data_ptr(),

@@ -107,13 +107,18 @@ typedef struct ep_bin_params {
     double scale_x, scale_y;     /* events_reshape fused (dataset/augmentation/events_augment.py:22-26):
                                     x*scale_x, y*scale_y in fp64, then truncation; 1.0 = none */
     int time_f32;                /* 1 = do the time arithmetic in fp32 (what torch does for float32 event arrays) */
-    int flags;                   /* reserved, 0 */
+    int flags;                   /* 0 = choose; EP_BIN_FORCE_GLOBAL / EP_BIN_FORCE_BANDED pin the kernel family */
 } ep_bin_params;
+#define EP_BIN_FORCE_GLOBAL 1    /* packed-u64 global RED + finalize (any layout, any size) */
+#define EP_BIN_FORCE_BANDED 2    /* banded shared-memory sweep (canonical SoA layout only) */
 
 /* Scratch for ep_bin_events*: per-sample accumulator slots.  Returns the recommended size (enough
  * slots to keep one group of samples L2-resident); any size >= the minimum (one slot + per-sample
  * metadata), returned through *min_bytes when non-NULL, works. */
 EP_API size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch, size_t* min_bytes);
+/* Same, knowing the batch (reads offsets_host only): also covers the routed-record buffer of the banded
+ * fast path, which is chosen when the layout is canonical and the workspace is large enough. */
+EP_API size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_params* prm);
 
 /* Replaces, for a whole ragged batch in one call:
  *   events_to_voxel_grid(args, events, size)   dataset/dataset_utils/events_to_voxel_grid.py:4-61

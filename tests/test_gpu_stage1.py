@@ -186,3 +186,82 @@ def test_evrep_batch(ep):
     out = ep.evrep(ev, (H, W), check=True).cpu().numpy()
     for b, p in enumerate(parts):
         assert np.array_equal(out[b], oe.evrep(p[0], p[1], p[2], p[3], (W, H))), b
+
+
+def _random_batch(ep, rng, counts, H, W, t_span=50_000, hot=None, unsorted=False):
+    xs, ys, ts, ps = [], [], [], []
+    for n in counts:
+        x = rng.integers(0, W, n); y = rng.integers(0, H, n); p = rng.integers(0, 2, n)
+        t = rng.integers(0, t_span, n).astype(np.int64)
+        if not unsorted:
+            t = np.sort(t)
+        if hot is not None and n > 4 * hot:
+            x[n // 4: n // 4 + hot] = 3
+            y[n // 4: n // 4 + hot] = 2
+            p[n // 4: n // 4 + hot] = 1
+        xs.append(x); ys.append(y); ts.append(t); ps.append(p)
+    off = np.cumsum([0] + list(counts))
+    ev = ep.from_soa(np.concatenate(xs).astype(np.uint16), np.concatenate(ys).astype(np.uint16), np.concatenate(ts),
+                     np.concatenate(ps).astype(np.uint8), off, t_div=1e6)
+    samples = [np.stack([xs[b], ys[b], ts[b].astype(np.float64) / 1e6, ps[b]], 1).astype(np.float64) for b in range(len(counts))]
+    return ev.to("cuda"), samples
+
+
+@pytest.mark.parametrize("H,W,bins", [(224, 224, 5), (480, 640, 5), (44, 64, 15), (65, 87, 9)])
+def test_banded_equals_global_and_oracle(ep, H, W, bins):
+    """The banded shared-memory sweep and the global-RED kernels are the same integer arithmetic: identical bits;
+    both within tolerance of the oracle.  Ragged batch with an empty sample, a 1-event sample and a hot pixel
+    (2000 same-polarity events on one cell: exercises the spill table beyond the 127 admitted events)."""
+    from oracle import events as oe
+    rng = np.random.default_rng(H * 1000 + bins)
+    counts = [30000, 0, 1, 70001, 4099, 12288]
+    ev, samples = _random_batch(ep, rng, counts, H, W, hot=2000)
+    kw = dict(num_bins=bins, count_channels=2, voxel_sum=True, check=True)
+    a = ep.bin_events(ev, (H, W), method="global", **kw)
+    b = ep.bin_events(ev, (H, W), method="banded", **kw)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b[key]), key
+    for i, s in enumerate(samples):
+        if len(s) == 0:
+            assert not b["voxel"][i].any() and not b["count"][i].any()
+            continue
+        assert close(b["voxel"][i].cpu().numpy(), oe.voxel_grid(s, bins, (H, W))), i
+        assert np.array_equal(b["count"][i].cpu().numpy(), oe.count_frame(s, (H, W), 2)), i
+    # shard with offsets[0] > 0, count-only and voxel-only variants, fused scale
+    sh = ev.shard(1, 2)
+    c = ep.bin_events(sh, (H, W), num_bins=bins, method="banded", check=True)
+    assert torch.equal(c["voxel"], a["voxel"][3:])
+    d = ep.bin_events(ev, (H, W), count_channels=3, method="banded", check=True)
+    assert torch.equal(d["count"][:, 0], a["count"][:, 0]) and torch.equal(d["count"][:, 2], a["count"][:, 1])
+    assert not d["count"][:, 1].any()
+    sc = (0.5, 0.75)
+    e1 = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, scale=sc, method="global", check=True)
+    e2 = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, scale=sc, method="banded", check=True)
+    assert torch.equal(e1["voxel"], e2["voxel"]) and torch.equal(e1["count"], e2["count"])
+
+
+def test_banded_unsorted_and_out_of_window(ep):
+    """Unsorted stamps: first/last rows are not min/max, so some events fall outside the bins (dropped from the voxel
+    grid, still counted in the count frame); chunks then span several intervals."""
+    from oracle import events as oe
+    rng = np.random.default_rng(31)
+    H, W, bins = 48, 64, 5
+    ev, samples = _random_batch(ep, rng, [20000, 9000], H, W, unsorted=True)
+    a = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, method="global", check=True)
+    b = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, method="banded", check=True)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b[key]), key
+    for i, s in enumerate(samples):
+        assert close(b["voxel"][i].cpu().numpy(), oe.voxel_grid(s, bins, (H, W)))
+        assert np.array_equal(b["count"][i].cpu().numpy(), oe.count_frame(s, (H, W), 2))
+
+
+def test_banded_bad_events_raise(ep):
+    rng = np.random.default_rng(3)
+    ev, _ = _random_batch(ep, rng, [5000] * 40, 48, 64)
+    ev.x[17] = 64 + 63 * 64          # flat index far outside the 48x64 grid
+    ev.y[17] = 47
+    with pytest.raises(IndexError):
+        ep.bin_events(ev, (48, 64), num_bins=5, method="banded", check=True)
+    with pytest.raises(IndexError):
+        ep.bin_events(ev, (48, 64), num_bins=5, check=True)
