@@ -10,10 +10,13 @@ from .augmentation import events_reshape, get_random_index, reshape_scale  # noq
 from .dataset_utils import (events_to_EvRep, events_to_image_ecdp, events_to_image_mem,  # noqa: F401
                             events_to_voxel_grid, remove_hot_pixel_mem)
 from .events import (BadEventsError, RaggedEvents, bin_events, bin_events_aos, evrep, from_soa,  # noqa: F401
-                     mem_hotpixel, normalise, pack_events)
+                     mem_hotpixel, normalise, pack_events, time_surface)
 from .masking import (block_mask_expand, convvit_keep_masks, gather_tokens, len_keep_of,  # noqa: F401
                       mask_from_noise, patch_density, random_masking, swin_apply_mask, unshuffle_tokens)
 from .reshape import (diffmap_frames, frame2emb, patchify_gather, reconstruct_loss, target_normpix,  # noqa: F401
                       target_patch_loss)
+
+from .view_augment import (ViewChoice, apply_views, draw_crop, draw_evg_choice, draw_frame_choice,  # noqa: F401
+                           evg_augment, frame_augment)
 
 __version__ = "0.1.0"

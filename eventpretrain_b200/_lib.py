@@ -14,6 +14,7 @@ EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64 = range(1, 9)
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
 EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_BANDED = 1, 2
+EP_RESIZE_NEAREST, EP_RESIZE_BILINEAR, EP_RESIZE_BICUBIC = 0, 1, 2
 
 c_void_p, c_int, c_int64, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                          ctypes.c_size_t, ctypes.c_float, ctypes.c_double)
@@ -34,6 +35,11 @@ class EventsAos(ctypes.Structure):
 
 class ProfileStats(ctypes.Structure):
     _fields_ = [("ms", c_double * 3), ("launches", c_int * 3)]
+
+
+class ViewParams(ctypes.Structure):
+    _fields_ = [("crop_x", c_int), ("crop_y", c_int), ("crop_w", c_int), ("crop_h", c_int), ("hflip", c_int),
+                ("time_flip", c_int), ("negate", c_int), ("reserved", c_int)]
 
 
 class BinParams(ctypes.Structure):
@@ -60,6 +66,9 @@ SIGNATURES = {
     "ep_mem_hotpixel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_size_t]),
     "ep_evrep_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
     "ep_evrep": (c_int, [c_void_p, P(EventsSoa), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ep_time_surface_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ep_time_surface": (c_int, [c_void_p, P(EventsSoa), c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ep_view_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ep_diffmap_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),
     "ep_patchify_normpix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ep_target_patch_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) k_finalize_voxel(BinArgs a, float* __restrict__ out_voxel,
+__global__ void __launch_bounds__(kThreads, 4) k_finalize_voxel(BinArgs a, float* __restrict__ out_voxel,
                                                              float* __restrict__ out_sum) {
     finalize_voxel_block<VEC>(a, out_voxel, out_sum, blockIdx.y, blockIdx.x);
 }

@@ -262,3 +262,25 @@ def evrep(ev, size, check=False):
     if check:
         _raise_bad(bad)
     return out
+
+
+def time_surface(ev, size, tau, t_ref=None, check=False):
+    """(B,2,H,W) f32 exponential time surface, exp(-(t_ref - t_last)/tau) per polarity and pixel (0 where no event).
+    No counterpart exists in the reference (parity unpinned; self-oracle oracle/stage3_np.py:time_surface)."""
+    require_cuda(ev.x)
+    dev = ev.device
+    H, W = size
+    B = ev.batch
+    out = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+    L = lib()
+    ws = workspace(L.ep_time_surface_workspace_bytes(B, H, W), dev, "tsurf")
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    tr = None if t_ref is None else torch.as_tensor(t_ref, dtype=torch.float64, device=dev).contiguous()
+    desc = ev._desc()
+    with torch.cuda.device(dev):
+        rc = L.ep_time_surface(stream_ptr(dev), ctypes.byref(desc), H, W, float(tau), ptr(tr), out.data_ptr(), ws.data_ptr(),
+                               ws.numel(), ptr(bad))
+    _lib.check(rc, "ep_time_surface")
+    if check:
+        _raise_bad(bad)
+    return out

@@ -165,6 +165,31 @@ EP_API size_t ep_evrep_workspace_bytes(int batch, int height, int width, int64_t
 EP_API int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, double* out,
              void* workspace, size_t workspace_bytes, unsigned int* bad_count);
 
+/* Time surface (PARITY UNPINNED: the reference has no such routine; self-oracle in oracle/stage3_np.py).
+ * out (B,2,H,W) f32: channel 0 positive, 1 negative; exp(-(t_ref - t_last)/tau) of the latest event per pixel, 0 where
+ * none.  t_ref: device array of B doubles, or NULL = each sample's last-row timestamp. */
+EP_API size_t ep_time_surface_workspace_bytes(int batch, int height, int width);
+EP_API int ep_time_surface(void* stream, const ep_events_soa* ev, int height, int width, double tau, const double* t_ref,
+                    float* out, void* workspace, size_t workspace_bytes, unsigned int* bad_count);
+
+/* View augmentation, fused: crop -> resize -> horizontal flip -> time flip.
+ *   evg_augment / frame_augment   dataset/augmentation/view_augment.py:9-89
+ * The stochastic choices stay on the host (the reference draws them from the global numpy RNG, re-seeded with the
+ * same seed for a voxel grid and its sub_frame so that crops coincide, pr_ef_imagenet_dataset.py:187-206) and are
+ * passed per sample.  in (B,C,H,W) f32 -> out (B,C,out_h,out_w) f32.  Resize = F.interpolate(align_corners=None). */
+typedef struct ep_view_params {
+    int crop_x, crop_y, crop_w, crop_h;   /* view_crop box (:26-28); full frame when no crop was drawn */
+    int hflip;                            /* view_horizontal_flip (:41-47) */
+    int time_flip;                        /* evg_time_flip: reverse the channel (bin) axis (:49-58) */
+    int negate;                           /* evg_time_flip's sign change for 5/6 bins, or frame_time_flip (:60-63) */
+    int reserved;
+} ep_view_params;
+#define EP_RESIZE_NEAREST 0
+#define EP_RESIZE_BILINEAR 1
+#define EP_RESIZE_BICUBIC 2
+EP_API int ep_view_augment(void* stream, const float* in, int batch, int channels, int height, int width,
+                    const ep_view_params* params /* device, B entries */, int out_h, int out_w, int mode, float* out);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 2 — difference-map target
  * ------------------------------------------------------------------------------------------- */

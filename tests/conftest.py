@@ -33,6 +33,11 @@ def golden_stage3():
 
 
 @pytest.fixture(scope="session")
+def golden_views():
+    return _load("views.npz")
+
+
+@pytest.fixture(scope="session")
 def native_lib():
     """Builds (if stale) and loads the CUDA C-ABI library; nvcc cross-compiles without a GPU."""
     from eventpretrain_b200 import build, _lib

@@ -325,6 +325,33 @@ def stage3_cases(ref):
     return out
 
 
+def view_cases(ref):
+    """evg_augment / frame_augment (dataset/augmentation/view_augment.py:65-89) with seeds: crop box, resize mode,
+    horizontal flip and time flip all come from the reference's own RNG sequence."""
+    out = {}
+    va = ref.view_augment
+    for bins, mode, seeds in ((5, "nearest", (1, 2, 3, 4, 5, 6)), (5, "bilinear", (7, 8, 9)), (15, "bilinear", (10, 11)),
+                              (2, "bicubic", (12,))):
+        args = SimpleNamespace(crop_min=0.2, num_bins=bins, input_size=32)
+        grid = torch.from_numpy(hash_uniform((bins, 60, 80), 4000 + bins)) * 8
+        for sd in seeds:
+            o, flag = va.evg_augment(args, grid.clone(), (32, 32), mode=mode, seed=sd)
+            out[f"evg_{mode}_b{bins}_s{sd}"] = dict(out=o.numpy(), flag=np.asarray(flag), bins=np.asarray(bins), seed=np.asarray(sd),
+                                                  mode=np.asarray(["nearest", "bilinear", "bicubic"].index(mode)))
+    args = SimpleNamespace(crop_min=0.2, num_bins=5, input_size=32)
+    frame = torch.from_numpy(hash_uniform((1, 60, 80), 4100))
+    for sd, tf in ((21, False), (22, True), (23, True), (24, False)):
+        o = va.frame_augment(args, frame.clone(), seed=sd, time_flip_flag=tf)
+        out[f"frame_s{sd}"] = dict(out=o.numpy(), seed=np.asarray(sd), tflip=np.asarray(tf))
+    # a grid and its sub_frame augmented with the same seed share the crop (pr_ef_imagenet_dataset.py:187-206)
+    # no-crop fallback: crop_min so large that 10 attempts fail for a tiny frame
+    args = SimpleNamespace(crop_min=0.999, num_bins=5, input_size=8)
+    tiny = torch.from_numpy(hash_uniform((5, 3, 3), 4200))
+    o, flag = va.evg_augment(args, tiny.clone(), (8, 8), mode="nearest", seed=31)
+    out["evg_nocrop"] = dict(out=o.numpy(), flag=np.asarray(flag))
+    return out
+
+
 def main():
     ref = _import_reference()
     torch.set_num_threads(1)
@@ -334,7 +361,10 @@ def main():
     s3 = stage3_cases(ref)
     flat = {f"{case}/{k}": v for case, rec in s3.items() for k, v in rec.items()}
     np.savez_compressed(os.path.join(HERE, "stage3_mask_patch.npz"), **flat)
-    for f in ("stage1_events.npz", "stage3_mask_patch.npz"):
+    vc = view_cases(ref)
+    flat = {f"{case}/{k}": v for case, rec in vc.items() for k, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "views.npz"), **flat)
+    for f in ("stage1_events.npz", "stage3_mask_patch.npz", "views.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
     print("torch", torch.__version__, "numpy", np.__version__)
 

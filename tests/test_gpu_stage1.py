@@ -265,3 +265,15 @@ def test_banded_bad_events_raise(ep):
         ep.bin_events(ev, (48, 64), num_bins=5, method="banded", check=True)
     with pytest.raises(IndexError):
         ep.bin_events(ev, (48, 64), num_bins=5, check=True)
+
+
+def test_time_surface_self_oracle(ep):
+    """No reference routine exists: checked against the numpy self-oracle."""
+    from oracle import stage3_np as s3
+    rng = np.random.default_rng(12)
+    H, W = 30, 40
+    ev, samples = _random_batch(ep, rng, [4000, 1, 900], H, W)
+    out = ep.time_surface(ev, (H, W), tau=0.01, check=True).cpu().numpy()
+    for b, s in enumerate(samples):
+        ref = s3.time_surface(s[:, 0], s[:, 1], s[:, 2], s[:, 3], (H, W), 0.01)
+        assert np.allclose(out[b], ref, rtol=1e-6, atol=1e-7), b
