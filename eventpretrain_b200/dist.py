@@ -7,6 +7,7 @@ max: MAX), the analogue of misc.all_reduce_mean (utils/misc.py:406-414), issued 
 never gates the binning kernels.  torch.distributed is the transport: NCCL over NVLink on GPUs, gloo in
 the CPU tests.
 """
+import datetime
 import os
 
 import torch
@@ -23,9 +24,9 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=datetime.timedelta(seconds=180))
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, world, local

@@ -1,0 +1,51 @@
+"""Masked-modelling input pipeline as one CUDA graph (BASELINE.json configs[2]).
+
+At ViT-S/16 sizes every stage-3 kernel runs for a few microseconds, so a Python call per kernel is launch-bound.
+`MaskedInputPipeline` captures mask -> visible-patch gather -> patchified normalised target into a CUDA graph over
+static buffers; `run()` is a single graph launch.
+"""
+import torch
+
+from .masking import len_keep_of, mask_from_noise
+from .reshape import patchify_gather, target_normpix
+
+
+class MaskedInputPipeline:
+    def __init__(self, batch, channels, size, patch, mask_ratio, device, target_channels=1, norm_pix_loss=True, order="cpq"):
+        H, W = size
+        self.L = (H // patch) * (W // patch)
+        self.keep = len_keep_of(self.L, mask_ratio)
+        self.patch, self.order, self.norm = patch, order, norm_pix_loss
+        dev = torch.device(device)
+        # static inputs: fill them in place (copy_) before run()
+        self.noise = torch.zeros(batch, self.L, device=dev)
+        self.x = torch.zeros(batch, channels, H, W, device=dev)
+        self.sub_frame = torch.zeros(batch, target_channels, H, W, device=dev)
+        self.out = None
+        self.graph = None
+        self._warm(dev)
+
+    def _body(self):
+        ids_keep, mask, ids_restore = mask_from_noise(self.noise, self.keep)
+        patches = patchify_gather(self.x, self.patch, ids_keep, self.order)
+        target = target_normpix(self.sub_frame, self.patch, self.norm)
+        return {"ids_keep": ids_keep, "mask": mask, "ids_restore": ids_restore, "visible_patches": patches, "target": target}
+
+    def _warm(self, dev):
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._body()
+
+    def run(self, draw_noise=True):
+        """One graph launch; with draw_noise the mask noise is redrawn with torch.rand (outside the graph, like
+        the reference's random_masking)."""
+        if draw_noise:
+            self.noise.copy_(torch.rand(self.noise.shape, device=self.noise.device))
+        self.graph.replay()
+        return self.out

@@ -180,3 +180,18 @@ def test_diffmap(ep, golden_stage3):
         assert np.array_equal(lin[i], s3.diffmap_frames(a[i], b[i], "linear", negate=bool(neg[i])))
     lg = ep.diffmap_frames(cu(a), cu(b), "log", eps=1e-3).cpu().numpy()
     np.testing.assert_allclose(lg, s3.diffmap_frames(a, b, "log", 1e-3), rtol=1e-5, atol=1e-6)
+
+
+def test_masked_input_pipeline_graph(ep):
+    """The CUDA-graph pipeline equals the individual calls, replay after replay."""
+    pipe = ep.MaskedInputPipeline(8, 5, (224, 224), 16, 0.75, "cuda")
+    for it in range(3):
+        torch.manual_seed(it)
+        pipe.x.copy_(torch.randn(8, 5, 224, 224, device="cuda"))
+        pipe.sub_frame.copy_(torch.randn(8, 1, 224, 224, device="cuda"))
+        pipe.noise.copy_(torch.rand(8, 196, device="cuda"))
+        out = pipe.run(draw_noise=False)
+        ik, m, ir = ep.mask_from_noise(pipe.noise, 49)
+        assert torch.equal(out["ids_keep"], ik) and torch.equal(out["mask"], m) and torch.equal(out["ids_restore"], ir)
+        assert torch.equal(out["visible_patches"], ep.patchify_gather(pipe.x, 16, ik, "cpq"))
+        assert torch.equal(out["target"], ep.target_normpix(pipe.sub_frame, 16))

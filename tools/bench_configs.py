@@ -104,6 +104,11 @@ def c3():
     ms = timeit(pipeline)
     report("C3 input pipeline: mask + patch gather + target (3 launches)", ms,
            B * (4 * L + 8 * K + 12 * L + 2 * 4 * K * C * p * p + 2 * 4 * 224 * 224), B, "samples", launches=3)
+    pipe = ep.MaskedInputPipeline(B, C, (224, 224), p, 0.75, dev)
+    pipe.noise.copy_(noise); pipe.x.copy_(x); pipe.sub_frame.copy_(sub)
+    ms = timeit(lambda: pipe.run(draw_noise=False))
+    report("C3 input pipeline as one CUDA graph (mask + patch gather + target)", ms,
+           B * (4 * L + 8 * K + 12 * L + 2 * 4 * K * C * p * p + 2 * 4 * 224 * 224), B, "samples", launches=3)
     # reference formulation in stock torch on the same GPU, for scale
     def torch_ref():
         ids_shuffle = torch.argsort(noise, dim=1)
