@@ -20,6 +20,8 @@
 //
 // Integer accumulation => the result is order-independent and bit-identical to the global-RED path.
 // Unsorted input is handled (chunks are revisited for every interval they contain), just slower.
+#include <stdio.h>
+
 #include "ep_binning_common.cuh"
 
 namespace ep {
@@ -32,14 +34,30 @@ constexpr int kSweepThreads = 512;
 constexpr int kCPT4 = 3;                // quads of cells per sweep thread (register-resident A_{k-1} and sum)
 constexpr int kCPT = 4 * kCPT4;
 constexpr int kMaxCellsPerBand = kCPT * kSweepThreads;   // 6144 cells -> 48 KB of tile, two CTAs per SM
-constexpr int kTeam = 16;               // threads that walk one chunk's run of records together
-constexpr int kUnroll = 3;              // records in flight per thread in the sweep
+constexpr int kTeam = 8;                // lanes that walk one chunk's run of records together
+constexpr int kUnroll = 12;             // records in flight per lane: a typical run (4096 / 50 bands) is one round
 constexpr int kAdmit = 127;             // events per (cell, interval) accumulated in the 32-bit A word
 constexpr int kSpill = 256;             // spill-table slots per CTA (power of two)
 constexpr int kRowStride = kMaxBands + 2;   // u16 entries per chunk row: offsets[0..NB], then kmin|kmax<<8
 constexpr int kMaxTableChunks = 1024;   // chunk rows of one sample staged in shared memory at a time
 constexpr uint32_t kKShift = 25, kPolShift = 30;
 constexpr uint32_t kKCountOnly = 31;    // interval code of events outside the time bins (count frame only)
+
+// Optional per-phase cycle accounting (build with -DEP_PHASE_TIMING; tools only, never in the shipped library).
+#ifdef EP_PHASE_TIMING
+#define EP_TICK(slot)                                                                      \
+    do {                                                                                   \
+        if (threadIdx.x == 0) {                                                            \
+            const long long _now = clock64();                                              \
+            atomicAdd(g.dbg + (slot), (unsigned long long)(_now - _t_last));               \
+            _t_last = _now;                                                                \
+        }                                                                                  \
+    } while (0)
+#define EP_TICK_INIT() long long _t_last = clock64()
+#else
+#define EP_TICK(slot) do { } while (0)
+#define EP_TICK_INIT() do { } while (0)
+#endif
 
 struct BandArgs {
     BinArgs bin;                 // offsets, meta, geometry, bad_count (begin/end/g0/g1 describe the group)
@@ -53,6 +71,7 @@ struct BandArgs {
     uint32_t* rec_val;           // [chunks_in_group][kChunk]
     uint16_t* rec_cell;          // [chunks_in_group][kChunk]
     float* out_voxel; float* out_sum; float* out_count;
+    unsigned long long* dbg;     // phase cycle counters (EP_PHASE_TIMING builds), else unused
 };
 
 __device__ __forceinline__ int64_t sample_chunk_origin(const BinArgs& a, int b) {
@@ -127,7 +146,9 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs 
         s_kmin = 255; s_kmax = 0;
     }
     if (threadIdx.x < kMaxBands) { s_cnt[threadIdx.x] = 0; s_cur[threadIdx.x] = 0; }
+    EP_TICK_INIT();
     __syncthreads();
+    EP_TICK(0);
 
     const int64_t c_lo = s_info.c_lo, ev_lo = s_info.ev_lo, ev_hi = s_info.ev_hi;
     const int64_t HW = (int64_t)a.H * a.W;
@@ -225,6 +246,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs 
     kmax = warp_reduce(kmax, [](int x, int y) { return max(x, y); });
     if ((threadIdx.x & 31) == 0) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); }
     __syncthreads();
+    EP_TICK(1);
     if (threadIdx.x < 32) {      // exclusive scan of the (<= 64) band counts: two per lane
         const int l = threadIdx.x;
         const int c0 = s_cnt[2 * l], c1 = s_cnt[2 * l + 1];
@@ -234,6 +256,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs 
         if (l == 31) s_base[kMaxBands] = incl;
     }
     __syncthreads();
+    EP_TICK(2);
 #pragma unroll
     for (int q = 0; q < 2 * kEvPerThread; ++q) {
         if (cb[q] == 0xffffffffu) continue;
@@ -243,6 +266,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs 
         s_cell[pos] = (uint16_t)cb[q];
     }
     __syncthreads();
+    EP_TICK(3);
     // write the sorted chunk back: 4 records per thread per step, 16-byte / 8-byte vectors (the tail of the
     // last vector may carry stale staging data; the band offsets in the row delimit what is read)
     const int n_vec = (s_base[kMaxBands] + 3) >> 2;
@@ -255,6 +279,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs 
     uint16_t* row = g.rows + (int64_t)blockIdx.x * kRowStride;
     if (threadIdx.x <= g.nb) row[threadIdx.x] = (uint16_t)s_base[threadIdx.x < g.nb ? threadIdx.x : kMaxBands];
     if (threadIdx.x == 0) row[kMaxBands + 1] = (uint16_t)((s_kmin & 0xff) | (s_kmax << 8));
+    EP_TICK(4);
 }
 
 // ---- sweep ------------------------------------------------------------------------------------------------
@@ -322,8 +347,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
     uint2* sCnt = sCS + g.cpb;                                              // [cpb] {count_pos, count_neg} (COUNT only)
     SpillTable* spill = reinterpret_cast<SpillTable*>(sCnt + (COUNT ? g.cpb : 0));   // [3]: roles rotate, see below
     uint32_t* s_run = reinterpret_cast<uint32_t*>(spill + 3);              // lo | hi << 16 per staged chunk
-    uint16_t* s_rel = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks); // staged chunks relevant to this pass
-    __shared__ int s_spilled[3], s_nrel;
+    uint16_t* s_kk = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks);  // kmin | kmax << 8 per staged chunk
+    __shared__ int s_spilled[3];
 
     const int tid = threadIdx.x;
     const int team = tid / kTeam, tl = tid % kTeam;
@@ -332,20 +357,32 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
     const int B = a.num_bins;
     const int n_pass = B + (COUNT ? 1 : 0);
 
+    EP_TICK_INIT();
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
         const int band = task % g.nb;
         const int b = a.g0 + task / g.nb;
         const int64_t band_base = (int64_t)band * g.cpb;
         const int ncell = (int)((band_base + g.cpb <= HW) ? g.cpb : (HW > band_base ? HW - band_base : 0));
         const int ch0 = g.chunk_first[b] - g.chunk_begin, nch = g.chunk_first[b + 1] - g.chunk_first[b];
+        // the sample's chunk table (this band's run offsets + interval span) is staged in shared memory once per
+        // task when it fits (<= kMaxTableChunks chunks = 4.2 M events), else re-staged tile by tile in every pass
+        const bool table_once = nch <= kMaxTableChunks;
 
         __syncthreads();                                   // previous task fully flushed
+        EP_TICK(8);                                        // tail of the previous task (sum / count write-out + wait)
         for (int i = tid; i < g.cpb; i += kSweepThreads) {
             sN[i] = 0; sA[i] = 0; sCS[i] = make_uint2(0u, 0u);
             if (COUNT) sCnt[i] = make_uint2(0u, 0u);
         }
         for (int t = 0; t < 3; ++t) spill_clear(spill + t, tid);
         if (tid == 0) { s_spilled[0] = 0; s_spilled[1] = 0; s_spilled[2] = 0; }
+        if (table_once) {
+            for (int c = tid; c < nch; c += kSweepThreads) {
+                const uint16_t* row = g.rows + (int64_t)(ch0 + c) * kRowStride;
+                s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
+                s_kk[c] = row[kMaxBands + 1];
+            }
+        }
         // spill-table roles: cur = A excess of the running interval, prev = carry excess (read at flush),
         // next = carry excess for the following interval (written at flush)
         int cur = 0, prev = 1, next = 2;
@@ -355,25 +392,23 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
             const int k = pass < B ? pass : (int)kKCountOnly;
             for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
                 const int nt = min(kMaxTableChunks, nch - t0);
-                __syncthreads();
-                if (tid == 0) s_nrel = 0;
-                __syncthreads();
-                for (int c = tid; c < nt; c += kSweepThreads) {
-                    const uint16_t* row = g.rows + (int64_t)(ch0 + t0 + c) * kRowStride;
-                    const uint32_t kk = row[kMaxBands + 1];
-                    const int kmin = kk & 0xff, kmax = kk >> 8;
-                    const uint32_t lo = row[band], hi = row[band + 1];
-                    // count-only records are not covered by [kmin, kmax]: every chunk is scanned in that pass
-                    if (hi > lo && (k == (int)kKCountOnly || (k >= kmin && k <= kmax))) {
-                        const int slot = atomicAdd(&s_nrel, 1);
-                        s_rel[slot] = (uint16_t)c;
-                        s_run[c] = lo | (hi << 16);
+                __syncthreads();                           // tile zeroed / flushed, table visible
+                EP_TICK(pass == 0 ? 5 : 7);                // 5: task set-up; 7: flush of the previous pass
+                if (!table_once) {
+                    for (int c = tid; c < nt; c += kSweepThreads) {
+                        const uint16_t* row = g.rows + (int64_t)(ch0 + t0 + c) * kRowStride;
+                        s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
+                        s_kk[c] = row[kMaxBands + 1];
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
-                const int nrel = s_nrel;
-                for (int ri = team; ri < nrel; ri += kTeams) {
-                    const int c = s_rel[ri];
+                // one team of kTeam lanes per chunk; chunks are time-ordered, so the chunks relevant to interval k are
+                // (for sorted input) consecutive and land on distinct teams: one round of loads per pass
+                for (int c = team; c < nt; c += kTeams) {
+                    const uint32_t kk = s_kk[c];
+                    const int kmin = kk & 0xff, kmax = kk >> 8;
+                    // count-only records are not covered by [kmin, kmax]: every chunk is scanned in that pass
+                    if (k != (int)kKCountOnly && (k < kmin || k > kmax)) continue;
                     const uint32_t run = s_run[c];
                     const int lo = run & 0xffff, hi = run >> 16;
                     const uint32_t* rv = g.rec_val + (int64_t)(ch0 + t0 + c) * kChunk;
@@ -392,6 +427,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
                 }
             }
             __syncthreads();
+            EP_TICK(6);                                    // record phase (incl. waiting for the slowest warp)
             const bool spill_cur = s_spilled[cur] != 0, spill_prev = s_spilled[prev] != 0;
             float* o = (pass < B) ? g.out_voxel + ((int64_t)b * B + k) * HW + band_base : nullptr;
             for (int cell = tid; cell < ncell; cell += kSweepThreads) {
@@ -465,7 +501,7 @@ bool plan_bands(const ep_bin_params* p, BandPlan* bp) {
     while ((1ll << sh) < cpb) ++sh;
     bp->magic = (uint32_t)(((1ull << (31 + sh)) / (uint64_t)cpb) + 1);
     bp->shift = sh - 1;
-    bp->sweep_smem = (size_t)cpb * 16 + 3 * sizeof(SpillTable) + kMaxTableChunks * (4 + 2) + 64;   // + cpb * 8 with a count frame
+    bp->sweep_smem = (size_t)cpb * 16 + 3 * sizeof(SpillTable) + kMaxTableChunks * (4 + 2) + 64;     // + cpb * 8 with a count frame
     return true;
 }
 
@@ -550,6 +586,13 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
     g.rec_val = reinterpret_cast<uint32_t*>(w + L.rec_val);
     g.rec_cell = reinterpret_cast<uint16_t*>(w + L.rec_cell);
     g.out_voxel = out_voxel; g.out_sum = out_sum; g.out_count = out_count;
+    g.dbg = nullptr;
+#ifdef EP_PHASE_TIMING
+    static unsigned long long* s_dbg = nullptr;
+    if (!s_dbg) cudaMalloc(&s_dbg, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(s_dbg, 0, 16 * sizeof(unsigned long long), st);
+    g.dbg = s_dbg;
+#endif
 
     profile_begin(st, kProfOther);
     k_sample_meta<Loader><<<(B + 127) / 128, 128, 0, st>>>(ld, a, B);
@@ -569,15 +612,30 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
 
     int64_t chunk_begin = 0;
     int g0 = 0;
+    const int slots = 2 * kNumSMs;                 // resident sweep CTAs
     while (g0 < B) {
-        int g1 = g0;
+        // largest group the record budget allows ...
+        int g_max = g0;
         int64_t cur = 0;
-        while (g1 < B) {
-            const int64_t c = chunks_of(off, g1);
+        while (g_max < B) {
+            const int64_t c = chunks_of(off, g_max);
             if (cur > 0 && ((size_t)(cur + c) * kBytesPerChunk > budget || cur + c > gchunks)) break;
             cur += c;
-            ++g1;
+            ++g_max;
         }
+        // ... then trimmed so that its (sample, band) tasks fill whole waves of the resident sweep CTAs: a group of 12
+        // samples x 50 bands = 600 tasks on 296 slots runs 3 rounds (2.03 needed), 11 samples run 2
+        int g1 = g_max;
+        if (g_max < B || true) {
+            double best = -1.0;
+            for (int cand = g_max; cand > g0 && cand >= g0 + (g_max - g0 + 1) / 2; --cand) {
+                const int64_t tasks = (int64_t)(cand - g0) * bp.nb;
+                const double eff = (double)tasks / (double)(ceil_div64(tasks, slots) * slots);
+                if (eff > best + 1e-9) { best = eff; g1 = cand; }
+            }
+        }
+        cur = 0;
+        for (int b = g0; b < g1; ++b) cur += chunks_of(off, b);
         a.g0 = g0; a.g1 = g1;
         a.begin = off[g0]; a.end = off[g1];
         g.chunk_begin = (int)chunk_begin;
@@ -597,6 +655,19 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
         chunk_begin += cur;
         g0 = g1;
     }
+#ifdef EP_PHASE_TIMING
+    if (getenv("EP_PRINT_TIMING")) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, g.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[9] = {"route: setup", "route: load+compute+count", "route: scan", "route: place", "route: writeout",
+                                "sweep: task setup", "sweep: records", "sweep: flush", "sweep: task tail"};
+        double rt = 0, sw = 0;
+        for (int i = 0; i < 5; ++i) rt += (double)h[i];
+        for (int i = 5; i < 9; ++i) sw += (double)h[i];
+        for (int i = 0; i < 9; ++i) fprintf(stderr, "  %-28s %12.3f Mcycles  %5.1f%%\n", names[i], h[i] * 1e-6, 100.0 * h[i] / (i < 5 ? rt : sw));
+    }
+#endif
     return EP_OK;
 }
 
