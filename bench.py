@@ -324,15 +324,17 @@ def run_ours(args):
     del pipe
 
     # ---- e2e: pinned host SoA -> H2D -> bin -> D2H of the per-sample checksum, all inside the timed region ----
-    host = ep.RaggedEvents(ev.x.cpu().pin_memory(), ev.y.cpu().pin_memory(), ev.t.cpu().pin_memory(),
-                           ev.p.cpu().pin_memory(), ev.offsets.cpu().pin_memory(), ev.offsets_host, ev.t_div)
+    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the 8 B/event
+    # transport layout (u16 x,y + u32 relative ticks | polarity << 31; RaggedEvents.compact(), bit-identical results)
+    host13 = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
+    host = host13.compact().pin_memory()
     h2d = host.nbytes()
     del ev
     torch.cuda.empty_cache()
 
     def e2e_step():
         d = host.to(dev, non_blocking=True)
-        o = ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method)
+        o = ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method if args.method != "banded" else "auto")
         return o["voxel_sum"].sum(dim=(1, 2, 3)).cpu()       # (B,) fp32: sum of polarities per sample
 
     for _ in range(2):
@@ -347,7 +349,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e = {"value": total_events * args.steps / float(tm.item()) / 1e9, "unit": "Gevents/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * float(tm.item()) / args.steps}
+           "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * float(tm.item()) / args.steps,
+           "host_layout": "pinned SoA, 8 B/event transport layout (u16 x, u16 y, u32 relative ticks | polarity << 31)"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port on the host cores, bounded sample + parity check ----
     cpu = None
@@ -356,8 +359,8 @@ def run_ours(args):
         oe.build()
         threads = os.cpu_count() or 1
         n_s = min(BATCH, max(8, min(threads, 64)))
-        hx, hy, ht, hp = (a.numpy() for a in (host.x, host.y, host.t, host.p))
-        off = host.offsets_host
+        hx, hy, ht, hp = (a.numpy() for a in (host13.x, host13.y, host13.t, host13.p))
+        off = host13.offsets_host
         aos = np.ascontiguousarray(np.concatenate([aos_sample((hx, hy, ht, hp), off, b) for b in range(n_s)], 0))
         soff = (off[: n_s + 1] - off[0]).astype(np.int64)
         t0 = time.perf_counter()

@@ -6,7 +6,8 @@ functions that keep the reference's call signatures.  No CPU fallback.
 """
 from . import config  # noqa: F401
 from ._lib import LIB_PATH, NativeLibraryMissing, load as load_library  # noqa: F401
-from .augmentation import events_reshape, get_random_index, reshape_scale  # noqa: F401
+from .augmentation import (add_noise_events, erase_and_add_events, events_augment, events_reshape,  # noqa: F401
+                           get_random_index, reshape_scale)
 from .dataset_utils import (events_to_EvRep, events_to_image_ecdp, events_to_image_mem,  # noqa: F401
                             events_to_voxel_grid, remove_hot_pixel_mem)
 from .events import (BadEventsError, RaggedEvents, bin_events, bin_events_aos, evrep, from_soa,  # noqa: F401

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeventpretrain_b200.so")
 
-EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64 = range(1, 9)
+EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64, EP_U32 = range(1, 10)
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
 EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_BANDED = 1, 2
@@ -26,7 +26,7 @@ P = ctypes.POINTER
 class EventsSoa(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("y", c_void_p), ("t", c_void_p), ("p", c_void_p),
                 ("xy_dtype", c_int), ("t_dtype", c_int), ("p_dtype", c_int), ("batch", c_int),
-                ("t_div", c_double), ("offsets", c_void_p), ("offsets_host", c_void_p)]
+                ("t_div", c_double), ("offsets", c_void_p), ("offsets_host", c_void_p), ("t_base", c_void_p)]
 
 
 class EventsAos(ctypes.Structure):

@@ -232,6 +232,11 @@ size_t l2_group_budget() {
     return (size_t)mb << 20;
 }
 
+bool persist_l2_enabled() {
+    const char* e = getenv("EP_PERSIST_L2");
+    return e ? atoi(e) != 0 : false;
+}
+
 int scatter_ctas_per_sm() {
     const char* e = getenv("EP_SCATTER_CTAS_PER_SM");
     int v = e ? atoi(e) : 8;
@@ -281,6 +286,35 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
     cudaError_t ce = cudaMemsetAsync(slots, 0, (size_t)G * L.slot_bytes, st);
     if (ce != cudaSuccess) return (int)ce;
 
+    // Pin the accumulator slots in the persisting part of L2 for the duration of the call (B200: 126 MB L2, up to
+    // 79 MB persisting): the event stream (13 B/event, read once) and the fp32 outputs (written once) otherwise
+    // compete with them for residency, and a RED that misses L2 costs a DRAM round trip.
+    bool window_set = false;
+    cudaStreamAttrValue old_attr;
+    if (persist_l2_enabled()) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t want = (size_t)G * L.slot_bytes;
+        if (max_persist > 0 && max_window > 0) {
+            if (want > (size_t)max_persist) want = (size_t)max_persist;
+            if (want > (size_t)max_window) want = (size_t)max_window;
+            size_t cur_limit = 0;
+            cudaDeviceGetLimit(&cur_limit, cudaLimitPersistingL2CacheSize);
+            if (cur_limit < want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamGetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &old_attr);
+            cudaStreamAttrValue attr;
+            attr.accessPolicyWindow.base_ptr = slots;
+            attr.accessPolicyWindow.num_bytes = want;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
+
     const int64_t HW = (int64_t)p->height * p->width;
     for (int g0 = 0; g0 < B; g0 += G) {
         const int g1 = (g0 + G < B) ? g0 + G : B;
@@ -319,6 +353,7 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
             EP_LAUNCH_CHECK();
         }
     }
+    if (window_set) cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &old_attr);
     return EP_OK;
 }
 
@@ -354,12 +389,22 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     int rc = check_params(prm);
     if (rc != EP_OK) return rc;
     if (!ev || ev->batch <= 0 || !ev->offsets || !ev->offsets_host) return EP_EINVAL;
-    if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype)) return EP_EINVAL;
+    if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || (!valid_dtype(ev->p_dtype) && ev->t_dtype != EP_U32)) return EP_EINVAL;
     if (!(ev->t_div != 0.0)) return EP_EINVAL;
     const int B = ev->batch;
     for (int b = 0; b < B; ++b) if (ev->offsets_host[b + 1] < ev->offsets_host[b]) return EP_EINVAL;
-    if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || !ev->y || !ev->t || !ev->p)) return EP_EINVAL;
+    if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || !ev->y || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ev->t_dtype == EP_U32) {
+        // compact transport layout: u16 x,y + u32 (relative ticks | polarity << 31) + per-sample int64 base
+        if (ev->xy_dtype != EP_U16 || ev->p != nullptr || !ev->t_base || prm->time_f32) return EP_EINVAL;
+        if (!aligned16(ev->x) || !aligned16(ev->y) || !aligned16(ev->t)) return EP_EALIGN;
+        if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
+        SoaCompactLoader ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y),
+                            static_cast<const uint32_t*>(ev->t), ev->t_base, ev->t_div};
+        return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
+                           workspace_bytes, bad_count);
+    }
     const bool canon = ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && !prm->time_f32 &&
                        (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64) && aligned16(ev->x) && aligned16(ev->y) &&
                        aligned16(ev->t) && aligned16(ev->p);

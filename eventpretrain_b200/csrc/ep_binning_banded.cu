@@ -310,30 +310,71 @@ __device__ __forceinline__ long long spill_get(const SpillTable* t, unsigned int
 }
 
 // Tile, structure of arrays over the band's cells:
-//   N[cell]  = n_pos | n_neg << 16 of the current interval          (ATOMS, returning)
-//   A[cell]  = sum p*r mod 2^32 over the admitted events            (ATOMS)
+//   N[cell]  = n_pos | n_neg << 16 of the current interval          (ATOMS, fire and forget)
+//   A[cell]  = sum p*r mod 2^32 over the interval's events          (ATOMS, fire and forget)
 //   CS[cell] = { carry = A of the previous interval (low 32 bits), running fp32 sum over bins }
-// Cells whose A does not fit 32 bits (more than kAdmit events in one interval) keep the excess in two
-// small 64-bit hash tables: spill[cur] for the running interval, spill[prev] for the carry.
-__device__ __forceinline__ void sweep_record(uint32_t v, uint32_t cell, int k, uint32_t* sN, uint32_t* sA,
-                                             SpillTable* spill, int* s_spilled, unsigned int* bad) {
-    if ((int)((v >> kKShift) & 31u) != k) return;
-    const bool pos = (v >> kPolShift) & 1u;
-    const uint32_t old = atomicAdd(sN + cell, pos ? 1u : 0x10000u);
-    if (k == (int)kKCountOnly) return;
-    const uint32_t seen = (old & 0xffffu) + (old >> 16);
-    const int r = (int)(v & 0x1ffffffu);
-    if (seen < (uint32_t)kAdmit) {
-        atomicAdd(sA + cell, (uint32_t)(pos ? r : -r));
-    } else {
-        if ((pos ? (old & 0xffffu) : (old >> 16)) >= 0xfff0u && bad) atomicOr(bad, 0x80000000u);
-        spill_add(spill, cell, pos ? (long long)r : -(long long)r, bad);
-        *s_spilled = 1;
+// A is exact as a signed 32-bit value while the cell holds at most kAdmit (127) events of the interval
+// (|A| <= 127 * 2^24 < 2^31).  Cells that received more ("hot") are detected at flush time from the exact count and
+// recomputed: the interval's records are re-scanned and the hot cells' weights are summed in a small 64-bit hash
+// table.  Carries that do not fit 32 bits live in two more such tables (prev / next).  Both paths are rare, so the
+// common path has no returning atomics and no dependent chains.
+// Counter fields are 16 bits: a pass whose per-cell counts do not add up to the number of records it consumed has
+// wrapped a field (> 65535 events of one polarity on one pixel in one interval) and is reported through bad_count.
+template <bool RESCAN>
+__device__ __forceinline__ int scan_records(const BandArgs& g, int k, int ch0, int t0, int nt, int team, int tl,
+                                            const uint32_t* s_run, const uint16_t* s_kk, uint32_t* sN, uint32_t* sA,
+                                            SpillTable* hot, unsigned int* bad) {
+    constexpr int kTeams = kSweepThreads / kTeam;
+    int matched = 0;
+    // one team of kTeam lanes per chunk; chunks are time-ordered, so the chunks relevant to interval k are (for sorted
+    // input) consecutive and land on distinct teams: one round of loads per pass
+    for (int c = team; c < nt; c += kTeams) {
+        const uint32_t kk = s_kk[c];
+        const int kmin = kk & 0xff, kmax = kk >> 8;
+        // count-only records are not covered by [kmin, kmax]: every chunk is scanned in that pass
+        if (k != (int)kKCountOnly && (k < kmin || k > kmax)) continue;
+        const uint32_t run = s_run[c];
+        const int lo = run & 0xffff, hi = run >> 16;
+        const uint32_t* rv = g.rec_val + (int64_t)(ch0 + t0 + c) * kChunk;
+        const uint16_t* rc = g.rec_cell + (int64_t)(ch0 + t0 + c) * kChunk;
+        for (int i0 = lo + tl; i0 < hi; i0 += kUnroll * kTeam) {
+            uint32_t v[kUnroll], cl[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = i0 + u * kTeam;
+                v[u] = 0xffffffffu;            // interval field 31 + polarity bit: never equals a voxel pass's k ...
+                cl[u] = 0;
+                if (i < hi) { v[u] = __ldcs(rv + i); cl[u] = __ldcs(rc + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (i0 + u * kTeam >= hi) continue;   // ... but the count-only pass has k == 31, so test the bound too
+                if ((int)((v[u] >> kKShift) & 31u) != k) continue;
+                const bool pos = (v[u] >> kPolShift) & 1u;
+                const int r = (int)(v[u] & 0x1ffffffu);
+                if (!RESCAN) {
+                    ++matched;
+                    atomicAdd(sN + cl[u], pos ? 1u : 0x10000u);
+                    if (k != (int)kKCountOnly) atomicAdd(sA + cl[u], (uint32_t)(pos ? r : -r));
+                } else {
+                    const uint32_t n = sN[cl[u]];
+                    if ((n & 0xffffu) + (n >> 16) > (uint32_t)kAdmit) spill_add(hot, cl[u], pos ? (long long)r : -(long long)r, bad);
+                }
+            }
+        }
     }
+    return matched;
 }
 
 __device__ __forceinline__ void spill_clear(SpillTable* t, int tid) {
     for (int i = tid; i < kSpill; i += kSweepThreads) { t->key[i] = 0; t->acc[i] = 0ull; }
+}
+
+__device__ __forceinline__ float q24_to_float(long long val) {
+    // one rounding from the exact fixed-point value; the 32-bit conversion is the same rounding when it applies
+    const int lo = (int)val;
+    const float f = ((long long)lo == val) ? (float)lo : __ll2float_rn(val);
+    return f * (1.0f / 16777216.0f);
 }
 
 // Persistent over the (sample, band) tasks of a group: grid = min(tasks, 2 x SMs).
@@ -345,17 +386,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
     uint32_t* sA = sN + g.cpb;                                              // [cpb]
     uint2* sCS = reinterpret_cast<uint2*>(sA + g.cpb);                      // [cpb] {carry, sum}
     uint2* sCnt = sCS + g.cpb;                                              // [cpb] {count_pos, count_neg} (COUNT only)
-    SpillTable* spill = reinterpret_cast<SpillTable*>(sCnt + (COUNT ? g.cpb : 0));   // [3]: roles rotate, see below
+    SpillTable* spill = reinterpret_cast<SpillTable*>(sCnt + (COUNT ? g.cpb : 0));   // [3]: hot, carry prev, carry next
     uint32_t* s_run = reinterpret_cast<uint32_t*>(spill + 3);              // lo | hi << 16 per staged chunk
     uint16_t* s_kk = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks);  // kmin | kmax << 8 per staged chunk
-    __shared__ int s_spilled[3];
+    __shared__ int s_hot, s_carry[2];          // flags: hot cells in this pass; wide carries in tables prev / next
+    __shared__ unsigned int s_check[2];        // records consumed / events counted in the tile, per pass
 
     const int tid = threadIdx.x;
     const int team = tid / kTeam, tl = tid % kTeam;
-    constexpr int kTeams = kSweepThreads / kTeam;
     const int64_t HW = (int64_t)a.H * a.W;
     const int B = a.num_bins;
     const int n_pass = B + (COUNT ? 1 : 0);
+    SpillTable* hot = spill;
 
     EP_TICK_INIT();
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
@@ -375,7 +417,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
             if (COUNT) sCnt[i] = make_uint2(0u, 0u);
         }
         for (int t = 0; t < 3; ++t) spill_clear(spill + t, tid);
-        if (tid == 0) { s_spilled[0] = 0; s_spilled[1] = 0; s_spilled[2] = 0; }
+        if (tid == 0) { s_hot = 0; s_carry[0] = 0; s_carry[1] = 0; s_check[0] = 0; s_check[1] = 0; }
         if (table_once) {
             for (int c = tid; c < nch; c += kSweepThreads) {
                 const uint16_t* row = g.rows + (int64_t)(ch0 + c) * kRowStride;
@@ -383,13 +425,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
                 s_kk[c] = row[kMaxBands + 1];
             }
         }
-        // spill-table roles: cur = A excess of the running interval, prev = carry excess (read at flush),
-        // next = carry excess for the following interval (written at flush)
-        int cur = 0, prev = 1, next = 2;
+        int prev = 0, next = 1;                            // roles of the two carry tables (spill[1 + prev], spill[1 + next])
 
         // intervals 0..B-1 produce voxel planes; the pseudo-interval kKCountOnly only feeds the count frame
         for (int pass = 0; pass < n_pass; ++pass) {
             const int k = pass < B ? pass : (int)kKCountOnly;
+            int matched = 0;
             for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
                 const int nt = min(kMaxTableChunks, nch - t0);
                 __syncthreads();                           // tile zeroed / flushed, table visible
@@ -402,67 +443,101 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
                     }
                     __syncthreads();
                 }
-                // one team of kTeam lanes per chunk; chunks are time-ordered, so the chunks relevant to interval k are
-                // (for sorted input) consecutive and land on distinct teams: one round of loads per pass
-                for (int c = team; c < nt; c += kTeams) {
-                    const uint32_t kk = s_kk[c];
-                    const int kmin = kk & 0xff, kmax = kk >> 8;
-                    // count-only records are not covered by [kmin, kmax]: every chunk is scanned in that pass
-                    if (k != (int)kKCountOnly && (k < kmin || k > kmax)) continue;
-                    const uint32_t run = s_run[c];
-                    const int lo = run & 0xffff, hi = run >> 16;
-                    const uint32_t* rv = g.rec_val + (int64_t)(ch0 + t0 + c) * kChunk;
-                    const uint16_t* rc = g.rec_cell + (int64_t)(ch0 + t0 + c) * kChunk;
-                    for (int i0 = lo + tl; i0 < hi; i0 += kUnroll * kTeam) {
-                        uint32_t v[kUnroll], cl[kUnroll];
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) {
-                            const int i = i0 + u * kTeam;
-                            if (i < hi) { v[u] = __ldcs(rv + i); cl[u] = __ldcs(rc + i); }
-                        }
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u)
-                            if (i0 + u * kTeam < hi) sweep_record(v[u], cl[u], k, sN, sA, spill + cur, &s_spilled[cur], a.bad_count);
-                    }
-                }
+                matched += scan_records<false>(g, k, ch0, t0, nt, team, tl, s_run, s_kk, sN, sA, hot, a.bad_count);
             }
+            matched = warp_reduce(matched, [](int x, int y) { return x + y; });
+            if ((tid & 31) == 0 && matched) atomicAdd(&s_check[0], (unsigned int)matched);
             __syncthreads();
             EP_TICK(6);                                    // record phase (incl. waiting for the slowest warp)
-            const bool spill_cur = s_spilled[cur] != 0, spill_prev = s_spilled[prev] != 0;
+
+            // ---- flush: every cell of the band emits voxel[k]; hot cells are deferred to the exact path below
+            const bool wide_prev = s_carry[prev] != 0;
             float* o = (pass < B) ? g.out_voxel + ((int64_t)b * B + k) * HW + band_base : nullptr;
+            unsigned int counted = 0;
+#pragma unroll 2
             for (int cell = tid; cell < ncell; cell += kSweepThreads) {
                 const uint32_t n = sN[cell];
-                const int np = (int)(n & 0xffffu), nn = (int)(n >> 16);
-                if (COUNT) { uint2 c = sCnt[cell]; c.x += np; c.y += nn; sCnt[cell] = c; }
-                if (pass < B) {
-                    const uint32_t aw = sA[cell];
-                    const uint2 cs = sCS[cell];
-                    long long A = (long long)(int32_t)aw, carry = (long long)(int32_t)cs.x;
-                    if (spill_cur | spill_prev) {          // rare: some cell of this band exceeded the 32-bit words
-                        if (spill_cur && np + nn > kAdmit) A += spill_get(spill + cur, (unsigned int)cell);
-                        if (spill_prev) carry += spill_get(spill + prev, (unsigned int)cell);
-                        const long long rest = A - (long long)(int32_t)(uint32_t)A;     // carry = low 32 bits + rest
-                        if (rest != 0) { spill_add(spill + next, (unsigned int)cell, rest, a.bad_count); s_spilled[next] = 1; }
+                if (pass >= B) {                           // count-only pseudo-interval
+                    if (n) {
+                        counted += (n & 0xffffu) + (n >> 16);
+                        uint2 c = sCnt[cell]; c.x += n & 0xffffu; c.y += n >> 16; sCnt[cell] = c;
+                        sN[cell] = 0;
                     }
-                    const long long val = ((long long)(np - nn) << kQ) - A + carry;
-                    const float r = __ll2float_rn(val) * (1.0f / 16777216.0f);
-                    st_stream(o + cell, r);
-                    sCS[cell] = make_uint2((uint32_t)A, __float_as_uint(__uint_as_float(cs.y) + r));
-                    if (n) sA[cell] = 0;
+                    continue;
                 }
-                if (n) sN[cell] = 0;
+                const uint2 cs = sCS[cell];
+                if (n == 0 && !wide_prev) {                // no event in this interval: voxel[k] = carry
+                    if (cs.x == 0) { st_stream(o + cell, 0.0f); continue; }
+                    const float r = (float)(int32_t)cs.x * (1.0f / 16777216.0f);
+                    st_stream(o + cell, r);
+                    sCS[cell] = make_uint2(0u, __float_as_uint(__uint_as_float(cs.y) + r));
+                    continue;
+                }
+                const int np = (int)(n & 0xffffu), nn = (int)(n >> 16);
+                counted += (unsigned int)(np + nn);
+                if (np + nn > kAdmit) { s_hot = 1; continue; }       // exact path below; N and A stay for the re-scan
+                if (COUNT) { uint2 c = sCnt[cell]; c.x += np; c.y += nn; sCnt[cell] = c; }
+                const int32_t A = (int32_t)sA[cell];
+                long long carry = (long long)(int32_t)cs.x;
+                if (wide_prev) carry += spill_get(spill + 1 + prev, (unsigned int)cell);
+                const float r = q24_to_float(((long long)(np - nn) << kQ) - (long long)A + carry);
+                st_stream(o + cell, r);
+                sCS[cell] = make_uint2((uint32_t)A, __float_as_uint(__uint_as_float(cs.y) + r));
+                if (n) { sN[cell] = 0; sA[cell] = 0; }
             }
-            if (pass < B && (spill_cur | spill_prev)) {
+            counted = warp_reduce(counted, [](unsigned int x, unsigned int y) { return x + y; });
+            if ((tid & 31) == 0 && counted) atomicAdd(&s_check[1], counted);
+            __syncthreads();
+            if (pass < B && s_hot) {
+                // ---- exact path for hot cells: re-scan the interval's records, 64-bit sums in the hash table
+                for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
+                    const int nt = min(kMaxTableChunks, nch - t0);
+                    if (!table_once) {
+                        __syncthreads();
+                        for (int c = tid; c < nt; c += kSweepThreads) {
+                            const uint16_t* row = g.rows + (int64_t)(ch0 + t0 + c) * kRowStride;
+                            s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
+                            s_kk[c] = row[kMaxBands + 1];
+                        }
+                        __syncthreads();
+                    }
+                    scan_records<true>(g, k, ch0, t0, nt, team, tl, s_run, s_kk, sN, sA, hot, a.bad_count);
+                }
                 __syncthreads();
-                if (spill_cur) spill_clear(spill + cur, tid);
-                if (spill_prev) spill_clear(spill + prev, tid);
-                if (tid == 0) { s_spilled[cur] = 0; s_spilled[prev] = 0; }
-                const int t = prev; prev = next; next = t;     // cur stays (cleared), old prev becomes next (cleared)
-            } else if (pass < B && s_spilled[next]) {
-                const int t = prev; prev = next; next = t;     // unreachable: next is only written on the slow path
+                for (int cell = tid; cell < ncell; cell += kSweepThreads) {
+                    const uint32_t n = sN[cell];
+                    const int np = (int)(n & 0xffffu), nn = (int)(n >> 16);
+                    if (np + nn <= kAdmit) continue;
+                    if (COUNT) { uint2 c = sCnt[cell]; c.x += np; c.y += nn; sCnt[cell] = c; }
+                    const uint2 cs = sCS[cell];
+                    const long long A = spill_get(hot, (unsigned int)cell);
+                    long long carry = (long long)(int32_t)cs.x;
+                    if (wide_prev) carry += spill_get(spill + 1 + prev, (unsigned int)cell);
+                    const float r = q24_to_float(((long long)(np - nn) << kQ) - A + carry);
+                    st_stream(o + cell, r);
+                    const long long rest = A - (long long)(int32_t)(uint32_t)A;      // carry = low 32 bits + rest
+                    if (rest != 0) { spill_add(spill + 1 + next, (unsigned int)cell, rest, a.bad_count); s_carry[next] = 1; }
+                    sCS[cell] = make_uint2((uint32_t)A, __float_as_uint(__uint_as_float(cs.y) + r));
+                    sN[cell] = 0; sA[cell] = 0;
+                }
+                __syncthreads();
+                spill_clear(hot, tid);
+                if (tid == 0) s_hot = 0;
+            }
+            if (pass < B && (wide_prev || s_carry[next])) {
+                // rotate the carry tables: "next" becomes "prev" for the following interval, the old "prev" is cleared
+                __syncthreads();
+                if (wide_prev) spill_clear(spill + 1 + prev, tid);
+                if (tid == 0) s_carry[prev] = 0;
+                const int t = prev; prev = next; next = t;
+            }
+            if (tid == 0) {
+                if (s_check[0] != s_check[1] && a.bad_count) atomicOr(a.bad_count, 0x80000000u);   // a 16-bit count wrapped
+                s_check[0] = 0; s_check[1] = 0;
             }
             // the next pass starts with a __syncthreads() before the tile and the tables are touched again
         }
+        __syncthreads();
         if (g.out_sum && B > 0) {
             float* sp = g.out_sum + (int64_t)b * HW + band_base;
             for (int cell = tid; cell < ncell; cell += kSweepThreads) st_stream(sp + cell, __uint_as_float(sCS[cell].y));

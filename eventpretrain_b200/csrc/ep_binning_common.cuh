@@ -121,12 +121,68 @@ struct SoaCanonLoader {
         double v = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
         return (t_div != 1.0) ? v / t_div : v;
     }
+    __device__ __forceinline__ double time_of(int64_t i, int) const { return time_at(i); }
     __device__ __forceinline__ double raw_at(int64_t i) const {
         return T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
     }
     __device__ __forceinline__ int64_t ticks_at(int64_t i) const {
         return T_IS_I64 ? static_cast<const int64_t*>(t)[i] : 0;
     }
+    __device__ __forceinline__ double div() const { return t_div; }
+};
+
+// compact transport layout (8 B/event): x,y u16; tp u32 = ticks relative to the sample's base in bits 0..30 and the
+// polarity in bit 31; t_base[b] int64 ticks per sample.  Same arithmetic as the int64 canonical layout: the metadata
+// uses (t_base + rel) / t_div like SoaCanonLoader<true>, and the per-event difference rel - rel_first is the same exact
+// integer, so both layouts give bit-identical results.
+struct SoaCompactLoader {
+    const uint16_t* x;
+    const uint16_t* y;
+    const uint32_t* tp;
+    const int64_t* t_base;
+    double t_div;
+    typedef double time_t_;
+    static constexpr bool kFastTime = true;
+    static constexpr bool kTicks = true;
+    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        (void)hi;
+        uint2 xv, yv;
+        uint4 tv;
+        if (i0 + 4 <= a.n_total) {
+            xv = ld_stream(reinterpret_cast<const uint2*>(x + i0));
+            yv = ld_stream(reinterpret_cast<const uint2*>(y + i0));
+            tv = ld_stream(reinterpret_cast<const uint4*>(tp + i0));
+        } else {
+            uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0}, ts_[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < a.n_total) { xs_[j] = x[i0 + j]; ys_[j] = y[i0 + j]; ts_[j] = tp[i0 + j]; }
+            xv = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
+            yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
+            tv = make_uint4(ts_[0], ts_[1], ts_[2], ts_[3]);
+        }
+        const uint32_t raw[4] = {tv.x, tv.y, tv.z, tv.w};
+        const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
+        const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (a.scaled) {
+                e.x[j] = __double2ll_rz(__dmul_rn((double)xs[j], a.sx));
+                e.y[j] = __double2ll_rz(__dmul_rn((double)ys[j], a.sy));
+            } else {
+                e.x[j] = xs[j];
+                e.y[j] = ys[j];
+            }
+            e.ti[j] = (int64_t)(raw[j] & 0x7fffffffu);
+            e.t[j] = 0.0;
+            e.cls[j] = (raw[j] >> 31) ? 0 : 1;           // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
+        }
+    }
+    __device__ __forceinline__ double time_of(int64_t i, int b) const {
+        const double v = (double)(t_base[b] + (int64_t)(tp[i] & 0x7fffffffu));
+        return (t_div != 1.0) ? v / t_div : v;
+    }
+    __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
+    __device__ __forceinline__ int64_t ticks_at(int64_t i) const { return (int64_t)(tp[i] & 0x7fffffffu); }
     __device__ __forceinline__ double div() const { return t_div; }
 };
 
@@ -145,6 +201,7 @@ struct SoaGenericLoader {
     __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
     __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
     __device__ __forceinline__ double div() const { return 1.0; }
+    __device__ __forceinline__ TT time_of(int64_t i, int) const { return time_at(i); }
     __device__ __forceinline__ TT time_at(int64_t i) const {
         if (sizeof(TT) == 4) {
             float v = (t_dtype == EP_F32) ? static_cast<const float*>(t)[i] : (float)load_as_double(t, t_dtype, i);
@@ -187,6 +244,7 @@ struct AosLoader {
     __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
     __device__ __forceinline__ double div() const { return 1.0; }
     __device__ __forceinline__ ET time_at(int64_t i) const { return ev[i * 4 + 2]; }
+    __device__ __forceinline__ ET time_of(int64_t i, int) const { return time_at(i); }
     __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const {
 #pragma unroll
         for (int j = 0; j < kEvPerThread; ++j) {
@@ -255,7 +313,7 @@ __global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
     SampleMeta m;
     m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.pad = 0; m.scale_raw = 0.0; m.t0_raw = 0.0; m.t0_ticks = 0;
     if (hi > lo) {
-        const TT first = ld.time_at(lo), last = ld.time_at(hi - 1);
+        const TT first = ld.time_of(lo, b), last = ld.time_of(hi - 1, b);
         TT d = last - first;
         if (d == (TT)0) d = (TT)1;
         m.t0 = (double)first;

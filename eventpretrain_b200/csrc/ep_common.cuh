@@ -64,12 +64,13 @@ __device__ __forceinline__ double load_as_double(const void* base, int dtype, in
         case EP_U16: return (double)static_cast<const uint16_t*>(base)[i];
         case EP_I16: return (double)static_cast<const int16_t*>(base)[i];
         case EP_I32: return (double)static_cast<const int32_t*>(base)[i];
+        case EP_U32: return (double)static_cast<const uint32_t*>(base)[i];
         case EP_I64: return (double)static_cast<const int64_t*>(base)[i];
         case EP_F32: return (double)static_cast<const float*>(base)[i];
         default: return static_cast<const double*>(base)[i];
     }
 }
 
-inline bool valid_dtype(int d) { return d >= EP_U8 && d <= EP_F64; }
+inline bool valid_dtype(int d) { return d >= EP_U8 && d <= EP_U32; }
 
 }  // namespace ep

@@ -18,7 +18,7 @@ _NP_TAG = {np.dtype(np.uint8): _lib.EP_U8, np.dtype(np.int8): _lib.EP_I8, np.dty
            np.dtype(np.float32): _lib.EP_F32, np.dtype(np.float64): _lib.EP_F64}
 _TORCH_TAG = {torch.uint8: _lib.EP_U8, torch.int8: _lib.EP_I8, torch.uint16: _lib.EP_U16, torch.int16: _lib.EP_I16,
               torch.int32: _lib.EP_I32, torch.int64: _lib.EP_I64, torch.float32: _lib.EP_F32,
-              torch.float64: _lib.EP_F64}
+              torch.float64: _lib.EP_F64, torch.uint32: _lib.EP_U32}
 
 
 @dataclass
@@ -31,6 +31,8 @@ class RaggedEvents:
     offsets: torch.Tensor          # int64 (B+1), same device as the data
     offsets_host: np.ndarray       # int64 (B+1)
     t_div: float = 1.0             # timestamp value = t / t_div (int64 microseconds, t_div=1e6 -> seconds)
+    t_base: torch.Tensor = None    # compact layout only: int64 (B,) per-sample base ticks; then t is uint32
+                                   # (relative ticks | polarity << 31) and p is None
 
     @property
     def batch(self):
@@ -44,18 +46,49 @@ class RaggedEvents:
     def device(self):
         return self.x.device
 
+    def _arrays(self):
+        return [a for a in (self.x, self.y, self.t, self.p, self.offsets, self.t_base) if a is not None]
+
     def nbytes(self):
-        return sum(int(a.numel()) * a.element_size() for a in (self.x, self.y, self.t, self.p, self.offsets))
+        return sum(int(a.numel()) * a.element_size() for a in self._arrays())
+
+    def _map(self, f):
+        g = lambda a: None if a is None else f(a)
+        return RaggedEvents(g(self.x), g(self.y), g(self.t), g(self.p), g(self.offsets), self.offsets_host, self.t_div,
+                            g(self.t_base))
 
     def to(self, device, non_blocking=True):
-        mv = lambda a: a.to(device, non_blocking=non_blocking)
-        return RaggedEvents(mv(self.x), mv(self.y), mv(self.t), mv(self.p), mv(self.offsets), self.offsets_host,
-                            self.t_div)
+        return self._map(lambda a: a.to(device, non_blocking=non_blocking))
 
     def pin_memory(self):
-        pm = lambda a: a.pin_memory()
-        return RaggedEvents(pm(self.x), pm(self.y), pm(self.t), pm(self.p), pm(self.offsets), self.offsets_host,
-                            self.t_div)
+        return self._map(lambda a: a.pin_memory())
+
+    def compact(self):
+        """Host-side repack into the 8 B/event transport layout: u16 x,y + u32 (ticks relative to the sample's first
+        stamp | polarity << 31).  Needs int64 tick stamps, p in {0,1} and < 2^31 ticks between a sample's smallest and
+        largest stamp.  Binning results are bit-identical to the int64 layout; H2D traffic drops from 13 to 8 B/event."""
+        if self.t_base is not None:
+            return self
+        if self.t.dtype != torch.int64 or self.p.dtype != torch.uint8 or self.x.dtype != torch.uint16:
+            raise TypeError("compact() needs the canonical u16 / int64-tick / u8 layout")
+        off = self.offsets_host
+        t = self.t.cpu().numpy()
+        p = self.p.cpu().numpy()
+        B = self.batch
+        base = np.zeros(B, np.int64)
+        rel = np.empty(t.shape[0], np.uint32)
+        for b in range(B):
+            lo, hi = int(off[b]), int(off[b + 1])
+            if hi > lo:
+                base[b] = t[lo:hi].min()
+                d = t[lo:hi] - base[b]
+                if d.max() >= (1 << 31):
+                    raise ValueError("sample spans more than 2^31 ticks")
+                rel[lo:hi] = d.astype(np.uint32)
+        rel |= p.astype(np.uint32) << np.uint32(31)
+        mk = (lambda a: a.pin_memory()) if (self.x.is_pinned() or self.x.is_cuda) and torch.cuda.is_available() else (lambda a: a)
+        return RaggedEvents(self.x, self.y, mk(torch.from_numpy(rel)).to(self.x.device), None, self.offsets, off, self.t_div,
+                            mk(torch.from_numpy(base)).to(self.x.device))
 
     def shard(self, rank, world_size):
         """Samples [rank*B/G, (rank+1)*B/G): DistributedSampler-style contiguous split (main_pretrain.py:218-220).
@@ -63,7 +96,7 @@ class RaggedEvents:
         B = self.batch
         lo, hi = (B * rank) // world_size, (B * (rank + 1)) // world_size
         return RaggedEvents(self.x, self.y, self.t, self.p, self.offsets[lo:hi + 1], self.offsets_host[lo:hi + 1],
-                            self.t_div)
+                            self.t_div, None if self.t_base is None else self.t_base[lo:hi])
 
     def _desc(self):
         d = _lib.EventsSoa()
@@ -72,7 +105,8 @@ class RaggedEvents:
             raise TypeError("x and y must share a dtype")
         d.xy_dtype = _TORCH_TAG[self.x.dtype]
         d.t_dtype = _TORCH_TAG[self.t.dtype]
-        d.p_dtype = _TORCH_TAG[self.p.dtype]
+        d.p_dtype = _TORCH_TAG[self.p.dtype] if self.p is not None else 0
+        d.t_base = ptr(self.t_base)
         d.batch = self.batch
         d.t_div = float(self.t_div)
         d.offsets = ptr(self.offsets)

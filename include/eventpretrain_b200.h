@@ -48,7 +48,7 @@ extern "C" {
 
 /* dtype tags for ragged event buffers */
 enum ep_dtype {
-    EP_U8 = 1, EP_I8 = 2, EP_U16 = 3, EP_I16 = 4, EP_I32 = 5, EP_I64 = 6, EP_F32 = 7, EP_F64 = 8
+    EP_U8 = 1, EP_I8 = 2, EP_U16 = 3, EP_I16 = 4, EP_I32 = 5, EP_I64 = 6, EP_F32 = 7, EP_F64 = 8, EP_U32 = 9
 };
 
 EP_API int ep_abi_version(void);
@@ -90,6 +90,10 @@ typedef struct ep_events_soa {
     double t_div;
     const int64_t* offsets;      /* device, B+1 entries, offsets[0] may be > 0 */
     const int64_t* offsets_host; /* host copy of the same B+1 entries (required: sizes the launches) */
+    const int64_t* t_base;       /* device, B entries, or NULL.  Compact transport layout (8 B/event, ep_bin_events only):
+                                    t_dtype = EP_U32 holds ticks relative to t_base[b] in bits 0..30 and the polarity in
+                                    bit 31, p = NULL; timestamp value = (t_base[b] + ticks) / t_div.  Bit-identical
+                                    results to the int64 canonical layout. */
 } ep_events_soa;
 
 /* Array-of-structures single sample: the reference's own (N,4) x,y,t,p array

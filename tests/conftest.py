@@ -33,6 +33,11 @@ def golden_stage3():
 
 
 @pytest.fixture(scope="session")
+def golden_stream_aug():
+    return _load("stream_aug.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_views():
     return _load("views.npz")
 

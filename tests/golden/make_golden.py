@@ -352,6 +352,27 @@ def view_cases(ref):
     return out
 
 
+def stream_aug_cases(ref):
+    """events_augment / add_noise_events (dataset/augmentation/events_augment.py:28-86) with seeds, then binned by the
+    reference: pins the RNG order of the host-side mirror and the binning of the fractional coordinates it produces."""
+    import importlib
+    ea = importlib.import_module("dataset.augmentation.events_augment")
+    rng = np.random.default_rng(6001)
+    ev = uniform_stream(rng, 5000, 64, 48)
+    args = SimpleNamespace(num_bins=5)
+    out = {}
+    for sd in (1, 2):
+        aug = ea.events_augment(args, ev.copy(), size=(48, 64), seed=sd)
+        out[f"erase_add_s{sd}"] = dict(events=ev, seed=np.asarray(sd), aug=aug, voxel=ref.voxel(args, aug.copy(), (48, 64)).numpy(),
+                                       ecdp=ref.eti.events_to_image_ecdp(args, aug.copy(), (48, 64)).numpy())
+    np.random.seed(3)
+    noisy = ea.add_noise_events(args, ev.copy(), (48, 64))
+    out["add_noise_s3"] = dict(events=ev, seed=np.asarray(3), aug=noisy)
+    tiny = uniform_stream(rng, 50, 16, 12)
+    out["erase_add_tiny"] = dict(events=tiny, seed=np.asarray(4), aug=ea.events_augment(args, tiny.copy(), size=(12, 16), seed=4))
+    return out
+
+
 def main():
     ref = _import_reference()
     torch.set_num_threads(1)
@@ -364,7 +385,10 @@ def main():
     vc = view_cases(ref)
     flat = {f"{case}/{k}": v for case, rec in vc.items() for k, v in rec.items()}
     np.savez_compressed(os.path.join(HERE, "views.npz"), **flat)
-    for f in ("stage1_events.npz", "stage3_mask_patch.npz", "views.npz"):
+    sa = stream_aug_cases(ref)
+    flat = {f"{case}/{k}": v for case, rec in sa.items() for k, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "stream_aug.npz"), **flat)
+    for f in ("stage1_events.npz", "stage3_mask_patch.npz", "views.npz", "stream_aug.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
     print("torch", torch.__version__, "numpy", np.__version__)
 

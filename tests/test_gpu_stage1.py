@@ -277,3 +277,20 @@ def test_time_surface_self_oracle(ep):
     for b, s in enumerate(samples):
         ref = s3.time_surface(s[:, 0], s[:, 1], s[:, 2], s[:, 3], (H, W), 0.01)
         assert np.allclose(out[b], ref, rtol=1e-6, atol=1e-7), b
+
+
+def test_compact_transport_layout(ep):
+    """8 B/event transport layout (u16 x,y + u32 relative ticks | polarity << 31) gives bit-identical tensors."""
+    rng = np.random.default_rng(41)
+    H, W = 60, 80
+    ev, _ = _random_batch(ep, rng, [30000, 0, 1, 5003], H, W)
+    host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu() + 1_700_000_000_000_000, ev.p.cpu(), ev.offsets.cpu(),
+                           ev.offsets_host, ev.t_div)
+    comp = host.compact()
+    assert comp.p is None and comp.t.dtype == torch.uint32 and comp.nbytes() < 0.65 * host.nbytes()
+    a = ep.bin_events(host.to("cuda"), (H, W), num_bins=5, count_channels=2, voxel_sum=True, check=True)
+    b = ep.bin_events(comp.to("cuda"), (H, W), num_bins=5, count_channels=2, voxel_sum=True, check=True)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b[key]), key
+    c = ep.bin_events(comp.to("cuda").shard(1, 2), (H, W), num_bins=5, check=True)
+    assert torch.equal(c["voxel"], a["voxel"][2:])

@@ -82,3 +82,30 @@ def test_batched_views_and_shared_seed(native_lib):
     for i in range(4):
         ref = _torch_apply(grids[i].cpu(), choices[i], (224, 224), "bilinear")
         assert torch.allclose(out[i].cpu(), ref, rtol=1e-5, atol=2e-6)
+
+
+def test_event_stream_augmentation_rng_mirror(golden_stream_aug):
+    """Row f2: erase_and_add_events / add_noise_events drop-ins reproduce the reference's seeded output bit for bit."""
+    import eventpretrain_b200 as ep
+    args = SimpleNamespace(num_bins=5)
+    for name, c in golden_stream_aug.items():
+        ev, sd = c["events"].copy(), int(c["seed"])
+        if name.startswith("add_noise"):
+            np.random.seed(sd)
+            got = ep.add_noise_events(args, ev, (48, 64))
+        else:
+            size = (12, 16) if name.endswith("tiny") else (48, 64)
+            got = ep.events_augment(args, ev, size=size, seed=sd)
+        assert np.array_equal(got, c["aug"]), name
+
+
+@pytest.mark.gpu
+def test_augmented_streams_bin_like_reference(golden_stream_aug, native_lib):
+    import eventpretrain_b200 as ep
+    args = SimpleNamespace(num_bins=5)
+    for name in ("erase_add_s1", "erase_add_s2"):
+        c = golden_stream_aug[name]
+        aug = ep.events_augment(args, c["events"].copy(), size=(48, 64), seed=int(c["seed"]))
+        v = ep.events_to_voxel_grid(args, aug, (48, 64)).numpy()
+        assert np.all(np.abs(v - c["voxel"]) <= 1e-5 * np.abs(c["voxel"]) + 1e-6)
+        assert np.array_equal(ep.events_to_image_ecdp(args, aug, (48, 64)).numpy(), c["ecdp"])
