@@ -1,22 +1,22 @@
-// Stage 1, fast path — banded shared-memory sweep (sm_100a).
+// Stage 1, alternative path — banded shared-memory sweep (sm_100a).  EXPERIMENTAL in round 1: correct and bit-identical
+// to the global-RED path (tests/test_gpu_stage1.py::test_banded_*), selected only with EP_BIN_FORCE_BANDED because it is
+// still slower on the benchmark workload (3.8 ms vs 2.9 ms per step; analysis in profiles/r01_banded_phase_timing.txt).
 //
-// Same arithmetic and outputs as the global-RED path in ep_binning.cu (events_to_voxel_grid.py:4-61,
-// events_to_image.py:6-62), but no global atomics and no accumulator round trip:
+// Same arithmetic and outputs as ep_binning.cu (events_to_voxel_grid.py:4-61, events_to_image.py:6-62), but no global
+// atomics and no accumulator round trip:
 //
 //   route  (k_route)   one pass over the events of a sample group: each CTA takes a 4096-event chunk, computes
-//                      (cell, interval k, r = rn(d*2^24), polarity) per event, counting-sorts the chunk by
-//                      spatial band in shared memory and writes it back as 6-byte records
-//                      (u16 cell-in-band + u32 r|k<<25|p<<30) with a per-chunk band-offset row.  The record
-//                      buffer of a group is sized to stay L2-resident.
-//   sweep  (k_sweep)   one CTA per (sample, band) owns its band for every interval: per interval it pulls the
-//                      band's records, accumulates them with shared-memory ATOMS.ADD.u32 (measured ~8x the
-//                      throughput of global RED on B200) into two words per cell,
+//                      (cell, interval k, r = rn(d*2^24), polarity) per event, counting-sorts the chunk by spatial band
+//                      in shared memory and writes it back as 6-byte records (u16 cell-in-band + u32 r|k<<25|p<<30)
+//                      with a per-chunk band-offset row.  The record buffer of a group is sized to stay L2-resident.
+//   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks and own the band for every interval: per interval they
+//                      pull the band's records, accumulate them with fire-and-forget shared-memory ATOMS.ADD.u32
+//                      (measured ~8x the throughput of global RED on B200) into two words per cell,
 //                          N = n_pos | n_neg << 16     (exact polarity counts)
-//                          A = sum p*r  (mod 2^32)     (only the first 127 events of the cell are admitted,
-//                                                       which keeps |A| < 2^31; later ones go to a small
-//                                                       64-bit spill table keyed by cell)
-//                      then emits voxel[k] = (C_k*2^24 - A_k + A_{k-1}) * 2^-24 for its rows straight to the
-//                      fp32 output (coalesced, streaming), carrying A_{k-1} in registers.
+//                          A = sum p*r  (mod 2^32)     (exact while the cell holds <= 127 events of the interval)
+//                      then emit voxel[k] = (C_k*2^24 - A_k + A_{k-1}) * 2^-24 for their cells straight to the fp32 output
+//                      (coalesced, streaming).  Cells with more than 127 events in an interval are detected from the
+//                      exact count and recomputed by re-scanning the interval into a 64-bit hash table.
 //
 // Integer accumulation => the result is order-independent and bit-identical to the global-RED path.
 // Unsorted input is handled (chunks are revisited for every interval they contain), just slower.
@@ -701,13 +701,11 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
         // ... then trimmed so that its (sample, band) tasks fill whole waves of the resident sweep CTAs: a group of 12
         // samples x 50 bands = 600 tasks on 296 slots runs 3 rounds (2.03 needed), 11 samples run 2
         int g1 = g_max;
-        if (g_max < B || true) {
-            double best = -1.0;
-            for (int cand = g_max; cand > g0 && cand >= g0 + (g_max - g0 + 1) / 2; --cand) {
-                const int64_t tasks = (int64_t)(cand - g0) * bp.nb;
-                const double eff = (double)tasks / (double)(ceil_div64(tasks, slots) * slots);
-                if (eff > best + 1e-9) { best = eff; g1 = cand; }
-            }
+        double best = -1.0;
+        for (int cand = g_max; cand > g0 && cand >= g0 + (g_max - g0 + 1) / 2; --cand) {
+            const int64_t tasks = (int64_t)(cand - g0) * bp.nb;
+            const double eff = (double)tasks / (double)(ceil_div64(tasks, slots) * slots);
+            if (eff > best + 1e-9) { best = eff; g1 = cand; }
         }
         cur = 0;
         for (int b = g0; b < g1; ++b) cur += chunks_of(off, b);
