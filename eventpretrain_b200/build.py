@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-lcudart"]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 
