@@ -32,6 +32,7 @@ namespace ep {
 int run_banded_canon(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
                      float* out_count, void* ws, size_t ws_bytes, unsigned int* bad);
 size_t banded_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
+bool banded_worthwhile(const ep_events_soa* ev, const ep_bin_params* p);
 
 namespace {
 
@@ -395,33 +396,30 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     for (int b = 0; b < B; ++b) if (ev->offsets_host[b + 1] < ev->offsets_host[b]) return EP_EINVAL;
     if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || !ev->y || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (ev->t_dtype == EP_U32) {
+    const bool compact = ev->t_dtype == EP_U32;
+    if (compact) {
         // compact transport layout: u16 x,y + u32 (relative ticks | polarity << 31) + per-sample int64 base
         if (ev->xy_dtype != EP_U16 || ev->p != nullptr || !ev->t_base || prm->time_f32) return EP_EINVAL;
         if (!aligned16(ev->x) || !aligned16(ev->y) || !aligned16(ev->t)) return EP_EALIGN;
-        if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
-        SoaCompactLoader ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y),
-                            static_cast<const uint32_t*>(ev->t), ev->t_base, ev->t_div};
-        return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
-                           workspace_bytes, bad_count);
     }
-    const bool canon = ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && !prm->time_f32 &&
+    const bool canon = !compact && ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && !prm->time_f32 &&
                        (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64) && aligned16(ev->x) && aligned16(ev->y) &&
                        aligned16(ev->t) && aligned16(ev->p);
-    if (canon && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
-        // fast path: banded shared-memory sweep.  Falls through to the global-RED path when the shape does not
+    if ((canon || compact) && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
+        // fast path: route + banded shared-memory sweep.  Falls through to the global-RED path when the shape does not
         // qualify, the batch is too small to fill the machine, or the caller's workspace is too small for it.
-        const int64_t HWc = (int64_t)prm->height * prm->width;
-        // round 1: the banded sweep is correct but still slower than the global-RED path on B200 (3.8 vs 3.05 ms per
-        // step on the benchmark workload), so it is used only on request
-        const bool worth = (prm->flags & EP_BIN_FORCE_BANDED) != 0;
-        (void)HWc;
-        if (worth) {
+        if ((prm->flags & EP_BIN_FORCE_BANDED) || banded_worthwhile(ev, prm)) {
             rc = run_banded_canon(st, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count);
             if (rc == EP_OK || (rc != EP_EUNSUPPORTED && rc != EP_EWORKSPACE) || (prm->flags & EP_BIN_FORCE_BANDED)) return rc;
         }
     } else if (prm->flags & EP_BIN_FORCE_BANDED) {
         return EP_EUNSUPPORTED;
+    }
+    if (compact) {
+        SoaCompactLoader ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y),
+                            static_cast<const uint32_t*>(ev->t), ev->t_base, ev->t_div};
+        return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
+                           workspace_bytes, bad_count);
     }
     if (canon) {
         if (ev->t_dtype == EP_I64) {

@@ -1,25 +1,25 @@
-// Stage 1, alternative path — banded shared-memory sweep (sm_100a).  EXPERIMENTAL in round 1: correct and bit-identical
-// to the global-RED path (tests/test_gpu_stage1.py::test_banded_*), selected only with EP_BIN_FORCE_BANDED because it is
-// still slower on the benchmark workload (3.8 ms vs 2.9 ms per step; analysis in profiles/r01_banded_phase_timing.txt).
+// Stage 1, fast path — route + banded shared-memory sweep (sm_100a).
 //
-// Same arithmetic and outputs as ep_binning.cu (events_to_voxel_grid.py:4-61, events_to_image.py:6-62), but no global
-// atomics and no accumulator round trip:
+// Same arithmetic and outputs as ep_binning.cu (events_to_voxel_grid.py:4-61, events_to_image.py:6-62), bit for bit,
+// but no global atomics and no accumulator round trip through L2:
 //
-//   route  (k_route)   one pass over the events of a sample group: each CTA takes a 4096-event chunk, computes
-//                      (cell, interval k, r = rn(d*2^24), polarity) per event, counting-sorts the chunk by spatial band
-//                      in shared memory and writes it back as 6-byte records (u16 cell-in-band + u32 r|k<<25|p<<30)
-//                      with a per-chunk band-offset row.  The record buffer of a group is sized to stay L2-resident.
-//   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks and own the band for every interval: per interval they
-//                      pull the band's records, accumulate them with fire-and-forget shared-memory ATOMS.ADD.u32
-//                      (measured ~8x the throughput of global RED on B200) into two words per cell,
-//                          N = n_pos | n_neg << 16     (exact polarity counts)
-//                          A = sum p*r  (mod 2^32)     (exact while the cell holds <= 127 events of the interval)
-//                      then emit voxel[k] = (C_k*2^24 - A_k + A_{k-1}) * 2^-24 for their cells straight to the fp32 output
-//                      (coalesced, streaming).  Cells with more than 127 events in an interval are detected from the
-//                      exact count and recomputed by re-scanning the interval into a 64-bit hash table.
+//   route  (k_route)   one pass over the events of a sample group.  A CTA takes a chunk of consecutive events of one
+//                      sample, computes per event (cell, interval k, r = rn(d * 2^24), polarity) — integer fixed-point
+//                      time arithmetic for tick stamps (ticks_to_v) — counting-sorts the chunk by spatial band in shared
+//                      memory and writes it back, coalesced, as 8-byte records {cell, r | k << 25 | negative << 31}
+//                      plus one (begin, end) entry per band.  The record buffer of a group is sized to stay L2-resident.
+//   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks and own the band's cells for a window of up to 6 voxel
+//                      planes in shared memory: int32 Q24 planes + one count word per cell.  Per record: two
+//                      fire-and-forget ATOMS.ADD on the planes k and k+1 (p * (2^24 - r), p * r) and one on the count
+//                      word (n_pos | n_neg << 16).  The flush converts the planes to fp32 (one rounding from the exact
+//                      integer), adds the fused voxel.sum(0) plane and the polarity count frame, and writes every
+//                      output element exactly once with 16-byte streaming stores.
 //
-// Integer accumulation => the result is order-independent and bit-identical to the global-RED path.
-// Unsorted input is handled (chunks are revisited for every interval they contain), just slower.
+// Exactness: a plane word is exact while the cell saw at most 127 records in the window (127 * 2^24 < 2^31); the
+// count word tells (fields are 16 bits; a band whose counts do not add up to the records it consumed has wrapped a
+// field and is reported through bad_count bit 31).  A band with a hotter cell is redone with 64-bit planes (atom.u64
+// in shared memory), so results never depend on the distribution.  Integer accumulation => order independent,
+// bit-reproducible, and identical to the global-RED path.
 #include <stdio.h>
 
 #include "ep_binning_common.cuh"
@@ -27,24 +27,21 @@
 namespace ep {
 namespace {
 
-constexpr int kChunk = 4096;            // events per routed chunk
-constexpr int kRouteThreads = 512;      // 2 quads (8 events) per thread
-constexpr int kMaxBands = 64;
-constexpr int kSweepThreads = 512;
-constexpr int kCPT4 = 3;                // quads of cells per sweep thread (register-resident A_{k-1} and sum)
-constexpr int kCPT = 4 * kCPT4;
-constexpr int kMaxCellsPerBand = kCPT * kSweepThreads;   // 6144 cells -> 48 KB of tile, two CTAs per SM
-constexpr int kTeam = 8;                // lanes that walk one chunk's run of records together
-constexpr int kUnroll = 12;             // records in flight per lane: a typical run (4096 / 50 bands) is one round
-constexpr int kAdmit = 127;             // events per (cell, interval) accumulated in the 32-bit A word
-constexpr int kSpill = 256;             // spill-table slots per CTA (power of two)
-constexpr int kRowStride = kMaxBands + 2;   // u16 entries per chunk row: offsets[0..NB], then kmin|kmax<<8
-constexpr int kMaxTableChunks = 1024;   // chunk rows of one sample staged in shared memory at a time
-constexpr uint32_t kKShift = 25, kPolShift = 30;
-constexpr uint32_t kKCountOnly = 31;    // interval code of events outside the time bins (count frame only)
+constexpr int kMaxBands = 255;
+constexpr uint32_t kKShift = 25;            // record value: r (25 bits) | k << 25 (5 bits) | negative << 31
+constexpr uint32_t kKCountOnly = 31;        // interval code of events outside the time bins (count frame only)
+constexpr int kAdmit = 127;                 // records per cell and window the int32 planes hold exactly
+constexpr int kMaxWindowPlanes = 6;
+constexpr int kBufSets = 2;                 // record buffers: the route of group g + 1 runs while group g is swept
+constexpr int kMaxTableChunks = 1024;       // chunk-table entries of one sample staged in shared memory at a time
+constexpr int kSweepSmemBudget = 232448 - 1024;   // opt-in shared memory per CTA minus static use
 
-// Optional per-phase cycle accounting (build with -DEP_PHASE_TIMING; tools only, never in the shipped library).
+enum { kKindTicks64 = 0, kKindF64 = 1, kKindCompact = 2 };
+
+// Optional per-phase cycle accounting (build with EP_PHASE_TIMING=1; tools only, never in the shipped library):
+// thread 0 of every CTA adds the cycles between phase boundaries to g.dbg[slot].
 #ifdef EP_PHASE_TIMING
+#define EP_TICK_INIT() long long _t_last = clock64()
 #define EP_TICK(slot)                                                                      \
     do {                                                                                   \
         if (threadIdx.x == 0) {                                                            \
@@ -53,23 +50,44 @@ constexpr uint32_t kKCountOnly = 31;    // interval code of events outside the t
             _t_last = _now;                                                                \
         }                                                                                  \
     } while (0)
-#define EP_TICK_INIT() long long _t_last = clock64()
 #else
-#define EP_TICK(slot) do { } while (0)
 #define EP_TICK_INIT() do { } while (0)
+#define EP_TICK(slot) do { } while (0)
 #endif
 
+struct __align__(16) ChunkInfo {
+    int64_t c_lo;            // first event slot of the chunk (multiple of 4; may precede the sample's first event)
+    int32_t b;               // owning sample
+    uint16_t lo_off, hi_off; // the sample's events inside the chunk: [c_lo + lo_off, c_lo + hi_off)
+    // copy of the owning sample's integer-time constants (SampleMeta), so the steady-state path needs this one load
+    int64_t t0_ticks;
+    uint32_t tmul, tshift;
+    uint32_t thalf, flags;
+    uint32_t pad[2];
+};
+
+struct RouteSrc {
+    const uint16_t* x;
+    const uint16_t* y;
+    const void* t;           // int64 ticks | fp64 | uint32 (relative ticks | p << 31)
+    const uint8_t* p;
+};
+
 struct BandArgs {
-    BinArgs bin;                 // offsets, meta, geometry, bad_count (begin/end/g0/g1 describe the group)
+    BinArgs bin;                 // offsets, meta, geometry, bad_count (g0/g1 describe the group)
     int nb;                      // bands
-    int cpb;                     // cells per band
+    int cpb;                     // cells per band (multiple of 4)
     uint32_t cpb_magic;          // flat / cpb == umulhi(flat, cpb_magic) >> cpb_shift  for flat < 2^31
     int cpb_shift;
+    int P;                       // voxel planes per window
+    int chunk;                   // events per routed chunk
     const int32_t* chunk_first;  // [B+1] first chunk id of each sample (global numbering)
+    const ChunkInfo* info;       // [total chunks]
     int chunk_begin;             // first chunk id of this group
-    uint16_t* rows;              // [chunks_in_group][kRowStride]
-    uint32_t* rec_val;           // [chunks_in_group][kChunk]
-    uint16_t* rec_cell;          // [chunks_in_group][kChunk]
+    int gchunks;                 // row length of runs
+    uint32_t* runs;              // [nb][gchunks]  begin | end << 16 of the band's records inside the chunk
+    uint16_t* kk;                // [gchunks]      kmin | kmax << 8 of the chunk's in-bins records (255 | 0 when none)
+    uint2* rec;                  // [gchunks][chunk]
     float* out_voxel; float* out_sum; float* out_count;
     unsigned long long* dbg;     // phase cycle counters (EP_PHASE_TIMING builds), else unused
 };
@@ -78,8 +96,13 @@ __device__ __forceinline__ int64_t sample_chunk_origin(const BinArgs& a, int b) 
     return off_at(a, b) / kEvPerThread * kEvPerThread;   // chunks start on the 4-event grid of the arrays
 }
 
-// ---- chunk numbering: chunks of sample b = ceil((off[b+1] - align4(off[b])) / kChunk) ------------------
-__global__ void __launch_bounds__(1024) k_chunk_prefix(BinArgs a, int B, int32_t* __restrict__ chunk_first) {
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// ---- chunk numbering: chunks of sample b = ceil((off[b+1] - align4(off[b])) / chunk) --------------------
+__global__ void __launch_bounds__(1024) k_chunk_prefix(BinArgs a, int B, int chunk, int32_t* __restrict__ chunk_first) {
     __shared__ int s_warp[32];
     __shared__ int s_base, s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -90,7 +113,7 @@ __global__ void __launch_bounds__(1024) k_chunk_prefix(BinArgs a, int B, int32_t
         int v = 0;
         if (b < B) {
             const int64_t lo = sample_chunk_origin(a, b), hi = off_at(a, b + 1);
-            v = hi > off_at(a, b) ? (int)ceil_div64(hi - lo, kChunk) : 0;
+            v = hi > off_at(a, b) ? (int)ceil_div64(hi - lo, chunk) : 0;
         }
         const int incl = warp_incl_scan(v, lane);
         if (lane == 31) s_warp[warp] = incl;
@@ -109,265 +132,730 @@ __global__ void __launch_bounds__(1024) k_chunk_prefix(BinArgs a, int B, int32_t
     }
 }
 
+__global__ void __launch_bounds__(256) k_chunk_info(BinArgs a, int B, int chunk, const int32_t* __restrict__ chunk_first,
+                                                    int n_chunks, ChunkInfo* __restrict__ info) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    int lo = 0, hi = B;                   // smallest j in (0, B] with chunk_first[j] > c; owner = j - 1 (never empty)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_first[mid] > c) hi = mid; else lo = mid;
+    }
+    const int b = lo;
+    const int64_t s_lo = off_at(a, b), s_hi = off_at(a, b + 1);
+    const int64_t c_lo = sample_chunk_origin(a, b) + (int64_t)(c - chunk_first[b]) * chunk;
+    ChunkInfo ci;
+    ci.c_lo = c_lo;
+    ci.b = b;
+    ci.lo_off = (uint16_t)(c_lo < s_lo ? s_lo - c_lo : 0);
+    ci.hi_off = (uint16_t)(c_lo + chunk < s_hi ? chunk : s_hi - c_lo);
+    const SampleMeta m = a.meta[b];
+    ci.t0_ticks = m.t0_ticks; ci.tmul = m.tmul; ci.tshift = m.tshift; ci.thalf = m.thalf; ci.flags = m.flags;
+    ci.pad[0] = ci.pad[1] = 0;
+    info[c] = ci;
+}
+
+// ---- shared-memory access through 32-bit window addresses (computed once per kernel; keeps the per-event code free
+// of address-space conversions) -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_add64(uint32_t addr, unsigned long long v) {
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
 // ---- route ------------------------------------------------------------------------------------------------
-struct RouteInfo {          // per-CTA facts computed once by thread 0
-    int b;
-    int lean;
-    int64_t c_lo, ev_lo, ev_hi;
-    SampleMeta m;
+struct RouteConst {
+    uint32_t W, HW;
+    uint32_t tmul, tshift, thalf, v_end, v_last;
+    uint32_t cpb_magic, cpb_shift, drop_band;
+    int64_t t0_ticks;
+    const SampleMeta* meta;      // the owning sample's metadata: fp64 time constants, read on the non-lean paths only
+    int num_bins, count;
+    bool int_time, scaled;
 };
 
-template <class Loader>
-__global__ void __launch_bounds__(kRouteThreads, 2) k_route(Loader ld, BandArgs g) {
-    __shared__ __align__(16) uint32_t s_val[kChunk];
-    __shared__ __align__(16) uint16_t s_cell[kChunk];
-    __shared__ int s_cnt[kMaxBands], s_base[kMaxBands + 1], s_cur[kMaxBands];
-    __shared__ int s_kmin, s_kmax;
-    __shared__ RouteInfo s_info;
-    const BinArgs& a = g.bin;
-    if (threadIdx.x == 0) {
-        const int chunk = g.chunk_begin + blockIdx.x;
-        int lo = a.g0, hi = a.g1;          // owning sample: last b in [g0, g1) with chunk_first[b] <= chunk
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (g.chunk_first[mid] <= chunk) lo = mid; else hi = mid;
-        }
-        const int b = lo;
-        const int64_t s_lo = off_at(a, b), s_hi = off_at(a, b + 1);
-        const int64_t c_lo = sample_chunk_origin(a, b) + (int64_t)(chunk - g.chunk_first[b]) * kChunk;
-        s_info.b = b;
-        s_info.c_lo = c_lo;
-        s_info.ev_lo = c_lo > s_lo ? c_lo : s_lo;
-        s_info.ev_hi = (c_lo + kChunk < s_hi) ? c_lo + kChunk : s_hi;
-        // interior chunk (all 4096 events belong to sample b, hence lie inside the arrays), unscaled coordinates:
-        // lean 32-bit path without per-event range checks; everything else takes the general loader path
-        s_info.lean = Loader::kFastTime && !a.scaled && c_lo >= s_lo && c_lo + kChunk <= s_hi && a.W < 65536;
-        s_info.m = a.meta[b];
-        s_kmin = 255; s_kmax = 0;
+// One event -> record words, branch-free on the steady-state path.  v = rn(ts * 2^24) (interval k = v >> 24, right
+// weight r = v & 0xffffff); the record is {flat cell index, r | k << 25 | negative << 31}, with an event exactly on the last
+// node filed under the interval before it (k - 1, r = 2^24), which is the same integer contribution.  Returns the band
+// the record goes to, or rc.drop_band for events that produce none; `bad` is set for events the reference raises on.
+// LEAN: integer-tick time arithmetic and unscaled coordinates (the uniform branches are hoisted to the CTA level).
+template <int KIND, bool LEAN, bool TRACK>
+__device__ __forceinline__ uint32_t route_event(const RouteConst& rc, const BinArgs& a, uint32_t xs, uint32_t ys, uint32_t pb, uint32_t tlo,
+                                                uint32_t thi, bool live, uint32_t& flat, uint32_t& val, uint32_t& vmin,
+                                                uint32_t& vmax, bool& bad) {
+    if (!LEAN && rc.scaled) {   // events_reshape fused: fp64 multiply, truncation (events_augment.py:22-26)
+        const int64_t xi = __double2ll_rz(__dmul_rn((double)xs, a.sx)), yi = __double2ll_rz(__dmul_rn((double)ys, a.sy));
+        const int64_t f = xi + yi * (int64_t)rc.W;
+        flat = (f < 0 || f >= (int64_t)rc.HW) ? 0xffffffffu : (uint32_t)f;
+    } else {
+        flat = ys * rc.W + xs;
     }
-    if (threadIdx.x < kMaxBands) { s_cnt[threadIdx.x] = 0; s_cur[threadIdx.x] = 0; }
-    EP_TICK_INIT();
-    __syncthreads();
-    EP_TICK(0);
+    const bool valid = live && flat < rc.HW && pb <= 1u;     // `live` is false for slots of a neighbouring sample (edge chunks)
+    bad = live && !valid;
+    uint32_t v = 0;
+    bool in_bins;
+    if (KIND != kKindF64 && (LEAN || rc.int_time)) {
+        const int64_t t = (KIND == kKindCompact) ? (int64_t)tlo : (int64_t)(((uint64_t)thi << 32) | tlo);
+        in_bins = ticks_to_v(t - rc.t0_ticks, rc.tmul, rc.tshift, rc.thalf, rc.v_end, v);
+    } else {
+        double dt;
+        if (KIND == kKindF64) dt = __longlong_as_double((long long)(((uint64_t)thi << 32) | tlo)) - rc.meta->t0_raw;
+        else if (KIND == kKindCompact) dt = (double)((int64_t)tlo - rc.t0_ticks);
+        else dt = (double)((int64_t)(((uint64_t)thi << 32) | tlo) - rc.t0_ticks);
+        const double ts = dt * rc.meta->scale_raw, tis = floor(ts);
+        in_bins = tis >= 0.0 && tis < (double)rc.num_bins;
+        if (in_bins)   // same fp32 fraction as quantise_ts; a fraction that rounds to 1.0 carries into k
+            v = ((uint32_t)(int)tis << kQ) + (uint32_t)__float2int_rn((float)(ts - tis) * 16777216.0f);
+    }
+    if (TRACK && in_bins && valid) { vmin = min(vmin, v); vmax = max(vmax, v); }
+    uint32_t kr = v + (v & 0xff000000u);                       // r | k << 25
+    if (v == rc.v_last) kr -= 1u << kQ;                        // (k, 0) on the last node -> (k - 1, 2^24)
+    if (!in_bins) kr = kKCountOnly << kKShift;
+    val = kr | ((pb ^ 1u) << 31);                          // bit 31 set = negative polarity
+    const uint32_t band = __umulhi(flat, rc.cpb_magic) >> rc.cpb_shift;
+    return (valid && (in_bins || rc.count != 0)) ? band : rc.drop_band;
+}
 
-    const int64_t c_lo = s_info.c_lo, ev_lo = s_info.ev_lo, ev_hi = s_info.ev_hi;
-    const int64_t HW = (int64_t)a.H * a.W;
-    uint32_t val[2 * kEvPerThread];
-    uint32_t cb[2 * kEvPerThread];        // cell-in-band | band << 16, 0xffffffff = dropped
-    int kmin = 255, kmax = 0;
-    if (s_info.lean) {
-        const uint32_t W32 = (uint32_t)a.W, HW32 = (uint32_t)HW;
-        const int nbm1 = a.num_bins - 1;
-        const double nb_d = (double)a.num_bins, scale = s_info.m.scale_raw, t0_raw = s_info.m.t0_raw;
-        const long long t0_ticks = s_info.m.t0_ticks;
-        // all loads of both quads first, so their latency overlaps
-        uint2 xv[2], yv[2];
-        uint32_t pv[2];
-        longlong2 tq[2][2];
+// loads of one thread: QUADS quads of 4 consecutive events, all issued before the first use
+template <int KIND, int QUADS>
+struct RawEvents {
+    uint2 xv[QUADS], yv[QUADS];
+    uint32_t pv[QUADS];
+    uint4 ta[QUADS], tb[QUADS];
+};
+
+template <int KIND, int CHUNK, int THREADS, bool EDGE>
+__device__ __forceinline__ void route_load(const RouteSrc& src, const BinArgs& a, int64_t c_lo,
+                                           RawEvents<KIND, CHUNK / (THREADS * 4)>& e) {
+    constexpr int QUADS = CHUNK / (THREADS * 4);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int64_t i0 = c_lo + ((int64_t)h * kRouteThreads + threadIdx.x) * kEvPerThread;
-            xv[h] = ld_stream(reinterpret_cast<const uint2*>(ld.x + i0));
-            yv[h] = ld_stream(reinterpret_cast<const uint2*>(ld.y + i0));
-            pv[h] = ld_stream(reinterpret_cast<const uint32_t*>(ld.p + i0));
-            tq[h][0] = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(ld.t) + i0));
-            tq[h][1] = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(ld.t) + i0 + 2));
+    for (int h = 0; h < QUADS; ++h) {
+        const int64_t i0 = c_lo + (int64_t)(h * THREADS + threadIdx.x) * 4;
+        if (!EDGE || i0 + 4 <= a.n_total) {
+            e.xv[h] = ld_stream(reinterpret_cast<const uint2*>(src.x + i0));
+            e.yv[h] = ld_stream(reinterpret_cast<const uint2*>(src.y + i0));
+            if (KIND == kKindCompact) {
+                e.ta[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(src.t) + i0));
+                e.pv[h] = 0;
+            } else {
+                e.pv[h] = ld_stream(reinterpret_cast<const uint32_t*>(src.p + i0));
+                e.ta[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0));
+                e.tb[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0 + 2));
+            }
+        } else {     // last, partial quad of the arrays: scalar loads, nothing read past the end
+            uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0}, lo_[4] = {0, 0, 0, 0}, hi_[4] = {0, 0, 0, 0};
+            e.pv[h] = 0;
+            for (int j = 0; j < 4; ++j) {
+                if (i0 + j < a.n_total) {
+                    xs_[j] = src.x[i0 + j]; ys_[j] = src.y[i0 + j];
+                    if (KIND == kKindCompact) {
+                        lo_[j] = static_cast<const uint32_t*>(src.t)[i0 + j];
+                    } else {
+                        e.pv[h] |= (uint32_t)src.p[i0 + j] << (8 * j);
+                        const uint64_t tv = (uint64_t)static_cast<const int64_t*>(src.t)[i0 + j];
+                        lo_[j] = (uint32_t)tv; hi_[j] = (uint32_t)(tv >> 32);
+                    }
+                }
+            }
+            e.xv[h] = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
+            e.yv[h] = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
+            if (KIND == kKindCompact) e.ta[h] = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+            else { e.ta[h] = make_uint4(lo_[0], hi_[0], lo_[1], hi_[1]); e.tb[h] = make_uint4(lo_[2], hi_[2], lo_[3], hi_[3]); }
+        }
+    }
+}
+
+// compute + rank: every event slot of the thread gets (flat, val, band | rank << 16); slots that produce no record go to
+// the extra band rc.drop_band, whose records land behind the real ones in the staging buffer and are never read
+template <int KIND, int CHUNK, int THREADS, bool EDGE, bool LEAN, bool TRACK>
+__device__ __forceinline__ void route_rank(const RawEvents<KIND, CHUNK / (THREADS * 4)>& e, uint32_t lo_off, uint32_t hi_off,
+                                           const RouteConst& rc, const BinArgs& a, uint32_t cnt_addr, uint32_t (&flat)[CHUNK / THREADS],
+                                           uint32_t (&val)[CHUNK / THREADS], uint32_t (&bp)[CHUNK / THREADS], uint32_t& vmin,
+                                           uint32_t& vmax, unsigned& nbad) {
+    constexpr int QUADS = CHUNK / (THREADS * 4);
+#pragma unroll
+    for (int h = 0; h < QUADS; ++h) {
+        const uint32_t xs[4] = {e.xv[h].x & 0xffffu, e.xv[h].x >> 16, e.xv[h].y & 0xffffu, e.xv[h].y >> 16};
+        const uint32_t ys[4] = {e.yv[h].x & 0xffffu, e.yv[h].x >> 16, e.yv[h].y & 0xffffu, e.yv[h].y >> 16};
+        uint32_t tlo[4], thi[4], pb[4];
+        if (KIND == kKindCompact) {
+            const uint32_t raw[4] = {e.ta[h].x, e.ta[h].y, e.ta[h].z, e.ta[h].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tlo[j] = raw[j] & 0x7fffffffu; thi[j] = 0; pb[j] = raw[j] >> 31; }
+        } else {
+            tlo[0] = e.ta[h].x; thi[0] = e.ta[h].y; tlo[1] = e.ta[h].z; thi[1] = e.ta[h].w;
+            tlo[2] = e.tb[h].x; thi[2] = e.tb[h].y; tlo[3] = e.tb[h].z; thi[3] = e.tb[h].w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = (e.pv[h] >> (8 * j)) & 0xffu;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const long long raw[4] = {tq[h][0].x, tq[h][0].y, tq[h][1].x, tq[h][1].y};
-            const uint32_t xs[4] = {xv[h].x & 0xffffu, xv[h].x >> 16, xv[h].y & 0xffffu, xv[h].y >> 16};
-            const uint32_t ys[4] = {yv[h].x & 0xffffu, yv[h].x >> 16, yv[h].y & 0xffffu, yv[h].y >> 16};
-#pragma unroll
-            for (int j = 0; j < kEvPerThread; ++j) {
-                const int q = h * kEvPerThread + j;
-                cb[q] = 0xffffffffu;
-                const uint32_t flat = ys[j] * W32 + xs[j];
-                const uint32_t pb = (pv[h] >> (8 * j)) & 0xffu;
-                if (flat >= HW32 || pb > 1u) {
-                    if (a.bad_count) atomicAdd(a.bad_count, 1u);
-                    continue;
-                }
-                const double dt = Loader::kTicks ? (double)(raw[j] - t0_ticks) : (__longlong_as_double(raw[j]) - t0_raw);
-                const double ts = dt * scale;
-                int k = (int)kKCountOnly, r = 0;
-                if (nbm1 >= 0 && ts >= 0.0 && ts < nb_d) {
-                    k = __double2int_rd(ts);
-                    r = __float2int_rn((float)(ts - (double)k) * 16777216.0f);
-                    const bool on_last = (k == nbm1) & (r == 0) & (nbm1 > 0);     // exactly on the last node
-                    k -= on_last;
-                    r = on_last ? (1 << kQ) : r;
-                    kmin = min(kmin, k); kmax = max(kmax, k);
-                } else if (!a.count_channels) {
-                    continue;                                  // contributes to nothing
-                }
-                const uint32_t bd = __umulhi(flat, g.cpb_magic) >> g.cpb_shift;
-                cb[q] = (flat - bd * (uint32_t)g.cpb) | (bd << 16);
-                val[q] = (uint32_t)r | ((uint32_t)k << kKShift) | (pb << kPolShift);
-                atomicAdd(&s_cnt[bd], 1);
+        for (int j = 0; j < 4; ++j) {
+            const int q = h * 4 + j;
+            bool live = true, bad;
+            if (EDGE) {
+                const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
+                live = e_off - lo_off < hi_off - lo_off;
             }
+            const uint32_t band = route_event<KIND, LEAN, TRACK>(rc, a, xs[j], ys[j], pb[j], tlo[j], thi[j], live, flat[q], val[q],
+                                                                 vmin, vmax, bad);
+            nbad += bad ? 1u : 0u;
+            bp[q] = band | (atoms_add(cnt_addr + band * 4u, 1u) << 16);
+        }
+    }
+}
+
+// Persistent: grid = MINB CTAs per SM, each walks the group's chunks with stride gridDim.x.  Per chunk: rank (the events
+// were loaded during the previous chunk's tail), barrier, per-warp scan + place, barrier, write-out, barrier.
+template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
+__global__ void __launch_bounds__(THREADS, MINB) k_route(RouteSrc src, BandArgs g, int n_chunks) {
+    constexpr int EPT = CHUNK / THREADS;
+    constexpr int kWarps = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);          // [CHUNK]
+    __shared__ int s_cnt[kMaxBands + 1], s_base[kMaxBands + 1];  // per band, plus the drop band at index nb
+    __shared__ int s_kmin, s_kmax;
+    __shared__ ChunkInfo s_info[3];                              // ring: this chunk, the next one, the one being fetched
+    const BinArgs& a = g.bin;
+    const int stride = (int)gridDim.x;
+    int chunk = (int)blockIdx.x;                                 // chunk id inside the group
+    if (chunk >= n_chunks) return;
+    {
+        const uint4* ip = reinterpret_cast<const uint4*>(g.info + g.chunk_begin);
+        constexpr int kV = (int)(sizeof(ChunkInfo) / 16);
+        if (threadIdx.x < kV) reinterpret_cast<uint4*>(&s_info[0])[threadIdx.x] = ip[(int64_t)chunk * kV + threadIdx.x];
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + kV && chunk + stride < n_chunks)
+            reinterpret_cast<uint4*>(&s_info[1])[threadIdx.x - 32] = ip[(int64_t)(chunk + stride) * kV + threadIdx.x - 32];
+    }
+    for (int i = threadIdx.x; i <= g.nb; i += THREADS) s_cnt[i] = 0;
+    if (threadIdx.x == 0) { s_kmin = TRACK ? 255 : 0; s_kmax = TRACK ? 0 : 31; }
+    __syncthreads();
+
+    RouteConst rc;
+    rc.W = (uint32_t)a.W; rc.HW = (uint32_t)(a.H * a.W);
+    rc.v_end = (uint32_t)a.num_bins << kQ;
+    rc.v_last = a.num_bins >= 2 ? (uint32_t)(a.num_bins - 1) << kQ : 0xffffffffu;
+    rc.cpb_magic = g.cpb_magic; rc.cpb_shift = (uint32_t)g.cpb_shift; rc.drop_band = (uint32_t)g.nb;
+    rc.num_bins = a.num_bins; rc.count = a.count_channels;
+    rc.scaled = a.scaled != 0;
+    const uint32_t cnt_addr = smem_u32(s_cnt), base_addr = smem_u32(s_base), rec_addr = smem_u32(s_rec);
+
+    RawEvents<KIND, EPT / 4> ev;
+    {
+        const ChunkInfo& c0 = s_info[0];
+        if (c0.lo_off == 0 && c0.hi_off == CHUNK) route_load<KIND, CHUNK, THREADS, false>(src, a, c0.c_lo, ev);
+        else route_load<KIND, CHUNK, THREADS, true>(src, a, c0.c_lo, ev);
+    }
+    EP_TICK_INIT();
+    for (int it = 0; chunk < n_chunks; ++it, chunk += stride) {
+        const ChunkInfo& ci = s_info[it % 3];
+        {   // fetch the descriptor two chunks ahead (the next chunk's is already in the ring)
+            constexpr int kV = (int)(sizeof(ChunkInfo) / 16);
+            const int64_t c2 = (int64_t)chunk + 2 * (int64_t)stride;
+            if (threadIdx.x < kV && c2 < n_chunks)
+                reinterpret_cast<uint4*>(&s_info[(it + 2) % 3])[threadIdx.x] =
+                    reinterpret_cast<const uint4*>(g.info + g.chunk_begin)[c2 * kV + threadIdx.x];
+        }
+        rc.tmul = ci.tmul; rc.tshift = ci.tshift; rc.thalf = ci.thalf;
+        rc.t0_ticks = ci.t0_ticks;
+        rc.meta = a.meta + ci.b;
+        rc.int_time = (ci.flags & kFlagIntTime) != 0 && a.num_bins > 0;
+        const uint32_t lo_off = ci.lo_off, hi_off = ci.hi_off;
+        const bool interior = lo_off == 0 && hi_off == CHUNK;      // all slots belong to the sample, hence lie inside the arrays
+        const bool lean = KIND != kKindF64 && rc.int_time && !rc.scaled;
+
+        uint32_t val[EPT], flat[EPT], bp[EPT];
+        uint32_t vmin = 0xffffffffu, vmax = 0;
+        unsigned nbad = 0;
+#ifdef EP_COUNT_LEAN   // tools only: keep just the steady-state path to count its SASS
+        route_rank<KIND, CHUNK, THREADS, false, true, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
+#else
+        if (interior && lean) route_rank<KIND, CHUNK, THREADS, false, true, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
+        else if (interior) route_rank<KIND, CHUNK, THREADS, false, false, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
+        else route_rank<KIND, CHUNK, THREADS, true, false, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
+#endif
+        if (TRACK) {
+            // interval span of the chunk's in-bins records (conservative: an event on the last node counts for both sides)
+            vmin = warp_reduce(vmin, [](uint32_t x, uint32_t y) { return min(x, y); });
+            vmax = warp_reduce(vmax, [](uint32_t x, uint32_t y) { return max(x, y); });
+            if ((threadIdx.x & 31) == 0 && vmin <= vmax) { atomicMin(&s_kmin, (int)(vmin >> kQ)); atomicMax(&s_kmax, (int)(vmax >> kQ)); }
+        }
+        if (nbad && a.bad_count) atomicAdd(a.bad_count, nbad);
+        __syncthreads();
+        EP_TICK(1);
+        {
+            // exclusive scan of the (<= 256) band counts, eight per lane.  Every warp computes it for itself (same values)
+            // and stores the bases it will look up, so no warp waits for another; the runs go out spread over the warps.
+            const int l = threadIdx.x & 31, wp = threadIdx.x >> 5;
+            int c[8], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = (8 * l + i <= g.nb) ? s_cnt[8 * l + i] : 0; tot += c[i]; }
+            int run = warp_incl_scan(tot, l) - tot;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int bd = 8 * l + i;
+                if (bd <= g.nb) s_base[bd] = run;
+                if (bd < g.nb && (bd % kWarps) == wp)
+                    g.runs[(int64_t)bd * g.gchunks + chunk] = (uint32_t)run | ((uint32_t)(run + c[i]) << 16);
+                run += c[i];
+            }
+            __syncwarp();
+        }
+        EP_TICK(2);
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const uint32_t dst = lds_u32(base_addr + (bp[q] & 0xffffu) * 4u) + (bp[q] >> 16);
+            sts_v2(rec_addr + dst * 8u, flat[q], val[q]);
+        }
+        // the next chunk's events: in flight during this chunk's write-out (issued here, where the records' registers
+        // are free again: issuing them earlier makes ptxas spill load destinations, which serialises the loads)
+        if (chunk + stride < n_chunks) {
+            const ChunkInfo& cn = s_info[(it + 1) % 3];
+            if (cn.lo_off == 0 && cn.hi_off == CHUNK) route_load<KIND, CHUNK, THREADS, false>(src, a, cn.c_lo, ev);
+            else route_load<KIND, CHUNK, THREADS, true>(src, a, cn.c_lo, ev);
+        }
+        __syncthreads();
+        EP_TICK(3);
+        // every warp has scanned and placed: counters and span can be reset for the next chunk
+        const int n_vec = (s_base[g.nb] + 1) >> 1;
+        if (threadIdx.x == 32) {
+            g.kk[chunk] = (uint16_t)((s_kmin & 0xff) | (s_kmax << 8));
+            if (TRACK) { s_kmin = 255; s_kmax = 0; }
+        }
+        for (int i = threadIdx.x; i <= g.nb; i += THREADS) s_cnt[i] = 0;
+        // sorted chunk back to global, 16 bytes per thread and step (a trailing half vector may carry a dropped slot's
+        // data; the band runs delimit what is read)
+        uint4* gv = reinterpret_cast<uint4*>(g.rec + (int64_t)chunk * CHUNK);
+        for (int i = threadIdx.x; i < n_vec; i += THREADS) gv[i] = reinterpret_cast<const uint4*>(s_rec)[i];
+        __syncthreads();                                           // staging buffer, counters and descriptor ring reusable
+        EP_TICK(4);
+    }
+}
+
+// ---- route, two-pass form ---------------------------------------------------------------------------------
+// Same output as k_route.  Small CTAs that keep nothing in registers across a barrier: pass A reads x, y, p and
+// histograms the chunk by band (fire-and-forget RED), a scan turns the histogram into cursors, pass B reads the events
+// again (x, y, p from L2/L1; the stamps were prefetched into L2 at CTA start), builds the records and claims their slots
+// with one returning ATOMS on the band's cursor.  Low register count => 5-6 CTAs per SM whose phases drift apart and
+// hide each other's barriers and load latencies.
+template <int KIND>
+__device__ __forceinline__ void load_quad_xyp(const RouteSrc& src, const BinArgs& a, int64_t i0, bool guard, uint2& xv, uint2& yv,
+                                              uint32_t& pv) {
+    if (!guard || i0 + 4 <= a.n_total) {
+        xv = __ldg(reinterpret_cast<const uint2*>(src.x + i0));
+        yv = __ldg(reinterpret_cast<const uint2*>(src.y + i0));
+        pv = (KIND == kKindCompact) ? 0u : __ldg(reinterpret_cast<const uint32_t*>(src.p + i0));
+    } else {
+        uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0};
+        pv = 0;
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < a.n_total) {
+                xs_[j] = src.x[i0 + j]; ys_[j] = src.y[i0 + j];
+                if (KIND != kKindCompact) pv |= (uint32_t)src.p[i0 + j] << (8 * j);
+            }
+        xv = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
+        yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void load_quad_t(const RouteSrc& src, const BinArgs& a, int64_t i0, bool guard, uint4& ta, uint4& tb) {
+    if (!guard || i0 + 4 <= a.n_total) {
+        if (KIND == kKindCompact) {
+            ta = ld_stream(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(src.t) + i0));
+        } else {
+            ta = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0));
+            tb = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0 + 2));
         }
     } else {
-        const SampleMeta m = s_info.m;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int64_t i0 = c_lo + ((int64_t)h * kRouteThreads + threadIdx.x) * kEvPerThread;
-            Ev<double> e;
-            if (i0 < ev_hi && i0 + kEvPerThread > ev_lo) ld.load(i0, ev_hi, a, e);
-#pragma unroll
-            for (int j = 0; j < kEvPerThread; ++j) {
-                const int q = h * kEvPerThread + j;
-                const int64_t i = i0 + j;
-                cb[q] = 0xffffffffu;
-                if (i < ev_lo || i >= ev_hi) continue;
-                const int cls = e.cls[j];
-                const int64_t flat64 = e.x[j] + e.y[j] * (int64_t)a.W;
-                if (cls == 3 || flat64 < 0 || flat64 >= HW) {
-                    if (a.bad_count) atomicAdd(a.bad_count, 1u);
-                    continue;
+        uint32_t lo_[4] = {0, 0, 0, 0}, hi_[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < a.n_total) {
+                if (KIND == kKindCompact) {
+                    lo_[j] = static_cast<const uint32_t*>(src.t)[i0 + j];
+                } else {
+                    const uint64_t tv = (uint64_t)static_cast<const int64_t*>(src.t)[i0 + j];
+                    lo_[j] = (uint32_t)tv; hi_[j] = (uint32_t)(tv >> 32);
                 }
-                int k, r;
-                bool last_plane;
-                const bool in_bins = a.num_bins > 0 && voxel_weights<Loader, double>(e, j, m, a.num_bins, k, r, last_plane);
-                if (!in_bins) {
-                    if (!a.count_channels) continue;     // contributes to nothing
-                    k = kKCountOnly; r = 0;
-                }
-                const uint32_t flat = (uint32_t)flat64;
-                const uint32_t bd = __umulhi(flat, g.cpb_magic) >> g.cpb_shift;
-                cb[q] = (flat - bd * (uint32_t)g.cpb) | (bd << 16);
-                val[q] = (uint32_t)r | ((uint32_t)k << kKShift) | ((cls == 0 ? 1u : 0u) << kPolShift);
-                if (k != (int)kKCountOnly) { kmin = min(kmin, k); kmax = max(kmax, k); }
-                atomicAdd(&s_cnt[bd], 1);
+            }
+        if (KIND == kKindCompact) ta = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
+        else { ta = make_uint4(lo_[0], hi_[0], lo_[1], hi_[1]); tb = make_uint4(lo_[2], hi_[2], lo_[3], hi_[3]); }
+    }
+}
+
+// pass A of one quad: band histogram
+template <int KIND, int THREADS, bool EDGE, bool LEAN>
+__device__ __forceinline__ void route2_count(const RouteConst& rc, const BinArgs& a, int h, uint32_t lo_off, uint32_t hi_off,
+                                             uint2 xv, uint2 yv, uint32_t pv, uint32_t cnt_addr) {
+    const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
+    const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t flat;
+        if (!LEAN && rc.scaled) {
+            const int64_t xi = __double2ll_rz(__dmul_rn((double)xs[j], a.sx)), yi = __double2ll_rz(__dmul_rn((double)ys[j], a.sy));
+            const int64_t f = xi + yi * (int64_t)rc.W;
+            flat = (f < 0 || f >= (int64_t)rc.HW) ? 0xffffffffu : (uint32_t)f;
+        } else {
+            flat = ys[j] * rc.W + xs[j];
+        }
+        bool keep = flat < rc.HW && ((pv >> (8 * j)) & 0xffu) <= 1u;
+        if (EDGE) {
+            const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
+            keep = keep && (e_off - lo_off < hi_off - lo_off);
+        }
+        const uint32_t band = keep ? (__umulhi(flat, rc.cpb_magic) >> rc.cpb_shift) : rc.drop_band;
+        reds_add(cnt_addr + band * 4u, 1u);
+    }
+}
+
+// pass B of one quad: records into their slots
+template <int KIND, int THREADS, bool EDGE, bool LEAN, bool TRACK>
+__device__ __forceinline__ void route2_place(const RouteConst& rc, const BinArgs& a, int h, uint32_t lo_off, uint32_t hi_off,
+                                             uint2 xv, uint2 yv, uint32_t pv, uint4 ta, uint4 tb, uint32_t cur_addr,
+                                             uint32_t rec_addr, uint32_t& vmin, uint32_t& vmax, unsigned& nbad) {
+    const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
+    const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
+    uint32_t tlo[4], thi[4], pb[4];
+    if (KIND == kKindCompact) {
+        const uint32_t raw[4] = {ta.x, ta.y, ta.z, ta.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tlo[j] = raw[j] & 0x7fffffffu; thi[j] = 0; pb[j] = raw[j] >> 31; }
+    } else {
+        tlo[0] = ta.x; thi[0] = ta.y; tlo[1] = ta.z; thi[1] = ta.w;
+        tlo[2] = tb.x; thi[2] = tb.y; tlo[3] = tb.z; thi[3] = tb.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = (pv >> (8 * j)) & 0xffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bool live = true, bad;
+        if (EDGE) {
+            const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
+            live = e_off - lo_off < hi_off - lo_off;
+        }
+        uint32_t flat, val;
+        route_event<KIND, LEAN, TRACK>(rc, a, xs[j], ys[j], pb[j], tlo[j], thi[j], live, flat, val, vmin, vmax, bad);
+        nbad += bad ? 1u : 0u;
+        // same keep rule as pass A (events outside the time bins keep their slot as count-only records)
+        const bool keep = live && !bad;
+        const uint32_t band = keep ? (__umulhi(flat, rc.cpb_magic) >> rc.cpb_shift) : rc.drop_band;
+        const uint32_t dst = atoms_add(cur_addr + band * 4u, 1u);
+        sts_v2(rec_addr + dst * 8u, flat, val);
+    }
+}
+
+template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
+__global__ void __launch_bounds__(THREADS, MINB) k_route2(RouteSrc src, BandArgs g) {
+    constexpr int QUADS = CHUNK / (THREADS * 4);
+    constexpr int kWarps = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_cnt[kMaxBands + 1], s_cur[kMaxBands + 1];   // per band, plus the drop band at index nb
+    __shared__ int s_kmin, s_kmax, s_total;
+    const BinArgs& a = g.bin;
+    const int chunk = (int)blockIdx.x;
+    const ChunkInfo ci = g.info[g.chunk_begin + chunk];
+    for (int i = threadIdx.x; i <= g.nb; i += THREADS) s_cnt[i] = 0;
+    if (threadIdx.x == 0) { s_kmin = TRACK ? 255 : 0; s_kmax = TRACK ? 0 : 31; }
+    const uint32_t lo_off = ci.lo_off, hi_off = ci.hi_off;
+    const bool interior = lo_off == 0 && hi_off == CHUNK;
+    // the chunk's stamps -> L2 while pass A runs (one 128-byte line per thread and step)
+    {
+        const int t_bytes = (KIND == kKindCompact) ? 4 : 8;
+        const char* tp = static_cast<const char*>(src.t) + ci.c_lo * t_bytes;
+        const int64_t lim = (a.n_total - ci.c_lo) * t_bytes;
+        for (int64_t o = (int64_t)threadIdx.x * 128; o < (int64_t)CHUNK * t_bytes && o < lim; o += (int64_t)THREADS * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
+    }
+    RouteConst rc;
+    rc.W = (uint32_t)a.W; rc.HW = (uint32_t)(a.H * a.W);
+    rc.tmul = ci.tmul; rc.tshift = ci.tshift; rc.thalf = ci.thalf;
+    rc.v_end = (uint32_t)a.num_bins << kQ;
+    rc.v_last = a.num_bins >= 2 ? (uint32_t)(a.num_bins - 1) << kQ : 0xffffffffu;
+    rc.cpb_magic = g.cpb_magic; rc.cpb_shift = (uint32_t)g.cpb_shift; rc.drop_band = (uint32_t)g.nb;
+    rc.t0_ticks = ci.t0_ticks;
+    rc.meta = a.meta + ci.b;
+    rc.num_bins = a.num_bins; rc.count = a.count_channels;
+    rc.int_time = (ci.flags & kFlagIntTime) != 0 && a.num_bins > 0;
+    rc.scaled = a.scaled != 0;
+    const bool lean = KIND != kKindF64 && rc.int_time && !rc.scaled;
+    const uint32_t cnt_addr = smem_u32(s_cnt), cur_addr = smem_u32(s_cur), rec_addr = smem_u32(smem_raw);
+
+    // ---- pass A
+    {
+        uint2 xv[QUADS], yv[QUADS];
+        uint32_t pv[QUADS];
+#pragma unroll
+        for (int h = 0; h < QUADS; ++h)
+            load_quad_xyp<KIND>(src, a, ci.c_lo + (int64_t)(h * THREADS + threadIdx.x) * 4, !interior, xv[h], yv[h], pv[h]);
+        __syncthreads();                                           // histogram zeroed
+#pragma unroll
+        for (int h = 0; h < QUADS; ++h) {
+            if (interior && lean) route2_count<KIND, THREADS, false, true>(rc, a, h, lo_off, hi_off, xv[h], yv[h], pv[h], cnt_addr);
+            else if (interior) route2_count<KIND, THREADS, false, false>(rc, a, h, lo_off, hi_off, xv[h], yv[h], pv[h], cnt_addr);
+            else route2_count<KIND, THREADS, true, false>(rc, a, h, lo_off, hi_off, xv[h], yv[h], pv[h], cnt_addr);
+        }
+    }
+    __syncthreads();
+    {
+        // exclusive scan of the band counts, eight per lane, computed by every warp; warp w publishes the bands b with
+        // b % kWarps == w (cursor + run entry)
+        const int l = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        int c[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = (8 * l + i <= g.nb) ? s_cnt[8 * l + i] : 0; tot += c[i]; }
+        int run = warp_incl_scan(tot, l) - tot;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int bd = 8 * l + i;
+            if (bd <= g.nb && (bd % kWarps) == wp) {
+                s_cur[bd] = run;
+                if (bd < g.nb) g.runs[(int64_t)bd * g.gchunks + chunk] = (uint32_t)run | ((uint32_t)(run + c[i]) << 16);
+                else s_total = run;
+            }
+            run += c[i];
+        }
+    }
+    __syncthreads();
+    // ---- pass B
+    uint32_t vmin = 0xffffffffu, vmax = 0;
+    unsigned nbad = 0;
+#pragma unroll 1
+    for (int h0 = 0; h0 < QUADS; h0 += 2) {
+        uint2 xv[2], yv[2];
+        uint32_t pv[2];
+        uint4 ta[2], tb[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (h0 + u < QUADS) {
+                const int64_t i0 = ci.c_lo + (int64_t)((h0 + u) * THREADS + threadIdx.x) * 4;
+                load_quad_xyp<KIND>(src, a, i0, !interior, xv[u], yv[u], pv[u]);
+                load_quad_t<KIND>(src, a, i0, !interior, ta[u], tb[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (h0 + u < QUADS) {
+                const int h = h0 + u;
+                if (interior && lean) route2_place<KIND, THREADS, false, true, TRACK>(rc, a, h, lo_off, hi_off, xv[u], yv[u], pv[u], ta[u], tb[u], cur_addr, rec_addr, vmin, vmax, nbad);
+                else if (interior) route2_place<KIND, THREADS, false, false, TRACK>(rc, a, h, lo_off, hi_off, xv[u], yv[u], pv[u], ta[u], tb[u], cur_addr, rec_addr, vmin, vmax, nbad);
+                else route2_place<KIND, THREADS, true, false, TRACK>(rc, a, h, lo_off, hi_off, xv[u], yv[u], pv[u], ta[u], tb[u], cur_addr, rec_addr, vmin, vmax, nbad);
             }
         }
     }
-    kmin = warp_reduce(kmin, [](int x, int y) { return min(x, y); });
-    kmax = warp_reduce(kmax, [](int x, int y) { return max(x, y); });
-    if ((threadIdx.x & 31) == 0) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); }
-    __syncthreads();
-    EP_TICK(1);
-    if (threadIdx.x < 32) {      // exclusive scan of the (<= 64) band counts: two per lane
-        const int l = threadIdx.x;
-        const int c0 = s_cnt[2 * l], c1 = s_cnt[2 * l + 1];
-        const int incl = warp_incl_scan(c0 + c1, l);
-        s_base[2 * l] = incl - c0 - c1;
-        s_base[2 * l + 1] = incl - c1;
-        if (l == 31) s_base[kMaxBands] = incl;
+    if (TRACK) {
+        vmin = warp_reduce(vmin, [](uint32_t x, uint32_t y) { return min(x, y); });
+        vmax = warp_reduce(vmax, [](uint32_t x, uint32_t y) { return max(x, y); });
+        if ((threadIdx.x & 31) == 0 && vmin <= vmax) { atomicMin(&s_kmin, (int)(vmin >> kQ)); atomicMax(&s_kmax, (int)(vmax >> kQ)); }
     }
+    if (nbad && a.bad_count) atomicAdd(a.bad_count, nbad);
     __syncthreads();
-    EP_TICK(2);
-#pragma unroll
-    for (int q = 0; q < 2 * kEvPerThread; ++q) {
-        if (cb[q] == 0xffffffffu) continue;
-        const int bd = cb[q] >> 16;
-        const int pos = s_base[bd] + atomicAdd(&s_cur[bd], 1);
-        s_val[pos] = val[q];
-        s_cell[pos] = (uint16_t)cb[q];
+    if (threadIdx.x == 32) g.kk[chunk] = (uint16_t)((s_kmin & 0xff) | (s_kmax << 8));
+    const int n_vec = (s_total + 1) >> 1;
+    uint4* gv = reinterpret_cast<uint4*>(g.rec + (int64_t)chunk * CHUNK);
+    for (int i = threadIdx.x; i < n_vec; i += THREADS) gv[i] = reinterpret_cast<const uint4*>(smem_raw)[i];
+}
+
+template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
+cudaError_t launch_route2(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
+    static bool configured = false;
+    const size_t smem = (size_t)CHUNK * 8;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(k_route2<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        cudaFuncSetAttribute(k_route2<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
     }
-    __syncthreads();
-    EP_TICK(3);
-    // write the sorted chunk back: 4 records per thread per step, 16-byte / 8-byte vectors (the tail of the
-    // last vector may carry stale staging data; the band offsets in the row delimit what is read)
-    const int n_vec = (s_base[kMaxBands] + 3) >> 2;
-    uint4* gv = reinterpret_cast<uint4*>(g.rec_val + (int64_t)blockIdx.x * kChunk);
-    uint2* gc = reinterpret_cast<uint2*>(g.rec_cell + (int64_t)blockIdx.x * kChunk);
-    for (int i = threadIdx.x; i < n_vec; i += kRouteThreads) {
-        gv[i] = reinterpret_cast<const uint4*>(s_val)[i];
-        gc[i] = reinterpret_cast<const uint2*>(s_cell)[i];
-    }
-    uint16_t* row = g.rows + (int64_t)blockIdx.x * kRowStride;
-    if (threadIdx.x <= g.nb) row[threadIdx.x] = (uint16_t)s_base[threadIdx.x < g.nb ? threadIdx.x : kMaxBands];
-    if (threadIdx.x == 0) row[kMaxBands + 1] = (uint16_t)((s_kmin & 0xff) | (s_kmax << 8));
-    EP_TICK(4);
+    k_route2<KIND, CHUNK, THREADS, MINB, TRACK><<<grid, THREADS, smem, st>>>(src, g);
+    return cudaSuccess;
 }
 
 // ---- sweep ------------------------------------------------------------------------------------------------
-struct SpillTable {
-    unsigned int key[kSpill];              // cell + 1, 0 = empty
-    unsigned long long acc[kSpill];        // sum p*r of the events beyond the admitted ones
-};
+struct Window { int q0, q1; };   // voxel planes [q0, q1) held in shared memory
 
-__device__ __forceinline__ void spill_add(SpillTable* t, unsigned int cell, long long v, unsigned int* bad) {
-    unsigned int h = (cell * 2654435761u) >> (32 - 8);
-    for (int probe = 0; probe < kSpill; ++probe) {
-        const unsigned int prev = atomicCAS(&t->key[h], 0u, cell + 1);
-        if (prev == 0u || prev == cell + 1) { atomicAdd(&t->acc[h], (unsigned long long)v); return; }
-        h = (h + 1) & (kSpill - 1);
-    }
-    if (bad) atomicOr(bad, 0x80000000u);   // more than kSpill hot cells in one band and interval
-}
-
-__device__ __forceinline__ long long spill_get(const SpillTable* t, unsigned int cell) {
-    unsigned int h = (cell * 2654435761u) >> (32 - 8);
-    for (int probe = 0; probe < kSpill; ++probe) {
-        const unsigned int k = t->key[h];
-        if (k == cell + 1) return (long long)t->acc[h];
-        if (k == 0u) return 0;
-        h = (h + 1) & (kSpill - 1);
-    }
-    return 0;
-}
-
-// Tile, structure of arrays over the band's cells:
-//   N[cell]  = n_pos | n_neg << 16 of the current interval          (ATOMS, fire and forget)
-//   A[cell]  = sum p*r mod 2^32 over the interval's events          (ATOMS, fire and forget)
-//   CS[cell] = { carry = A of the previous interval (low 32 bits), running fp32 sum over bins }
-// A is exact as a signed 32-bit value while the cell holds at most kAdmit (127) events of the interval
-// (|A| <= 127 * 2^24 < 2^31).  Cells that received more ("hot") are detected at flush time from the exact count and
-// recomputed: the interval's records are re-scanned and the hot cells' weights are summed in a small 64-bit hash
-// table.  Carries that do not fit 32 bits live in two more such tables (prev / next).  Both paths are rare, so the
-// common path has no returning atomics and no dependent chains.
-// Counter fields are 16 bits: a pass whose per-cell counts do not add up to the number of records it consumed has
-// wrapped a field (> 65535 events of one polarity on one pixel in one interval) and is reported through bad_count.
-template <bool RESCAN>
-__device__ __forceinline__ int scan_records(const BandArgs& g, int k, int ch0, int t0, int nt, int team, int tl,
-                                            const uint32_t* s_run, const uint16_t* s_kk, uint32_t* sN, uint32_t* sA,
-                                            SpillTable* hot, unsigned int* bad) {
-    constexpr int kTeams = kSweepThreads / kTeam;
-    int matched = 0;
-    // one team of kTeam lanes per chunk; chunks are time-ordered, so the chunks relevant to interval k are (for sorted
-    // input) consecutive and land on distinct teams: one round of loads per pass
-    for (int c = team; c < nt; c += kTeams) {
-        const uint32_t kk = s_kk[c];
-        const int kmin = kk & 0xff, kmax = kk >> 8;
-        // count-only records are not covered by [kmin, kmax]: every chunk is scanned in that pass
-        if (k != (int)kKCountOnly && (k < kmin || k > kmax)) continue;
-        const uint32_t run = s_run[c];
-        const int lo = run & 0xffff, hi = run >> 16;
-        const uint32_t* rv = g.rec_val + (int64_t)(ch0 + t0 + c) * kChunk;
-        const uint16_t* rc = g.rec_cell + (int64_t)(ch0 + t0 + c) * kChunk;
-        for (int i0 = lo + tl; i0 < hi; i0 += kUnroll * kTeam) {
-            uint32_t v[kUnroll], cl[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int i = i0 + u * kTeam;
-                v[u] = 0xffffffffu;            // interval field 31 + polarity bit: never equals a voxel pass's k ...
-                cl[u] = 0;
-                if (i < hi) { v[u] = __ldcs(rv + i); cl[u] = __ldcs(rc + i); }
+// mode 0: int32 planes + count word (fast); mode 1: int64 planes (exact for any count); mode 2: count word only
+template <int MODE, int THREADS>
+__device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool count_all, bool filter, int band,
+                                               int64_t band_base, int ch0, int nch, uint32_t* s_run, uint16_t* s_kk,
+                                               uint32_t* slots) {
+    constexpr int kWarps = THREADS / 32;
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cpb = (uint32_t)g.cpb;
+    // slot addresses as functions of the record's flat cell index: count word [cpb] first, then the planes
+    const uint32_t n_addr0 = smem_u32(slots) - (uint32_t)band_base * 4u;
+    const uint32_t p_addr0 = smem_u32(slots + cpb) - ((uint32_t)band_base + (uint32_t)w.q0 * cpb) * 4u;   // int32 [P][cpb]
+    const uint32_t w_addr0 = smem_u32(slots) - ((uint32_t)band_base + (uint32_t)w.q0 * cpb) * 8u;         // int64 [Pw][cpb]
+    unsigned matched = 0;
+    for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
+        const int nt = min(kMaxTableChunks, nch - t0);
+        __syncthreads();                                    // previous tile of the table consumed / slots ready
+        for (int c = threadIdx.x; c < nt; c += THREADS) {
+            s_run[c] = g.runs[(int64_t)band * g.gchunks + ch0 + t0 + c];
+            s_kk[c] = g.kk[ch0 + t0 + c];
+        }
+        __syncthreads();
+        for (int c = warp; c < nt; c += kWarps) {
+            if (filter) {      // chunks are time ordered: most lie outside a window of a multi-window task
+                const int kmin = s_kk[c] & 0xff, kmax = s_kk[c] >> 8;
+                if (kmax + 1 < w.q0 || kmin >= w.q1) continue;
             }
+            const uint32_t run = s_run[c];
+            const int lo = run & 0xffff, hi = run >> 16;
+            const uint2* rp = g.rec + (int64_t)(ch0 + t0 + c) * g.chunk;
+            for (int i0 = lo + lane; i0 < hi; i0 += 32 * U) {
+                uint2 rv[U];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (i0 + u * kTeam >= hi) continue;   // ... but the count-only pass has k == 31, so test the bound too
-                if ((int)((v[u] >> kKShift) & 31u) != k) continue;
-                const bool pos = (v[u] >> kPolShift) & 1u;
-                const int r = (int)(v[u] & 0x1ffffffu);
-                if (!RESCAN) {
-                    ++matched;
-                    atomicAdd(sN + cl[u], pos ? 1u : 0x10000u);
-                    if (k != (int)kKCountOnly) atomicAdd(sA + cl[u], (uint32_t)(pos ? r : -r));
-                } else {
-                    const uint32_t n = sN[cl[u]];
-                    if ((n & 0xffffu) + (n >> 16) > (uint32_t)kAdmit) spill_add(hot, cl[u], pos ? (long long)r : -(long long)r, bad);
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + 32 * u;
+                    if (i < hi) rv[u] = __ldcs(rp + i);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (i0 + 32 * u >= hi) continue;
+                    const uint32_t flat = rv[u].x, v = rv[u].y;
+                    const uint32_t k = (v >> kKShift) & 31u;
+                    const bool pos = (v >> 31) == 0u;
+                    const uint32_t r = v & 0x1ffffffu;
+                    const bool left_ok = k >= (uint32_t)w.q0 && k < (uint32_t)w.q1;
+                    const bool right_ok = k + 1 >= (uint32_t)w.q0 && k + 1 < (uint32_t)w.q1;
+                    if (MODE == 2 || count_all || left_ok || right_ok) {
+                        ++matched;
+                        if (MODE != 1) reds_add(n_addr0 + flat * 4u, pos ? 1u : 0x10000u);
+                    }
+                    const uint32_t idx = k * cpb + flat;
+                    if (MODE == 0) {
+                        const uint32_t wl = (1u << kQ) - r;
+                        const uint32_t addr = p_addr0 + idx * 4u;
+                        if (left_ok) reds_add(addr, pos ? wl : 0u - wl);
+                        if (right_ok) reds_add(addr + cpb * 4u, pos ? r : 0u - r);
+                    } else if (MODE == 1) {
+                        const long long wl = (1ll << kQ) - (long long)r, wr = (long long)r;
+                        const uint32_t addr = w_addr0 + idx * 8u;
+                        if (left_ok) reds_add64(addr, (unsigned long long)(pos ? wl : -wl));
+                        if (right_ok) reds_add64(addr + cpb * 8u, (unsigned long long)(pos ? wr : -wr));
+                    }
                 }
             }
         }
     }
+    __syncthreads();
     return matched;
 }
 
-__device__ __forceinline__ void spill_clear(SpillTable* t, int tid) {
-    for (int i = tid; i < kSpill; i += kSweepThreads) { t->key[i] = 0; t->acc[i] = 0ull; }
+// Steady-state accumulate of window w with int32 planes + count word (same result as accumulate<0>): one branch per
+// record, every address a multiply-add from the record's flat cell index, the next chunk's rows already in flight
+// while the current ones are applied.
+struct FastAddr { uint32_t n0, p0, cpb, cpb4, q0, nfast, q1; };
+
+__device__ __noinline__ void apply_record_slow(uint32_t flat, uint32_t v, FastAddr fa, bool count_all, unsigned& skipped) {
+    const uint32_t k = (v >> kKShift) & 31u, r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);
+    const bool left_ok = k >= fa.q0 && k < fa.q1;
+    const bool right_ok = k + 1 >= fa.q0 && k + 1 < fa.q1;
+    if (!(count_all || left_ok || right_ok)) { ++skipped; return; }
+    reds_add(fa.n0 + flat * 4u, (m & 0xffffu) + 1u);
+    const uint32_t addr = fa.p0 + ((k - fa.q0) * fa.cpb + flat) * 4u, wl = (1u << kQ) - r;
+    if (left_ok) reds_add(addr, (wl ^ m) - m);
+    if (right_ok) reds_add(addr + fa.cpb4, (r ^ m) - m);
+}
+
+__device__ __forceinline__ void apply_record(uint32_t flat, uint32_t v, const FastAddr& fa, bool count_all, unsigned& skipped) {
+    const uint32_t kw = ((v >> kKShift) & 31u) - fa.q0;
+    if (kw < fa.nfast) {                                        // both planes k and k + 1 lie inside the window
+        const uint32_t r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);   // m = 0 (positive) | ~0 (negative)
+        const uint32_t n_addr = fa.n0 + flat * 4u;              // count word; plane j of the window sits (j + 1) * cpb words on
+        const uint32_t addr = (kw + 1u) * fa.cpb4 + n_addr, wl = (1u << kQ) - r;
+        reds_add(n_addr, (m & 0xffffu) + 1u);
+        reds_add(addr, (wl ^ m) - m);
+        reds_add(addr + fa.cpb4, (r ^ m) - m);
+    } else {
+        apply_record_slow(flat, v, fa, count_all, skipped);
+    }
+}
+
+template <int THREADS>
+__device__ __forceinline__ unsigned accumulate_fast(const BandArgs& g, Window w, bool count_all, bool filter, int band,
+                                                    int64_t band_base, int ch0, int nch, uint32_t* s_run, uint16_t* s_kk,
+                                                    uint32_t* slots) {
+    constexpr int kWarps = THREADS / 32;
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FastAddr fa;
+    fa.cpb = (uint32_t)g.cpb; fa.cpb4 = fa.cpb * 4u;
+    fa.q0 = (uint32_t)w.q0; fa.q1 = (uint32_t)w.q1;
+    fa.nfast = w.q1 - w.q0 >= 2 ? (uint32_t)(w.q1 - w.q0 - 1) : 0u;
+    fa.n0 = smem_u32(slots) - (uint32_t)band_base * 4u;               // count word [cpb], then int32 planes [P][cpb]
+    fa.p0 = smem_u32(slots + fa.cpb) - (uint32_t)band_base * 4u;
+    asm volatile("" : "+r"(fa.n0), "+r"(fa.p0), "+r"(fa.cpb4), "+r"(fa.cpb), "+r"(fa.q0), "+r"(fa.nfast));   // keep them in registers (no rematerialisation)
+    unsigned taken = 0, skipped = 0;
+    for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
+        const int nt = min(kMaxTableChunks, nch - t0);
+        __syncthreads();                                    // previous tile of the table consumed / slots ready
+        for (int c = threadIdx.x; c < nt; c += THREADS) {
+            s_run[c] = g.runs[(int64_t)band * g.gchunks + ch0 + t0 + c];
+            s_kk[c] = g.kk[ch0 + t0 + c];
+        }
+        __syncthreads();
+        const uint2* rec0 = g.rec + (int64_t)(ch0 + t0) * g.chunk;
+        // chunks are time ordered: most lie outside a window of a multi-window task
+        auto next_chunk = [&](int c) {
+            if (filter) {
+                while (c < nt) {
+                    const int kmin = s_kk[c] & 0xff, kmax = s_kk[c] >> 8;
+                    if (!(kmax + 1 < w.q0 || kmin >= w.q1)) break;
+                    c += kWarps;
+                }
+            }
+            return c;
+        };
+        auto load_rows = [&](int c, int& lo, int& hi, uint2 (&rv)[U]) {
+            const uint32_t run = s_run[c];
+            lo = (int)(run & 0xffffu) + lane; hi = (int)(run >> 16);
+            const uint2* rp = rec0 + (int64_t)c * g.chunk;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (lo + 32 * u < hi) rv[u] = __ldcs(rp + lo + 32 * u);
+        };
+        int c = next_chunk(warp), lo = 0, hi = 0;
+        uint2 rv[U];
+        if (c < nt) load_rows(c, lo, hi, rv);
+        while (c < nt) {
+            const int cn = next_chunk(c + kWarps);
+            int lon = 0, hin = 0;
+            uint2 rn[U];
+            if (cn < nt) load_rows(cn, lon, hin, rn);
+            if (lo < hi) taken += (unsigned)((hi - lo + 31) >> 5);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (lo + 32 * u < hi) apply_record(rv[u].x, rv[u].y, fa, count_all, skipped);
+            if (lo + 32 * U < hi) {                          // longer run than the rows in flight (skewed input)
+                const uint2* rp = rec0 + (int64_t)c * g.chunk;
+                for (int i = lo + 32 * U; i < hi; i += 32) {
+                    const uint2 q = __ldcs(rp + i);
+                    apply_record(q.x, q.y, fa, count_all, skipped);
+                }
+            }
+            c = cn; lo = lon; hi = hin;
+#pragma unroll
+            for (int u = 0; u < U; ++u) rv[u] = rn[u];
+        }
+    }
+    __syncthreads();
+    return taken - skipped;
 }
 
 __device__ __forceinline__ float q24_to_float(long long val) {
@@ -377,179 +865,245 @@ __device__ __forceinline__ float q24_to_float(long long val) {
     return f * (1.0f / 16777216.0f);
 }
 
-// Persistent over the (sample, band) tasks of a group: grid = min(tasks, 2 x SMs).
-template <bool COUNT>
-__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_tasks) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int VEC> struct VecF;
+template <> struct VecF<4> { typedef float4 type; typedef uint4 utype; };
+template <> struct VecF<1> { typedef float type; typedef uint32_t utype; };
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+    if (VEC == 4) st_stream(reinterpret_cast<float4*>(p), make_float4(v[0], v[VEC > 1 ? 1 : 0], v[VEC > 2 ? 2 : 0], v[VEC > 3 ? 3 : 0]));
+    else st_stream(p, v[0]);
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_u32(const uint32_t* p, uint32_t (&v)[VEC]) {
+    if (VEC == 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        v[0] = q.x; v[VEC > 1 ? 1 : 0] = q.y; v[VEC > 2 ? 2 : 0] = q.z; v[VEC > 3 ? 3 : 0] = q.w;
+    } else {
+        v[0] = *p;
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void zero_u32(uint32_t* p) {
+    if (VEC == 4) *reinterpret_cast<uint4*>(p) = make_uint4(0u, 0u, 0u, 0u);
+    else *p = 0u;
+}
+
+// Fast flush of window w (int32 planes): voxel planes, and when the task has a single window also the sum plane and the
+// count frame.  Slots are left zeroed.  Accumulates this thread's (hot, counted).
+template <int VEC, int THREADS, int NP>
+__device__ __forceinline__ void flush_fast_np(const BandArgs& g, int q0, bool single, bool count, int b, int64_t band_base,
+                                              int ncell, uint32_t* slots, bool& hot, unsigned& counted) {
     const BinArgs& a = g.bin;
-    uint32_t* sN = reinterpret_cast<uint32_t*>(smem_raw);                   // [cpb]
-    uint32_t* sA = sN + g.cpb;                                              // [cpb]
-    uint2* sCS = reinterpret_cast<uint2*>(sA + g.cpb);                      // [cpb] {carry, sum}
-    uint2* sCnt = sCS + g.cpb;                                              // [cpb] {count_pos, count_neg} (COUNT only)
-    SpillTable* spill = reinterpret_cast<SpillTable*>(sCnt + (COUNT ? g.cpb : 0));   // [3]: hot, carry prev, carry next
-    uint32_t* s_run = reinterpret_cast<uint32_t*>(spill + 3);              // lo | hi << 16 per staged chunk
-    uint16_t* s_kk = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks);  // kmin | kmax << 8 per staged chunk
-    __shared__ int s_hot, s_carry[2];          // flags: hot cells in this pass; wide carries in tables prev / next
-    __shared__ unsigned int s_check[2];        // records consumed / events counted in the tile, per pass
-
-    const int tid = threadIdx.x;
-    const int team = tid / kTeam, tl = tid % kTeam;
     const int64_t HW = (int64_t)a.H * a.W;
-    const int B = a.num_bins;
-    const int n_pass = B + (COUNT ? 1 : 0);
-    SpillTable* hot = spill;
+    const int cpb = g.cpb;
+    uint32_t* sN = slots;
+    uint32_t* sP = slots + cpb;
+    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + q0) * HW + band_base;
+    float* os = (single && g.out_sum && NP > 0) ? g.out_sum + (int64_t)b * HW + band_base : nullptr;
+    float* oc = (single && count) ? g.out_count + (int64_t)b * a.count_channels * HW + band_base : nullptr;
+    const int64_t neg_off = (int64_t)(a.count_channels - 1) * HW;
+    for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        uint32_t n[VEC], pw[NP > 0 ? NP : 1][VEC];
+        load_u32<VEC>(sN + c, n);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) load_u32<VEC>(sP + j * cpb + c, pw[j]);
+        zero_u32<VEC>(sN + c);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) zero_u32<VEC>(sP + j * cpb + c);
+        unsigned mx = 0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const unsigned tot = (n[v] & 0xffffu) + (n[v] >> 16);
+            mx = max(mx, tot);
+            counted += tot;
+        }
+        hot |= mx > (unsigned)kAdmit;
+        float sum[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
+        float* o = ov + c;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            float r[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                r[v] = (float)(int32_t)pw[j][v] * (1.0f / 16777216.0f);
+                sum[v] += r[v];                   // voxel.sum(dim=0): sequential fp32 over bins
+            }
+            store_vec<VEC>(o, r);
+            o += HW;
+        }
+        if (os) store_vec<VEC>(os + c, sum);
+        if (oc) {
+            float cp[VEC], cn[VEC], z[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { cp[v] = (float)(n[v] & 0xffffu); cn[v] = (float)(n[v] >> 16); z[v] = 0.f; }
+            store_vec<VEC>(oc + c, cp);
+            store_vec<VEC>(oc + neg_off + c, cn);
+            if (a.count_channels == 3) store_vec<VEC>(oc + HW + c, z);
+        }
+    }
+}
 
+template <int VEC, int THREADS>
+__device__ __forceinline__ void flush_fast(const BandArgs& g, Window w, bool single, bool count, int b, int64_t band_base,
+                                           int ncell, uint32_t* slots, bool& hot, unsigned& counted) {
+    switch (w.q1 - w.q0) {
+        case 0: flush_fast_np<VEC, THREADS, 0>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 1: flush_fast_np<VEC, THREADS, 1>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 2: flush_fast_np<VEC, THREADS, 2>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 3: flush_fast_np<VEC, THREADS, 3>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 4: flush_fast_np<VEC, THREADS, 4>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 5: flush_fast_np<VEC, THREADS, 5>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        default: flush_fast_np<VEC, THREADS, 6>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+    }
+}
+
+// flush of the count word only (dedicated count pass of multi-window tasks)
+template <int VEC, int THREADS>
+__device__ __forceinline__ void flush_count(const BandArgs& g, int b, int64_t band_base, int ncell, uint32_t* slots,
+                                            unsigned& counted) {
+    const BinArgs& a = g.bin;
+    const int64_t HW = (int64_t)a.H * a.W;
+    for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        uint32_t n[VEC];
+        load_u32<VEC>(slots + c, n);
+        zero_u32<VEC>(slots + c);
+        float cp[VEC], cn[VEC], z[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            counted += (n[v] & 0xffffu) + (n[v] >> 16);
+            cp[v] = (float)(n[v] & 0xffffu); cn[v] = (float)(n[v] >> 16); z[v] = 0.f;
+        }
+        float* oc = g.out_count + (int64_t)b * a.count_channels * HW + band_base + c;
+        store_vec<VEC>(oc, cp);
+        store_vec<VEC>(oc + (int64_t)(a.count_channels - 1) * HW, cn);
+        if (a.count_channels == 3) store_vec<VEC>(oc + HW, z);
+    }
+}
+
+// exact flush of int64 planes [w.q0, w.q1): voxel planes only
+template <int VEC, int THREADS>
+__device__ __forceinline__ void flush_wide(const BandArgs& g, Window w, int b, int64_t band_base, int ncell, uint32_t* slots) {
+    const BinArgs& a = g.bin;
+    const int64_t HW = (int64_t)a.H * a.W;
+    const int cpb = g.cpb, np = w.q1 - w.q0;
+    unsigned long long* sW = reinterpret_cast<unsigned long long*>(slots);
+    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + w.q0) * HW + band_base;
+    for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        for (int j = 0; j < np; ++j) {
+            float r[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                r[v] = q24_to_float((long long)sW[(int64_t)j * cpb + c + v]);
+                sW[(int64_t)j * cpb + c + v] = 0ull;
+            }
+            store_vec<VEC>(ov + (int64_t)j * HW + c, r);
+        }
+    }
+}
+
+// voxel.sum(0) from the planes this thread wrote itself (same cell mapping as the flushes)
+template <int VEC, int THREADS>
+__device__ __forceinline__ void sum_pass(const BandArgs& g, int b, int64_t band_base, int ncell) {
+    const BinArgs& a = g.bin;
+    const int64_t HW = (int64_t)a.H * a.W;
+    const float* ov = g.out_voxel + (int64_t)b * a.num_bins * HW + band_base;
+    for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        float sum[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
+        for (int q = 0; q < a.num_bins; ++q) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sum[v] += __ldcg(ov + (int64_t)q * HW + c + v);
+        }
+        store_vec<VEC>(g.out_sum + (int64_t)b * HW + band_base + c, sum);
+    }
+}
+
+// Persistent over the (sample, band) tasks of a group: grid = min(tasks, SMs), one CTA per SM.
+template <int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_sweep(BandArgs g, int n_tasks, int slot_words) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* slots = reinterpret_cast<uint32_t*>(smem_raw);                 // [(P + 1) * cpb] (count word + P planes)
+    uint32_t* s_run = slots + slot_words;                                    // [kMaxTableChunks]
+    uint16_t* s_kk = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks);   // [kMaxTableChunks]
+    __shared__ unsigned s_check[2];
+    const BinArgs& a = g.bin;
+    const int64_t HW = (int64_t)a.H * a.W;
+    const int bins = a.num_bins;
+    const bool count = a.count_channels != 0;
+    const int n_win = bins > 0 ? (bins + g.P - 1) / g.P : 0;
+    const bool single = n_win <= 1;
+    const int Pw = ((g.P + 1) * 4) / 8;                                      // int64 planes the same slots hold
+
+    for (int i = threadIdx.x; i < slot_words; i += THREADS) slots[i] = 0u;
+    if (threadIdx.x < 2) s_check[threadIdx.x] = 0u;
     EP_TICK_INIT();
+
     for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
         const int band = task % g.nb;
         const int b = a.g0 + task / g.nb;
         const int64_t band_base = (int64_t)band * g.cpb;
         const int ncell = (int)((band_base + g.cpb <= HW) ? g.cpb : (HW > band_base ? HW - band_base : 0));
         const int ch0 = g.chunk_first[b] - g.chunk_begin, nch = g.chunk_first[b + 1] - g.chunk_first[b];
-        // the sample's chunk table (this band's run offsets + interval span) is staged in shared memory once per
-        // task when it fits (<= kMaxTableChunks chunks = 4.2 M events), else re-staged tile by tile in every pass
-        const bool table_once = nch <= kMaxTableChunks;
+        bool any_hot = false;
 
-        __syncthreads();                                   // previous task fully flushed
-        EP_TICK(8);                                        // tail of the previous task (sum / count write-out + wait)
-        for (int i = tid; i < g.cpb; i += kSweepThreads) {
-            sN[i] = 0; sA[i] = 0; sCS[i] = make_uint2(0u, 0u);
-            if (COUNT) sCnt[i] = make_uint2(0u, 0u);
-        }
-        for (int t = 0; t < 3; ++t) spill_clear(spill + t, tid);
-        if (tid == 0) { s_hot = 0; s_carry[0] = 0; s_carry[1] = 0; s_check[0] = 0; s_check[1] = 0; }
-        if (table_once) {
-            for (int c = tid; c < nch; c += kSweepThreads) {
-                const uint16_t* row = g.rows + (int64_t)(ch0 + c) * kRowStride;
-                s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
-                s_kk[c] = row[kMaxBands + 1];
+        for (int wi = 0; wi < (n_win > 0 ? n_win : 1); ++wi) {
+            Window w;
+            w.q0 = wi * g.P;
+            w.q1 = min(w.q0 + g.P, bins);
+            const bool count_here = single && count;                  // the count word doubles as the count frame
+            EP_TICK(5);
+            unsigned matched = accumulate_fast<THREADS>(g, w, count_here, !single, band, band_base, ch0, nch, s_run, s_kk, slots);
+            bool hot = false;
+            unsigned counted = 0;
+            EP_TICK(6);
+            flush_fast<VEC, THREADS>(g, w, single, count_here, b, band_base, ncell, slots, hot, counted);
+            matched = warp_reduce(matched, [](unsigned x, unsigned y) { return x + y; });
+            counted = warp_reduce(counted, [](unsigned x, unsigned y) { return x + y; });
+            if ((threadIdx.x & 31) == 0) {
+                if (matched) atomicAdd(&s_check[0], matched);
+                if (counted) atomicAdd(&s_check[1], counted);
             }
-        }
-        int prev = 0, next = 1;                            // roles of the two carry tables (spill[1 + prev], spill[1 + next])
-
-        // intervals 0..B-1 produce voxel planes; the pseudo-interval kKCountOnly only feeds the count frame
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const int k = pass < B ? pass : (int)kKCountOnly;
-            int matched = 0;
-            for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
-                const int nt = min(kMaxTableChunks, nch - t0);
-                __syncthreads();                           // tile zeroed / flushed, table visible
-                EP_TICK(pass == 0 ? 5 : 7);                // 5: task set-up; 7: flush of the previous pass
-                if (!table_once) {
-                    for (int c = tid; c < nt; c += kSweepThreads) {
-                        const uint16_t* row = g.rows + (int64_t)(ch0 + t0 + c) * kRowStride;
-                        s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
-                        s_kk[c] = row[kMaxBands + 1];
-                    }
-                    __syncthreads();
-                }
-                matched += scan_records<false>(g, k, ch0, t0, nt, team, tl, s_run, s_kk, sN, sA, hot, a.bad_count);
-            }
-            matched = warp_reduce(matched, [](int x, int y) { return x + y; });
-            if ((tid & 31) == 0 && matched) atomicAdd(&s_check[0], (unsigned int)matched);
-            __syncthreads();
-            EP_TICK(6);                                    // record phase (incl. waiting for the slowest warp)
-
-            // ---- flush: every cell of the band emits voxel[k]; hot cells are deferred to the exact path below
-            const bool wide_prev = s_carry[prev] != 0;
-            float* o = (pass < B) ? g.out_voxel + ((int64_t)b * B + k) * HW + band_base : nullptr;
-            unsigned int counted = 0;
-#pragma unroll 2
-            for (int cell = tid; cell < ncell; cell += kSweepThreads) {
-                const uint32_t n = sN[cell];
-                if (pass >= B) {                           // count-only pseudo-interval
-                    if (n) {
-                        counted += (n & 0xffffu) + (n >> 16);
-                        uint2 c = sCnt[cell]; c.x += n & 0xffffu; c.y += n >> 16; sCnt[cell] = c;
-                        sN[cell] = 0;
-                    }
-                    continue;
-                }
-                const uint2 cs = sCS[cell];
-                if (n == 0 && !wide_prev) {                // no event in this interval: voxel[k] = carry
-                    if (cs.x == 0) { st_stream(o + cell, 0.0f); continue; }
-                    const float r = (float)(int32_t)cs.x * (1.0f / 16777216.0f);
-                    st_stream(o + cell, r);
-                    sCS[cell] = make_uint2(0u, __float_as_uint(__uint_as_float(cs.y) + r));
-                    continue;
-                }
-                const int np = (int)(n & 0xffffu), nn = (int)(n >> 16);
-                counted += (unsigned int)(np + nn);
-                if (np + nn > kAdmit) { s_hot = 1; continue; }       // exact path below; N and A stay for the re-scan
-                if (COUNT) { uint2 c = sCnt[cell]; c.x += np; c.y += nn; sCnt[cell] = c; }
-                const int32_t A = (int32_t)sA[cell];
-                long long carry = (long long)(int32_t)cs.x;
-                if (wide_prev) carry += spill_get(spill + 1 + prev, (unsigned int)cell);
-                const float r = q24_to_float(((long long)(np - nn) << kQ) - (long long)A + carry);
-                st_stream(o + cell, r);
-                sCS[cell] = make_uint2((uint32_t)A, __float_as_uint(__uint_as_float(cs.y) + r));
-                if (n) { sN[cell] = 0; sA[cell] = 0; }
-            }
-            counted = warp_reduce(counted, [](unsigned int x, unsigned int y) { return x + y; });
-            if ((tid & 31) == 0 && counted) atomicAdd(&s_check[1], counted);
-            __syncthreads();
-            if (pass < B && s_hot) {
-                // ---- exact path for hot cells: re-scan the interval's records, 64-bit sums in the hash table
-                for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
-                    const int nt = min(kMaxTableChunks, nch - t0);
-                    if (!table_once) {
-                        __syncthreads();
-                        for (int c = tid; c < nt; c += kSweepThreads) {
-                            const uint16_t* row = g.rows + (int64_t)(ch0 + t0 + c) * kRowStride;
-                            s_run[c] = (uint32_t)row[band] | ((uint32_t)row[band + 1] << 16);
-                            s_kk[c] = row[kMaxBands + 1];
-                        }
-                        __syncthreads();
-                    }
-                    scan_records<true>(g, k, ch0, t0, nt, team, tl, s_run, s_kk, sN, sA, hot, a.bad_count);
-                }
-                __syncthreads();
-                for (int cell = tid; cell < ncell; cell += kSweepThreads) {
-                    const uint32_t n = sN[cell];
-                    const int np = (int)(n & 0xffffu), nn = (int)(n >> 16);
-                    if (np + nn <= kAdmit) continue;
-                    if (COUNT) { uint2 c = sCnt[cell]; c.x += np; c.y += nn; sCnt[cell] = c; }
-                    const uint2 cs = sCS[cell];
-                    const long long A = spill_get(hot, (unsigned int)cell);
-                    long long carry = (long long)(int32_t)cs.x;
-                    if (wide_prev) carry += spill_get(spill + 1 + prev, (unsigned int)cell);
-                    const float r = q24_to_float(((long long)(np - nn) << kQ) - A + carry);
-                    st_stream(o + cell, r);
-                    const long long rest = A - (long long)(int32_t)(uint32_t)A;      // carry = low 32 bits + rest
-                    if (rest != 0) { spill_add(spill + 1 + next, (unsigned int)cell, rest, a.bad_count); s_carry[next] = 1; }
-                    sCS[cell] = make_uint2((uint32_t)A, __float_as_uint(__uint_as_float(cs.y) + r));
-                    sN[cell] = 0; sA[cell] = 0;
-                }
-                __syncthreads();
-                spill_clear(hot, tid);
-                if (tid == 0) s_hot = 0;
-            }
-            if (pass < B && (wide_prev || s_carry[next])) {
-                // rotate the carry tables: "next" becomes "prev" for the following interval, the old "prev" is cleared
-                __syncthreads();
-                if (wide_prev) spill_clear(spill + 1 + prev, tid);
-                if (tid == 0) s_carry[prev] = 0;
-                const int t = prev; prev = next; next = t;
-            }
-            if (tid == 0) {
+            const int hot_any = __syncthreads_or(hot ? 1 : 0);
+            EP_TICK(7);
+            if (threadIdx.x == 0) {
                 if (s_check[0] != s_check[1] && a.bad_count) atomicOr(a.bad_count, 0x80000000u);   // a 16-bit count wrapped
-                s_check[0] = 0; s_check[1] = 0;
+                s_check[0] = 0u; s_check[1] = 0u;
             }
-            // the next pass starts with a __syncthreads() before the tile and the tables are touched again
+            if (hot_any) {
+                // a cell saw more than kAdmit records: redo the window's planes exactly with int64 accumulators
+                any_hot = true;
+                for (int s0 = w.q0; s0 < w.q1; s0 += Pw) {
+                    Window ws;
+                    ws.q0 = s0;
+                    ws.q1 = min(s0 + Pw, w.q1);
+                    accumulate<1, THREADS>(g, ws, false, false, band, band_base, ch0, nch, s_run, s_kk, slots);
+                    flush_wide<VEC, THREADS>(g, ws, b, band_base, ncell, slots);
+                }
+            }
         }
-        __syncthreads();
-        if (g.out_sum && B > 0) {
-            float* sp = g.out_sum + (int64_t)b * HW + band_base;
-            for (int cell = tid; cell < ncell; cell += kSweepThreads) st_stream(sp + cell, __uint_as_float(sCS[cell].y));
-        }
-        if (COUNT) {
-            float* c0 = g.out_count + (int64_t)b * a.count_channels * HW + band_base;
-            float* cn = c0 + (int64_t)(a.count_channels - 1) * HW;
-            for (int cell = tid; cell < ncell; cell += kSweepThreads) {
-                const uint2 c = sCnt[cell];
-                st_stream(c0 + cell, (float)c.x);
-                st_stream(cn + cell, (float)c.y);
-                if (a.count_channels == 3) st_stream(c0 + HW + cell, 0.0f);
+        if (g.out_sum && bins > 0 && (!single || any_hot)) sum_pass<VEC, THREADS>(g, b, band_base, ncell);
+        if (count && !single) {
+            Window w;
+            w.q0 = 0; w.q1 = 0;
+            unsigned matched = accumulate<2, THREADS>(g, w, true, false, band, band_base, ch0, nch, s_run, s_kk, slots);
+            unsigned counted = 0;
+            flush_count<VEC, THREADS>(g, b, band_base, ncell, slots, counted);
+            matched = warp_reduce(matched, [](unsigned x, unsigned y) { return x + y; });
+            counted = warp_reduce(counted, [](unsigned x, unsigned y) { return x + y; });
+            if ((threadIdx.x & 31) == 0) {
+                if (matched) atomicAdd(&s_check[0], matched);
+                if (counted) atomicAdd(&s_check[1], counted);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (s_check[0] != s_check[1] && a.bad_count) atomicOr(a.bad_count, 0x80000000u);
+                s_check[0] = 0u; s_check[1] = 0u;
             }
         }
     }
@@ -557,90 +1111,216 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(BandArgs g, int n_ta
 
 // ---- host side ----------------------------------------------------------------------------------------------
 struct BandPlan {
-    int nb, cpb, shift;
+    int nb, cpb, shift, P, chunk, route_threads;
     uint32_t magic;
+    int slot_words;
     size_t sweep_smem;
 };
 
-bool plan_bands(const ep_bin_params* p, BandPlan* bp) {
-    const int64_t HW = (int64_t)p->height * p->width;
-    int nb = (int)ceil_div64(HW, kMaxCellsPerBand);
-    if (nb > kMaxBands) return false;
-    int cpb = (int)ceil_div64(HW, nb);
-    cpb = (cpb + 3) / 4 * 4;
-    if (cpb > kMaxCellsPerBand || cpb > 65536) return false;
-    bp->nb = (int)ceil_div64(HW, cpb);
-    bp->cpb = cpb;
-    // exact flat / cpb for flat < 2^31: s = ceil(log2 cpb), magic = floor(2^(31+s) / cpb) + 1, q = umulhi(n, magic) >> (s-1)
-    int sh = 0;
-    while ((1ll << sh) < cpb) ++sh;
-    bp->magic = (uint32_t)(((1ull << (31 + sh)) / (uint64_t)cpb) + 1);
-    bp->shift = sh - 1;
-    bp->sweep_smem = (size_t)cpb * 16 + 3 * sizeof(SpillTable) + kMaxTableChunks * (4 + 2) + 64;     // + cpb * 8 with a count frame
-    return true;
-}
 
 size_t banded_group_budget() {
-    const char* e = getenv("EP_BANDED_GROUP_MB");
-    long mb = e ? atol(e) : 72;
+    long mb = env_int("EP_BANDED_GROUP_MB", 64);
     if (mb < 1) mb = 1;
     return (size_t)mb << 20;
 }
 
-int64_t chunks_of(const int64_t* off, int b) {
-    const int64_t lo = off[b] / kEvPerThread * kEvPerThread;
-    return off[b + 1] > off[b] ? ceil_div64(off[b + 1] - lo, kChunk) : 0;
+bool plan_bands(const ep_bin_params* p, int batch, int64_t n_events, BandPlan* bp) {
+    const int64_t HW = (int64_t)p->height * p->width;
+    if (HW >= (1ll << 31) || p->width >= 65536 || p->num_bins > 30) return false;
+    const int bins = p->num_bins;
+    const int n_win = bins > 0 ? (bins + kMaxWindowPlanes - 1) / kMaxWindowPlanes : 1;
+    const int P = bins > 0 ? (bins + n_win - 1) / n_win : 0;
+    const int words_per_cell = P + 1;
+    const int table_bytes = kMaxTableChunks * 6;
+    int cpb_max = (kSweepSmemBudget - table_bytes) / (4 * words_per_cell);
+    const int cap = env_int("EP_BANDED_CPB", 0);
+    if (cap > 0 && cap < cpb_max) cpb_max = cap;
+    cpb_max = cpb_max / 4 * 4;
+    const int nb_min = (int)ceil_div64(HW, cpb_max);
+    if (nb_min > kMaxBands) return false;
+    int nb = nb_min;
+    if ((int64_t)nb * batch < kNumSMs) {
+        // small batches: more, smaller bands so that the (sample, band) tasks cover the SMs
+        while ((int64_t)nb * batch < kNumSMs && nb < kMaxBands && ceil_div64(HW, nb + 1) >= 1024) ++nb;
+    } else {
+        // a group of s samples gives s * nb sweep tasks for one CTA per SM: pick the band count whose groups fill whole
+        // waves (e.g. 640x480, 5 bins: 33 bands would do, 37 make 8 samples exactly two waves of 148)
+        const int64_t per_sample = n_events > 0 ? n_events / batch : 1;
+        int s_max = (int)(banded_group_budget() / (size_t)(per_sample * 8 + 1));
+        if (s_max < 1) s_max = 1;
+        if (s_max > batch) s_max = batch;
+        double best = -1.0;
+        for (int cand = nb_min; cand <= kMaxBands && cand <= nb_min + nb_min / 2 + 4; ++cand) {
+            double eff = 0.0;
+            for (int sg = (s_max + 1) / 2; sg <= s_max; ++sg) {
+                const int64_t tasks = (int64_t)sg * cand;
+                const double e = (double)tasks / (double)(ceil_div64(tasks, kNumSMs) * kNumSMs);
+                if (e > eff) eff = e;
+            }
+            const double score = eff - 0.004 * (cand - nb_min);
+            if (score > best + 1e-9) { best = score; nb = cand; }
+        }
+    }
+    const int force_nb = env_int("EP_BANDED_NB", 0);
+    if (force_nb >= nb_min && force_nb <= kMaxBands) nb = force_nb;
+    int cpb = (int)ceil_div64(HW, nb);
+    cpb = (cpb + 3) / 4 * 4;
+    bp->nb = (int)ceil_div64(HW, cpb);
+    bp->cpb = cpb;
+    bp->P = P;
+    // exact flat / cpb for flat < 2^31: s = ceil(log2 cpb), magic = floor(2^(31+s) / cpb) + 1, q = umulhi(n, magic) >> (s-1)
+    int sh = 0;
+    while ((1ll << sh) < cpb) ++sh;
+    if (sh < 1) sh = 1;
+    bp->magic = (uint32_t)(((1ull << (31 + sh)) / (uint64_t)cpb) + 1);
+    bp->shift = sh - 1;
+    bp->slot_words = words_per_cell * cpb;
+    bp->sweep_smem = (size_t)bp->slot_words * 4 + table_bytes;
+    const int variant = env_int("EP_ROUTE_VARIANT", 4);
+    bp->chunk = (variant == 1 || variant == 5 || variant == 6) ? 8192 : 4096;
+    bp->route_threads = variant == 1 ? 1024 : 512;
+    return true;
 }
 
-constexpr size_t kBytesPerChunk = (size_t)kChunk * 6 + kRowStride * 2;
+int64_t chunks_of(const int64_t* off, int b, int chunk) {
+    const int64_t lo = off[b] / kEvPerThread * kEvPerThread;
+    return off[b + 1] > off[b] ? ceil_div64(off[b + 1] - lo, chunk) : 0;
+}
 
-struct BandLayout { size_t meta, chunk_first, rows, rec_val, rec_cell, total; int64_t max_group_chunks; };
+size_t bytes_per_chunk(const BandPlan& bp) { return (size_t)bp.chunk * 8 + (size_t)bp.nb * 4 + 2; }   // per buffer set
 
-// groups: consecutive samples while the record buffer stays within the L2 budget (at least one sample)
-int64_t max_group_chunks(const int64_t* off, int B, size_t budget, size_t ws_cap_chunks) {
+// Second stream + events for the route / sweep overlap, one set per host thread (calls are re-entrant across threads).
+struct OverlapCtx {
+    int device = -1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t start = nullptr, routed[kBufSets] = {nullptr, nullptr}, swept[kBufSets] = {nullptr, nullptr};
+    bool ok = false;
+};
+OverlapCtx* overlap_ctx() {
+    static thread_local OverlapCtx ctx;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (ctx.ok && ctx.device == dev) return &ctx;
+    if (ctx.ok) return nullptr;                       // one device per process (and thread); anything else runs unoverlapped
+    ctx.device = dev;
+    bool good = cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&ctx.start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kBufSets; ++i) {
+        good = good && cudaEventCreateWithFlags(&ctx.routed[i], cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&ctx.swept[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ctx.ok = good;
+    if (!good) cudaGetLastError();
+    return good ? &ctx : nullptr;
+}
+
+struct BandLayout { size_t meta, chunk_first, info, runs[kBufSets], kk[kBufSets], rec[kBufSets], total; };
+
+BandLayout band_layout(int B, int64_t total_chunks, int64_t group_chunks, const BandPlan& bp) {
+    BandLayout L;
+    L.meta = 0;
+    L.chunk_first = align_up(sizeof(SampleMeta) * (size_t)B, 256);
+    L.info = L.chunk_first + align_up(sizeof(int32_t) * (size_t)(B + 1), 256);
+    size_t at = L.info + align_up(sizeof(ChunkInfo) * (size_t)total_chunks, 256);
+    for (int i = 0; i < kBufSets; ++i) {
+        L.runs[i] = at; at += align_up((size_t)group_chunks * bp.nb * 4, 256);
+        L.kk[i] = at;   at += align_up((size_t)group_chunks * 2, 256);
+        L.rec[i] = at;  at += align_up((size_t)group_chunks * bp.chunk * 8, 256);
+    }
+    L.total = at;
+    return L;
+}
+
+// largest group (in chunks) over a greedy split into consecutive samples within the record budget
+int64_t max_group_chunks(const int64_t* off, int B, const BandPlan& bp, size_t budget) {
     int64_t best = 0, cur = 0;
     for (int b = 0; b < B; ++b) {
-        const int64_t c = chunks_of(off, b);
-        if (cur > 0 && ((size_t)(cur + c) * kBytesPerChunk > budget || (size_t)(cur + c) > ws_cap_chunks)) cur = 0;
+        const int64_t c = chunks_of(off, b, bp.chunk);
+        if (cur > 0 && (size_t)(cur + c) * bytes_per_chunk(bp) > budget) cur = 0;
         cur += c;
         if (cur > best) best = cur;
     }
     return best;
 }
 
-BandLayout band_layout(int B, int64_t group_chunks) {
-    BandLayout L;
-    L.meta = 0;
-    L.chunk_first = align_up(sizeof(SampleMeta) * (size_t)B, 256);
-    L.rows = L.chunk_first + align_up(sizeof(int32_t) * (size_t)(B + 1), 256);
-    L.rec_val = L.rows + align_up((size_t)group_chunks * kRowStride * 2, 256);
-    L.rec_cell = L.rec_val + align_up((size_t)group_chunks * kChunk * 4, 256);
-    L.total = L.rec_cell + align_up((size_t)group_chunks * kChunk * 2, 256);
-    L.max_group_chunks = group_chunks;
-    return L;
+int64_t total_chunks_of(const int64_t* off, int B, int chunk) {
+    int64_t t = 0;
+    for (int b = 0; b < B; ++b) t += chunks_of(off, b, chunk);
+    return t;
 }
 
-bool banded_eligible(const ep_events_soa* ev, const ep_bin_params* p) {
-    if (p->time_f32 || p->num_bins > 30) return false;
-    if (!(ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64))) return false;
-    if (!aligned16(ev->x) || !aligned16(ev->y) || !aligned16(ev->t) || !aligned16(ev->p)) return false;
-    return true;
+int banded_kind(const ep_events_soa* ev, const ep_bin_params* p) {
+    if (p->time_f32 || ev->xy_dtype != EP_U16 || !aligned16(ev->x) || !aligned16(ev->y) || !aligned16(ev->t)) return -1;
+    if (ev->t_dtype == EP_U32) return (ev->p == nullptr && ev->t_base) ? kKindCompact : -1;
+    if (ev->p_dtype != EP_U8 || !aligned16(ev->p)) return -1;
+    if (ev->t_dtype == EP_I64) return kKindTicks64;
+    if (ev->t_dtype == EP_F64) return kKindF64;
+    return -1;
 }
 
-template <class Loader>
-int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin_params* p, const BandPlan& bp,
-               float* out_voxel, float* out_sum, float* out_count, void* ws, size_t ws_bytes, unsigned int* bad) {
+template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
+cudaError_t launch_route(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
+    static bool configured = false;
+    const size_t smem = (size_t)CHUNK * 8;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    const unsigned resident = (unsigned)(MINB * kNumSMs);
+    k_route<KIND, CHUNK, THREADS, MINB, TRACK><<<grid < resident ? grid : resident, THREADS, smem, st>>>(src, g, (int)grid);
+    return cudaSuccess;
+}
+
+template <int KIND>
+cudaError_t launch_route_kind(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
+    const bool track = g.bin.num_bins > g.P;      // multi-window sweeps filter chunks by their interval span
+    const int variant = env_int("EP_ROUTE_VARIANT", 4);
+    if (variant == 3) return track ? launch_route2<KIND, 4096, 256, 6, true>(st, src, g, grid) : launch_route2<KIND, 4096, 256, 6, false>(st, src, g, grid);
+    if (variant == 4) return track ? launch_route2<KIND, 4096, 256, 4, true>(st, src, g, grid) : launch_route2<KIND, 4096, 256, 4, false>(st, src, g, grid);
+    if (variant == 5) return track ? launch_route2<KIND, 8192, 512, 3, true>(st, src, g, grid) : launch_route2<KIND, 8192, 512, 3, false>(st, src, g, grid);
+    if (variant == 6) return track ? launch_route2<KIND, 8192, 256, 3, true>(st, src, g, grid) : launch_route2<KIND, 8192, 256, 3, false>(st, src, g, grid);
+    if (g.chunk == 8192) return track ? launch_route<KIND, 8192, 1024, 1, true>(st, src, g, grid)
+                                      : launch_route<KIND, 8192, 1024, 1, false>(st, src, g, grid);
+    if (variant == 2)
+        return track ? launch_route<KIND, 4096, 512, 3, true>(st, src, g, grid)
+                     : launch_route<KIND, 4096, 512, 3, false>(st, src, g, grid);
+    return track ? launch_route<KIND, 4096, 512, 2, true>(st, src, g, grid)
+                 : launch_route<KIND, 4096, 512, 2, false>(st, src, g, grid);
+}
+
+template <int VEC, int THREADS>
+cudaError_t launch_sweep(cudaStream_t st, const BandArgs& g, int n_tasks, const BandPlan& bp) {
+    static size_t configured = 0;
+    if (configured < bp.sweep_smem) {
+        cudaError_t ce = cudaFuncSetAttribute(k_sweep<VEC, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.sweep_smem);
+        if (ce != cudaSuccess) return ce;
+        configured = bp.sweep_smem;
+    }
+    const int grid = n_tasks < kNumSMs ? n_tasks : kNumSMs;
+    k_sweep<VEC, THREADS><<<(unsigned)grid, THREADS, bp.sweep_smem, st>>>(g, n_tasks, bp.slot_words);
+    return cudaSuccess;
+}
+
+template <class MetaLoader>
+int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, const ep_events_soa* ev, const ep_bin_params* p,
+               const BandPlan& bp, float* out_voxel, float* out_sum, float* out_count, void* ws, size_t ws_bytes,
+               unsigned int* bad) {
     const int B = ev->batch;
     const int64_t* off = ev->offsets_host;
-    // how many chunks fit the caller's workspace
-    const size_t fixed = band_layout(B, 0).total;
-    if (ws_bytes < fixed + kBytesPerChunk + 1024) return EP_EWORKSPACE;
-    const size_t cap_chunks = (ws_bytes - fixed - 1024) / kBytesPerChunk;
+    const int64_t total_chunks = total_chunks_of(off, B, bp.chunk);
+    if (total_chunks >= (1ll << 31)) return EP_EUNSUPPORTED;
+    const size_t fixed = band_layout(B, total_chunks, 0, bp).total;
+    const size_t bpc = bytes_per_chunk(bp);
+    if (ws_bytes < fixed + kBufSets * bpc + 4096) return EP_EWORKSPACE;
+    const size_t cap_chunks = (ws_bytes - fixed - 4096) / (kBufSets * bpc);
+    size_t budget = banded_group_budget();
+    if (budget > cap_chunks * bpc) budget = cap_chunks * bpc;
     for (int b = 0; b < B; ++b)
-        if ((size_t)chunks_of(off, b) > cap_chunks) return EP_EWORKSPACE;
-    const size_t budget = banded_group_budget();
-    const int64_t gchunks = max_group_chunks(off, B, budget, cap_chunks);
-    const BandLayout L = band_layout(B, gchunks);
+        if ((size_t)chunks_of(off, b, bp.chunk) > cap_chunks) return EP_EWORKSPACE;
+    const int64_t gchunks = max_group_chunks(off, B, bp, budget);
+    const BandLayout L = band_layout(B, total_chunks, gchunks, bp);
     if (L.total > ws_bytes) return EP_EWORKSPACE;
     char* w = static_cast<char*>(ws);
 
@@ -653,13 +1333,16 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
     a.bad_count = bad;
     a.vox_acc = nullptr; a.cnt_acc = nullptr;
     a.n_total = off[B];
-    a.begin = off[0]; a.end = off[B]; a.start4 = 0; a.g0 = 0; a.g1 = B;
-    g.nb = bp.nb; g.cpb = bp.cpb; g.cpb_magic = bp.magic; g.cpb_shift = bp.shift;
+    a.begin = off[0]; a.end = off[B]; a.start4 = 0; a.n_tiles = 0; a.g0 = 0; a.g1 = B;
+    g.nb = bp.nb; g.cpb = bp.cpb; g.cpb_magic = bp.magic; g.cpb_shift = bp.shift; g.P = bp.P; g.chunk = bp.chunk;
     int32_t* chunk_first = reinterpret_cast<int32_t*>(w + L.chunk_first);
+    ChunkInfo* info = reinterpret_cast<ChunkInfo*>(w + L.info);
     g.chunk_first = chunk_first;
-    g.rows = reinterpret_cast<uint16_t*>(w + L.rows);
-    g.rec_val = reinterpret_cast<uint32_t*>(w + L.rec_val);
-    g.rec_cell = reinterpret_cast<uint16_t*>(w + L.rec_cell);
+    g.info = info;
+    g.gchunks = (int)gchunks;
+    g.runs = reinterpret_cast<uint32_t*>(w + L.runs[0]);
+    g.kk = reinterpret_cast<uint16_t*>(w + L.kk[0]);
+    g.rec = reinterpret_cast<uint2*>(w + L.rec[0]);
     g.out_voxel = out_voxel; g.out_sum = out_sum; g.out_count = out_count;
     g.dbg = nullptr;
 #ifdef EP_PHASE_TIMING
@@ -670,75 +1353,101 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
 #endif
 
     profile_begin(st, kProfOther);
-    k_sample_meta<Loader><<<(B + 127) / 128, 128, 0, st>>>(ld, a, B);
+    k_sample_meta<MetaLoader><<<(B + 127) / 128, 128, 0, st>>>(mld, a, B);
+    EP_LAUNCH_CHECK();
+    k_chunk_prefix<<<1, 1024, 0, st>>>(a, B, bp.chunk, chunk_first);
+    EP_LAUNCH_CHECK();
+    if (total_chunks > 0) {
+        k_chunk_info<<<(unsigned)ceil_div64(total_chunks, 256), 256, 0, st>>>(a, B, bp.chunk, chunk_first, (int)total_chunks, info);
+        EP_LAUNCH_CHECK();
+    }
     profile_end(st);
-    EP_LAUNCH_CHECK();
-    k_chunk_prefix<<<1, 1024, 0, st>>>(a, B, chunk_first);
-    EP_LAUNCH_CHECK();
 
-    const bool count = p->count_channels != 0;
-    const size_t sweep_smem = bp.sweep_smem + (count ? (size_t)bp.cpb * 8 : 0);
-    cudaError_t ce = count ? cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem)
-                           : cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
-    if (ce != cudaSuccess) return (int)ce;
-    cudaFuncSetAttribute(k_route<Loader>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const bool vec4 = ((int64_t)p->height * p->width) % 4 == 0 && !(reinterpret_cast<uintptr_t>(out_voxel) & 15u) &&
+                      !(reinterpret_cast<uintptr_t>(out_sum) & 15u) && !(reinterpret_cast<uintptr_t>(out_count) & 15u);
+    const int sweep_threads = env_int("EP_SWEEP_THREADS", 512);
+
+    // Routes run on the caller's stream, sweeps on a side stream: the route of group g + 1 fills the SMs the sweep of
+    // group g leaves idle (its tail, launch gaps), and vice versa.  Everything is ordered after the caller's earlier work
+    // and joined back before returning; no host synchronisation.
+    OverlapCtx* ov = env_int("EP_BANDED_OVERLAP", 1) ? overlap_ctx() : nullptr;
+    cudaStream_t st_sweep = ov ? ov->side : st;
+    if (ov) {
+        cudaEventRecord(ov->start, st);
+        cudaStreamWaitEvent(ov->side, ov->start, 0);
+    }
+    int n_groups = 0;
 
     int64_t chunk_begin = 0;
     int g0 = 0;
-    const int slots = 2 * kNumSMs;                 // resident sweep CTAs
     while (g0 < B) {
         // largest group the record budget allows ...
         int g_max = g0;
         int64_t cur = 0;
         while (g_max < B) {
-            const int64_t c = chunks_of(off, g_max);
-            if (cur > 0 && ((size_t)(cur + c) * kBytesPerChunk > budget || cur + c > gchunks)) break;
+            const int64_t c = chunks_of(off, g_max, bp.chunk);
+            if (cur > 0 && ((size_t)(cur + c) * bpc > budget || cur + c > gchunks)) break;
             cur += c;
             ++g_max;
         }
-        // ... then trimmed so that its (sample, band) tasks fill whole waves of the resident sweep CTAs: a group of 12
-        // samples x 50 bands = 600 tasks on 296 slots runs 3 rounds (2.03 needed), 11 samples run 2
+        // ... then trimmed so that its (sample, band) tasks fill whole waves of the resident sweep CTAs
         int g1 = g_max;
         double best = -1.0;
         for (int cand = g_max; cand > g0 && cand >= g0 + (g_max - g0 + 1) / 2; --cand) {
             const int64_t tasks = (int64_t)(cand - g0) * bp.nb;
-            const double eff = (double)tasks / (double)(ceil_div64(tasks, slots) * slots);
+            const double eff = (double)tasks / (double)(ceil_div64(tasks, kNumSMs) * kNumSMs);
             if (eff > best + 1e-9) { best = eff; g1 = cand; }
         }
         cur = 0;
-        for (int b = g0; b < g1; ++b) cur += chunks_of(off, b);
+        for (int b = g0; b < g1; ++b) cur += chunks_of(off, b, bp.chunk);
         a.g0 = g0; a.g1 = g1;
         a.begin = off[g0]; a.end = off[g1];
         g.chunk_begin = (int)chunk_begin;
+        const int buf = ov ? (n_groups % kBufSets) : 0;
+        g.runs = reinterpret_cast<uint32_t*>(w + L.runs[buf]);
+        g.kk = reinterpret_cast<uint16_t*>(w + L.kk[buf]);
+        g.rec = reinterpret_cast<uint2*>(w + L.rec[buf]);
+        if (ov && n_groups >= kBufSets) cudaStreamWaitEvent(st, ov->swept[buf], 0);     // the buffer set is free again
         if (cur > 0) {
             profile_begin(st, kProfScatter);
-            k_route<Loader><<<(unsigned)cur, kRouteThreads, 0, st>>>(ld, g);
+            cudaError_t ce;
+            if (kind == kKindTicks64) ce = launch_route_kind<kKindTicks64>(st, src, g, (unsigned)cur);
+            else if (kind == kKindF64) ce = launch_route_kind<kKindF64>(st, src, g, (unsigned)cur);
+            else ce = launch_route_kind<kKindCompact>(st, src, g, (unsigned)cur);
             profile_end(st);
+            if (ce != cudaSuccess) return (int)ce;
             EP_LAUNCH_CHECK();
         }
-        profile_begin(st, kProfFinalize);
+        if (ov) {
+            cudaEventRecord(ov->routed[buf], st);
+            cudaStreamWaitEvent(st_sweep, ov->routed[buf], 0);
+        }
+        profile_begin(st_sweep, kProfFinalize);
         const int n_tasks = (g1 - g0) * bp.nb;
-        const int sweep_grid = n_tasks < 2 * kNumSMs ? n_tasks : 2 * kNumSMs;
-        if (count) k_sweep<true><<<(unsigned)sweep_grid, kSweepThreads, sweep_smem, st>>>(g, n_tasks);
-        else k_sweep<false><<<(unsigned)sweep_grid, kSweepThreads, sweep_smem, st>>>(g, n_tasks);
-        profile_end(st);
+        cudaError_t ce;
+        if (sweep_threads == 512) ce = vec4 ? launch_sweep<4, 512>(st_sweep, g, n_tasks, bp) : launch_sweep<1, 512>(st_sweep, g, n_tasks, bp);
+        else ce = vec4 ? launch_sweep<4, 1024>(st_sweep, g, n_tasks, bp) : launch_sweep<1, 1024>(st_sweep, g, n_tasks, bp);
+        profile_end(st_sweep);
+        if (ov) cudaEventRecord(ov->swept[buf], st_sweep);
+        if (ce != cudaSuccess) return (int)ce;
         EP_LAUNCH_CHECK();
         chunk_begin += cur;
         g0 = g1;
+        ++n_groups;
     }
+    if (ov)      // join: the caller's stream continues after the last sweeps
+        for (int i = 0; i < kBufSets && i < n_groups; ++i) cudaStreamWaitEvent(st, ov->swept[(n_groups - 1 - i) % kBufSets], 0);
 #ifdef EP_PHASE_TIMING
     if (getenv("EP_PRINT_TIMING")) {
         unsigned long long h[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, g.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[9] = {"route: setup", "route: load+compute+count", "route: scan", "route: place", "route: writeout",
-                                "sweep: task setup", "sweep: records", "sweep: flush", "sweep: task tail"};
+        const char* names[8] = {"route: setup + zero", "route: load wait + rank", "route: scan", "route: place", "route: writeout",
+                                "sweep: between windows", "sweep: accumulate", "sweep: flush"};
         double rt = 0, sw = 0;
         for (int i = 0; i < 5; ++i) rt += (double)h[i];
-        for (int i = 5; i < 9; ++i) sw += (double)h[i];
-        for (int i = 0; i < 9; ++i) fprintf(stderr, "  %-28s %12.3f Mcycles  %5.1f%%\n", names[i], h[i] * 1e-6, 100.0 * h[i] / (i < 5 ? rt : sw));
+        for (int i = 5; i < 8; ++i) sw += (double)h[i];
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "  %-28s %12.3f Mcycles  %5.1f%%\n", names[i], h[i] * 1e-6, 100.0 * h[i] / (i < 5 ? rt : sw));
     }
 #endif
     return EP_OK;
@@ -748,25 +1457,39 @@ int run_banded(cudaStream_t st, Loader ld, const ep_events_soa* ev, const ep_bin
 
 size_t banded_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p) {
     BandPlan bp;
-    if (!ev || !ev->offsets_host || ev->batch <= 0 || !plan_bands(p, &bp)) return 0;
-    const int64_t gchunks = max_group_chunks(ev->offsets_host, ev->batch, banded_group_budget(), (size_t)1 << 40);
-    return band_layout(ev->batch, gchunks).total + kBytesPerChunk + 2048;
+    if (!ev || !ev->offsets_host || ev->batch <= 0 || !plan_bands(p, ev->batch, ev->offsets_host[ev->batch] - ev->offsets_host[0], &bp)) return 0;
+    const int64_t total = total_chunks_of(ev->offsets_host, ev->batch, bp.chunk);
+    const int64_t gchunks = max_group_chunks(ev->offsets_host, ev->batch, bp, banded_group_budget());
+    return band_layout(ev->batch, total, gchunks, bp).total + kBufSets * bytes_per_chunk(bp) + 8192;
+}
+
+// true when the banded path can take this call and the batch is large enough for it to pay
+bool banded_worthwhile(const ep_events_soa* ev, const ep_bin_params* p) {
+    BandPlan bp;
+    if (banded_kind(ev, p) < 0 || !ev->offsets_host || !plan_bands(p, ev->batch, ev->offsets_host[ev->batch] - ev->offsets_host[0], &bp)) return false;
+    const int64_t n = ev->offsets_host[ev->batch] - ev->offsets_host[0];
+    return n >= (int64_t)env_int("EP_BANDED_MIN_EVENTS", 4000000) && (int64_t)ev->batch * bp.nb >= kNumSMs;
 }
 
 int run_banded_canon(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
                      float* out_count, void* ws, size_t ws_bytes, unsigned int* bad) {
     BandPlan bp;
-    if (!banded_eligible(ev, p) || !plan_bands(p, &bp)) return EP_EUNSUPPORTED;
-    if (ev->offsets_host[ev->batch] - ev->offsets_host[0] > 0x7fffffffLL * (int64_t)kChunk / 2) return EP_EUNSUPPORTED;
+    const int kind = banded_kind(ev, p);
+    if (kind < 0 || !plan_bands(p, ev->batch, ev->offsets_host[ev->batch] - ev->offsets_host[0], &bp)) return EP_EUNSUPPORTED;
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u)) return EP_EALIGN;
-    if (ev->t_dtype == EP_I64) {
-        SoaCanonLoader<true> ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y), ev->t,
-                                static_cast<const uint8_t*>(ev->p), ev->t_div};
-        return run_banded(st, ld, ev, p, bp, out_voxel, out_sum, out_count, ws, ws_bytes, bad);
+    if ((p->num_bins > 0 && !out_voxel) || (p->count_channels > 0 && !out_count)) return EP_EINVAL;
+    RouteSrc src{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y), ev->t,
+                 static_cast<const uint8_t*>(ev->p)};
+    if (kind == kKindCompact) {
+        SoaCompactLoader ld{src.x, src.y, static_cast<const uint32_t*>(ev->t), ev->t_base, ev->t_div};
+        return run_banded(st, ld, kind, src, ev, p, bp, out_voxel, out_sum, out_count, ws, ws_bytes, bad);
     }
-    SoaCanonLoader<false> ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y), ev->t,
-                             static_cast<const uint8_t*>(ev->p), ev->t_div};
-    return run_banded(st, ld, ev, p, bp, out_voxel, out_sum, out_count, ws, ws_bytes, bad);
+    if (kind == kKindTicks64) {
+        SoaCanonLoader<true> ld{src.x, src.y, ev->t, src.p, ev->t_div};
+        return run_banded(st, ld, kind, src, ev, p, bp, out_voxel, out_sum, out_count, ws, ws_bytes, bad);
+    }
+    SoaCanonLoader<false> ld{src.x, src.y, ev->t, src.p, ev->t_div};
+    return run_banded(st, ld, kind, src, ev, p, bp, out_voxel, out_sum, out_count, ws, ws_bytes, bad);
 }
 
 }  // namespace ep

@@ -15,6 +15,7 @@ constexpr int kThreads = 256;
 constexpr int kEvPerThread = 4;
 constexpr uint32_t kFlagLastPlane = 1u;      // an event landed in interval num_bins-1 with d > 0
 constexpr uint32_t kFlagZeroPol = 2u;        // the sample has p == 0 events (count-frame neg class)
+constexpr uint32_t kFlagIntTime = 4u;        // integer-tick stamps spanning < 2^32 ticks: fixed-point time arithmetic
 
 struct __align__(16) SampleMeta {
     double t0;        // first row's timestamp (events_to_voxel_grid.py:19)
@@ -23,7 +24,8 @@ struct __align__(16) SampleMeta {
     double t0_raw;    // first row's raw stamp (before t_div) when the stamps are fp64
     int64_t t0_ticks; // first row's raw stamp when the stamps are int64 ticks
     uint32_t flags;
-    uint32_t pad;
+    // kFlagIntTime: rn(ts * 2^24) = (dt * tmul + thalf) >> tshift for 0 <= dt < 2^32 ticks (ticks_to_v)
+    uint32_t tmul, tshift, thalf;
 };
 
 struct BinArgs {
@@ -291,10 +293,42 @@ __device__ __forceinline__ bool quantise_ts(TT ts, int num_bins, int& k, int& r,
     return true;
 }
 
+// Integer-tick layouts: v = rn(ts * 2^24) in fixed point.  ts = (bins-1) * dt / dT with dt, dT integer ticks, so
+//   v = (dt * tmul + thalf) >> tshift,   tmul = floor((bins-1) * 2^(24+tshift) / dT) < 2^32,  thalf = 2^(tshift-1):
+// one 32x32->64 multiply-add and a funnel shift per event instead of the reference's fp64 chain.  tmul is short of the
+// exact ratio by < 1, so v is short of the exact rn() by < dT / 2^tshift <= 1/2 weight quantum of 2^-24 (checked in k_sample_meta; and
+// v(dT) is exactly (bins-1) << 24): against the fp64 expression this moves a weight by at most one quantum, 6e-8.
+// Returns false when the event lies outside [0, bins) (events_to_voxel_grid.py:44-45).
+__device__ __forceinline__ bool ticks_to_v(int64_t dt, uint32_t tmul, uint32_t tshift, uint32_t thalf, uint32_t v_end,
+                                           uint32_t& v) {
+    const uint64_t q = (uint64_t)(uint32_t)dt * tmul + thalf;
+    const uint32_t hi = (uint32_t)(q >> 32);
+    v = __funnelshift_r((uint32_t)q, hi, tshift);
+    return (((uint32_t)((uint64_t)dt >> 32)) | (hi >> tshift)) == 0u && v < v_end;
+}
+
+// v -> (k, r) with the last-node fold of quantise_ts
+__device__ __forceinline__ void split_v(uint32_t v, int num_bins, int& k, int& r, bool& last_plane) {
+    k = (int)(v >> kQ);
+    r = (int)(v & ((1u << kQ) - 1u));
+    last_plane = false;
+    if (k == num_bins - 1) {
+        if (r == 0 && num_bins >= 2) { k -= 1; r = 1 << kQ; }
+        else last_plane = true;
+    }
+}
+
 // event j of a loaded quad -> (k, r); Loader::kFastTime selects the multiply form (canonical layout)
 template <class Loader, typename TT>
 __device__ __forceinline__ bool voxel_weights(const Ev<TT>& e, int j, const SampleMeta& m, int num_bins, int& k, int& r,
                                               bool& last_plane) {
+    if (Loader::kFastTime && Loader::kTicks && (m.flags & kFlagIntTime)) {
+        uint32_t v;
+        last_plane = false;
+        if (!ticks_to_v(e.ti[j] - m.t0_ticks, m.tmul, m.tshift, m.thalf, (uint32_t)num_bins << kQ, v)) return false;
+        split_v(v, num_bins, k, r, last_plane);
+        return true;
+    }
     if (Loader::kFastTime) {
         const double dt = Loader::kTicks ? (double)(e.ti[j] - m.t0_ticks) : ((double)e.t[j] - m.t0_raw);
         return quantise_ts<double>(dt * m.scale_raw, num_bins, k, r, last_plane);
@@ -311,7 +345,8 @@ __global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
     typedef typename Loader::time_t_ TT;
     const int64_t lo = off_at(a, b), hi = off_at(a, b + 1);
     SampleMeta m;
-    m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.pad = 0; m.scale_raw = 0.0; m.t0_raw = 0.0; m.t0_ticks = 0;
+    m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.tmul = 0; m.tshift = 0; m.thalf = 0; m.scale_raw = 0.0; m.t0_raw = 0.0;
+    m.t0_ticks = 0;
     if (hi > lo) {
         const TT first = ld.time_of(lo, b), last = ld.time_of(hi - 1, b);
         TT d = last - first;
@@ -321,6 +356,23 @@ __global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
         m.t0_raw = ld.raw_at(lo);
         m.t0_ticks = ld.ticks_at(lo);
         m.scale_raw = (double)(a.num_bins - 1) / ((double)d * ld.div());
+        if (Loader::kTicks && a.num_bins >= 1 && a.num_bins <= 64) {
+            // deltaT == 0 (-> 1.0 s, :24-25) and last < first (unsorted rows) keep the fp64 expression
+            const int64_t dticks = ld.ticks_at(hi - 1) - m.t0_ticks;
+            if (dticks > 0 && dticks < (1ll << 32)) {
+                const uint64_t nbm1 = (uint64_t)(a.num_bins - 1);
+                int s = 31;
+                uint64_t mul = 0;
+                for (; s >= 0; --s) {
+                    mul = (nbm1 << (kQ + s)) / (uint64_t)dticks;
+                    if (mul < (1ull << 32)) break;
+                }
+                if (s >= 0 && (uint64_t)dticks <= ((1ull << s) >> 1) + (s == 0)) {   // truncation of tmul costs < 1/2 quantum
+                    m.tmul = (uint32_t)mul; m.tshift = (uint32_t)s; m.thalf = s ? (1u << (s - 1)) : 0u;
+                    m.flags |= kFlagIntTime;
+                }
+            }
+        }
     }
     a.meta[b] = m;
 }
