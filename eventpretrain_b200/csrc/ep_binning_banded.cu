@@ -3,23 +3,31 @@
 // Same arithmetic and outputs as ep_binning.cu (events_to_voxel_grid.py:4-61, events_to_image.py:6-62), bit for bit,
 // but no global atomics and no accumulator round trip through L2:
 //
-//   route  (k_route)   one pass over the events of a sample group.  A CTA takes a chunk of consecutive events of one
-//                      sample, computes per event (cell, interval k, r = rn(d * 2^24), polarity) — integer fixed-point
-//                      time arithmetic for tick stamps (ticks_to_v) — counting-sorts the chunk by spatial band in shared
-//                      memory and writes it back, coalesced, as 8-byte records {cell, r | k << 25 | negative << 31}
-//                      plus one (begin, end) entry per band.  The record buffer of a group is sized to stay L2-resident.
+//   route  (k_route)   one pass over the events of a sample group.  A CTA takes a chunk of 4096 consecutive events of one
+//                      sample: pass A histograms them by spatial band (shared-memory RED), a scan turns the histogram
+//                      into cursors, pass B computes per event (cell, interval k, r = rn(d * 2^24), polarity) — integer
+//                      fixed-point time arithmetic for tick stamps (ticks_to_v) — and claims a slot with one returning
+//                      ATOMS; the chunk goes back to global memory sorted by band, coalesced, as 8-byte records
+//                      {cell, r | k << 25 | negative << 31}, plus one (begin, end) entry per band.  The record buffer
+//                      of a group is sized to stay L2-resident.
 //   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks and own the band's cells for a window of up to 6 voxel
-//                      planes in shared memory: int32 Q24 planes + one count word per cell.  Per record: two
-//                      fire-and-forget ATOMS.ADD on the planes k and k+1 (p * (2^24 - r), p * r) and one on the count
-//                      word (n_pos | n_neg << 16).  The flush converts the planes to fp32 (one rounding from the exact
-//                      integer), adds the fused voxel.sum(0) plane and the polarity count frame, and writes every
-//                      output element exactly once with 16-byte streaming stores.
+//                      planes in shared memory: int32 Q24 planes + one count word per cell.  A warp takes the band's run
+//                      of one chunk at a time (the next run's rows already in flight); per record: two fire-and-forget
+//                      ATOMS.ADD on the planes k and k + 1 (p * (2^24 - r), p * r) and one on the count word
+//                      (n_pos | n_neg << 16).  The flush converts
+//                      the planes to fp32 (one rounding from the exact integer), adds the fused voxel.sum(0) plane and
+//                      the polarity count frame, and writes every output element exactly once with 16-byte streaming
+//                      stores.
+//   Routes run on the caller's stream and sweeps on a side stream, so the route of group g + 1 fills the SMs the sweep
+//   of group g leaves idle.
 //
-// Exactness: a plane word is exact while the cell saw at most 127 records in the window (127 * 2^24 < 2^31); the
-// count word tells (fields are 16 bits; a band whose counts do not add up to the records it consumed has wrapped a
-// field and is reported through bad_count bit 31).  A band with a hotter cell is redone with 64-bit planes (atom.u64
-// in shared memory), so results never depend on the distribution.  Integer accumulation => order independent,
-// bit-reproducible, and identical to the global-RED path.
+// Exactness: the count word's ATOMS returns how many records the cell had before; the first 127 contributions of a cell
+// go to its int32 plane words (127 * 2^24 < 2^31: they never wrap), later ones to a small 64-bit side table keyed by
+// (cell, plane), so dense cells (hot pixels, strong edges) cost a few slow adds, not a second pass.  If the side table
+// overflows the window is redone with each plane split into two int32 words (sums of w >> 12 and w & 0xfff: exact for
+// any count).  Count fields are 16 bits; a band whose counts do not add up to the records it consumed has wrapped a
+// field and is reported through bad_count bit 31.  Integer accumulation => order independent, bit-reproducible, and
+// identical to the global-RED path.
 #include <stdio.h>
 
 #include "ep_binning_common.cuh"
@@ -33,8 +41,9 @@ constexpr uint32_t kKCountOnly = 31;        // interval code of events outside t
 constexpr int kAdmit = 127;                 // records per cell and window the int32 planes hold exactly
 constexpr int kMaxWindowPlanes = 6;
 constexpr int kBufSets = 2;                 // record buffers: the route of group g + 1 runs while group g is swept
+constexpr int kSweepThreads = 512;
 constexpr int kMaxTableChunks = 1024;       // chunk-table entries of one sample staged in shared memory at a time
-constexpr int kSweepSmemBudget = 232448 - 1024;   // opt-in shared memory per CTA minus static use
+constexpr int kSweepSmemBudget = 232448 - 7168;   // opt-in shared memory per CTA minus static use (side table, flags)
 
 enum { kKindTicks64 = 0, kKindF64 = 1, kKindCompact = 2 };
 
@@ -75,10 +84,13 @@ struct RouteSrc {
 
 struct BandArgs {
     BinArgs bin;                 // offsets, meta, geometry, bad_count (g0/g1 describe the group)
-    int nb;                      // bands
-    int cpb;                     // cells per band (multiple of 4)
-    uint32_t cpb_magic;          // flat / cpb == umulhi(flat, cpb_magic) >> cpb_shift  for flat < 2^31
-    int cpb_shift;
+    // Bands are row-cyclic: band b owns the rows b, b + nb, b + 2 nb, ... (dense image regions — edges, blobs — are
+    // dealt out over all bands, so the sweep tasks of a sample carry about the same number of records whatever the
+    // spatial distribution).  A record addresses its cell inside the band: (row / nb) * W + column.
+    int nb;                      // bands (>= 2)
+    int cpb;                     // cell slots per band: ceil(H / nb) * W rounded up to a multiple of 4
+    uint32_t w_magic, w_shift;   // n / W  == umulhi(n, w_magic) >> w_shift    for n < 2^31  (W >= 2)
+    uint32_t nb_magic, nb_shift; // n / nb == umulhi(n, nb_magic) >> nb_shift
     int P;                       // voxel planes per window
     int chunk;                   // events per routed chunk
     const int32_t* chunk_first;  // [B+1] first chunk id of each sample (global numbering)
@@ -89,6 +101,7 @@ struct BandArgs {
     uint16_t* kk;                // [gchunks]      kmin | kmax << 8 of the chunk's in-bins records (255 | 0 when none)
     uint2* rec;                  // [gchunks][chunk]
     float* out_voxel; float* out_sum; float* out_count;
+    unsigned int* task_counter;  // sweep: next task of this launch (zeroed before the launch)
     unsigned long long* dbg;     // phase cycle counters (EP_PHASE_TIMING builds), else unused
 };
 
@@ -166,14 +179,6 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void reds_add64(uint32_t addr, unsigned long long v) {
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
-    return r;
-}
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
@@ -182,17 +187,26 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
 struct RouteConst {
     uint32_t W, HW;
     uint32_t tmul, tshift, thalf, v_end, v_last;
-    uint32_t cpb_magic, cpb_shift, drop_band;
+    uint32_t w_magic, w_shift, nb, nb_magic, nb_shift, drop_band;
     int64_t t0_ticks;
     const SampleMeta* meta;      // the owning sample's metadata: fp64 time constants, read on the non-lean paths only
     int num_bins, count;
     bool int_time, scaled;
 };
 
+// flat cell index -> (band, cell inside the band) of the row-cyclic banding
+__device__ __forceinline__ uint32_t band_of(const RouteConst& rc, uint32_t flat, uint32_t& local) {
+    const uint32_t row = __umulhi(flat, rc.w_magic) >> rc.w_shift, col = flat - row * rc.W;
+    const uint32_t q = __umulhi(row, rc.nb_magic) >> rc.nb_shift;
+    local = q * rc.W + col;
+    return row - q * rc.nb;
+}
+
 // One event -> record words, branch-free on the steady-state path.  v = rn(ts * 2^24) (interval k = v >> 24, right
 // weight r = v & 0xffffff); the record is {flat cell index, r | k << 25 | negative << 31}, with an event exactly on the last
 // node filed under the interval before it (k - 1, r = 2^24), which is the same integer contribution.  Returns the band
-// the record goes to, or rc.drop_band for events that produce none; `bad` is set for events the reference raises on.
+// the record goes to (rc.drop_band for slots that hold no valid event of this sample); `bad` is set for events the
+// reference raises on.
 // LEAN: integer-tick time arithmetic and unscaled coordinates (the uniform branches are hoisted to the CTA level).
 template <int KIND, bool LEAN, bool TRACK>
 __device__ __forceinline__ uint32_t route_event(const RouteConst& rc, const BinArgs& a, uint32_t xs, uint32_t ys, uint32_t pb, uint32_t tlo,
@@ -227,227 +241,13 @@ __device__ __forceinline__ uint32_t route_event(const RouteConst& rc, const BinA
     if (v == rc.v_last) kr -= 1u << kQ;                        // (k, 0) on the last node -> (k - 1, 2^24)
     if (!in_bins) kr = kKCountOnly << kKShift;
     val = kr | ((pb ^ 1u) << 31);                          // bit 31 set = negative polarity
-    const uint32_t band = __umulhi(flat, rc.cpb_magic) >> rc.cpb_shift;
-    return (valid && (in_bins || rc.count != 0)) ? band : rc.drop_band;
+    uint32_t local;
+    const uint32_t band = band_of(rc, valid ? flat : 0u, local);
+    flat = local;                                              // the record carries the cell inside its band
+    return valid ? band : rc.drop_band;      // events outside the time bins keep a slot (count-only record), like in pass A
 }
 
-// loads of one thread: QUADS quads of 4 consecutive events, all issued before the first use
-template <int KIND, int QUADS>
-struct RawEvents {
-    uint2 xv[QUADS], yv[QUADS];
-    uint32_t pv[QUADS];
-    uint4 ta[QUADS], tb[QUADS];
-};
-
-template <int KIND, int CHUNK, int THREADS, bool EDGE>
-__device__ __forceinline__ void route_load(const RouteSrc& src, const BinArgs& a, int64_t c_lo,
-                                           RawEvents<KIND, CHUNK / (THREADS * 4)>& e) {
-    constexpr int QUADS = CHUNK / (THREADS * 4);
-#pragma unroll
-    for (int h = 0; h < QUADS; ++h) {
-        const int64_t i0 = c_lo + (int64_t)(h * THREADS + threadIdx.x) * 4;
-        if (!EDGE || i0 + 4 <= a.n_total) {
-            e.xv[h] = ld_stream(reinterpret_cast<const uint2*>(src.x + i0));
-            e.yv[h] = ld_stream(reinterpret_cast<const uint2*>(src.y + i0));
-            if (KIND == kKindCompact) {
-                e.ta[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(src.t) + i0));
-                e.pv[h] = 0;
-            } else {
-                e.pv[h] = ld_stream(reinterpret_cast<const uint32_t*>(src.p + i0));
-                e.ta[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0));
-                e.tb[h] = ld_stream(reinterpret_cast<const uint4*>(static_cast<const int64_t*>(src.t) + i0 + 2));
-            }
-        } else {     // last, partial quad of the arrays: scalar loads, nothing read past the end
-            uint32_t xs_[4] = {0, 0, 0, 0}, ys_[4] = {0, 0, 0, 0}, lo_[4] = {0, 0, 0, 0}, hi_[4] = {0, 0, 0, 0};
-            e.pv[h] = 0;
-            for (int j = 0; j < 4; ++j) {
-                if (i0 + j < a.n_total) {
-                    xs_[j] = src.x[i0 + j]; ys_[j] = src.y[i0 + j];
-                    if (KIND == kKindCompact) {
-                        lo_[j] = static_cast<const uint32_t*>(src.t)[i0 + j];
-                    } else {
-                        e.pv[h] |= (uint32_t)src.p[i0 + j] << (8 * j);
-                        const uint64_t tv = (uint64_t)static_cast<const int64_t*>(src.t)[i0 + j];
-                        lo_[j] = (uint32_t)tv; hi_[j] = (uint32_t)(tv >> 32);
-                    }
-                }
-            }
-            e.xv[h] = make_uint2(xs_[0] | (xs_[1] << 16), xs_[2] | (xs_[3] << 16));
-            e.yv[h] = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
-            if (KIND == kKindCompact) e.ta[h] = make_uint4(lo_[0], lo_[1], lo_[2], lo_[3]);
-            else { e.ta[h] = make_uint4(lo_[0], hi_[0], lo_[1], hi_[1]); e.tb[h] = make_uint4(lo_[2], hi_[2], lo_[3], hi_[3]); }
-        }
-    }
-}
-
-// compute + rank: every event slot of the thread gets (flat, val, band | rank << 16); slots that produce no record go to
-// the extra band rc.drop_band, whose records land behind the real ones in the staging buffer and are never read
-template <int KIND, int CHUNK, int THREADS, bool EDGE, bool LEAN, bool TRACK>
-__device__ __forceinline__ void route_rank(const RawEvents<KIND, CHUNK / (THREADS * 4)>& e, uint32_t lo_off, uint32_t hi_off,
-                                           const RouteConst& rc, const BinArgs& a, uint32_t cnt_addr, uint32_t (&flat)[CHUNK / THREADS],
-                                           uint32_t (&val)[CHUNK / THREADS], uint32_t (&bp)[CHUNK / THREADS], uint32_t& vmin,
-                                           uint32_t& vmax, unsigned& nbad) {
-    constexpr int QUADS = CHUNK / (THREADS * 4);
-#pragma unroll
-    for (int h = 0; h < QUADS; ++h) {
-        const uint32_t xs[4] = {e.xv[h].x & 0xffffu, e.xv[h].x >> 16, e.xv[h].y & 0xffffu, e.xv[h].y >> 16};
-        const uint32_t ys[4] = {e.yv[h].x & 0xffffu, e.yv[h].x >> 16, e.yv[h].y & 0xffffu, e.yv[h].y >> 16};
-        uint32_t tlo[4], thi[4], pb[4];
-        if (KIND == kKindCompact) {
-            const uint32_t raw[4] = {e.ta[h].x, e.ta[h].y, e.ta[h].z, e.ta[h].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { tlo[j] = raw[j] & 0x7fffffffu; thi[j] = 0; pb[j] = raw[j] >> 31; }
-        } else {
-            tlo[0] = e.ta[h].x; thi[0] = e.ta[h].y; tlo[1] = e.ta[h].z; thi[1] = e.ta[h].w;
-            tlo[2] = e.tb[h].x; thi[2] = e.tb[h].y; tlo[3] = e.tb[h].z; thi[3] = e.tb[h].w;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pb[j] = (e.pv[h] >> (8 * j)) & 0xffu;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = h * 4 + j;
-            bool live = true, bad;
-            if (EDGE) {
-                const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
-                live = e_off - lo_off < hi_off - lo_off;
-            }
-            const uint32_t band = route_event<KIND, LEAN, TRACK>(rc, a, xs[j], ys[j], pb[j], tlo[j], thi[j], live, flat[q], val[q],
-                                                                 vmin, vmax, bad);
-            nbad += bad ? 1u : 0u;
-            bp[q] = band | (atoms_add(cnt_addr + band * 4u, 1u) << 16);
-        }
-    }
-}
-
-// Persistent: grid = MINB CTAs per SM, each walks the group's chunks with stride gridDim.x.  Per chunk: rank (the events
-// were loaded during the previous chunk's tail), barrier, per-warp scan + place, barrier, write-out, barrier.
-template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
-__global__ void __launch_bounds__(THREADS, MINB) k_route(RouteSrc src, BandArgs g, int n_chunks) {
-    constexpr int EPT = CHUNK / THREADS;
-    constexpr int kWarps = THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* s_rec = reinterpret_cast<uint2*>(smem_raw);          // [CHUNK]
-    __shared__ int s_cnt[kMaxBands + 1], s_base[kMaxBands + 1];  // per band, plus the drop band at index nb
-    __shared__ int s_kmin, s_kmax;
-    __shared__ ChunkInfo s_info[3];                              // ring: this chunk, the next one, the one being fetched
-    const BinArgs& a = g.bin;
-    const int stride = (int)gridDim.x;
-    int chunk = (int)blockIdx.x;                                 // chunk id inside the group
-    if (chunk >= n_chunks) return;
-    {
-        const uint4* ip = reinterpret_cast<const uint4*>(g.info + g.chunk_begin);
-        constexpr int kV = (int)(sizeof(ChunkInfo) / 16);
-        if (threadIdx.x < kV) reinterpret_cast<uint4*>(&s_info[0])[threadIdx.x] = ip[(int64_t)chunk * kV + threadIdx.x];
-        if (threadIdx.x >= 32 && threadIdx.x < 32 + kV && chunk + stride < n_chunks)
-            reinterpret_cast<uint4*>(&s_info[1])[threadIdx.x - 32] = ip[(int64_t)(chunk + stride) * kV + threadIdx.x - 32];
-    }
-    for (int i = threadIdx.x; i <= g.nb; i += THREADS) s_cnt[i] = 0;
-    if (threadIdx.x == 0) { s_kmin = TRACK ? 255 : 0; s_kmax = TRACK ? 0 : 31; }
-    __syncthreads();
-
-    RouteConst rc;
-    rc.W = (uint32_t)a.W; rc.HW = (uint32_t)(a.H * a.W);
-    rc.v_end = (uint32_t)a.num_bins << kQ;
-    rc.v_last = a.num_bins >= 2 ? (uint32_t)(a.num_bins - 1) << kQ : 0xffffffffu;
-    rc.cpb_magic = g.cpb_magic; rc.cpb_shift = (uint32_t)g.cpb_shift; rc.drop_band = (uint32_t)g.nb;
-    rc.num_bins = a.num_bins; rc.count = a.count_channels;
-    rc.scaled = a.scaled != 0;
-    const uint32_t cnt_addr = smem_u32(s_cnt), base_addr = smem_u32(s_base), rec_addr = smem_u32(s_rec);
-
-    RawEvents<KIND, EPT / 4> ev;
-    {
-        const ChunkInfo& c0 = s_info[0];
-        if (c0.lo_off == 0 && c0.hi_off == CHUNK) route_load<KIND, CHUNK, THREADS, false>(src, a, c0.c_lo, ev);
-        else route_load<KIND, CHUNK, THREADS, true>(src, a, c0.c_lo, ev);
-    }
-    EP_TICK_INIT();
-    for (int it = 0; chunk < n_chunks; ++it, chunk += stride) {
-        const ChunkInfo& ci = s_info[it % 3];
-        {   // fetch the descriptor two chunks ahead (the next chunk's is already in the ring)
-            constexpr int kV = (int)(sizeof(ChunkInfo) / 16);
-            const int64_t c2 = (int64_t)chunk + 2 * (int64_t)stride;
-            if (threadIdx.x < kV && c2 < n_chunks)
-                reinterpret_cast<uint4*>(&s_info[(it + 2) % 3])[threadIdx.x] =
-                    reinterpret_cast<const uint4*>(g.info + g.chunk_begin)[c2 * kV + threadIdx.x];
-        }
-        rc.tmul = ci.tmul; rc.tshift = ci.tshift; rc.thalf = ci.thalf;
-        rc.t0_ticks = ci.t0_ticks;
-        rc.meta = a.meta + ci.b;
-        rc.int_time = (ci.flags & kFlagIntTime) != 0 && a.num_bins > 0;
-        const uint32_t lo_off = ci.lo_off, hi_off = ci.hi_off;
-        const bool interior = lo_off == 0 && hi_off == CHUNK;      // all slots belong to the sample, hence lie inside the arrays
-        const bool lean = KIND != kKindF64 && rc.int_time && !rc.scaled;
-
-        uint32_t val[EPT], flat[EPT], bp[EPT];
-        uint32_t vmin = 0xffffffffu, vmax = 0;
-        unsigned nbad = 0;
-#ifdef EP_COUNT_LEAN   // tools only: keep just the steady-state path to count its SASS
-        route_rank<KIND, CHUNK, THREADS, false, true, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
-#else
-        if (interior && lean) route_rank<KIND, CHUNK, THREADS, false, true, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
-        else if (interior) route_rank<KIND, CHUNK, THREADS, false, false, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
-        else route_rank<KIND, CHUNK, THREADS, true, false, TRACK>(ev, lo_off, hi_off, rc, a, cnt_addr, flat, val, bp, vmin, vmax, nbad);
-#endif
-        if (TRACK) {
-            // interval span of the chunk's in-bins records (conservative: an event on the last node counts for both sides)
-            vmin = warp_reduce(vmin, [](uint32_t x, uint32_t y) { return min(x, y); });
-            vmax = warp_reduce(vmax, [](uint32_t x, uint32_t y) { return max(x, y); });
-            if ((threadIdx.x & 31) == 0 && vmin <= vmax) { atomicMin(&s_kmin, (int)(vmin >> kQ)); atomicMax(&s_kmax, (int)(vmax >> kQ)); }
-        }
-        if (nbad && a.bad_count) atomicAdd(a.bad_count, nbad);
-        __syncthreads();
-        EP_TICK(1);
-        {
-            // exclusive scan of the (<= 256) band counts, eight per lane.  Every warp computes it for itself (same values)
-            // and stores the bases it will look up, so no warp waits for another; the runs go out spread over the warps.
-            const int l = threadIdx.x & 31, wp = threadIdx.x >> 5;
-            int c[8], tot = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c[i] = (8 * l + i <= g.nb) ? s_cnt[8 * l + i] : 0; tot += c[i]; }
-            int run = warp_incl_scan(tot, l) - tot;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int bd = 8 * l + i;
-                if (bd <= g.nb) s_base[bd] = run;
-                if (bd < g.nb && (bd % kWarps) == wp)
-                    g.runs[(int64_t)bd * g.gchunks + chunk] = (uint32_t)run | ((uint32_t)(run + c[i]) << 16);
-                run += c[i];
-            }
-            __syncwarp();
-        }
-        EP_TICK(2);
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            const uint32_t dst = lds_u32(base_addr + (bp[q] & 0xffffu) * 4u) + (bp[q] >> 16);
-            sts_v2(rec_addr + dst * 8u, flat[q], val[q]);
-        }
-        // the next chunk's events: in flight during this chunk's write-out (issued here, where the records' registers
-        // are free again: issuing them earlier makes ptxas spill load destinations, which serialises the loads)
-        if (chunk + stride < n_chunks) {
-            const ChunkInfo& cn = s_info[(it + 1) % 3];
-            if (cn.lo_off == 0 && cn.hi_off == CHUNK) route_load<KIND, CHUNK, THREADS, false>(src, a, cn.c_lo, ev);
-            else route_load<KIND, CHUNK, THREADS, true>(src, a, cn.c_lo, ev);
-        }
-        __syncthreads();
-        EP_TICK(3);
-        // every warp has scanned and placed: counters and span can be reset for the next chunk
-        const int n_vec = (s_base[g.nb] + 1) >> 1;
-        if (threadIdx.x == 32) {
-            g.kk[chunk] = (uint16_t)((s_kmin & 0xff) | (s_kmax << 8));
-            if (TRACK) { s_kmin = 255; s_kmax = 0; }
-        }
-        for (int i = threadIdx.x; i <= g.nb; i += THREADS) s_cnt[i] = 0;
-        // sorted chunk back to global, 16 bytes per thread and step (a trailing half vector may carry a dropped slot's
-        // data; the band runs delimit what is read)
-        uint4* gv = reinterpret_cast<uint4*>(g.rec + (int64_t)chunk * CHUNK);
-        for (int i = threadIdx.x; i < n_vec; i += THREADS) gv[i] = reinterpret_cast<const uint4*>(s_rec)[i];
-        __syncthreads();                                           // staging buffer, counters and descriptor ring reusable
-        EP_TICK(4);
-    }
-}
-
-// ---- route, two-pass form ---------------------------------------------------------------------------------
-// Same output as k_route.  Small CTAs that keep nothing in registers across a barrier: pass A reads x, y, p and
+// Two passes over the chunk.  Small CTAs that keep nothing in registers across a barrier: pass A reads x, y, p and
 // histograms the chunk by band (fire-and-forget RED), a scan turns the histogram into cursors, pass B reads the events
 // again (x, y, p from L2/L1; the stamps were prefetched into L2 at CTA start), builds the records and claims their slots
 // with one returning ATOMS on the band's cursor.  Low register count => 5-6 CTAs per SM whose phases drift apart and
@@ -518,7 +318,9 @@ __device__ __forceinline__ void route2_count(const RouteConst& rc, const BinArgs
             const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
             keep = keep && (e_off - lo_off < hi_off - lo_off);
         }
-        const uint32_t band = keep ? (__umulhi(flat, rc.cpb_magic) >> rc.cpb_shift) : rc.drop_band;
+        uint32_t local;
+        const uint32_t bd = band_of(rc, keep ? flat : 0u, local);
+        const uint32_t band = keep ? bd : rc.drop_band;
         reds_add(cnt_addr + band * 4u, 1u);
     }
 }
@@ -548,19 +350,16 @@ __device__ __forceinline__ void route2_place(const RouteConst& rc, const BinArgs
             const uint32_t e_off = (uint32_t)((h * THREADS + threadIdx.x) * 4 + j);
             live = e_off - lo_off < hi_off - lo_off;
         }
-        uint32_t flat, val;
-        route_event<KIND, LEAN, TRACK>(rc, a, xs[j], ys[j], pb[j], tlo[j], thi[j], live, flat, val, vmin, vmax, bad);
+        uint32_t cell, val;
+        const uint32_t band = route_event<KIND, LEAN, TRACK>(rc, a, xs[j], ys[j], pb[j], tlo[j], thi[j], live, cell, val, vmin, vmax, bad);
         nbad += bad ? 1u : 0u;
-        // same keep rule as pass A (events outside the time bins keep their slot as count-only records)
-        const bool keep = live && !bad;
-        const uint32_t band = keep ? (__umulhi(flat, rc.cpb_magic) >> rc.cpb_shift) : rc.drop_band;
         const uint32_t dst = atoms_add(cur_addr + band * 4u, 1u);
-        sts_v2(rec_addr + dst * 8u, flat, val);
+        sts_v2(rec_addr + dst * 8u, cell, val);
     }
 }
 
 template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
-__global__ void __launch_bounds__(THREADS, MINB) k_route2(RouteSrc src, BandArgs g) {
+__global__ void __launch_bounds__(THREADS, MINB) k_route(RouteSrc src, BandArgs g) {
     constexpr int QUADS = CHUNK / (THREADS * 4);
     constexpr int kWarps = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -586,7 +385,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_route2(RouteSrc src, BandArgs
     rc.tmul = ci.tmul; rc.tshift = ci.tshift; rc.thalf = ci.thalf;
     rc.v_end = (uint32_t)a.num_bins << kQ;
     rc.v_last = a.num_bins >= 2 ? (uint32_t)(a.num_bins - 1) << kQ : 0xffffffffu;
-    rc.cpb_magic = g.cpb_magic; rc.cpb_shift = (uint32_t)g.cpb_shift; rc.drop_band = (uint32_t)g.nb;
+    rc.w_magic = g.w_magic; rc.w_shift = g.w_shift; rc.nb = (uint32_t)g.nb; rc.nb_magic = g.nb_magic; rc.nb_shift = g.nb_shift;
+    rc.drop_band = (uint32_t)g.nb;
     rc.t0_ticks = ci.t0_ticks;
     rc.meta = a.meta + ci.b;
     rc.num_bins = a.num_bins; rc.count = a.count_channels;
@@ -671,23 +471,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_route2(RouteSrc src, BandArgs
 }
 
 template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
-cudaError_t launch_route2(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
+cudaError_t launch_route(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
     static bool configured = false;
     const size_t smem = (size_t)CHUNK * 8;
     if (!configured) {
-        cudaError_t ce = cudaFuncSetAttribute(k_route2<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t ce = cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        cudaFuncSetAttribute(k_route2<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    k_route2<KIND, CHUNK, THREADS, MINB, TRACK><<<grid, THREADS, smem, st>>>(src, g);
+    k_route<KIND, CHUNK, THREADS, MINB, TRACK><<<grid, THREADS, smem, st>>>(src, g);
     return cudaSuccess;
 }
 
 // ---- sweep ------------------------------------------------------------------------------------------------
 struct Window { int q0, q1; };   // voxel planes [q0, q1) held in shared memory
 
-// mode 0: int32 planes + count word (fast); mode 1: int64 planes (exact for any count); mode 2: count word only
+// mode 0: int32 planes + count word (fast); mode 1: hi/lo split planes (exact for any count); mode 2: count word only
 template <int MODE, int THREADS>
 __device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool count_all, bool filter, int band,
                                                int64_t band_base, int ch0, int nch, uint32_t* s_run, uint16_t* s_kk,
@@ -699,7 +499,7 @@ __device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool
     // slot addresses as functions of the record's flat cell index: count word [cpb] first, then the planes
     const uint32_t n_addr0 = smem_u32(slots) - (uint32_t)band_base * 4u;
     const uint32_t p_addr0 = smem_u32(slots + cpb) - ((uint32_t)band_base + (uint32_t)w.q0 * cpb) * 4u;   // int32 [P][cpb]
-    const uint32_t w_addr0 = smem_u32(slots) - ((uint32_t)band_base + (uint32_t)w.q0 * cpb) * 8u;         // int64 [Pw][cpb]
+    const uint32_t w_addr0 = smem_u32(slots) - ((uint32_t)band_base + 2u * (uint32_t)w.q0 * cpb) * 4u;    // hi/lo int32 [Pw][2][cpb]
     unsigned matched = 0;
     for (int t0 = 0; t0 < nch; t0 += kMaxTableChunks) {
         const int nt = min(kMaxTableChunks, nch - t0);
@@ -744,10 +544,18 @@ __device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool
                         if (left_ok) reds_add(addr, pos ? wl : 0u - wl);
                         if (right_ok) reds_add(addr + cpb * 4u, pos ? r : 0u - r);
                     } else if (MODE == 1) {
-                        const long long wl = (1ll << kQ) - (long long)r, wr = (long long)r;
-                        const uint32_t addr = w_addr0 + idx * 8u;
-                        if (left_ok) reds_add64(addr, (unsigned long long)(pos ? wl : -wl));
-                        if (right_ok) reds_add64(addr + cpb * 8u, (unsigned long long)(pos ? wr : -wr));
+                        // plane j of the window as two int32 words per cell: [2j] sum of p * (w >> 12), [2j+1] sum of
+                        // p * (w & 0xfff); w <= 2^24, so both are exact for more events than a count field can hold
+                        const uint32_t wl = (1u << kQ) - r, m = pos ? 0u : ~0u;
+                        const uint32_t addr = w_addr0 + (2u * idx - flat) * 4u;     // (2 * (k * cpb) + flat) words
+                        if (left_ok) {
+                            reds_add(addr, ((wl >> 12) ^ m) - m);
+                            reds_add(addr + cpb * 4u, ((wl & 0xfffu) ^ m) - m);
+                        }
+                        if (right_ok) {
+                            reds_add(addr + cpb * 8u, ((r >> 12) ^ m) - m);
+                            reds_add(addr + cpb * 12u, ((r & 0xfffu) ^ m) - m);
+                        }
                     }
                 }
             }
@@ -760,41 +568,104 @@ __device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool
 // Steady-state accumulate of window w with int32 planes + count word (same result as accumulate<0>): one branch per
 // record, every address a multiply-add from the record's flat cell index, the next chunk's rows already in flight
 // while the current ones are applied.
-struct FastAddr { uint32_t n0, p0, cpb, cpb4, q0, nfast, q1; };
+// Side table for cells that receive more than kAdmit records in a window: the first kAdmit contributions of a cell go
+// to its int32 plane words (which therefore never wrap), every later one is added here in 64 bits, keyed by
+// (cell, plane).  Which records are "later" is decided by the value the count word's ATOMS returns, so it is exact
+// under any interleaving.  Only dense cells (hot pixels, strong edges) ever come here.
+constexpr int kSpill = 512;                 // slots (power of two)
+struct SpillTable {
+    unsigned int key[kSpill];               // cell * 8 + plane + 1, 0 = empty
+    unsigned long long acc[kSpill];
+    int state;                              // 0 clean, 1 in use, 2 overflowed (the window is redone exactly)
+};
 
-__device__ __noinline__ void apply_record_slow(uint32_t flat, uint32_t v, FastAddr fa, bool count_all, unsigned& skipped) {
+__device__ __noinline__ void spill_add(SpillTable* t, uint32_t cell, uint32_t plane, int32_t v) {
+    const unsigned int key = cell * 8u + plane + 1u;
+    unsigned int h = (key * 2654435761u) >> (32 - 9);
+    if (t->state == 0) atomicMax(&t->state, 1);
+    for (int probe = 0; probe < kSpill; ++probe) {
+        const unsigned int prev = atomicCAS(&t->key[h], 0u, key);
+        if (prev == 0u || prev == key) { atomicAdd(&t->acc[h], (unsigned long long)(long long)v); return; }
+        h = (h + 1) & (kSpill - 1);
+    }
+    atomicMax(&t->state, 2);
+}
+
+__device__ __noinline__ long long spill_get(const SpillTable* t, uint32_t cell, uint32_t plane) {
+    const unsigned int key = cell * 8u + plane + 1u;
+    unsigned int h = (key * 2654435761u) >> (32 - 9);
+    for (int probe = 0; probe < kSpill; ++probe) {
+        const unsigned int k = t->key[h];
+        if (k == key) return (long long)t->acc[h];
+        if (k == 0u) return 0;
+        h = (h + 1) & (kSpill - 1);
+    }
+    return 0;
+}
+
+// Steady-state accumulate of window w with int32 planes + count word (same result as accumulate<0>): one branch per
+// record, every address a multiply-add from the record's cell index, the next chunk's rows already in flight
+// while the current ones are applied.
+struct FastAddr { uint32_t n0, p0, cpb, cpb4, q0, nfast, q1; SpillTable* spill; };
+
+__device__ __forceinline__ bool admitted(uint32_t old_n) { return (old_n & 0xffffu) + (old_n >> 16) < (uint32_t)kAdmit; }
+
+__device__ __noinline__ void apply_record_slow(uint32_t cell, uint32_t v, FastAddr fa, bool count_all, unsigned& skipped) {
     const uint32_t k = (v >> kKShift) & 31u, r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);
     const bool left_ok = k >= fa.q0 && k < fa.q1;
     const bool right_ok = k + 1 >= fa.q0 && k + 1 < fa.q1;
     if (!(count_all || left_ok || right_ok)) { ++skipped; return; }
-    reds_add(fa.n0 + flat * 4u, (m & 0xffffu) + 1u);
-    const uint32_t addr = fa.p0 + ((k - fa.q0) * fa.cpb + flat) * 4u, wl = (1u << kQ) - r;
-    if (left_ok) reds_add(addr, (wl ^ m) - m);
-    if (right_ok) reds_add(addr + fa.cpb4, (r ^ m) - m);
+    const uint32_t old_n = atoms_add(fa.n0 + cell * 4u, (m & 0xffffu) + 1u);
+    const uint32_t addr = fa.p0 + ((k - fa.q0) * fa.cpb + cell) * 4u, wl = (1u << kQ) - r;
+    if (admitted(old_n)) {
+        if (left_ok) reds_add(addr, (wl ^ m) - m);
+        if (right_ok) reds_add(addr + fa.cpb4, (r ^ m) - m);
+    } else {
+        if (left_ok) spill_add(fa.spill, cell, k - fa.q0, (int32_t)((wl ^ m) - m));
+        if (right_ok) spill_add(fa.spill, cell, k + 1 - fa.q0, (int32_t)((r ^ m) - m));
+    }
 }
 
-__device__ __forceinline__ void apply_record(uint32_t flat, uint32_t v, const FastAddr& fa, bool count_all, unsigned& skipped) {
+__device__ __noinline__ void spill_record(uint32_t cell, uint32_t v, FastAddr fa) {
+    const uint32_t kw = ((v >> kKShift) & 31u) - fa.q0, r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);
+    const uint32_t wl = (1u << kQ) - r;
+    spill_add(fa.spill, cell, kw, (int32_t)((wl ^ m) - m));
+    spill_add(fa.spill, cell, kw + 1u, (int32_t)((r ^ m) - m));
+}
+
+// step 1 of a record: bump the count word (returning ATOMS); records off the fast path are finished right here
+__device__ __forceinline__ uint32_t apply_begin(uint32_t cell, uint32_t v, const FastAddr& fa, bool count_all, unsigned& skipped) {
     const uint32_t kw = ((v >> kKShift) & 31u) - fa.q0;
     if (kw < fa.nfast) {                                        // both planes k and k + 1 lie inside the window
-        const uint32_t r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);   // m = 0 (positive) | ~0 (negative)
-        const uint32_t n_addr = fa.n0 + flat * 4u;              // count word; plane j of the window sits (j + 1) * cpb words on
-        const uint32_t addr = (kw + 1u) * fa.cpb4 + n_addr, wl = (1u << kQ) - r;
-        reds_add(n_addr, (m & 0xffffu) + 1u);
+        const uint32_t m = (uint32_t)((int32_t)v >> 31);        // 0 (positive) | ~0 (negative)
+        return atoms_add(fa.n0 + cell * 4u, (m & 0xffffu) + 1u);
+    }
+    apply_record_slow(cell, v, fa, count_all, skipped);
+    return 0xffffffffu;
+}
+
+// step 2: the two plane contributions, into the plane words while the cell is within kAdmit records, else the side table
+__device__ __forceinline__ void apply_finish(uint32_t cell, uint32_t v, uint32_t old_n, const FastAddr& fa) {
+    if (old_n == 0xffffffffu) return;
+    if (admitted(old_n)) {
+        const uint32_t kw = ((v >> kKShift) & 31u) - fa.q0, r = v & 0x1ffffffu, m = (uint32_t)((int32_t)v >> 31);
+        const uint32_t addr = (kw + 1u) * fa.cpb4 + fa.n0 + cell * 4u, wl = (1u << kQ) - r;   // plane j sits (j + 1) * cpb words after the count word
         reds_add(addr, (wl ^ m) - m);
         reds_add(addr + fa.cpb4, (r ^ m) - m);
     } else {
-        apply_record_slow(flat, v, fa, count_all, skipped);
+        spill_record(cell, v, fa);
     }
 }
 
 template <int THREADS>
 __device__ __forceinline__ unsigned accumulate_fast(const BandArgs& g, Window w, bool count_all, bool filter, int band,
                                                     int64_t band_base, int ch0, int nch, uint32_t* s_run, uint16_t* s_kk,
-                                                    uint32_t* slots) {
+                                                    uint32_t* slots, SpillTable* spill) {
     constexpr int kWarps = THREADS / 32;
     constexpr int U = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FastAddr fa;
+    fa.spill = spill;
     fa.cpb = (uint32_t)g.cpb; fa.cpb4 = fa.cpb * 4u;
     fa.q0 = (uint32_t)w.q0; fa.q1 = (uint32_t)w.q1;
     fa.nfast = w.q1 - w.q0 >= 2 ? (uint32_t)(w.q1 - w.q0 - 1) : 0u;
@@ -839,14 +710,18 @@ __device__ __forceinline__ unsigned accumulate_fast(const BandArgs& g, Window w,
             uint2 rn[U];
             if (cn < nt) load_rows(cn, lon, hin, rn);
             if (lo < hi) taken += (unsigned)((hi - lo + 31) >> 5);
+            uint32_t old_n[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (lo + 32 * u < hi) apply_record(rv[u].x, rv[u].y, fa, count_all, skipped);
-            if (lo + 32 * U < hi) {                          // longer run than the rows in flight (skewed input)
+                if (lo + 32 * u < hi) old_n[u] = apply_begin(rv[u].x, rv[u].y, fa, count_all, skipped);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (lo + 32 * u < hi) apply_finish(rv[u].x, rv[u].y, old_n[u], fa);
+            if (lo + 32 * U < hi) {                          // longer run than the rows in flight
                 const uint2* rp = rec0 + (int64_t)c * g.chunk;
                 for (int i = lo + 32 * U; i < hi; i += 32) {
                     const uint2 q = __ldcs(rp + i);
-                    apply_record(q.x, q.y, fa, count_all, skipped);
+                    apply_finish(q.x, q.y, apply_begin(q.x, q.y, fa, count_all, skipped), fa);
                 }
             }
             c = cn; lo = lon; hi = hin;
@@ -863,6 +738,12 @@ __device__ __forceinline__ float q24_to_float(long long val) {
     const int lo = (int)val;
     const float f = ((long long)lo == val) ? (float)lo : __ll2float_rn(val);
     return f * (1.0f / 16777216.0f);
+}
+
+// cell slot c of a band (c a multiple of VEC inside a row) -> offset in an (H, W) output plane: row-cyclic banding
+__device__ __forceinline__ int64_t out_offset(const BandArgs& g, int band, int c) {
+    const uint32_t q = __umulhi((uint32_t)c, g.w_magic) >> g.w_shift;
+    return (int64_t)(q * (uint32_t)g.nb + (uint32_t)band) * g.bin.W + ((uint32_t)c - q * (uint32_t)g.bin.W);
 }
 
 template <int VEC> struct VecF;
@@ -894,16 +775,17 @@ __device__ __forceinline__ void zero_u32(uint32_t* p) {
 // Fast flush of window w (int32 planes): voxel planes, and when the task has a single window also the sum plane and the
 // count frame.  Slots are left zeroed.  Accumulates this thread's (hot, counted).
 template <int VEC, int THREADS, int NP>
-__device__ __forceinline__ void flush_fast_np(const BandArgs& g, int q0, bool single, bool count, int b, int64_t band_base,
-                                              int ncell, uint32_t* slots, bool& hot, unsigned& counted) {
+__device__ __forceinline__ void flush_fast_np(const BandArgs& g, int q0, bool single, bool count, int b, int band,
+                                              int ncell, uint32_t* slots, const SpillTable* spill, unsigned& counted) {
     const BinArgs& a = g.bin;
     const int64_t HW = (int64_t)a.H * a.W;
     const int cpb = g.cpb;
+    const bool spilled = spill->state != 0;
     uint32_t* sN = slots;
     uint32_t* sP = slots + cpb;
-    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + q0) * HW + band_base;
-    float* os = (single && g.out_sum && NP > 0) ? g.out_sum + (int64_t)b * HW + band_base : nullptr;
-    float* oc = (single && count) ? g.out_count + (int64_t)b * a.count_channels * HW + band_base : nullptr;
+    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + q0) * HW;
+    float* os = (single && g.out_sum && NP > 0) ? g.out_sum + (int64_t)b * HW : nullptr;
+    float* oc = (single && count) ? g.out_count + (int64_t)b * a.count_channels * HW : nullptr;
     const int64_t neg_off = (int64_t)(a.count_channels - 1) * HW;
     for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
         uint32_t n[VEC], pw[NP > 0 ? NP : 1][VEC];
@@ -920,51 +802,54 @@ __device__ __forceinline__ void flush_fast_np(const BandArgs& g, int q0, bool si
             mx = max(mx, tot);
             counted += tot;
         }
-        hot |= mx > (unsigned)kAdmit;
+        const bool dense = spilled && mx > (unsigned)kAdmit;      // some cell here has contributions in the side table
         float sum[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
-        float* o = ov + c;
+        const int64_t off = out_offset(g, band, c);
+        float* o = ov + off;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
             float r[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 r[v] = (float)(int32_t)pw[j][v] * (1.0f / 16777216.0f);
+                if (dense && (n[v] & 0xffffu) + (n[v] >> 16) > (unsigned)kAdmit)
+                    r[v] = q24_to_float((long long)(int32_t)pw[j][v] + spill_get(spill, (uint32_t)(c + v), (uint32_t)j));
                 sum[v] += r[v];                   // voxel.sum(dim=0): sequential fp32 over bins
             }
             store_vec<VEC>(o, r);
             o += HW;
         }
-        if (os) store_vec<VEC>(os + c, sum);
+        if (os) store_vec<VEC>(os + off, sum);
         if (oc) {
             float cp[VEC], cn[VEC], z[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { cp[v] = (float)(n[v] & 0xffffu); cn[v] = (float)(n[v] >> 16); z[v] = 0.f; }
-            store_vec<VEC>(oc + c, cp);
-            store_vec<VEC>(oc + neg_off + c, cn);
-            if (a.count_channels == 3) store_vec<VEC>(oc + HW + c, z);
+            store_vec<VEC>(oc + off, cp);
+            store_vec<VEC>(oc + neg_off + off, cn);
+            if (a.count_channels == 3) store_vec<VEC>(oc + HW + off, z);
         }
     }
 }
 
 template <int VEC, int THREADS>
-__device__ __forceinline__ void flush_fast(const BandArgs& g, Window w, bool single, bool count, int b, int64_t band_base,
-                                           int ncell, uint32_t* slots, bool& hot, unsigned& counted) {
+__device__ __forceinline__ void flush_fast(const BandArgs& g, Window w, bool single, bool count, int b, int band,
+                                           int ncell, uint32_t* slots, const SpillTable* spill, unsigned& counted) {
     switch (w.q1 - w.q0) {
-        case 0: flush_fast_np<VEC, THREADS, 0>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        case 1: flush_fast_np<VEC, THREADS, 1>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        case 2: flush_fast_np<VEC, THREADS, 2>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        case 3: flush_fast_np<VEC, THREADS, 3>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        case 4: flush_fast_np<VEC, THREADS, 4>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        case 5: flush_fast_np<VEC, THREADS, 5>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
-        default: flush_fast_np<VEC, THREADS, 6>(g, w.q0, single, count, b, band_base, ncell, slots, hot, counted); break;
+        case 0: flush_fast_np<VEC, THREADS, 0>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        case 1: flush_fast_np<VEC, THREADS, 1>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        case 2: flush_fast_np<VEC, THREADS, 2>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        case 3: flush_fast_np<VEC, THREADS, 3>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        case 4: flush_fast_np<VEC, THREADS, 4>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        case 5: flush_fast_np<VEC, THREADS, 5>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
+        default: flush_fast_np<VEC, THREADS, 6>(g, w.q0, single, count, b, band, ncell, slots, spill, counted); break;
     }
 }
 
 // flush of the count word only (dedicated count pass of multi-window tasks)
 template <int VEC, int THREADS>
-__device__ __forceinline__ void flush_count(const BandArgs& g, int b, int64_t band_base, int ncell, uint32_t* slots,
+__device__ __forceinline__ void flush_count(const BandArgs& g, int b, int band, int ncell, uint32_t* slots,
                                             unsigned& counted) {
     const BinArgs& a = g.bin;
     const int64_t HW = (int64_t)a.H * a.W;
@@ -978,49 +863,52 @@ __device__ __forceinline__ void flush_count(const BandArgs& g, int b, int64_t ba
             counted += (n[v] & 0xffffu) + (n[v] >> 16);
             cp[v] = (float)(n[v] & 0xffffu); cn[v] = (float)(n[v] >> 16); z[v] = 0.f;
         }
-        float* oc = g.out_count + (int64_t)b * a.count_channels * HW + band_base + c;
+        float* oc = g.out_count + (int64_t)b * a.count_channels * HW + out_offset(g, band, c);
         store_vec<VEC>(oc, cp);
         store_vec<VEC>(oc + (int64_t)(a.count_channels - 1) * HW, cn);
         if (a.count_channels == 3) store_vec<VEC>(oc + HW, z);
     }
 }
 
-// exact flush of int64 planes [w.q0, w.q1): voxel planes only
+// exact flush of hi/lo split planes [w.q0, w.q1): voxel planes only
 template <int VEC, int THREADS>
-__device__ __forceinline__ void flush_wide(const BandArgs& g, Window w, int b, int64_t band_base, int ncell, uint32_t* slots) {
+__device__ __forceinline__ void flush_wide(const BandArgs& g, Window w, int b, int band, int ncell, uint32_t* slots) {
     const BinArgs& a = g.bin;
     const int64_t HW = (int64_t)a.H * a.W;
     const int cpb = g.cpb, np = w.q1 - w.q0;
-    unsigned long long* sW = reinterpret_cast<unsigned long long*>(slots);
-    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + w.q0) * HW + band_base;
+    float* ov = g.out_voxel + ((int64_t)b * a.num_bins + w.q0) * HW;
     for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        const int64_t off = out_offset(g, band, c);
         for (int j = 0; j < np; ++j) {
+            uint32_t hi[VEC], lo[VEC];
+            load_u32<VEC>(slots + (2 * j) * cpb + c, hi);
+            load_u32<VEC>(slots + (2 * j + 1) * cpb + c, lo);
+            zero_u32<VEC>(slots + (2 * j) * cpb + c);
+            zero_u32<VEC>(slots + (2 * j + 1) * cpb + c);
             float r[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                r[v] = q24_to_float((long long)sW[(int64_t)j * cpb + c + v]);
-                sW[(int64_t)j * cpb + c + v] = 0ull;
-            }
-            store_vec<VEC>(ov + (int64_t)j * HW + c, r);
+            for (int v = 0; v < VEC; ++v) r[v] = q24_to_float((long long)(int32_t)hi[v] * 4096 + (long long)(int32_t)lo[v]);
+            store_vec<VEC>(ov + (int64_t)j * HW + off, r);
         }
     }
 }
 
 // voxel.sum(0) from the planes this thread wrote itself (same cell mapping as the flushes)
 template <int VEC, int THREADS>
-__device__ __forceinline__ void sum_pass(const BandArgs& g, int b, int64_t band_base, int ncell) {
+__device__ __forceinline__ void sum_pass(const BandArgs& g, int b, int band, int ncell) {
     const BinArgs& a = g.bin;
     const int64_t HW = (int64_t)a.H * a.W;
-    const float* ov = g.out_voxel + (int64_t)b * a.num_bins * HW + band_base;
+    const float* ov = g.out_voxel + (int64_t)b * a.num_bins * HW;
     for (int c = threadIdx.x * VEC; c < ncell; c += THREADS * VEC) {
+        const int64_t off = out_offset(g, band, c);
         float sum[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
         for (int q = 0; q < a.num_bins; ++q) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) sum[v] += __ldcg(ov + (int64_t)q * HW + c + v);
+            for (int v = 0; v < VEC; ++v) sum[v] += __ldcg(ov + (int64_t)q * HW + off + v);
         }
-        store_vec<VEC>(g.out_sum + (int64_t)b * HW + band_base + c, sum);
+        store_vec<VEC>(g.out_sum + (int64_t)b * HW + off, sum);
     }
 }
 
@@ -1032,23 +920,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_sweep(BandArgs g, int n_tasks, i
     uint32_t* s_run = slots + slot_words;                                    // [kMaxTableChunks]
     uint16_t* s_kk = reinterpret_cast<uint16_t*>(s_run + kMaxTableChunks);   // [kMaxTableChunks]
     __shared__ unsigned s_check[2];
+    __shared__ int s_task;
+    __shared__ SpillTable s_spill;
     const BinArgs& a = g.bin;
-    const int64_t HW = (int64_t)a.H * a.W;
     const int bins = a.num_bins;
     const bool count = a.count_channels != 0;
     const int n_win = bins > 0 ? (bins + g.P - 1) / g.P : 0;
     const bool single = n_win <= 1;
-    const int Pw = ((g.P + 1) * 4) / 8;                                      // int64 planes the same slots hold
+    const int Pw = (g.P + 1) / 2;                                            // hi/lo split planes the same slots hold
 
     for (int i = threadIdx.x; i < slot_words; i += THREADS) slots[i] = 0u;
+    for (int i = threadIdx.x; i < kSpill; i += THREADS) { s_spill.key[i] = 0u; s_spill.acc[i] = 0ull; }
     if (threadIdx.x < 2) s_check[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_spill.state = 0;
     EP_TICK_INIT();
 
-    for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    // tasks are handed out dynamically: uneven bands (events concentrated on edges) do not pin the launch to the
+    // slowest CTA of a static split
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_task = (int)atomicAdd(g.task_counter, 1u);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= n_tasks) break;
         const int band = task % g.nb;
         const int b = a.g0 + task / g.nb;
-        const int64_t band_base = (int64_t)band * g.cpb;
-        const int ncell = (int)((band_base + g.cpb <= HW) ? g.cpb : (HW > band_base ? HW - band_base : 0));
+        const int64_t band_base = 0;                                      // records address cells inside the band
+        const int ncell = band < a.H ? ((a.H - band + g.nb - 1) / g.nb) * a.W : 0;   // rows band, band + nb, ... of the image
         const int ch0 = g.chunk_first[b] - g.chunk_begin, nch = g.chunk_first[b + 1] - g.chunk_first[b];
         bool any_hot = false;
 
@@ -1058,42 +956,52 @@ __global__ void __launch_bounds__(THREADS, 1) k_sweep(BandArgs g, int n_tasks, i
             w.q1 = min(w.q0 + g.P, bins);
             const bool count_here = single && count;                  // the count word doubles as the count frame
             EP_TICK(5);
-            unsigned matched = accumulate_fast<THREADS>(g, w, count_here, !single, band, band_base, ch0, nch, s_run, s_kk, slots);
-            bool hot = false;
+            unsigned matched = accumulate_fast<THREADS>(g, w, count_here, !single, band, band_base, ch0, nch, s_run, s_kk, slots, &s_spill);
             unsigned counted = 0;
             EP_TICK(6);
-            flush_fast<VEC, THREADS>(g, w, single, count_here, b, band_base, ncell, slots, hot, counted);
+            const int spill_state = s_spill.state;                    // uniform: accumulate ended with a barrier
+            flush_fast<VEC, THREADS>(g, w, single, count_here, b, band, ncell, slots, &s_spill, counted);
             matched = warp_reduce(matched, [](unsigned x, unsigned y) { return x + y; });
             counted = warp_reduce(counted, [](unsigned x, unsigned y) { return x + y; });
             if ((threadIdx.x & 31) == 0) {
                 if (matched) atomicAdd(&s_check[0], matched);
                 if (counted) atomicAdd(&s_check[1], counted);
             }
-            const int hot_any = __syncthreads_or(hot ? 1 : 0);
+            __syncthreads();
+            const int hot_any = spill_state == 2;                     // the side table overflowed: redo the window exactly
+            if (spill_state != 0) {
+                for (int i = threadIdx.x; i < kSpill; i += THREADS) { s_spill.key[i] = 0u; s_spill.acc[i] = 0ull; }
+                if (threadIdx.x == 0) s_spill.state = 0;
+                __syncthreads();
+            }
             EP_TICK(7);
             if (threadIdx.x == 0) {
                 if (s_check[0] != s_check[1] && a.bad_count) atomicOr(a.bad_count, 0x80000000u);   // a 16-bit count wrapped
                 s_check[0] = 0u; s_check[1] = 0u;
             }
             if (hot_any) {
-                // a cell saw more than kAdmit records: redo the window's planes exactly with int64 accumulators
+                // more dense (cell, plane) pairs than the side table holds: redo the window's planes with hi/lo split accumulators
                 any_hot = true;
                 for (int s0 = w.q0; s0 < w.q1; s0 += Pw) {
                     Window ws;
                     ws.q0 = s0;
                     ws.q1 = min(s0 + Pw, w.q1);
                     accumulate<1, THREADS>(g, ws, false, false, band, band_base, ch0, nch, s_run, s_kk, slots);
-                    flush_wide<VEC, THREADS>(g, ws, b, band_base, ncell, slots);
+                    flush_wide<VEC, THREADS>(g, ws, b, band, ncell, slots);
                 }
+                EP_TICK(8);
+#ifdef EP_PHASE_TIMING
+                if (threadIdx.x == 0) atomicAdd(g.dbg + 9, 1ull);
+#endif
             }
         }
-        if (g.out_sum && bins > 0 && (!single || any_hot)) sum_pass<VEC, THREADS>(g, b, band_base, ncell);
+        if (g.out_sum && bins > 0 && (!single || any_hot)) sum_pass<VEC, THREADS>(g, b, band, ncell);
         if (count && !single) {
             Window w;
             w.q0 = 0; w.q1 = 0;
             unsigned matched = accumulate<2, THREADS>(g, w, true, false, band, band_base, ch0, nch, s_run, s_kk, slots);
             unsigned counted = 0;
-            flush_count<VEC, THREADS>(g, b, band_base, ncell, slots, counted);
+            flush_count<VEC, THREADS>(g, b, band, ncell, slots, counted);
             matched = warp_reduce(matched, [](unsigned x, unsigned y) { return x + y; });
             counted = warp_reduce(counted, [](unsigned x, unsigned y) { return x + y; });
             if ((threadIdx.x & 31) == 0) {
@@ -1111,22 +1019,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_sweep(BandArgs g, int n_tasks, i
 
 // ---- host side ----------------------------------------------------------------------------------------------
 struct BandPlan {
-    int nb, cpb, shift, P, chunk, route_threads;
-    uint32_t magic;
+    int nb, cpb, P, chunk, route_threads;
+    uint32_t w_magic, w_shift, nb_magic, nb_shift;
     int slot_words;
     size_t sweep_smem;
 };
 
 
 size_t banded_group_budget() {
-    long mb = env_int("EP_BANDED_GROUP_MB", 64);
+    long mb = env_int("EP_BANDED_GROUP_MB", 72);
     if (mb < 1) mb = 1;
     return (size_t)mb << 20;
 }
 
+// exact n / d for n < 2^31, d >= 2: s = ceil(log2 d), magic = floor(2^(31+s) / d) + 1, q = umulhi(n, magic) >> (s - 1)
+void make_div(uint32_t d, uint32_t* magic, uint32_t* shift) {
+    int sh = 1;
+    while ((1ll << sh) < (int64_t)d) ++sh;
+    *magic = (uint32_t)(((1ull << (31 + sh)) / (uint64_t)d) + 1);
+    *shift = (uint32_t)(sh - 1);
+}
+
 bool plan_bands(const ep_bin_params* p, int batch, int64_t n_events, BandPlan* bp) {
     const int64_t HW = (int64_t)p->height * p->width;
-    if (HW >= (1ll << 31) || p->width >= 65536 || p->num_bins > 30) return false;
+    const int H = p->height, W = p->width;
+    if (HW >= (1ll << 31) || W >= 65536 || W < 2 || p->num_bins > 30) return false;
     const int bins = p->num_bins;
     const int n_win = bins > 0 ? (bins + kMaxWindowPlanes - 1) / kMaxWindowPlanes : 1;
     const int P = bins > 0 ? (bins + n_win - 1) / n_win : 0;
@@ -1136,15 +1053,18 @@ bool plan_bands(const ep_bin_params* p, int batch, int64_t n_events, BandPlan* b
     const int cap = env_int("EP_BANDED_CPB", 0);
     if (cap > 0 && cap < cpb_max) cpb_max = cap;
     cpb_max = cpb_max / 4 * 4;
-    const int nb_min = (int)ceil_div64(HW, cpb_max);
+    const int rows_max = cpb_max / W;                 // rows of the image one band can hold
+    if (rows_max < 1) return false;
+    int nb_min = (H + rows_max - 1) / rows_max;
+    if (nb_min < 2) nb_min = 2;
     if (nb_min > kMaxBands) return false;
     int nb = nb_min;
     if ((int64_t)nb * batch < kNumSMs) {
         // small batches: more, smaller bands so that the (sample, band) tasks cover the SMs
-        while ((int64_t)nb * batch < kNumSMs && nb < kMaxBands && ceil_div64(HW, nb + 1) >= 1024) ++nb;
+        while ((int64_t)nb * batch < kNumSMs && nb < kMaxBands && nb < H && (int64_t)((H + nb) / (nb + 1)) * W >= 1024) ++nb;
     } else {
         // a group of s samples gives s * nb sweep tasks for one CTA per SM: pick the band count whose groups fill whole
-        // waves (e.g. 640x480, 5 bins: 33 bands would do, 37 make 8 samples exactly two waves of 148)
+        // waves (e.g. 640x480, 5 bins: 37 bands make 8 samples exactly two waves of 148)
         const int64_t per_sample = n_events > 0 ? n_events / batch : 1;
         int s_max = (int)(banded_group_budget() / (size_t)(per_sample * 8 + 1));
         if (s_max < 1) s_max = 1;
@@ -1163,22 +1083,15 @@ bool plan_bands(const ep_bin_params* p, int batch, int64_t n_events, BandPlan* b
     }
     const int force_nb = env_int("EP_BANDED_NB", 0);
     if (force_nb >= nb_min && force_nb <= kMaxBands) nb = force_nb;
-    int cpb = (int)ceil_div64(HW, nb);
-    cpb = (cpb + 3) / 4 * 4;
-    bp->nb = (int)ceil_div64(HW, cpb);
-    bp->cpb = cpb;
+    bp->nb = nb;
+    bp->cpb = (((H + nb - 1) / nb) * W + 3) / 4 * 4;
     bp->P = P;
-    // exact flat / cpb for flat < 2^31: s = ceil(log2 cpb), magic = floor(2^(31+s) / cpb) + 1, q = umulhi(n, magic) >> (s-1)
-    int sh = 0;
-    while ((1ll << sh) < cpb) ++sh;
-    if (sh < 1) sh = 1;
-    bp->magic = (uint32_t)(((1ull << (31 + sh)) / (uint64_t)cpb) + 1);
-    bp->shift = sh - 1;
-    bp->slot_words = words_per_cell * cpb;
+    make_div((uint32_t)W, &bp->w_magic, &bp->w_shift);
+    make_div((uint32_t)nb, &bp->nb_magic, &bp->nb_shift);
+    bp->slot_words = words_per_cell * bp->cpb;
     bp->sweep_smem = (size_t)bp->slot_words * 4 + table_bytes;
-    const int variant = env_int("EP_ROUTE_VARIANT", 4);
-    bp->chunk = (variant == 1 || variant == 5 || variant == 6) ? 8192 : 4096;
-    bp->route_threads = variant == 1 ? 1024 : 512;
+    bp->chunk = 4096;
+    bp->route_threads = 256;
     return true;
 }
 
@@ -1214,13 +1127,14 @@ OverlapCtx* overlap_ctx() {
     return good ? &ctx : nullptr;
 }
 
-struct BandLayout { size_t meta, chunk_first, info, runs[kBufSets], kk[kBufSets], rec[kBufSets], total; };
+struct BandLayout { size_t meta, chunk_first, counters, info, runs[kBufSets], kk[kBufSets], rec[kBufSets], total; };
 
 BandLayout band_layout(int B, int64_t total_chunks, int64_t group_chunks, const BandPlan& bp) {
     BandLayout L;
     L.meta = 0;
     L.chunk_first = align_up(sizeof(SampleMeta) * (size_t)B, 256);
-    L.info = L.chunk_first + align_up(sizeof(int32_t) * (size_t)(B + 1), 256);
+    L.counters = L.chunk_first + align_up(sizeof(int32_t) * (size_t)(B + 1), 256);      // one sweep task counter per group
+    L.info = L.counters + align_up(sizeof(unsigned int) * (size_t)B, 256);
     size_t at = L.info + align_up(sizeof(ChunkInfo) * (size_t)total_chunks, 256);
     for (int i = 0; i < kBufSets; ++i) {
         L.runs[i] = at; at += align_up((size_t)group_chunks * bp.nb * 4, 256);
@@ -1258,36 +1172,10 @@ int banded_kind(const ep_events_soa* ev, const ep_bin_params* p) {
     return -1;
 }
 
-template <int KIND, int CHUNK, int THREADS, int MINB, bool TRACK>
-cudaError_t launch_route(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
-    static bool configured = false;
-    const size_t smem = (size_t)CHUNK * 8;
-    if (!configured) {
-        cudaError_t ce = cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ce != cudaSuccess) return ce;
-        cudaFuncSetAttribute(k_route<KIND, CHUNK, THREADS, MINB, TRACK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
-    const unsigned resident = (unsigned)(MINB * kNumSMs);
-    k_route<KIND, CHUNK, THREADS, MINB, TRACK><<<grid < resident ? grid : resident, THREADS, smem, st>>>(src, g, (int)grid);
-    return cudaSuccess;
-}
-
 template <int KIND>
 cudaError_t launch_route_kind(cudaStream_t st, const RouteSrc& src, const BandArgs& g, unsigned grid) {
     const bool track = g.bin.num_bins > g.P;      // multi-window sweeps filter chunks by their interval span
-    const int variant = env_int("EP_ROUTE_VARIANT", 4);
-    if (variant == 3) return track ? launch_route2<KIND, 4096, 256, 6, true>(st, src, g, grid) : launch_route2<KIND, 4096, 256, 6, false>(st, src, g, grid);
-    if (variant == 4) return track ? launch_route2<KIND, 4096, 256, 4, true>(st, src, g, grid) : launch_route2<KIND, 4096, 256, 4, false>(st, src, g, grid);
-    if (variant == 5) return track ? launch_route2<KIND, 8192, 512, 3, true>(st, src, g, grid) : launch_route2<KIND, 8192, 512, 3, false>(st, src, g, grid);
-    if (variant == 6) return track ? launch_route2<KIND, 8192, 256, 3, true>(st, src, g, grid) : launch_route2<KIND, 8192, 256, 3, false>(st, src, g, grid);
-    if (g.chunk == 8192) return track ? launch_route<KIND, 8192, 1024, 1, true>(st, src, g, grid)
-                                      : launch_route<KIND, 8192, 1024, 1, false>(st, src, g, grid);
-    if (variant == 2)
-        return track ? launch_route<KIND, 4096, 512, 3, true>(st, src, g, grid)
-                     : launch_route<KIND, 4096, 512, 3, false>(st, src, g, grid);
-    return track ? launch_route<KIND, 4096, 512, 2, true>(st, src, g, grid)
-                 : launch_route<KIND, 4096, 512, 2, false>(st, src, g, grid);
+    return track ? launch_route<KIND, 4096, 256, 4, true>(st, src, g, grid) : launch_route<KIND, 4096, 256, 4, false>(st, src, g, grid);
 }
 
 template <int VEC, int THREADS>
@@ -1334,7 +1222,8 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
     a.vox_acc = nullptr; a.cnt_acc = nullptr;
     a.n_total = off[B];
     a.begin = off[0]; a.end = off[B]; a.start4 = 0; a.n_tiles = 0; a.g0 = 0; a.g1 = B;
-    g.nb = bp.nb; g.cpb = bp.cpb; g.cpb_magic = bp.magic; g.cpb_shift = bp.shift; g.P = bp.P; g.chunk = bp.chunk;
+    g.nb = bp.nb; g.cpb = bp.cpb; g.P = bp.P; g.chunk = bp.chunk;
+    g.w_magic = bp.w_magic; g.w_shift = bp.w_shift; g.nb_magic = bp.nb_magic; g.nb_shift = bp.nb_shift;
     int32_t* chunk_first = reinterpret_cast<int32_t*>(w + L.chunk_first);
     ChunkInfo* info = reinterpret_cast<ChunkInfo*>(w + L.info);
     g.chunk_first = chunk_first;
@@ -1345,6 +1234,12 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
     g.rec = reinterpret_cast<uint2*>(w + L.rec[0]);
     g.out_voxel = out_voxel; g.out_sum = out_sum; g.out_count = out_count;
     g.dbg = nullptr;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(w + L.counters);
+    g.task_counter = counters;
+    {
+        cudaError_t ce = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)B, st);
+        if (ce != cudaSuccess) return (int)ce;
+    }
 #ifdef EP_PHASE_TIMING
     static unsigned long long* s_dbg = nullptr;
     if (!s_dbg) cudaMalloc(&s_dbg, 16 * sizeof(unsigned long long));
@@ -1363,9 +1258,8 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
     }
     profile_end(st);
 
-    const bool vec4 = ((int64_t)p->height * p->width) % 4 == 0 && !(reinterpret_cast<uintptr_t>(out_voxel) & 15u) &&
+    const bool vec4 = p->width % 4 == 0 && !(reinterpret_cast<uintptr_t>(out_voxel) & 15u) &&
                       !(reinterpret_cast<uintptr_t>(out_sum) & 15u) && !(reinterpret_cast<uintptr_t>(out_count) & 15u);
-    const int sweep_threads = env_int("EP_SWEEP_THREADS", 512);
 
     // Routes run on the caller's stream, sweeps on a side stream: the route of group g + 1 fills the SMs the sweep of
     // group g leaves idle (its tail, launch gaps), and vice versa.  Everything is ordered after the caller's earlier work
@@ -1404,6 +1298,7 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
         a.begin = off[g0]; a.end = off[g1];
         g.chunk_begin = (int)chunk_begin;
         const int buf = ov ? (n_groups % kBufSets) : 0;
+        g.task_counter = counters + n_groups;
         g.runs = reinterpret_cast<uint32_t*>(w + L.runs[buf]);
         g.kk = reinterpret_cast<uint16_t*>(w + L.kk[buf]);
         g.rec = reinterpret_cast<uint2*>(w + L.rec[buf]);
@@ -1425,8 +1320,7 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
         profile_begin(st_sweep, kProfFinalize);
         const int n_tasks = (g1 - g0) * bp.nb;
         cudaError_t ce;
-        if (sweep_threads == 512) ce = vec4 ? launch_sweep<4, 512>(st_sweep, g, n_tasks, bp) : launch_sweep<1, 512>(st_sweep, g, n_tasks, bp);
-        else ce = vec4 ? launch_sweep<4, 1024>(st_sweep, g, n_tasks, bp) : launch_sweep<1, 1024>(st_sweep, g, n_tasks, bp);
+        ce = vec4 ? launch_sweep<4, kSweepThreads>(st_sweep, g, n_tasks, bp) : launch_sweep<1, kSweepThreads>(st_sweep, g, n_tasks, bp);
         profile_end(st_sweep);
         if (ov) cudaEventRecord(ov->swept[buf], st_sweep);
         if (ce != cudaSuccess) return (int)ce;
@@ -1442,12 +1336,13 @@ int run_banded(cudaStream_t st, MetaLoader mld, int kind, const RouteSrc& src, c
         unsigned long long h[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, g.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[8] = {"route: setup + zero", "route: load wait + rank", "route: scan", "route: place", "route: writeout",
-                                "sweep: between windows", "sweep: accumulate", "sweep: flush"};
+        const char* names[9] = {"route: setup + zero", "route: load wait + rank", "route: scan", "route: place", "route: writeout",
+                                "sweep: between windows", "sweep: accumulate", "sweep: flush", "sweep: exact redo"};
         double rt = 0, sw = 0;
         for (int i = 0; i < 5; ++i) rt += (double)h[i];
-        for (int i = 5; i < 8; ++i) sw += (double)h[i];
-        for (int i = 0; i < 8; ++i) fprintf(stderr, "  %-28s %12.3f Mcycles  %5.1f%%\n", names[i], h[i] * 1e-6, 100.0 * h[i] / (i < 5 ? rt : sw));
+        for (int i = 5; i < 9; ++i) sw += (double)h[i];
+        for (int i = 0; i < 9; ++i) fprintf(stderr, "  %-28s %12.3f Mcycles  %5.1f%%\n", names[i], h[i] * 1e-6, 100.0 * h[i] / (i < 5 ? rt : sw));
+        fprintf(stderr, "  sweep: windows redone exactly: %llu\n", h[9]);
     }
 #endif
     return EP_OK;

@@ -185,8 +185,8 @@ def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_s
 
     Returns a dict with the keys that were requested: 'voxel', 'voxel_sum', 'count'.
     check=True synchronises and raises for events the reference would have raised on.
-    method: None/"auto" (banded shared-memory sweep when the layout is canonical and the batch fills the GPU,
-    else the global-RED kernels), "global", "banded" — same results bit for bit.
+    method: None/"auto" (the global-RED kernels), "global", "banded" (route + shared-memory sweep; canonical and
+    compact layouts only) — same results bit for bit.
     """
     require_cuda(ev.x)
     dev = ev.device
