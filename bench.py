@@ -4,14 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload at every N (weak scaling: the same per-GPU batch on each rank): BASELINE.json configs[1] —
-an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), canonical
-SoA layout (x,y u16 | t i64 us | p u8 = 13 B/event), binned at sensor resolution into a 5-bin voxel grid
-plus the event-side difference-map target voxel.sum(0).  A "step" is one pass of the hot path over the
-batch.  Prints ONE JSON line on rank 0.
+an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), binned at sensor
+resolution into a 5-bin voxel grid plus the event-side difference-map target voxel.sum(0).  The batch is resident in
+the layout the collate step ships over PCIe (5 B/event: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 plus one tick byte,
+ticks relative to a base per 1024 events, RaggedEvents.packed(); lossless, results bit-identical to the 13 B/event
+canonical SoA, whose number is reported under "extra").  A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
 
   value     events/s with the batch already resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same metric through the public API from pinned HOST buffers: H2D of the SoA batch and a D2H read
-            of the per-sample checksum of the result are inside the timed region
+  e2e       the same metric through the public API from pinned HOST buffers: H2D of the SoA batch (in slices, so the
+            copy of slice i+1 overlaps the binning of slice i) and a D2H read of the per-sample checksum of the result
+            are inside the timed region
   roofline  binning kernels (scatter + finalize): algorithmic bytes / their summed device time (CUDA events
             recorded by the library around each launch: ep_profile_*), against the measured HBM copy peak
   cpu_baseline  the oracle C port of the reference routine on the host cores, bounded sample, rank 0 / N=1 only
@@ -208,8 +210,13 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     L = ep.load_library()
 
-    ev = make_batch_gpu(rank, dev)
-    n_events = ev.num_events
+    ev13 = make_batch_gpu(rank, dev)
+    n_events = ev13.num_events
+    host13 = ep.RaggedEvents(ev13.x.cpu(), ev13.y.cpu(), ev13.t.cpu(), ev13.p.cpu(), ev13.offsets.cpu(), ev13.offsets_host, ev13.t_div)
+    # resident copy in the transport layout (5 B/event; the opt-in banded path takes the 8 B/event one)
+    host = (host13.compact() if args.method == "banded" else host13.packed()).pin_memory()
+    ev = host.to(dev)
+    torch.cuda.synchronize()
     out = {"voxel": torch.empty((BATCH, BINS, H, W), dtype=torch.float32, device=dev),
            "voxel_sum": torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev)}
     stats_src = torch.tensor([n_events, BATCH], dtype=torch.int64, device=dev)
@@ -277,35 +284,56 @@ def run_ours(args):
     scatter_ms, finalize_ms = prof.ms[0] / args.steps, prof.ms[1] / args.steps
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(n_events, BATCH)
-    achieved = alg / ((scatter_ms + finalize_ms) * 1e-3) / 1e9
+    # the step IS the binning call: its device time (CUDA events around the K timed steps, above) is the kernels' time;
+    # the per-kernel figures come from the library's own events around each launch
+    kernel_ms = ms_total / args.steps if world == 1 else scatter_ms + finalize_ms
+    achieved = alg / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_per_step(), "peak_source": peak_src,
                 "frac_of_8TBs_spec": achieved / 8000.0,
-                "kernels": {"pass1_ms_per_step (k_route | k_scatter)": scatter_ms,
-                            "pass2_ms_per_step (k_sweep | k_finalize_voxel)": finalize_ms,
+                "kernels": {"pass1_ms_per_step (k_scatter | k_route)": scatter_ms,
+                            "pass2_ms_per_step (k_finalize_voxel | k_sweep)": finalize_ms,
                             "pass1_launches_per_step": prof.launches[0] // args.steps,
                             "pass1_Gevents_per_s": n_events / (scatter_ms * 1e-3) / 1e9},
-                "algorithmic_bytes_per_step": alg}
+                "algorithmic_bytes_per_step": alg,
+                "algorithmic_bytes_rule": "SURVEY.md 8(d): 13 B/event canonical record + 4 B per output element, whatever the resident layout (5 B/event here)"}
 
-    # ---- skewed distribution (contention evidence): same sizes, 70 % of events on 64 segments + hot pixels -----
+    # ---- the same step on the canonical 13 B/event layout, with the banded path, and on the skewed distribution
+    # (contention evidence: 70 % of events on 64 segments + hot pixels), same sizes
     extra = {}
-    if world == 1:
-        del ev
-        torch.cuda.empty_cache()
-        ev = make_batch_gpu(rank, dev, skewed=True)
+
+    def timed(evx, method):
         for _ in range(3):
-            step()
+            ep.bin_events(evx, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=method)
         torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(args.steps):
-            step()
+            ep.bin_events(evx, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=method)
         s1.record()
         torch.cuda.synchronize()
-        extra["skewed_distribution_Gevents_per_s"] = ev.num_events * args.steps / (s0.elapsed_time(s1) * 1e-3) / 1e9
-        del ev
+        return evx.num_events * args.steps / (s0.elapsed_time(s1) * 1e-3) / 1e9
+
+    if world == 1:
+        extra["canonical_13B_layout_Gevents_per_s"] = timed(ev13, args.method)
+        ev8 = host13.compact().to(dev)
+        extra["compact_8B_layout_Gevents_per_s"] = timed(ev8, args.method)
+        extra["banded_path_8B_layout_Gevents_per_s"] = timed(ev8, "banded")
+        del ev8
+        del ev13
         torch.cuda.empty_cache()
-        ev = make_batch_gpu(rank, dev)
+        sk13 = make_batch_gpu(rank, dev, skewed=True)
+        skh = ep.RaggedEvents(sk13.x.cpu(), sk13.y.cpu(), sk13.t.cpu(), sk13.p.cpu(), sk13.offsets.cpu(), sk13.offsets_host, sk13.t_div)
+        del sk13
+        sk = skh.packed().to(dev)
+        extra["skewed_distribution_Gevents_per_s"] = timed(sk, args.method)
+        del sk
+        sk = skh.compact().to(dev)
+        extra["skewed_distribution_banded_path_8B_layout_Gevents_per_s"] = timed(sk, "banded")
+        del sk, skh
+        torch.cuda.empty_cache()
+    else:
+        del ev13
 
     # ---- pretrain input pipeline (configs[2] per-GPU share: ViT-S/16 @224, 75 % mask, B=128): one CUDA graph ----------
     pipe = ep.MaskedInputPipeline(128, BINS, (224, 224), 16, 0.75, dev)
@@ -324,18 +352,45 @@ def run_ours(args):
     del pipe
 
     # ---- e2e: pinned host SoA -> H2D -> bin -> D2H of the per-sample checksum, all inside the timed region ----
-    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the 8 B/event
-    # transport layout (u16 x,y + u32 relative ticks | polarity << 31; RaggedEvents.compact(), bit-identical results)
-    host13 = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
-    host = host13.compact().pin_memory()
-    h2d = host.nbytes()
+    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the 5 B/event
+    # transport layout (RaggedEvents.packed(), lossless).  The batch crosses PCIe in E2E_SLICES slices of consecutive samples: the copy of slice i+1
+    # (copy stream) overlaps the binning of slice i (compute stream); two device staging sets, guarded by events.
     del ev
     torch.cuda.empty_cache()
+    E2E_SLICES = 8
+    bounds = [(BATCH * i) // E2E_SLICES for i in range(E2E_SLICES + 1)]
+    # every slice is packed on its own (the collate step would produce them like this): block offsets start at 0
+    slices = [host13.take(bounds[i], bounds[i + 1]).packed().pin_memory() for i in range(E2E_SLICES)]
+    h2d = sum(sl.nbytes() for sl in slices)
+    fields = ("x", "t", "p", "offsets", "t_base")
+    stage = [{f: torch.empty(max(getattr(sl, f).numel() for sl in slices), dtype=getattr(slices[0], f).dtype, device=dev)
+              for f in fields} for _ in range(2)]
+    copy_stream, comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(E2E_SLICES)]
+    binned = [torch.cuda.Event() for _ in range(E2E_SLICES)]
+    e2e_method = args.method if args.method != "banded" else "auto"
 
     def e2e_step():
-        d = host.to(dev, non_blocking=True)
-        o = ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method if args.method != "banded" else "auto")
-        return o["voxel_sum"].sum(dim=(1, 2, 3)).cpu()       # (B,) fp32: sum of polarities per sample
+        for i, sl in enumerate(slices):
+            st_ = stage[i % 2]
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(binned[i - 2])                 # the staging set is free again
+                view = {}
+                for f in fields:
+                    src = getattr(sl, f)
+                    view[f] = st_[f][:src.numel()]
+                    view[f].copy_(src, non_blocking=True)
+                copied[i].record(copy_stream)
+            with torch.cuda.stream(comp_stream):
+                comp_stream.wait_event(copied[i])
+                d = ep.RaggedEvents(view["x"], None, view["t"], view["p"], view["offsets"], sl.offsets_host, sl.t_div, view["t_base"])
+                o = {"voxel": out["voxel"][bounds[i]:bounds[i + 1]], "voxel_sum": out["voxel_sum"][bounds[i]:bounds[i + 1]]}
+                ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=o, method=e2e_method)
+                binned[i].record(comp_stream)
+        with torch.cuda.stream(comp_stream):
+            chk_ = out["voxel_sum"].sum(dim=(1, 2, 3)).cpu()          # (B,) fp32: sum of polarities per sample (synchronises)
+        return chk_
 
     for _ in range(2):
         chk = e2e_step()
@@ -350,7 +405,8 @@ def run_ours(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e = {"value": total_events * args.steps / float(tm.item()) / 1e9, "unit": "Gevents/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * float(tm.item()) / args.steps,
-           "host_layout": "pinned SoA, 8 B/event transport layout (u16 x, u16 y, u32 relative ticks | polarity << 31)"}
+           "host_layout": "pinned SoA, 5 B/event transport layout (u32 x | y << 11 | p << 22 | ticks >> 8 << 23, u8 ticks & 0xff; ticks relative to a base per 1024 events; lossless, include/eventpretrain_b200.h)",
+           "pipelining": f"{E2E_SLICES} slices of consecutive samples; H2D of slice i+1 overlaps the binning of slice i"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port on the host cores, bounded sample + parity check ----
     cpu = None
@@ -378,10 +434,10 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "events_binned_per_s", "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64 time / Q24 int64 fixed-point accumulate -> f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": "integer-tick time arithmetic, Q24 fixed-point int64 accumulate -> f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": "SoA x,y u16 | t i64 us | p u8 (13 B/event)",
-                           "cache": "inputs (3.3 GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
+                "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": "packed SoA: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 + u8 ticks & 0xff, ticks relative to a base per 1024 events (5 B/event, the transport layout; results bit-identical to the 13 B/event canonical SoA)",
+                           "cache": "inputs (1.3 GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"shard-by-sample x{world}, no data-path collective", "method": args.method},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -43,12 +43,32 @@ __device__ __forceinline__ void publish_zero_flag(const BinArgs& a, int b) {
     if (!(__ldcg(&a.meta[b].flags) & kFlagZeroPol)) atomicOr(&a.meta[b].flags, kFlagZeroPol);
 }
 
+constexpr int kOffCache = 256;     // offsets of the group's samples cached in shared memory (groups are a few samples)
+
 template <class Loader>
 __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a, int64_t first_tile, int64_t tile_stride) {
     typedef typename Loader::time_t_ TT;
-  // persistent stride loop over 1024-event tiles
+    // the owner lookup below runs once per tile and thread: keep the group's offsets on chip
+    __shared__ int64_t s_off[kOffCache + 1];
+    const bool cached = a.offsets != nullptr && a.g1 - a.g0 <= kOffCache;
+    if (cached) {
+        for (int i = threadIdx.x; i <= a.g1 - a.g0; i += kThreads) s_off[i] = a.offsets[a.g0 + i];
+        __syncthreads();
+    }
+    auto off_of = [&](int b) -> int64_t { return cached ? s_off[b - a.g0] : off_at(a, b); };
+    // persistent stride loop over 1024-event tiles; the next tile's loads are issued before this tile's REDs
+    typename Loader::Raw raw_next;
+    if (Loader::kPrefetch && first_tile < a.n_tiles) {
+        const int64_t i0 = a.start4 + (first_tile * kThreads + threadIdx.x) * kEvPerThread;
+        if (i0 < a.end) ld.load_raw(i0, a, raw_next);
+    }
   for (int64_t tile = first_tile; tile < a.n_tiles; tile += tile_stride) {
     const int64_t i0 = a.start4 + (tile * kThreads + threadIdx.x) * kEvPerThread;
+    typename Loader::Raw raw = raw_next;
+    if (Loader::kPrefetch && tile + tile_stride < a.n_tiles) {
+        const int64_t in = a.start4 + ((tile + tile_stride) * kThreads + threadIdx.x) * kEvPerThread;
+        if (in < a.end) ld.load_raw(in, a, raw_next);
+    }
     if (i0 >= a.end) continue;
 
     // sample that owns the first in-range event of this thread: last b with off[b] <= i
@@ -56,13 +76,13 @@ __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a
     int lo = a.g0, hi = a.g1;   // invariant: off[lo] <= ifirst < off[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (off_at(a, mid) <= ifirst) lo = mid; else hi = mid;
+        if (off_of(mid) <= ifirst) lo = mid; else hi = mid;
     }
     int b = lo;
-    int64_t b_end = off_at(a, b + 1);
+    int64_t b_end = off_of(b + 1);
 
     Ev<TT> e;
-    ld.load(i0, a.end, a, e);
+    ld.decode(raw, i0, a.end, a, e);
 
     const int64_t HW = (int64_t)a.H * a.W;
     SampleMeta m = a.meta[b];
@@ -74,9 +94,10 @@ __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a
         if (i < a.begin || i >= a.end) continue;
         if (i >= b_end) {
             if (zero_b >= 0) { publish_zero_flag(a, zero_b); zero_b = -1; }
-            do { ++b; b_end = off_at(a, b + 1); } while (i >= b_end);
+            do { ++b; b_end = off_of(b + 1); } while (i >= b_end);
             m = a.meta[b];
         }
+        if constexpr (Loader::kBlocked) e.ti[j] += ld.block_base(i, off_of(b));
         const int cls = e.cls[j];
         const int64_t flat = e.x[j] + e.y[j] * (int64_t)a.W;
         if (cls == 3 || flat < 0 || flat >= HW) {
@@ -399,8 +420,18 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     if (!(ev->t_div != 0.0)) return EP_EINVAL;
     const int B = ev->batch;
     for (int b = 0; b < B; ++b) if (ev->offsets_host[b + 1] < ev->offsets_host[b]) return EP_EINVAL;
-    if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || !ev->y || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
+    if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || (!ev->y && ev->t_dtype != EP_U8) || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ev->t_dtype == EP_U8) {
+        // packed transport layout (5 B/event): x -> uint32 words, t -> low tick bytes, p -> per-1024-block tick offsets
+        if (ev->xy_dtype != EP_U32 || ev->y != nullptr || !ev->p || ev->p_dtype != EP_U32 || !ev->t_base || prm->time_f32) return EP_EINVAL;
+        if (!aligned16(ev->x) || !aligned16(ev->t)) return EP_EALIGN;
+        if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
+        SoaPackedLoader ld{static_cast<const uint32_t*>(ev->x), static_cast<const uint8_t*>(ev->t),
+                           static_cast<const uint32_t*>(ev->p), ev->t_base, ev->t_div};
+        return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
+                           workspace_bytes, bad_count);
+    }
     const bool compact = ev->t_dtype == EP_U32;
     if (compact) {
         // compact transport layout: u16 x,y + u32 (relative ticks | polarity << 31) + per-sample int64 base

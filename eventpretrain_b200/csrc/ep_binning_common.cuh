@@ -76,11 +76,16 @@ struct SoaCanonLoader {
     // fp64 divisions; the two differ by O(1e-13) in ts, far below the 2^-25 weight quantum.
     static constexpr bool kFastTime = true;
     static constexpr bool kTicks = T_IS_I64;
+    static constexpr bool kPrefetch = true;      // load_raw / decode: the loads of the next tile fly during this tile's REDs
+    static constexpr bool kBlocked = false;
+    struct Raw { uint2 xv, yv; uint32_t pv; longlong2 a0, a1; };
     __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
-        (void)hi;
-        uint2 xv, yv;
-        uint32_t pv;
-        longlong2 a0, a1;     // raw 8-byte stamps (bit patterns)
+        Raw r;
+        load_raw(i0, a, r);
+        decode(r, i0, hi, a, e);
+    }
+    __device__ __forceinline__ void load_raw(int64_t i0, const BinArgs& a, Raw& r) const {
+        uint2& xv = r.xv; uint2& yv = r.yv; uint32_t& pv = r.pv; longlong2& a0 = r.a0; longlong2& a1 = r.a1;
         if (i0 + 4 <= a.n_total) {
             xv = ld_stream(reinterpret_cast<const uint2*>(x + i0));
             yv = ld_stream(reinterpret_cast<const uint2*>(y + i0));
@@ -102,6 +107,12 @@ struct SoaCanonLoader {
             yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
             a0 = make_longlong2(tv_[0], tv_[1]); a1 = make_longlong2(tv_[2], tv_[3]);
         }
+    }
+    __device__ __forceinline__ void decode(const Raw& r, int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        (void)i0; (void)hi;
+        const uint2 xv = r.xv, yv = r.yv;
+        const uint32_t pv = r.pv;
+        const longlong2 a0 = r.a0, a1 = r.a1;
         const long long raw[4] = {a0.x, a0.y, a1.x, a1.y};
         const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
         const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
@@ -123,11 +134,11 @@ struct SoaCanonLoader {
         double v = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
         return (t_div != 1.0) ? v / t_div : v;
     }
-    __device__ __forceinline__ double time_of(int64_t i, int) const { return time_at(i); }
+    __device__ __forceinline__ double time_of(int64_t i, int, int64_t) const { return time_at(i); }
     __device__ __forceinline__ double raw_at(int64_t i) const {
         return T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
     }
-    __device__ __forceinline__ int64_t ticks_at(int64_t i) const {
+    __device__ __forceinline__ int64_t ticks_at(int64_t i, int64_t) const {
         return T_IS_I64 ? static_cast<const int64_t*>(t)[i] : 0;
     }
     __device__ __forceinline__ double div() const { return t_div; }
@@ -146,10 +157,16 @@ struct SoaCompactLoader {
     typedef double time_t_;
     static constexpr bool kFastTime = true;
     static constexpr bool kTicks = true;
+    static constexpr bool kPrefetch = true;
+    static constexpr bool kBlocked = false;
+    struct Raw { uint2 xv, yv; uint4 tv; };
     __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
-        (void)hi;
-        uint2 xv, yv;
-        uint4 tv;
+        Raw r;
+        load_raw(i0, a, r);
+        decode(r, i0, hi, a, e);
+    }
+    __device__ __forceinline__ void load_raw(int64_t i0, const BinArgs& a, Raw& r) const {
+        uint2& xv = r.xv; uint2& yv = r.yv; uint4& tv = r.tv;
         if (i0 + 4 <= a.n_total) {
             xv = ld_stream(reinterpret_cast<const uint2*>(x + i0));
             yv = ld_stream(reinterpret_cast<const uint2*>(y + i0));
@@ -162,6 +179,11 @@ struct SoaCompactLoader {
             yv = make_uint2(ys_[0] | (ys_[1] << 16), ys_[2] | (ys_[3] << 16));
             tv = make_uint4(ts_[0], ts_[1], ts_[2], ts_[3]);
         }
+    }
+    __device__ __forceinline__ void decode(const Raw& r, int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        (void)i0; (void)hi;
+        const uint2 xv = r.xv, yv = r.yv;
+        const uint4 tv = r.tv;
         const uint32_t raw[4] = {tv.x, tv.y, tv.z, tv.w};
         const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
         const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
@@ -179,12 +201,79 @@ struct SoaCompactLoader {
             e.cls[j] = (raw[j] >> 31) ? 0 : 1;           // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
         }
     }
-    __device__ __forceinline__ double time_of(int64_t i, int b) const {
+    __device__ __forceinline__ double time_of(int64_t i, int b, int64_t) const {
         const double v = (double)(t_base[b] + (int64_t)(tp[i] & 0x7fffffffu));
         return (t_div != 1.0) ? v / t_div : v;
     }
     __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
-    __device__ __forceinline__ int64_t ticks_at(int64_t i) const { return (int64_t)(tp[i] & 0x7fffffffu); }
+    __device__ __forceinline__ int64_t ticks_at(int64_t i, int64_t) const { return (int64_t)(tp[i] & 0x7fffffffu); }
+    __device__ __forceinline__ double div() const { return t_div; }
+};
+
+// packed transport layout (5 B/event): one uint32 word x | y << 11 | polarity << 22 | (ticks >> 8) << 23 and one byte
+// (ticks & 0xff) per event, where `ticks` (17 bits) counts from a base that changes every 1024 events of the arrays:
+// for the events of a sample that share the 1024-block of the sample's first event the base is the sample's own
+// (t_base[b], int64), for every later block g = i >> 10 it is t_base[b] + blk_base[g].  Same integer time arithmetic as
+// the other tick layouts once the base is added, so results are bit-identical.
+struct SoaPackedLoader {
+    const uint32_t* w;          // [N]
+    const uint8_t* tl;          // [N]
+    const uint32_t* blk_base;   // [ceil(N / 1024)]
+    const int64_t* t_base;      // [B]
+    double t_div;
+    typedef double time_t_;
+    static constexpr bool kFastTime = true;
+    static constexpr bool kTicks = true;
+    static constexpr bool kPrefetch = true;
+    static constexpr bool kBlocked = true;       // e.ti holds block-relative ticks: the scatter loop adds block_base()
+    struct Raw { uint4 wv; uint32_t tv; };
+    __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        Raw r;
+        load_raw(i0, a, r);
+        decode(r, i0, hi, a, e);
+    }
+    __device__ __forceinline__ void load_raw(int64_t i0, const BinArgs& a, Raw& r) const {
+        if (i0 + 4 <= a.n_total) {
+            r.wv = ld_stream(reinterpret_cast<const uint4*>(w + i0));
+            r.tv = ld_stream(reinterpret_cast<const uint32_t*>(tl + i0));
+        } else {
+            uint32_t ws_[4] = {0, 0, 0, 0};
+            r.tv = 0;
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < a.n_total) { ws_[j] = w[i0 + j]; r.tv |= (uint32_t)tl[i0 + j] << (8 * j); }
+            r.wv = make_uint4(ws_[0], ws_[1], ws_[2], ws_[3]);
+        }
+    }
+    __device__ __forceinline__ void decode(const Raw& r, int64_t i0, int64_t hi, const BinArgs& a, Ev<double>& e) const {
+        (void)i0; (void)hi;
+        const uint32_t ws[4] = {r.wv.x, r.wv.y, r.wv.z, r.wv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t xs = ws[j] & 0x7ffu, ys = (ws[j] >> 11) & 0x7ffu;
+            if (a.scaled) {
+                e.x[j] = __double2ll_rz(__dmul_rn((double)xs, a.sx));
+                e.y[j] = __double2ll_rz(__dmul_rn((double)ys, a.sy));
+            } else {
+                e.x[j] = xs;
+                e.y[j] = ys;
+            }
+            e.ti[j] = (int64_t)(((ws[j] >> 23) << 8) | ((r.tv >> (8 * j)) & 0xffu));
+            e.t[j] = 0.0;
+            e.cls[j] = ((ws[j] >> 22) & 1u) ? 0 : 1;     // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
+        }
+    }
+    // ticks to add to an event's block-relative count: 0 inside the 1024-block where its sample starts
+    __device__ __forceinline__ int64_t block_base(int64_t i, int64_t s_lo) const {
+        return ((i >> 10) == (s_lo >> 10)) ? 0 : (int64_t)__ldg(blk_base + (i >> 10));
+    }
+    __device__ __forceinline__ int64_t ticks_at(int64_t i, int64_t s_lo) const {
+        return block_base(i, s_lo) + (int64_t)(((w[i] >> 23) << 8) | (uint32_t)tl[i]);
+    }
+    __device__ __forceinline__ double time_of(int64_t i, int b, int64_t s_lo) const {
+        const double v = (double)(t_base[b] + ticks_at(i, s_lo));
+        return (t_div != 1.0) ? v / t_div : v;
+    }
+    __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
     __device__ __forceinline__ double div() const { return t_div; }
 };
 
@@ -200,10 +289,15 @@ struct SoaGenericLoader {
     typedef TT time_t_;
     static constexpr bool kFastTime = false;
     static constexpr bool kTicks = false;
+    static constexpr bool kPrefetch = false;
+    static constexpr bool kBlocked = false;
+    struct Raw {};
+    __device__ __forceinline__ void load_raw(int64_t, const BinArgs&, Raw&) const {}
+    __device__ __forceinline__ void decode(const Raw&, int64_t i0, int64_t hi, const BinArgs& a, Ev<TT>& e) const { load(i0, hi, a, e); }
     __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
-    __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
+    __device__ __forceinline__ int64_t ticks_at(int64_t, int64_t) const { return 0; }
     __device__ __forceinline__ double div() const { return 1.0; }
-    __device__ __forceinline__ TT time_of(int64_t i, int) const { return time_at(i); }
+    __device__ __forceinline__ TT time_of(int64_t i, int, int64_t) const { return time_at(i); }
     __device__ __forceinline__ TT time_at(int64_t i) const {
         if (sizeof(TT) == 4) {
             float v = (t_dtype == EP_F32) ? static_cast<const float*>(t)[i] : (float)load_as_double(t, t_dtype, i);
@@ -242,11 +336,16 @@ struct AosLoader {
     typedef ET time_t_;
     static constexpr bool kFastTime = false;
     static constexpr bool kTicks = false;
+    static constexpr bool kPrefetch = false;
+    static constexpr bool kBlocked = false;
+    struct Raw {};
+    __device__ __forceinline__ void load_raw(int64_t, const BinArgs&, Raw&) const {}
+    __device__ __forceinline__ void decode(const Raw&, int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const { load(i0, hi, a, e); }
     __device__ __forceinline__ double raw_at(int64_t) const { return 0.0; }
-    __device__ __forceinline__ int64_t ticks_at(int64_t) const { return 0; }
+    __device__ __forceinline__ int64_t ticks_at(int64_t, int64_t) const { return 0; }
     __device__ __forceinline__ double div() const { return 1.0; }
     __device__ __forceinline__ ET time_at(int64_t i) const { return ev[i * 4 + 2]; }
-    __device__ __forceinline__ ET time_of(int64_t i, int) const { return time_at(i); }
+    __device__ __forceinline__ ET time_of(int64_t i, int, int64_t) const { return time_at(i); }
     __device__ __forceinline__ void load(int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const {
 #pragma unroll
         for (int j = 0; j < kEvPerThread; ++j) {
@@ -348,17 +447,17 @@ __global__ void k_sample_meta(Loader ld, BinArgs a, int B) {
     m.t0 = 0.0; m.dT = 1.0; m.flags = 0; m.tmul = 0; m.tshift = 0; m.thalf = 0; m.scale_raw = 0.0; m.t0_raw = 0.0;
     m.t0_ticks = 0;
     if (hi > lo) {
-        const TT first = ld.time_of(lo, b), last = ld.time_of(hi - 1, b);
+        const TT first = ld.time_of(lo, b, lo), last = ld.time_of(hi - 1, b, lo);
         TT d = last - first;
         if (d == (TT)0) d = (TT)1;
         m.t0 = (double)first;
         m.dT = (double)d;
         m.t0_raw = ld.raw_at(lo);
-        m.t0_ticks = ld.ticks_at(lo);
+        m.t0_ticks = ld.ticks_at(lo, lo);
         m.scale_raw = (double)(a.num_bins - 1) / ((double)d * ld.div());
         if (Loader::kTicks && a.num_bins >= 1 && a.num_bins <= 64) {
             // deltaT == 0 (-> 1.0 s, :24-25) and last < first (unsorted rows) keep the fp64 expression
-            const int64_t dticks = ld.ticks_at(hi - 1) - m.t0_ticks;
+            const int64_t dticks = ld.ticks_at(hi - 1, lo) - m.t0_ticks;
             if (dticks > 0 && dticks < (1ll << 32)) {
                 const uint64_t nbm1 = (uint64_t)(a.num_bins - 1);
                 int s = 31;

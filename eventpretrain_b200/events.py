@@ -31,8 +31,9 @@ class RaggedEvents:
     offsets: torch.Tensor          # int64 (B+1), same device as the data
     offsets_host: np.ndarray       # int64 (B+1)
     t_div: float = 1.0             # timestamp value = t / t_div (int64 microseconds, t_div=1e6 -> seconds)
-    t_base: torch.Tensor = None    # compact layout only: int64 (B,) per-sample base ticks; then t is uint32
-                                   # (relative ticks | polarity << 31) and p is None
+    t_base: torch.Tensor = None    # transport layouts only: int64 (B,) per-sample base ticks.  compact(): t is uint32
+                                   # (relative ticks | polarity << 31) and p is None.  packed(): x is one uint32 word
+                                   # per event, y is None, t the low tick byte, p the per-1024-block tick offsets
 
     @property
     def batch(self):
@@ -90,6 +91,94 @@ class RaggedEvents:
         return RaggedEvents(self.x, self.y, mk(torch.from_numpy(rel)).to(self.x.device), None, self.offsets, off, self.t_div,
                             mk(torch.from_numpy(base)).to(self.x.device))
 
+    def take(self, b0, b1):
+        """Standalone batch of the samples [b0, b1): copies of their array ranges, offsets rebased to 0 (canonical /
+        generic / compact layouts; a packed() batch cannot be cut, its block offsets are tied to array positions)."""
+        if self.t_base is not None and self.y is None:
+            raise TypeError("take() on a packed() batch: take first, pack afterwards")
+        lo, hi = int(self.offsets_host[b0]), int(self.offsets_host[b1])
+        cut = lambda a: None if a is None else a[lo:hi].clone()
+        off = (self.offsets_host[b0:b1 + 1] - lo).astype(np.int64)
+        return RaggedEvents(cut(self.x), cut(self.y), cut(self.t), cut(self.p), torch.from_numpy(off.copy()).to(self.offsets.device),
+                            off, self.t_div, None if self.t_base is None else self.t_base[b0:b1].clone())
+
+    PACK_BLOCK = 1024
+
+    def packed(self):
+        """Host-side repack into the 5 B/event transport layout (include/eventpretrain_b200.h, ep_events_soa.t_base):
+        one uint32 x | y << 11 | polarity << 22 | (ticks >> 8) << 23 plus one byte ticks & 0xff per event; `ticks`
+        (17 bits) counts from the sample's base inside the 1024-block of the arrays where the sample starts and from
+        base + a per-block offset afterwards.  Needs int64 tick stamps, p in {0,1}, x,y < 2048 and < 2^17 ticks between
+        the smallest and largest stamp a sample has inside one 1024-block (raises ValueError otherwise: use compact()).
+        Binning results are bit-identical to the int64 layout; H2D traffic drops from 13 to 5 B/event."""
+        if self.t_base is not None and self.y is None:
+            return self
+        if self.t_base is not None or self.t.dtype != torch.int64 or self.p.dtype != torch.uint8 or self.x.dtype != torch.uint16:
+            raise TypeError("packed() needs the canonical u16 / int64-tick / u8 layout")
+        if int(self.offsets_host[0]) != 0:
+            raise ValueError("packed() needs a whole batch (offsets[0] == 0): the block offsets are tied to array positions")
+        off = self.offsets_host
+        x = self.x.cpu().numpy().astype(np.uint32)
+        y = self.y.cpu().numpy().astype(np.uint32)
+        t = self.t.cpu().numpy()
+        p = self.p.cpu().numpy().astype(np.uint32)
+        n = t.shape[0]
+        if n and (x.max() >= 2048 or y.max() >= 2048):
+            raise ValueError("packed() needs x, y < 2048")
+        if n and p.max() > 1:
+            raise ValueError("packed() needs polarity in {0, 1}")
+        B, K = self.batch, self.PACK_BLOCK
+        counts = np.diff(off)
+        base = np.zeros(B, np.int64)
+        nz = counts > 0
+        if n:
+            base[nz] = np.minimum.reduceat(t, off[:-1][nz])     # per-sample smallest stamp (empty samples skipped)
+        sid = np.repeat(np.arange(B), counts)                    # owning sample of every event
+        rel = t - base[sid]
+        g = np.arange(n) // K                                    # 1024-block of every event
+        first_blk = (off[:-1] // K)[sid]                         # block where the event's sample starts
+        blk = np.zeros((n + K - 1) // K, np.uint32)
+        if n:
+            starts = np.arange(0, n, K)
+            own = sid == sid[starts][g]                          # event belongs to the sample owning its block's first slot
+            m = np.minimum.reduceat(np.where(own, rel, np.iinfo(np.int64).max), starts)
+            if m.max(initial=0) >= (1 << 32) and (m < np.iinfo(np.int64).max).any() and m[m < np.iinfo(np.int64).max].max() >= (1 << 32):
+                raise ValueError("sample spans more than 2^32 ticks")
+            blk = np.where(m < (1 << 32), m, 0).astype(np.uint32)
+        ticks = rel - np.where(g == first_blk, 0, blk[g].astype(np.int64)) if n else rel
+        if n and ticks.min() < 0:
+            raise ValueError("stamps too far out of order for the packed layout")
+        if n and ticks.max() >= (1 << 17):
+            raise ValueError("a 1024-event block spans 2^17 ticks or more")
+        tk = ticks.astype(np.uint32)
+        w = x | (y << np.uint32(11)) | (p << np.uint32(22)) | ((tk >> np.uint32(8)) << np.uint32(23))
+        tl = (tk & np.uint32(0xff)).astype(np.uint8)
+        dev = self.x.device
+        mk = (lambda a: a.pin_memory()) if (self.x.is_pinned() or self.x.is_cuda) and torch.cuda.is_available() else (lambda a: a)
+        cv = lambda a: mk(torch.from_numpy(np.ascontiguousarray(a))).to(dev)
+        return RaggedEvents(cv(w), None, cv(tl), cv(blk), self.offsets, off, self.t_div, cv(base))
+
+    def unpack_host(self):
+        """Decode a packed() batch back to (x, y, t_ticks, p) numpy arrays (tests / debugging)."""
+        if self.t_base is None or self.y is not None:
+            raise TypeError("not a packed() batch")
+        w = self.x.cpu().numpy().astype(np.uint32)
+        tl = self.t.cpu().numpy().astype(np.int64)
+        blk = self.p.cpu().numpy().astype(np.int64)
+        base = self.t_base.cpu().numpy()
+        off, K = self.offsets_host, self.PACK_BLOCK
+        ticks = ((w >> np.uint32(23)).astype(np.int64) << 8) | tl
+        t = np.zeros(w.shape[0], np.int64)
+        for b in range(self.batch):
+            lo, hi = int(off[b]), int(off[b + 1])
+            if hi <= lo:
+                continue
+            g = np.arange(lo, hi) // K
+            add = np.where(g == lo // K, 0, blk[g])
+            t[lo:hi] = base[b] + add + ticks[lo:hi]
+        return (w & np.uint32(0x7ff)).astype(np.uint16), ((w >> np.uint32(11)) & np.uint32(0x7ff)).astype(np.uint16), t, \
+            ((w >> np.uint32(22)) & np.uint32(1)).astype(np.uint8)
+
     def shard(self, rank, world_size):
         """Samples [rank*B/G, (rank+1)*B/G): DistributedSampler-style contiguous split (main_pretrain.py:218-220).
         Slices are views; offsets keep their absolute values (ep_events_soa allows offsets[0] > 0)."""
@@ -101,7 +190,7 @@ class RaggedEvents:
     def _desc(self):
         d = _lib.EventsSoa()
         d.x, d.y, d.t, d.p = ptr(self.x), ptr(self.y), ptr(self.t), ptr(self.p)
-        if self.x.dtype != self.y.dtype:
+        if self.y is not None and self.x.dtype != self.y.dtype:
             raise TypeError("x and y must share a dtype")
         d.xy_dtype = _TORCH_TAG[self.x.dtype]
         d.t_dtype = _TORCH_TAG[self.t.dtype]

@@ -294,3 +294,26 @@ def test_compact_transport_layout(ep):
         assert torch.equal(a[key], b[key]), key
     c = ep.bin_events(comp.to("cuda").shard(1, 2), (H, W), num_bins=5, check=True)
     assert torch.equal(c["voxel"], a["voxel"][2:])
+
+
+def test_packed_transport_layout(ep):
+    """5 B/event transport layout (uint32 x | y << 11 | p << 22 | ticks >> 8 << 23 + one tick byte, block-relative
+    ticks) gives bit-identical tensors; fused scale and count frames included."""
+    rng = np.random.default_rng(43)
+    H, W = 60, 80
+    ev, _ = _random_batch(ep, rng, [30000, 0, 1, 5003, 1024, 2047, 4097], H, W)
+    host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu() + 1_700_000_000_000_000, ev.p.cpu(), ev.offsets.cpu(),
+                           ev.offsets_host, ev.t_div)
+    pk = host.packed()
+    assert pk.y is None and pk.x.dtype == torch.uint32 and pk.nbytes() < 0.42 * host.nbytes()
+    a = ep.bin_events(host.to("cuda"), (H, W), num_bins=5, count_channels=2, voxel_sum=True, check=True)
+    b = ep.bin_events(pk.to("cuda"), (H, W), num_bins=5, count_channels=2, voxel_sum=True, check=True)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b[key]), key
+    sc = (0.5, 0.75)
+    a = ep.bin_events(host.to("cuda"), (H, W), num_bins=9, scale=sc, check=True)
+    b = ep.bin_events(pk.to("cuda"), (H, W), num_bins=9, scale=sc, check=True)
+    assert torch.equal(a["voxel"], b["voxel"])
+    c = ep.bin_events(pk.to("cuda").shard(1, 2), (H, W), num_bins=5, check=True)     # offsets[0] > 0 on the device side
+    a5 = ep.bin_events(host.to("cuda"), (H, W), num_bins=5, check=True)
+    assert torch.equal(c["voxel"], a5["voxel"][3:])

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--skewed", action="store_true")
     ap.add_argument("--compact", action="store_true")
+    ap.add_argument("--packed", action="store_true")
     ap.add_argument("--bins", type=int, default=bench.BINS)
     ap.add_argument("--count", type=int, default=0)
     args = ap.parse_args()
@@ -37,6 +38,9 @@ def main():
     if args.compact:
         host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
         ev = host.compact().to(dev)
+    if args.packed:
+        host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
+        ev = host.packed().to(dev)
     n = ev.num_events
     H, W = bench.H, bench.W
     results = {}
