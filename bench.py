@@ -6,9 +6,9 @@
 Workload at every N (weak scaling: the same per-GPU batch on each rank): BASELINE.json configs[1] —
 an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), binned at sensor
 resolution into a 5-bin voxel grid plus the event-side difference-map target voxel.sum(0).  The batch is resident in
-the layout the collate step ships over PCIe (5 B/event: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 plus one tick byte,
-ticks relative to a base per 1024 events, RaggedEvents.packed(); lossless, results bit-identical to the 13 B/event
-canonical SoA, whose number is reported under "extra").  A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
+the layout the collate step ships over PCIe: the densest lossless transport layout the stream fits
+(RaggedEvents.transport(): here 4 B/event, one u32 x | y << 11 | p << 22 | ticks << 23 with 9-bit ticks relative to a base
+per 256 events; results bit-identical to the 13 B/event canonical SoA, whose number is reported under "extra").  A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
 
   value     events/s with the batch already resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e       the same metric through the public API from pinned HOST buffers: H2D of the SoA batch (in slices, so the
@@ -213,9 +213,16 @@ def run_ours(args):
     ev13 = make_batch_gpu(rank, dev)
     n_events = ev13.num_events
     host13 = ep.RaggedEvents(ev13.x.cpu(), ev13.y.cpu(), ev13.t.cpu(), ev13.p.cpu(), ev13.offsets.cpu(), ev13.offsets_host, ev13.t_div)
-    # resident copy in the transport layout (5 B/event; the opt-in banded path takes the 8 B/event one)
-    host = (host13.compact() if args.method == "banded" else host13.packed()).pin_memory()
+    # resident copy in the transport layout: the densest lossless one the stream fits (4 B/event here; the opt-in
+    # banded path takes the 8 B/event one)
+    host = (host13.compact() if args.method == "banded" else host13.transport()).pin_memory()
     ev = host.to(dev)
+    bpe = host.nbytes() / max(n_events, 1)
+    host_gb = host.nbytes() / 1e9
+    layout_name = ("compact SoA: x,y u16 | u32 ticks relative to the sample | polarity << 31" if host.y is not None else
+                   "packed SoA: u32 x | y << 11 | p << 22 | ticks << 23 (9-bit ticks relative to a base per 256 events)" if host.t is None else
+                   "packed SoA: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 + u8 ticks & 0xff (ticks relative to a base per 1024 events)")
+    layout_name += f" ({bpe:.2f} B/event, the lossless transport layout; results bit-identical to the 13 B/event canonical SoA)"
     torch.cuda.synchronize()
     out = {"voxel": torch.empty((BATCH, BINS, H, W), dtype=torch.float32, device=dev),
            "voxel_sum": torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev)}
@@ -296,7 +303,7 @@ def run_ours(args):
                             "pass1_launches_per_step": prof.launches[0] // args.steps,
                             "pass1_Gevents_per_s": n_events / (scatter_ms * 1e-3) / 1e9},
                 "algorithmic_bytes_per_step": alg,
-                "algorithmic_bytes_rule": "SURVEY.md 8(d): 13 B/event canonical record + 4 B per output element, whatever the resident layout (5 B/event here)"}
+                "algorithmic_bytes_rule": f"SURVEY.md 8(d): 13 B/event canonical record + 4 B per output element, whatever the resident layout ({bpe:.1f} B/event here)"}
 
     # ---- the same step on the canonical 13 B/event layout, with the banded path, and on the skewed distribution
     # (contention evidence: 70 % of events on 64 segments + hot pixels), same sizes
@@ -325,7 +332,7 @@ def run_ours(args):
         sk13 = make_batch_gpu(rank, dev, skewed=True)
         skh = ep.RaggedEvents(sk13.x.cpu(), sk13.y.cpu(), sk13.t.cpu(), sk13.p.cpu(), sk13.offsets.cpu(), sk13.offsets_host, sk13.t_div)
         del sk13
-        sk = skh.packed().to(dev)
+        sk = skh.transport().to(dev)
         extra["skewed_distribution_Gevents_per_s"] = timed(sk, args.method)
         del sk
         sk = skh.compact().to(dev)
@@ -352,17 +359,19 @@ def run_ours(args):
     del pipe
 
     # ---- e2e: pinned host SoA -> H2D -> bin -> D2H of the per-sample checksum, all inside the timed region ----
-    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the 5 B/event
-    # transport layout (RaggedEvents.packed(), lossless).  The batch crosses PCIe in E2E_SLICES slices of consecutive samples: the copy of slice i+1
+    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the densest lossless
+    # transport layout that fits (RaggedEvents.transport()).  The batch crosses PCIe in E2E_SLICES slices of consecutive samples: the copy of slice i+1
     # (copy stream) overlaps the binning of slice i (compute stream); two device staging sets, guarded by events.
     del ev
     torch.cuda.empty_cache()
     E2E_SLICES = 8
     bounds = [(BATCH * i) // E2E_SLICES for i in range(E2E_SLICES + 1)]
     # every slice is packed on its own (the collate step would produce them like this): block offsets start at 0
-    slices = [host13.take(bounds[i], bounds[i + 1]).packed().pin_memory() for i in range(E2E_SLICES)]
+    slices = [host13.take(bounds[i], bounds[i + 1]).transport().pin_memory() for i in range(E2E_SLICES)]
+    if any((sl.t is None) != (slices[0].t is None) or (sl.y is None) != (slices[0].y is None) for sl in slices):
+        slices = [host13.take(bounds[i], bounds[i + 1]).packed(5).pin_memory() for i in range(E2E_SLICES)]
     h2d = sum(sl.nbytes() for sl in slices)
-    fields = ("x", "t", "p", "offsets", "t_base")
+    fields = tuple(f for f in ("x", "y", "t", "p", "offsets", "t_base") if getattr(slices[0], f) is not None)
     stage = [{f: torch.empty(max(getattr(sl, f).numel() for sl in slices), dtype=getattr(slices[0], f).dtype, device=dev)
               for f in fields} for _ in range(2)]
     copy_stream, comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -384,7 +393,8 @@ def run_ours(args):
                 copied[i].record(copy_stream)
             with torch.cuda.stream(comp_stream):
                 comp_stream.wait_event(copied[i])
-                d = ep.RaggedEvents(view["x"], None, view["t"], view["p"], view["offsets"], sl.offsets_host, sl.t_div, view["t_base"])
+                d = ep.RaggedEvents(view["x"], view.get("y"), view.get("t"), view.get("p"), view["offsets"], sl.offsets_host, sl.t_div,
+                                    view["t_base"])
                 o = {"voxel": out["voxel"][bounds[i]:bounds[i + 1]], "voxel_sum": out["voxel_sum"][bounds[i]:bounds[i + 1]]}
                 ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=o, method=e2e_method)
                 binned[i].record(comp_stream)
@@ -405,7 +415,7 @@ def run_ours(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e = {"value": total_events * args.steps / float(tm.item()) / 1e9, "unit": "Gevents/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * float(tm.item()) / args.steps,
-           "host_layout": "pinned SoA, 5 B/event transport layout (u32 x | y << 11 | p << 22 | ticks >> 8 << 23, u8 ticks & 0xff; ticks relative to a base per 1024 events; lossless, include/eventpretrain_b200.h)",
+           "host_layout": "pinned " + layout_name + "; include/eventpretrain_b200.h",
            "pipelining": f"{E2E_SLICES} slices of consecutive samples; H2D of slice i+1 overlaps the binning of slice i"}
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port on the host cores, bounded sample + parity check ----
@@ -436,8 +446,8 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "integer-tick time arithmetic, Q24 fixed-point int64 accumulate -> f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": "packed SoA: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 + u8 ticks & 0xff, ticks relative to a base per 1024 events (5 B/event, the transport layout; results bit-identical to the 13 B/event canonical SoA)",
-                           "cache": "inputs (1.3 GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
+                "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": layout_name,
+                           "cache": f"inputs ({host_gb:.1f} GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"shard-by-sample x{world}, no data-path collective", "method": args.method},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -416,19 +416,30 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     int rc = check_params(prm);
     if (rc != EP_OK) return rc;
     if (!ev || ev->batch <= 0 || !ev->offsets || !ev->offsets_host) return EP_EINVAL;
-    if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || (!valid_dtype(ev->p_dtype) && ev->t_dtype != EP_U32)) return EP_EINVAL;
+    const bool packed = ev->xy_dtype == EP_U32;       // packed transport layouts: their own pointer rules, checked below
+    if (!valid_dtype(ev->xy_dtype)) return EP_EINVAL;
+    if (!packed && (!valid_dtype(ev->t_dtype) || (!valid_dtype(ev->p_dtype) && ev->t_dtype != EP_U32))) return EP_EINVAL;
     if (!(ev->t_div != 0.0)) return EP_EINVAL;
     const int B = ev->batch;
     for (int b = 0; b < B; ++b) if (ev->offsets_host[b + 1] < ev->offsets_host[b]) return EP_EINVAL;
-    if (ev->offsets_host[B] > ev->offsets_host[0] && (!ev->x || (!ev->y && ev->t_dtype != EP_U8) || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
+    const int64_t n_events = ev->offsets_host[B] - ev->offsets_host[0];
+    if (n_events > 0 && !ev->x) return EP_EINVAL;
+    if (n_events > 0 && !packed && (!ev->y || !ev->t || (!ev->p && ev->t_dtype != EP_U32))) return EP_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (ev->t_dtype == EP_U8) {
-        // packed transport layout (5 B/event): x -> uint32 words, t -> low tick bytes, p -> per-1024-block tick offsets
-        if (ev->xy_dtype != EP_U32 || ev->y != nullptr || !ev->p || ev->p_dtype != EP_U32 || !ev->t_base || prm->time_f32) return EP_EINVAL;
+    if (ev->xy_dtype == EP_U32) {
+        // packed transport layouts: x -> uint32 words, p -> per-block tick offsets, t -> low tick bytes (5 B/event) or NULL (4 B/event)
+        const bool five = ev->t_dtype == EP_U8;
+        if ((!five && (ev->t_dtype != 0 || ev->t)) || (five && !ev->t && n_events > 0)) return EP_EINVAL;
+        if (ev->y != nullptr || (!ev->p && n_events > 0) || ev->p_dtype != EP_U32 || !ev->t_base || prm->time_f32) return EP_EINVAL;
         if (!aligned16(ev->x) || !aligned16(ev->t)) return EP_EALIGN;
         if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
-        SoaPackedLoader ld{static_cast<const uint32_t*>(ev->x), static_cast<const uint8_t*>(ev->t),
-                           static_cast<const uint32_t*>(ev->p), ev->t_base, ev->t_div};
+        if (five) {
+            SoaPackedLoader<true> ld{static_cast<const uint32_t*>(ev->x), static_cast<const uint8_t*>(ev->t),
+                                     static_cast<const uint32_t*>(ev->p), ev->t_base, ev->t_div};
+            return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
+                               workspace_bytes, bad_count);
+        }
+        SoaPackedLoader<false> ld{static_cast<const uint32_t*>(ev->x), nullptr, static_cast<const uint32_t*>(ev->p), ev->t_base, ev->t_div};
         return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
                            workspace_bytes, bad_count);
     }

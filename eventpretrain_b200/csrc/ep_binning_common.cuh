@@ -210,18 +210,22 @@ struct SoaCompactLoader {
     __device__ __forceinline__ double div() const { return t_div; }
 };
 
-// packed transport layout (5 B/event): one uint32 word x | y << 11 | polarity << 22 | (ticks >> 8) << 23 and one byte
-// (ticks & 0xff) per event, where `ticks` (17 bits) counts from a base that changes every 1024 events of the arrays:
-// for the events of a sample that share the 1024-block of the sample's first event the base is the sample's own
-// (t_base[b], int64), for every later block g = i >> 10 it is t_base[b] + blk_base[g].  Same integer time arithmetic as
-// the other tick layouts once the base is added, so results are bit-identical.
+// packed transport layouts: one uint32 word x | y << 11 | polarity << 22 | tick bits << 23 per event, the ticks counted
+// from a base that changes every BLOCK events of the arrays: for the events of a sample that share the block of the
+// sample's first event the base is the sample's own (t_base[b], int64), for every later block g = i / BLOCK it is
+// t_base[b] + blk_base[g].
+//   5 B/event (TICK_BYTE = true):  BLOCK = 1024, ticks = 17 bits = (word >> 23) << 8 | one extra byte per event
+//   4 B/event (TICK_BYTE = false): BLOCK = 256,  ticks = 9 bits  = word >> 23
+// Same integer time arithmetic as the other tick layouts once the base is added, so results are bit-identical.
+template <bool TICK_BYTE>
 struct SoaPackedLoader {
     const uint32_t* w;          // [N]
-    const uint8_t* tl;          // [N]
-    const uint32_t* blk_base;   // [ceil(N / 1024)]
+    const uint8_t* tl;          // [N] (5 B/event form only)
+    const uint32_t* blk_base;   // [ceil(N / BLOCK)]
     const int64_t* t_base;      // [B]
     double t_div;
     typedef double time_t_;
+    static constexpr int kBlockShift = TICK_BYTE ? 10 : 8;
     static constexpr bool kFastTime = true;
     static constexpr bool kTicks = true;
     static constexpr bool kPrefetch = true;
@@ -233,14 +237,17 @@ struct SoaPackedLoader {
         decode(r, i0, hi, a, e);
     }
     __device__ __forceinline__ void load_raw(int64_t i0, const BinArgs& a, Raw& r) const {
+        r.tv = 0;
         if (i0 + 4 <= a.n_total) {
             r.wv = ld_stream(reinterpret_cast<const uint4*>(w + i0));
-            r.tv = ld_stream(reinterpret_cast<const uint32_t*>(tl + i0));
+            if (TICK_BYTE) r.tv = ld_stream(reinterpret_cast<const uint32_t*>(tl + i0));
         } else {
             uint32_t ws_[4] = {0, 0, 0, 0};
-            r.tv = 0;
             for (int j = 0; j < 4; ++j)
-                if (i0 + j < a.n_total) { ws_[j] = w[i0 + j]; r.tv |= (uint32_t)tl[i0 + j] << (8 * j); }
+                if (i0 + j < a.n_total) {
+                    ws_[j] = w[i0 + j];
+                    if (TICK_BYTE) r.tv |= (uint32_t)tl[i0 + j] << (8 * j);
+                }
             r.wv = make_uint4(ws_[0], ws_[1], ws_[2], ws_[3]);
         }
     }
@@ -257,17 +264,18 @@ struct SoaPackedLoader {
                 e.x[j] = xs;
                 e.y[j] = ys;
             }
-            e.ti[j] = (int64_t)(((ws[j] >> 23) << 8) | ((r.tv >> (8 * j)) & 0xffu));
+            e.ti[j] = TICK_BYTE ? (int64_t)(((ws[j] >> 23) << 8) | ((r.tv >> (8 * j)) & 0xffu)) : (int64_t)(ws[j] >> 23);
             e.t[j] = 0.0;
             e.cls[j] = ((ws[j] >> 22) & 1u) ? 0 : 1;     // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
         }
     }
-    // ticks to add to an event's block-relative count: 0 inside the 1024-block where its sample starts
+    // ticks to add to an event's block-relative count: 0 inside the block where its sample starts
     __device__ __forceinline__ int64_t block_base(int64_t i, int64_t s_lo) const {
-        return ((i >> 10) == (s_lo >> 10)) ? 0 : (int64_t)__ldg(blk_base + (i >> 10));
+        return ((i >> kBlockShift) == (s_lo >> kBlockShift)) ? 0 : (int64_t)__ldg(blk_base + (i >> kBlockShift));
     }
     __device__ __forceinline__ int64_t ticks_at(int64_t i, int64_t s_lo) const {
-        return block_base(i, s_lo) + (int64_t)(((w[i] >> 23) << 8) | (uint32_t)tl[i]);
+        const int64_t rel = TICK_BYTE ? (int64_t)(((w[i] >> 23) << 8) | (uint32_t)tl[i]) : (int64_t)(w[i] >> 23);
+        return block_base(i, s_lo) + rel;
     }
     __device__ __forceinline__ double time_of(int64_t i, int b, int64_t s_lo) const {
         const double v = (double)(t_base[b] + ticks_at(i, s_lo));

@@ -216,6 +216,7 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
     using namespace ep;
     if (!ev || !out || !workspace || ev->batch <= 0 || height <= 0 || width <= 0) return EP_EINVAL;
     if (!ev->offsets || !ev->offsets_host) return EP_EINVAL;
+    if (ev->t_base || ev->xy_dtype == EP_U32 || ev->t_dtype == EP_U32) return EP_EUNSUPPORTED;   // transport layouts: ep_bin_events only
     if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype) || !(ev->t_div != 0.0))
         return EP_EINVAL;
     const int B = ev->batch;

@@ -79,6 +79,7 @@ int ep_time_surface(void* stream, const ep_events_soa* ev, int height, int width
     using namespace ep;
     if (!ev || !out || !workspace || ev->batch <= 0 || height <= 0 || width <= 0 || !(tau > 0.0)) return EP_EINVAL;
     if (!ev->offsets || !ev->offsets_host || !(ev->t_div != 0.0)) return EP_EINVAL;
+    if (ev->t_base || ev->xy_dtype == EP_U32 || ev->t_dtype == EP_U32) return EP_EUNSUPPORTED;   // transport layouts: ep_bin_events only
     if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype)) return EP_EINVAL;
     const size_t need = ep_time_surface_workspace_bytes(ev->batch, height, width);
     if (workspace_bytes < need) return EP_EWORKSPACE;

@@ -102,16 +102,33 @@ class RaggedEvents:
         return RaggedEvents(cut(self.x), cut(self.y), cut(self.t), cut(self.p), torch.from_numpy(off.copy()).to(self.offsets.device),
                             off, self.t_div, None if self.t_base is None else self.t_base[b0:b1].clone())
 
-    PACK_BLOCK = 1024
+    def pack_block(self):
+        """Events per tick-offset block of a packed() batch: 1024 (5 B/event form) or 256 (4 B/event form)."""
+        return 1024 if self.t is not None else 256
 
-    def packed(self):
-        """Host-side repack into the 5 B/event transport layout (include/eventpretrain_b200.h, ep_events_soa.t_base):
-        one uint32 x | y << 11 | polarity << 22 | (ticks >> 8) << 23 plus one byte ticks & 0xff per event; `ticks`
-        (17 bits) counts from the sample's base inside the 1024-block of the arrays where the sample starts and from
-        base + a per-block offset afterwards.  Needs int64 tick stamps, p in {0,1}, x,y < 2048 and < 2^17 ticks between
-        the smallest and largest stamp a sample has inside one 1024-block (raises ValueError otherwise: use compact()).
-        Binning results are bit-identical to the int64 layout; H2D traffic drops from 13 to 5 B/event."""
+    def transport(self):
+        """Densest lossless transport layout this batch fits: packed 4 B/event, else packed 5 B/event, else compact 8 B/event."""
+        for make in (lambda: self.packed(4), lambda: self.packed(5), self.compact):
+            try:
+                return make()
+            except ValueError:
+                continue
+        return self
+
+    def packed(self, nbytes=5):
+        """Host-side repack into a packed transport layout (include/eventpretrain_b200.h, ep_events_soa.t_base): one
+        uint32 x | y << 11 | polarity << 22 | tick bits << 23 per event; `ticks` count from the sample's base inside the
+        block of the arrays where the sample starts and from base + a per-block offset afterwards.
+          nbytes=5: blocks of 1024 events, 17-bit ticks = word bits | one extra byte per event
+          nbytes=4: blocks of 256 events, 9-bit ticks in the word (dense streams)
+        Needs int64 tick stamps, p in {0,1}, x,y < 2048 and a block's stamps (of one sample) within the tick range (raises
+        ValueError otherwise: use the next wider layout, see transport()).  Binning results are bit-identical to the int64
+        layout; H2D traffic drops from 13 to 5 or 4 B/event."""
+        if nbytes not in (4, 5):
+            raise ValueError("packed layouts have 4 or 5 bytes per event")
         if self.t_base is not None and self.y is None:
+            if (self.t is None) != (nbytes == 4):
+                raise TypeError("already packed with the other width")
             return self
         if self.t_base is not None or self.t.dtype != torch.int64 or self.p.dtype != torch.uint8 or self.x.dtype != torch.uint16:
             raise TypeError("packed() needs the canonical u16 / int64-tick / u8 layout")
@@ -127,7 +144,8 @@ class RaggedEvents:
             raise ValueError("packed() needs x, y < 2048")
         if n and p.max() > 1:
             raise ValueError("packed() needs polarity in {0, 1}")
-        B, K = self.batch, self.PACK_BLOCK
+        B, K = self.batch, (1024 if nbytes == 5 else 256)
+        tick_bits = 17 if nbytes == 5 else 9
         counts = np.diff(off)
         base = np.zeros(B, np.int64)
         nz = counts > 0
@@ -148,26 +166,31 @@ class RaggedEvents:
         ticks = rel - np.where(g == first_blk, 0, blk[g].astype(np.int64)) if n else rel
         if n and ticks.min() < 0:
             raise ValueError("stamps too far out of order for the packed layout")
-        if n and ticks.max() >= (1 << 17):
-            raise ValueError("a 1024-event block spans 2^17 ticks or more")
+        if n and ticks.max() >= (1 << tick_bits):
+            raise ValueError(f"a {K}-event block spans 2^{tick_bits} ticks or more")
         tk = ticks.astype(np.uint32)
-        w = x | (y << np.uint32(11)) | (p << np.uint32(22)) | ((tk >> np.uint32(8)) << np.uint32(23))
-        tl = (tk & np.uint32(0xff)).astype(np.uint8)
         dev = self.x.device
         mk = (lambda a: a.pin_memory()) if (self.x.is_pinned() or self.x.is_cuda) and torch.cuda.is_available() else (lambda a: a)
         cv = lambda a: mk(torch.from_numpy(np.ascontiguousarray(a))).to(dev)
-        return RaggedEvents(cv(w), None, cv(tl), cv(blk), self.offsets, off, self.t_div, cv(base))
+        if nbytes == 5:
+            w = x | (y << np.uint32(11)) | (p << np.uint32(22)) | ((tk >> np.uint32(8)) << np.uint32(23))
+            tl = cv((tk & np.uint32(0xff)).astype(np.uint8))
+        else:
+            w = x | (y << np.uint32(11)) | (p << np.uint32(22)) | (tk << np.uint32(23))
+            tl = None
+        return RaggedEvents(cv(w), None, tl, cv(blk), self.offsets, off, self.t_div, cv(base))
 
     def unpack_host(self):
         """Decode a packed() batch back to (x, y, t_ticks, p) numpy arrays (tests / debugging)."""
         if self.t_base is None or self.y is not None:
             raise TypeError("not a packed() batch")
         w = self.x.cpu().numpy().astype(np.uint32)
-        tl = self.t.cpu().numpy().astype(np.int64)
         blk = self.p.cpu().numpy().astype(np.int64)
         base = self.t_base.cpu().numpy()
-        off, K = self.offsets_host, self.PACK_BLOCK
-        ticks = ((w >> np.uint32(23)).astype(np.int64) << 8) | tl
+        off, K = self.offsets_host, self.pack_block()
+        ticks = (w >> np.uint32(23)).astype(np.int64)
+        if self.t is not None:
+            ticks = (ticks << 8) | self.t.cpu().numpy().astype(np.int64)
         t = np.zeros(w.shape[0], np.int64)
         for b in range(self.batch):
             lo, hi = int(off[b]), int(off[b + 1])
@@ -193,7 +216,7 @@ class RaggedEvents:
         if self.y is not None and self.x.dtype != self.y.dtype:
             raise TypeError("x and y must share a dtype")
         d.xy_dtype = _TORCH_TAG[self.x.dtype]
-        d.t_dtype = _TORCH_TAG[self.t.dtype]
+        d.t_dtype = _TORCH_TAG[self.t.dtype] if self.t is not None else 0
         d.p_dtype = _TORCH_TAG[self.p.dtype] if self.p is not None else 0
         d.t_base = ptr(self.t_base)
         d.batch = self.batch

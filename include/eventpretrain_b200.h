@@ -84,7 +84,7 @@ typedef struct ep_events_soa {
     const void* t;
     const void* p;
     int xy_dtype;                /* EP_U16 | EP_I16 | EP_I32 | EP_F32 | EP_F64 (fractional coords truncate toward 0); EP_U32 = packed layout */
-    int t_dtype;                 /* EP_I64 | EP_F64 | EP_F32; EP_U32 = compact layout, EP_U8 = packed layout */
+    int t_dtype;                 /* EP_I64 | EP_F64 | EP_F32; EP_U32 = compact layout; EP_U8 / 0 = packed layouts */
     int p_dtype;                 /* EP_U8 | EP_I8 | EP_F32 | EP_F64 */
     int batch;                   /* B */
     double t_div;
@@ -94,12 +94,14 @@ typedef struct ep_events_soa {
                                     in results to the int64 canonical layout; timestamp value = (t_base[b] + ticks) / t_div:
                                     - compact, 8 B/event: t_dtype = EP_U32 holds ticks relative to t_base[b] in bits
                                       0..30 and the polarity in bit 31, p = NULL;
-                                    - packed, 5 B/event: xy_dtype = EP_U32, x = one word per event
-                                      x | y << 11 | polarity << 22 | (ticks >> 8) << 23, y = NULL; t_dtype = EP_U8,
-                                      t = (ticks & 0xff) per event; p_dtype = EP_U32, p = one tick offset per 1024
-                                      events of the arrays.  `ticks` (17 bits) of event i of sample b counts from
-                                      t_base[b] when i lies in the 1024-block of the sample's first event, else from
-                                      t_base[b] + p[i >> 10].  x, y < 2048; both pointers 16-byte aligned. */
+                                    - packed, 5 or 4 B/event: xy_dtype = EP_U32, x = one word per event
+                                      x | y << 11 | polarity << 22 | tick bits << 23, y = NULL; p_dtype = EP_U32, p = one
+                                      tick offset per BLOCK events of the arrays.  `ticks` of event i of sample b count
+                                      from t_base[b] when i lies in the block of the sample's first event, else from
+                                      t_base[b] + p[i / BLOCK].  5 B form: t_dtype = EP_U8, t = (ticks & 0xff) per event,
+                                      word bits 23..31 = ticks >> 8 (17-bit ticks), BLOCK = 1024.  4 B form: t_dtype = 0,
+                                      t = NULL, word bits 23..31 = ticks (9 bits), BLOCK = 256.  x, y < 2048; x and t
+                                      16-byte aligned. */
 } ep_events_soa;
 
 /* Array-of-structures single sample: the reference's own (N,4) x,y,t,p array

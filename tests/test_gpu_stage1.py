@@ -317,3 +317,15 @@ def test_packed_transport_layout(ep):
     c = ep.bin_events(pk.to("cuda").shard(1, 2), (H, W), num_bins=5, check=True)     # offsets[0] > 0 on the device side
     a5 = ep.bin_events(host.to("cuda"), (H, W), num_bins=5, check=True)
     assert torch.equal(c["voxel"], a5["voxel"][3:])
+    # 4 B/event form (9-bit ticks per 256-event block) on a dense stream
+    ev, _ = _random_batch(ep, rng, [30000, 0, 1, 5003, 256, 255, 257], H, W, t_span=300)
+    host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu() + 1_700_000_000_000_000, ev.p.cpu(), ev.offsets.cpu(),
+                           ev.offsets_host, ev.t_div)
+    p4 = host.packed(4)
+    assert p4.t is None and p4.nbytes() < 0.33 * host.nbytes()
+    a = ep.bin_events(host.to("cuda"), (H, W), num_bins=5, count_channels=3, voxel_sum=True, check=True)
+    b = ep.bin_events(p4.to("cuda"), (H, W), num_bins=5, count_channels=3, voxel_sum=True, check=True)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b[key]), key
+    with pytest.raises(RuntimeError):
+        ep.evrep(p4.to("cuda"), (H, W))                 # transport layouts are for ep_bin_events only

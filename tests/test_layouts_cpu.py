@@ -27,6 +27,21 @@ def test_packed_round_trip():
     assert np.array_equal(x, ev.x.numpy()) and np.array_equal(y, ev.y.numpy())
     assert np.array_equal(t, ev.t.numpy()) and np.array_equal(p, ev.p.numpy())
     assert pk.packed() is pk
+    with pytest.raises(ValueError):
+        ev.packed(4)                                  # ~17 ticks per event on average: 256 events do not fit 9 bits
+    assert ev.transport().t is not None and ev.transport().y is None      # ... so the 5 B/event form is the densest that fits
+
+
+def test_packed4_round_trip():
+    rng = np.random.default_rng(2)
+    ev = _batch(rng, [3000, 0, 1, 5003, 256, 255, 257, 9999], span=400)    # dense stream: 256 events within 2^9 ticks
+    pk = ev.packed(4)
+    assert pk.y is None and pk.t is None and pk.x.dtype == torch.uint32 and pk.pack_block() == 256
+    assert pk.p.numel() == (ev.num_events + 255) // 256 and pk.nbytes() < 0.32 * ev.nbytes()
+    x, y, t, p = pk.unpack_host()
+    assert np.array_equal(x, ev.x.numpy()) and np.array_equal(y, ev.y.numpy())
+    assert np.array_equal(t, ev.t.numpy()) and np.array_equal(p, ev.p.numpy())
+    assert ev.transport().t is None
 
 
 def test_packed_mildly_unsorted_and_limits():

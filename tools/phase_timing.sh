@@ -1,3 +1,4 @@
 #!/bin/bash
-# per-phase cycle accounting of the banded kernels (library must be built with EP_PHASE_TIMING=1)
-EP_PROFILE_METHOD=banded EP_PRINT_TIMING=1 EP_PROFILE_BATCH=64 python tools/profile_binning.py 2>&1 | tail -12
+# per-phase cycle accounting of the banded kernels: rebuilds the library with EP_PHASE_TIMING=1 (tools only; run it on the GPU box)
+EP_PHASE_TIMING=1 python -m eventpretrain_b200.build --force > /dev/null 2>&1
+EP_PRINT_TIMING=1 python tools/quick_bin.py --batch 64 --methods banded --steps 1 "$@" 2>&1 | tail -12
