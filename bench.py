@@ -201,8 +201,8 @@ def run_ours(args):
     from eventpretrain_b200 import _lib
     from eventpretrain_b200.dist import init_from_env
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its banner on stdout; stdout carries exactly one JSON line
+    # stdout carries exactly one JSON line: NCCL's banner / debug output (printed at WARN level and above) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU port)")
