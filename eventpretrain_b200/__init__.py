@@ -15,6 +15,7 @@ from .events import (BadEventsError, RaggedEvents, bin_events, bin_events_aos, e
 from .masking import (block_mask_expand, convvit_keep_masks, gather_tokens, len_keep_of,  # noqa: F401
                       mask_from_noise, patch_density, random_masking, swin_apply_mask, unshuffle_tokens)
 from .pipeline import MaskedInputPipeline  # noqa: F401
+from .swin_grouping import GroupingModule, group_windows, knapsack, patch_merging_order  # noqa: F401
 from .reshape import (diffmap_frames, frame2emb, patchify_gather, reconstruct_loss, target_normpix,  # noqa: F401
                       target_patch_loss)
 

@@ -280,6 +280,15 @@ EP_API int ep_swin_apply_mask(void* stream, const float* x, const float* mask_ro
 EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask_token, const float* pos_embed,
                         const int64_t* ids_restore, int batch, int L, int K, int D, float* out);
 
+/* Swin sparse-token grouping, HOST function, no device work:
+ *   knapsack / group_windows   model/sub_module/swin_block.py:280-352 (called from GroupingModule._prepare_grouping :387-431)
+ * Packs windows holding num_ele_win[i] visible tokens (1 <= . <= group_size) into groups of at most group_size tokens,
+ * greedily, one 0/1 knapsack per group, with the reference's table, back-tracking and tie behaviour: identical groups.
+ * Outputs: num_ele_group[g] tokens of group g; the windows of group g are grouped_idx[group_first[g] .. group_first[g+1])
+ * in increasing order; *n_groups groups (<= n_win).  Arrays sized n_win (group_first: n_win + 1). */
+EP_API int ep_swin_group_windows_host(int group_size, const int* num_ele_win, int n_win, int* num_ele_group, int* group_first,
+                                      int* grouped_idx, int* n_groups);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,3 +172,40 @@ def time_surface(xs, ys, ts, ps, size, tau, t_ref=None):
     out = np.exp(-(t_ref - last) / tau)
     out[~np.isfinite(last)] = 0.0
     return out.astype(np.float32)
+
+
+# ---- Swin sparse-token grouping ---------------------------------------------------
+def swin_knapsack(W, wt):
+    """model/sub_module/swin_block.py:280-326 — 0/1 knapsack with value = weight; returns (best fill, selected indices in
+    increasing order).  Ties in the back-tracking go to "not taken" exactly like the reference (res == K[i-1][w])."""
+    n = len(wt)
+    K = np.zeros((n + 1, W + 1), np.int64)
+    for i in range(1, n + 1):
+        for w in range(1, W + 1):
+            K[i, w] = K[i - 1, w]
+            if wt[i - 1] <= w:
+                K[i, w] = max(wt[i - 1] + K[i - 1, w - wt[i - 1]], K[i - 1, w])
+    res = int(K[n, W])
+    left, w, idx = res, W, []
+    for i in range(n, 0, -1):
+        if left <= 0:
+            break
+        if left == K[i - 1, w]:
+            continue
+        idx.append(i - 1)
+        left -= wt[i - 1]
+        w -= wt[i - 1]
+    return res, idx[::-1]
+
+
+def swin_group_windows(group_size, num_ele_win):
+    """model/sub_module/swin_block.py:329-352 — greedy: one knapsack per group over the windows still ungrouped."""
+    wt, ori = list(num_ele_win), list(range(len(num_ele_win)))
+    groups, fills = [], []
+    while wt:
+        res, idx = swin_knapsack(group_size, wt)
+        fills.append(res)
+        groups.append([ori[i] for i in idx])
+        keep = [i for i in range(len(wt)) if i not in idx]
+        wt, ori = [wt[i] for i in keep], [ori[i] for i in keep]
+    return fills, groups

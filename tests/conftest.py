@@ -43,6 +43,11 @@ def golden_views():
 
 
 @pytest.fixture(scope="session")
+def golden_swin_grouping():
+    return _load("swin_grouping.npz")
+
+
+@pytest.fixture(scope="session")
 def native_lib():
     """Builds (if stale) and loads the CUDA C-ABI library; nvcc cross-compiles without a GPU."""
     from eventpretrain_b200 import build, _lib

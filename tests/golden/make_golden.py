@@ -373,6 +373,53 @@ def stream_aug_cases(ref):
     return out
 
 
+def swin_grouping_cases(ref):
+    """model/sub_module/swin_block.py:280-464 and :196-203 — knapsack / group_windows on random window fills, full
+    GroupingModule plans and PatchMerging's token order for masks of the Swin front-end.  The reference sorts tokens by
+    window id with torch.argsort's default; it is run here with stable=True (the order CUDA's radix sort gives on the
+    device the models run on), which fixes the order of tokens inside a window."""
+    from model.sub_module import swin_block as sb
+    out = {}
+    rng = np.random.default_rng(5100)
+    for c in range(24):
+        n, gs = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        wt = rng.integers(1, gs + 1, n).astype(np.int64)
+        fills, groups = sb.group_windows(gs, [int(v) for v in wt])
+        out[f"gw{c:02d}"] = dict(group_size=np.asarray(gs), wt=wt, fills=np.asarray(fills, np.int64),
+                                 first=np.cumsum([0] + [len(g) for g in groups]).astype(np.int64),
+                                 idx=np.asarray([i for g in groups for i in g], np.int64))
+    orig = torch.argsort
+    torch.argsort = lambda x, *a, **k: orig(x, *a, **{**k, "stable": True})
+    try:
+        gen = torch.Generator().manual_seed(5200)
+        for name, res, keep, ws, shift in (("g56_24_s0", 56, 24, 7, 0), ("g56_24_s3", 56, 24, 7, 3), ("g28_24_s3", 28, 24, 7, 3),
+                                           ("g56_12_s0", 56, 12, 7, 0), ("m14_24_s0", 14, 24, 7, 0)):
+            m = torch.zeros(49)
+            m[torch.randperm(49, generator=gen)[:49 - keep]] = 1
+            up = res // 7
+            mm = m.reshape(7, 7)[:, None, :, None].expand(7, up, 7, up).reshape(-1).bool()
+            ii, jj = torch.meshgrid(torch.arange(res), torch.arange(res), indexing="ij")
+            coords = torch.stack([ii, jj], -1).reshape(1, -1, 2)[:, ~mm]
+            gm = sb.GroupingModule(ws, shift)
+            attn_mask, rel_pos_idx = gm.prepare(coords.clone(), coords.shape[1])
+            rec = dict(res=np.asarray(res), window=np.asarray(ws), shift=np.asarray(shift), coords=coords.numpy(),
+                       grouping=np.asarray(gm._mode == "grouping"), attn_mask=attn_mask.numpy(), rel_pos_idx=rel_pos_idx.numpy())
+            if gm._mode == "grouping":
+                rec.update(idx_shuffle=gm.idx_shuffle.numpy(), idx_unshuffle=gm.idx_unshuffle.numpy(), group_size=np.asarray(gm.group_size))
+            # PatchMerging's order (swin_block.py:196-203) for the same visibility mask
+            vis = (~mm).reshape(1, -1)
+            mask = vis.reshape(res // 2, 2, res // 2, 2).permute(0, 2, 1, 3).reshape(-1)
+            cg = sb.get_coordinates(res, res).reshape(2, -1).permute(1, 0)
+            cg = cg.reshape(res // 2, 2, res // 2, 2, 2).permute(0, 2, 1, 3, 4).reshape(-1, 2)
+            cl = cg[mask].reshape(-1, 2)
+            cl = cl[:, 0] * res + cl[:, 1]
+            rec.update(vis=vis.numpy(), merge_order=torch.argsort(torch.argsort(cl)).numpy())
+            out[name] = rec
+    finally:
+        torch.argsort = orig
+    return out
+
+
 def main():
     ref = _import_reference()
     torch.set_num_threads(1)
@@ -388,7 +435,10 @@ def main():
     sa = stream_aug_cases(ref)
     flat = {f"{case}/{k}": v for case, rec in sa.items() for k, v in rec.items()}
     np.savez_compressed(os.path.join(HERE, "stream_aug.npz"), **flat)
-    for f in ("stage1_events.npz", "stage3_mask_patch.npz", "views.npz", "stream_aug.npz"):
+    sg = swin_grouping_cases(ref)
+    flat = {f"{case}/{k}": v for case, rec in sg.items() for k, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "swin_grouping.npz"), **flat)
+    for f in ("stage1_events.npz", "stage3_mask_patch.npz", "views.npz", "stream_aug.npz", "swin_grouping.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
     print("torch", torch.__version__, "numpy", np.__version__)
 

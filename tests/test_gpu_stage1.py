@@ -329,3 +329,34 @@ def test_packed_transport_layout(ep):
         assert torch.equal(a[key], b[key]), key
     with pytest.raises(RuntimeError):
         ep.evrep(p4.to("cuda"), (H, W))                 # transport layouts are for ep_bin_events only
+
+
+def test_full_size_properties(ep):
+    """BASELINE configs[1] sizes (640x480, ~1M events/sample, 5 bins; 24 samples here to keep the suite short): size-independent
+    properties instead of an oracle pass — conservation (every in-window event adds p in total, so the grid sums to the
+    sample's net polarity and voxel.sum(0) to the same), run-to-run bit identity, identical bits across the resident layouts
+    and both kernel families, shards equal to the rows of the whole batch."""
+    import bench
+    dev = torch.device("cuda", 0)
+    ev = bench.make_batch_gpu(0, dev, batch=24)
+    H, W, bins = bench.H, bench.W, bench.BINS
+    host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
+    a = ep.bin_events(ev, (H, W), num_bins=bins, voxel_sum=True, count_channels=2, check=True)
+    # conservation, per sample (events exactly at t_first .. t_last all lie inside the bins)
+    off = ev.offsets_host
+    pol = ev.p.to(torch.float64) * 2 - 1
+    for b in range(ev.batch):
+        net = float(pol[int(off[b]):int(off[b + 1])].sum())
+        assert abs(float(a["voxel"][b].double().sum()) - net) < 0.5
+        assert abs(float(a["voxel_sum"][b].double().sum()) - net) < 0.5
+        assert float(a["count"][b].sum()) == float(off[b + 1] - off[b])
+    b2 = ep.bin_events(ev, (H, W), num_bins=bins, voxel_sum=True, count_channels=2)
+    for key in ("voxel", "voxel_sum", "count"):
+        assert torch.equal(a[key], b2[key]), key
+    for other, method in ((host.transport().to(dev), None), (host.packed(5).to(dev), None), (host.compact().to(dev), None),
+                          (host.compact().to(dev), "banded"), (ev, "banded")):
+        o = ep.bin_events(other, (H, W), num_bins=bins, voxel_sum=True, count_channels=2, check=True, method=method)
+        for key in ("voxel", "voxel_sum", "count"):
+            assert torch.equal(a[key], o[key]), (key, method)
+    sh = ep.bin_events(ev.shard(1, 3), (H, W), num_bins=bins, check=True)
+    assert torch.equal(sh["voxel"], a["voxel"][8:16])
