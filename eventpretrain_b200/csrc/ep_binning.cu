@@ -45,17 +45,70 @@ __device__ __forceinline__ void publish_zero_flag(const BinArgs& a, int b) {
 
 constexpr int kOffCache = 256;     // offsets of the group's samples cached in shared memory (groups are a few samples)
 
+// per-sample constants of the lean path, cached in shared memory next to the offsets
+struct LeanMeta {
+    int64_t t0_ticks;
+    uint32_t tmul, tshift, thalf, flags;
+};
+
+// Lean path of one thread's 4 consecutive events: every event of the warp's 128 belongs to sample b, lies inside the
+// group, carries integer ticks (kFlagIntTime) and unscaled coordinates.  32-bit index arithmetic, no per-event
+// boundary tests, one slot base pointer per quad.  Same REDs as the general path.
+template <class Loader>
+__device__ __forceinline__ void scatter_quad_lean(const Loader& ld, const BinArgs& a, const typename Loader::Raw& raw, int64_t i0,
+                                                  int b, int64_t s_lo, const LeanMeta& lm, unsigned& nbad, bool& saw_zero) {
+    uint32_t xs[4], ys[4], pb[4];
+    int64_t ti[4];
+    ld.decode_lean(raw, xs, ys, pb, ti);
+    int64_t rebase = -lm.t0_ticks;
+    if constexpr (Loader::kBlocked) rebase += ld.block_base(i0, s_lo);      // a quad never straddles a block (i0 and the block size are multiples of 4)
+    const uint32_t W = (uint32_t)a.W, HW = (uint32_t)(a.H * a.W);
+    const uint32_t v_end = (uint32_t)a.num_bins << kQ;
+    const uint32_t v_last = a.num_bins >= 2 ? (uint32_t)(a.num_bins - 1) << kQ : 0xffffffffu;
+    const int slot = b - a.g0;
+    unsigned long long* acc = a.vox_acc + (int64_t)slot * a.num_bins * HW;
+    uint32_t* cnt = a.cnt_acc + (int64_t)slot * 3 * HW;
+#pragma unroll
+    for (int j = 0; j < kEvPerThread; ++j) {
+        const uint32_t flat = ys[j] * W + xs[j];
+        if (flat >= HW || pb[j] > 1u) { ++nbad; continue; }
+        if (a.count_channels) {
+            atomicAdd(cnt + (pb[j] ? 0u : HW) + flat, 1u);          // class planes: p == 1, p == 0
+            saw_zero |= pb[j] == 0u;
+        }
+        uint32_t v;
+        if (a.num_bins && ticks_to_v(ti[j] + rebase, lm.tmul, lm.tshift, lm.thalf, v_end, v)) {
+            const bool on_last = v == v_last;                     // exactly on the last node: file under the interval before
+            const uint32_t k = (v >> kQ) - (on_last ? 1u : 0u);
+            const uint32_t r = on_last ? (1u << kQ) : (v & ((1u << kQ) - 1u));
+            if (k == (uint32_t)(a.num_bins - 1) && !(__ldcg(&a.meta[b].flags) & kFlagLastPlane)) atomicOr(&a.meta[b].flags, kFlagLastPlane);
+            const long long w = (1ll << kABits) + (long long)r;
+            atomicAdd(acc + (k * HW + flat), (unsigned long long)(pb[j] ? w : -w));
+        }
+    }
+}
+
 template <class Loader>
 __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a, int64_t first_tile, int64_t tile_stride) {
     typedef typename Loader::time_t_ TT;
-    // the owner lookup below runs once per tile and thread: keep the group's offsets on chip
+    // the owner lookup below runs once per tile and thread: keep the group's offsets (and lean constants) on chip
     __shared__ int64_t s_off[kOffCache + 1];
+    __shared__ LeanMeta s_lm[Loader::kLean ? kOffCache : 1];
     const bool cached = a.offsets != nullptr && a.g1 - a.g0 <= kOffCache;
     if (cached) {
         for (int i = threadIdx.x; i <= a.g1 - a.g0; i += kThreads) s_off[i] = a.offsets[a.g0 + i];
+        if constexpr (Loader::kLean)
+            for (int i = threadIdx.x; i < a.g1 - a.g0; i += kThreads) {
+                const SampleMeta m = a.meta[a.g0 + i];
+                LeanMeta lm;
+                lm.t0_ticks = m.t0_ticks; lm.tmul = m.tmul; lm.tshift = m.tshift; lm.thalf = m.thalf; lm.flags = m.flags;
+                s_lm[i] = lm;
+            }
         __syncthreads();
     }
     auto off_of = [&](int b) -> int64_t { return cached ? s_off[b - a.g0] : off_at(a, b); };
+    const bool lean_ok = Loader::kLean && cached && !a.scaled && a.W < 65536 && (int64_t)a.H * a.W * (a.num_bins > 0 ? a.num_bins : 1) < (1ll << 32);
+    unsigned nbad = 0;
     // persistent stride loop over 1024-event tiles; the next tile's loads are issued before this tile's REDs
     typename Loader::Raw raw_next;
     if (Loader::kPrefetch && first_tile < a.n_tiles) {
@@ -68,6 +121,24 @@ __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a
     if (Loader::kPrefetch && tile + tile_stride < a.n_tiles) {
         const int64_t in = a.start4 + ((tile + tile_stride) * kThreads + threadIdx.x) * kEvPerThread;
         if (in < a.end) ld.load_raw(in, a, raw_next);
+    }
+    if constexpr (Loader::kLean) {
+        // warp-uniform test: all 128 events of the warp inside the group and inside one sample with integer-tick constants
+        const int64_t wf = a.start4 + (tile * kThreads + (threadIdx.x & ~31)) * kEvPerThread, wl = wf + 32 * kEvPerThread - 1;
+        if (lean_ok && wf >= a.begin && wl < a.end) {
+            int lo = a.g0, hi = a.g1;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid - a.g0] <= wf) lo = mid; else hi = mid;
+            }
+            const LeanMeta lm = s_lm[lo - a.g0];
+            if (wl < s_off[lo + 1 - a.g0] && (lm.flags & kFlagIntTime)) {
+                bool saw_zero = false;
+                scatter_quad_lean<Loader>(ld, a, raw, i0, lo, s_off[lo - a.g0], lm, nbad, saw_zero);
+                if (saw_zero) publish_zero_flag(a, lo);
+                continue;
+            }
+        }
     }
     if (i0 >= a.end) continue;
 
@@ -122,6 +193,7 @@ __device__ __forceinline__ void scatter_tiles(const Loader& ld, const BinArgs& a
     }
     if (zero_b >= 0) publish_zero_flag(a, zero_b);
   }
+    if (nbad && a.bad_count) atomicAdd(a.bad_count, nbad);
 }
 
 // ---- finalize: packed accumulators -> fp32 outputs, slots re-zeroed ---------------------------------

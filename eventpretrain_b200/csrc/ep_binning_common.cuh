@@ -130,6 +130,16 @@ struct SoaCanonLoader {
             e.cls[j] = pol_class_i((int)((pv >> (8 * j)) & 0xffu));
         }
     }
+    // 32-bit fields for the lean scatter path (integer ticks only): x, y, polarity byte, raw ticks
+    static constexpr bool kLean = T_IS_I64;
+    __device__ __forceinline__ void decode_lean(const Raw& r, uint32_t (&xs)[4], uint32_t (&ys)[4], uint32_t (&pb)[4],
+                                                int64_t (&ti)[4]) const {
+        xs[0] = r.xv.x & 0xffffu; xs[1] = r.xv.x >> 16; xs[2] = r.xv.y & 0xffffu; xs[3] = r.xv.y >> 16;
+        ys[0] = r.yv.x & 0xffffu; ys[1] = r.yv.x >> 16; ys[2] = r.yv.y & 0xffffu; ys[3] = r.yv.y >> 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = (r.pv >> (8 * j)) & 0xffu;
+        ti[0] = r.a0.x; ti[1] = r.a0.y; ti[2] = r.a1.x; ti[3] = r.a1.y;
+    }
     __device__ __forceinline__ double time_at(int64_t i) const {
         double v = T_IS_I64 ? (double)static_cast<const int64_t*>(t)[i] : static_cast<const double*>(t)[i];
         return (t_div != 1.0) ? v / t_div : v;
@@ -201,6 +211,15 @@ struct SoaCompactLoader {
             e.cls[j] = (raw[j] >> 31) ? 0 : 1;           // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
         }
     }
+    static constexpr bool kLean = true;
+    __device__ __forceinline__ void decode_lean(const Raw& r, uint32_t (&xs)[4], uint32_t (&ys)[4], uint32_t (&pb)[4],
+                                                int64_t (&ti)[4]) const {
+        xs[0] = r.xv.x & 0xffffu; xs[1] = r.xv.x >> 16; xs[2] = r.xv.y & 0xffffu; xs[3] = r.xv.y >> 16;
+        ys[0] = r.yv.x & 0xffffu; ys[1] = r.yv.x >> 16; ys[2] = r.yv.y & 0xffffu; ys[3] = r.yv.y >> 16;
+        const uint32_t raw[4] = {r.tv.x, r.tv.y, r.tv.z, r.tv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pb[j] = raw[j] >> 31; ti[j] = (int64_t)(raw[j] & 0x7fffffffu); }
+    }
     __device__ __forceinline__ double time_of(int64_t i, int b, int64_t) const {
         const double v = (double)(t_base[b] + (int64_t)(tp[i] & 0x7fffffffu));
         return (t_div != 1.0) ? v / t_div : v;
@@ -269,6 +288,16 @@ struct SoaPackedLoader {
             e.cls[j] = ((ws[j] >> 22) & 1u) ? 0 : 1;     // polarity bit: 1 = positive, 0 = negative (the p == 0 class)
         }
     }
+    static constexpr bool kLean = true;
+    __device__ __forceinline__ void decode_lean(const Raw& r, uint32_t (&xs)[4], uint32_t (&ys)[4], uint32_t (&pb)[4],
+                                                int64_t (&ti)[4]) const {
+        const uint32_t ws[4] = {r.wv.x, r.wv.y, r.wv.z, r.wv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            xs[j] = ws[j] & 0x7ffu; ys[j] = (ws[j] >> 11) & 0x7ffu; pb[j] = (ws[j] >> 22) & 1u;
+            ti[j] = TICK_BYTE ? (int64_t)(((ws[j] >> 23) << 8) | ((r.tv >> (8 * j)) & 0xffu)) : (int64_t)(ws[j] >> 23);
+        }
+    }
     // ticks to add to an event's block-relative count: 0 inside the block where its sample starts
     __device__ __forceinline__ int64_t block_base(int64_t i, int64_t s_lo) const {
         return ((i >> kBlockShift) == (s_lo >> kBlockShift)) ? 0 : (int64_t)__ldg(blk_base + (i >> kBlockShift));
@@ -299,6 +328,7 @@ struct SoaGenericLoader {
     static constexpr bool kTicks = false;
     static constexpr bool kPrefetch = false;
     static constexpr bool kBlocked = false;
+    static constexpr bool kLean = false;
     struct Raw {};
     __device__ __forceinline__ void load_raw(int64_t, const BinArgs&, Raw&) const {}
     __device__ __forceinline__ void decode(const Raw&, int64_t i0, int64_t hi, const BinArgs& a, Ev<TT>& e) const { load(i0, hi, a, e); }
@@ -346,6 +376,7 @@ struct AosLoader {
     static constexpr bool kTicks = false;
     static constexpr bool kPrefetch = false;
     static constexpr bool kBlocked = false;
+    static constexpr bool kLean = false;
     struct Raw {};
     __device__ __forceinline__ void load_raw(int64_t, const BinArgs&, Raw&) const {}
     __device__ __forceinline__ void decode(const Raw&, int64_t i0, int64_t hi, const BinArgs& a, Ev<ET>& e) const { load(i0, hi, a, e); }

@@ -19,8 +19,10 @@ struct TsArgs {
     double t_div;
     const int64_t* offsets;
     int B, H, W;
-    int64_t begin, end;
-    unsigned long long* keys;    // [B][2][HW]
+    int g0, g1;                  // samples [g0, g1) of this group; their key slots are keys[(b - g0) * 2 * HW ...]
+    int64_t begin, end;          // event range of the group
+    int64_t n_total;
+    unsigned long long* keys;    // [group][2][HW], L2-resident
     unsigned int* bad;
 };
 
@@ -37,23 +39,59 @@ __device__ __forceinline__ double ts_time(const TsArgs& a, int64_t i) {
     return a.t_div != 1.0 ? v / a.t_div : v;
 }
 
-__global__ void __launch_bounds__(256) k_ts_scatter(TsArgs a) {
-    const int64_t i = a.begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.end) return;
-    int lo = 0, hi = a.B;
+__device__ __forceinline__ int ts_owner(const TsArgs& a, int64_t i) {
+    int lo = a.g0, hi = a.g1;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.offsets[mid] <= i) lo = mid; else hi = mid; }
-    const int64_t x = __double2ll_rz(load_as_double(a.x, a.xy_dtype, i)), y = __double2ll_rz(load_as_double(a.y, a.xy_dtype, i));
-    const double p = load_as_double(a.p, a.p_dtype, i);
-    if (x < 0 || x >= a.W || y < 0 || y >= a.H || !(p == 1.0 || p == 0.0 || p == -1.0)) { if (a.bad) atomicAdd(a.bad, 1u); return; }
+    return lo;
+}
+
+__device__ __forceinline__ void ts_put(const TsArgs& a, int b, int64_t x, int64_t y, double p, double t, unsigned& nbad) {
+    if (x < 0 || x >= a.W || y < 0 || y >= a.H || !(p == 1.0 || p == 0.0 || p == -1.0)) { ++nbad; return; }
     const int64_t HW = (int64_t)a.H * a.W;
-    atomicMax(a.keys + ((int64_t)lo * 2 + (p == 1.0 ? 0 : 1)) * HW + y * a.W + x, f64_key(ts_time(a, i)));
+    atomicMax(a.keys + ((int64_t)(b - a.g0) * 2 + (p == 1.0 ? 0 : 1)) * HW + y * a.W + x, f64_key(t));
+}
+
+// CANON: x,y u16 | t i64 or f64 | p u8, 16-byte aligned: 4 consecutive events per thread with vector loads
+template <bool CANON>
+__global__ void __launch_bounds__(256) k_ts_scatter(TsArgs a, int64_t n_quads) {
+    unsigned nbad = 0;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = a.begin / 4 * 4 + q * 4;
+        if (CANON && i0 >= a.begin && i0 + 4 <= a.end && i0 + 4 <= a.n_total) {
+            const uint2 xv = ld_stream(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(a.x) + i0));
+            const uint2 yv = ld_stream(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(a.y) + i0));
+            const uint32_t pv = ld_stream(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(a.p) + i0));
+            const longlong2 t0 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(a.t) + i0));
+            const longlong2 t1 = ld_stream(reinterpret_cast<const longlong2*>(static_cast<const int64_t*>(a.t) + i0 + 2));
+            const uint32_t xs[4] = {xv.x & 0xffffu, xv.x >> 16, xv.y & 0xffffu, xv.y >> 16};
+            const uint32_t ys[4] = {yv.x & 0xffffu, yv.x >> 16, yv.y & 0xffffu, yv.y >> 16};
+            const long long tr[4] = {t0.x, t0.y, t1.x, t1.y};
+            int b = ts_owner(a, i0);
+            int64_t b_end = a.offsets[b + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                while (i0 + j >= b_end) { ++b; b_end = a.offsets[b + 1]; }
+                double t = a.t_dtype == EP_I64 ? (double)tr[j] : __longlong_as_double(tr[j]);
+                if (a.t_div != 1.0) t /= a.t_div;
+                ts_put(a, b, xs[j], ys[j], (double)((pv >> (8 * j)) & 0xffu), t, nbad);
+            }
+        } else {
+            for (int j = 0; j < 4; ++j) {
+                const int64_t i = i0 + j;
+                if (i < a.begin || i >= a.end) continue;
+                ts_put(a, ts_owner(a, i), __double2ll_rz(load_as_double(a.x, a.xy_dtype, i)), __double2ll_rz(load_as_double(a.y, a.xy_dtype, i)),
+                       load_as_double(a.p, a.p_dtype, i), ts_time(a, i), nbad);
+            }
+        }
+    }
+    if (nbad && a.bad) atomicAdd(a.bad, nbad);
 }
 
 __global__ void __launch_bounds__(256) k_ts_finish(TsArgs a, double tau, const double* t_ref_opt, float* __restrict__ out) {
     const int64_t HW = (int64_t)a.H * a.W;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.B * 2 * HW) return;
-    const int b = (int)(idx / (2 * HW));
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // cell of the group
+    if (idx >= (int64_t)(a.g1 - a.g0) * 2 * HW) return;
+    const int b = a.g0 + (int)(idx / (2 * HW));
     const unsigned long long k = a.keys[idx];
     a.keys[idx] = 0ull;
     float r = 0.f;
@@ -62,8 +100,10 @@ __global__ void __launch_bounds__(256) k_ts_finish(TsArgs a, double tau, const d
         const double t_ref = t_ref_opt ? t_ref_opt[b] : ts_time(a, hi - 1);      // default: the sample's last row
         r = (float)exp(-(t_ref - key_f64(k)) / tau);
     }
-    st_stream(out + idx, r);
+    st_stream(out + (int64_t)a.g0 * 2 * HW + idx, r);
 }
+
+constexpr size_t kTsGroupBytes = (size_t)64 << 20;      // key slots kept in flight: L2-resident, like the binning accumulators
 
 }  // namespace
 }  // namespace ep
@@ -71,7 +111,12 @@ __global__ void __launch_bounds__(256) k_ts_finish(TsArgs a, double tau, const d
 extern "C" {
 
 size_t ep_time_surface_workspace_bytes(int batch, int height, int width) {
-    return batch > 0 && height > 0 && width > 0 ? ep::align_up(sizeof(unsigned long long) * (size_t)batch * 2 * height * width, 256) : 0;
+    if (!(batch > 0 && height > 0 && width > 0)) return 0;
+    const size_t per = sizeof(unsigned long long) * 2 * (size_t)height * width;
+    size_t g = ep::kTsGroupBytes / per;
+    if (g < 1) g = 1;
+    if (g > (size_t)batch) g = (size_t)batch;
+    return ep::align_up(per * g, 256);
 }
 
 int ep_time_surface(void* stream, const ep_events_soa* ev, int height, int width, double tau, const double* t_ref,
@@ -81,21 +126,35 @@ int ep_time_surface(void* stream, const ep_events_soa* ev, int height, int width
     if (!ev->offsets || !ev->offsets_host || !(ev->t_div != 0.0)) return EP_EINVAL;
     if (ev->t_base || ev->xy_dtype == EP_U32 || ev->t_dtype == EP_U32) return EP_EUNSUPPORTED;   // transport layouts: ep_bin_events only
     if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype)) return EP_EINVAL;
-    const size_t need = ep_time_surface_workspace_bytes(ev->batch, height, width);
-    if (workspace_bytes < need) return EP_EWORKSPACE;
+    const size_t per = sizeof(unsigned long long) * 2 * (size_t)height * width;
+    if (workspace_bytes < per) return EP_EWORKSPACE;
+    int G = (int)(workspace_bytes / per);
+    if ((size_t)G > kTsGroupBytes / per && kTsGroupBytes / per >= 1) G = (int)(kTsGroupBytes / per);
+    if (G > ev->batch) G = ev->batch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool canon = ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64) &&
+                       aligned16(ev->x) && aligned16(ev->y) && aligned16(ev->t) && aligned16(ev->p);
     TsArgs a{ev->x, ev->y, ev->t, ev->p, ev->xy_dtype, ev->t_dtype, ev->p_dtype, ev->t_div, ev->offsets, ev->batch, height, width,
-             ev->offsets_host[0], ev->offsets_host[ev->batch], static_cast<unsigned long long*>(workspace), bad_count};
-    cudaError_t ce = cudaMemsetAsync(workspace, 0, need, st);
+             0, 0, 0, 0, ev->offsets_host[ev->batch], static_cast<unsigned long long*>(workspace), bad_count};
+    cudaError_t ce = cudaMemsetAsync(workspace, 0, per * (size_t)G, st);
     if (ce != cudaSuccess) return (int)ce;
-    const int64_t n = a.end - a.begin;
-    if (n > 0) {
-        k_ts_scatter<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a);
+    for (int g0 = 0; g0 < ev->batch; g0 += G) {
+        a.g0 = g0;
+        a.g1 = g0 + G < ev->batch ? g0 + G : ev->batch;
+        a.begin = ev->offsets_host[a.g0];
+        a.end = ev->offsets_host[a.g1];
+        const int64_t n_quads = a.end > a.begin ? ceil_div64(a.end - a.begin / 4 * 4, 4) : 0;
+        if (n_quads > 0) {
+            const int64_t blocks = ceil_div64(n_quads, 256), cap = (int64_t)kNumSMs * 8;
+            const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+            if (canon) k_ts_scatter<true><<<grid, 256, 0, st>>>(a, n_quads);
+            else k_ts_scatter<false><<<grid, 256, 0, st>>>(a, n_quads);
+            EP_LAUNCH_CHECK();
+        }
+        const int64_t cells = (int64_t)(a.g1 - a.g0) * 2 * height * width;
+        k_ts_finish<<<(unsigned)ceil_div64(cells, 256), 256, 0, st>>>(a, tau, t_ref, out);
         EP_LAUNCH_CHECK();
     }
-    const int64_t cells = (int64_t)ev->batch * 2 * height * width;
-    k_ts_finish<<<(unsigned)ceil_div64(cells, 256), 256, 0, st>>>(a, tau, t_ref, out);
-    EP_LAUNCH_CHECK();
     return EP_OK;
 }
 
