@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(kThreads) k_finalize_count(BinArgs a, float* _
 // ---- host side ----------------------------------------------------------------------------------------
 struct SlotLayout {
     size_t meta_bytes, vox_bytes, cnt_bytes, slot_bytes;
+    size_t touched_bytes;      // of a slot, in a normal run: the last interval's plane is neither written nor read (time-sorted input)
 };
 
 SlotLayout slot_layout(const ep_bin_params* p, int B) {
@@ -315,13 +316,15 @@ SlotLayout slot_layout(const ep_bin_params* p, int B) {
     s.vox_bytes = align_up(p->num_bins > 0 ? HW * p->num_bins * sizeof(unsigned long long) : 0, 256);
     s.cnt_bytes = align_up(p->count_channels > 0 ? HW * 3 * sizeof(uint32_t) : 0, 256);
     s.slot_bytes = s.vox_bytes + s.cnt_bytes;
+    s.touched_bytes = s.slot_bytes - (p->num_bins >= 2 ? HW * sizeof(unsigned long long) : 0);
     return s;
 }
 
 size_t l2_group_budget() {
-    // accumulator bytes kept in flight per group: 64 MB measured best on B200 (40 -> 78, 64 -> 84, 96 -> 71 Gev/s)
+    // accumulator bytes a group touches, kept L2-resident: measured on B200 with the bench workload (5 samples = 49 MB -> 97.2,
+    // 6 = 59 MB -> 99.1, 7 = 69 MB -> 93.1, 8 = 79 MB -> 86.5 Gev/s)
     const char* e = getenv("EP_L2_GROUP_MB");
-    long mb = e ? atol(e) : 64;
+    long mb = e ? atol(e) : 60;
     if (mb < 1) mb = 1;
     return (size_t)mb << 20;
 }
@@ -362,7 +365,7 @@ int run_binning(cudaStream_t st, Loader ld, const int64_t* off_dev, const int64_
     if ((reinterpret_cast<uintptr_t>(out_voxel) & 7u) || (reinterpret_cast<uintptr_t>(out_sum) & 7u)) return EP_EALIGN;
     int G = (int)((ws_bytes - L.meta_bytes) / L.slot_bytes);
     const size_t budget = l2_group_budget();
-    const int g_l2 = (int)(budget / L.slot_bytes) > 0 ? (int)(budget / L.slot_bytes) : 1;
+    const int g_l2 = (int)(budget / L.touched_bytes) > 0 ? (int)(budget / L.touched_bytes) : 1;
     if (G > g_l2) G = g_l2;
     if (G > B) G = B;
     if (G > 65535) G = 65535;
@@ -465,7 +468,7 @@ size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch, size_t
     if (ep::check_params(prm) != EP_OK || batch <= 0) { if (min_bytes) *min_bytes = 0; return 0; }
     const ep::SlotLayout L = ep::slot_layout(prm, batch);
     if (min_bytes) *min_bytes = L.meta_bytes + L.slot_bytes;
-    size_t g = ep::l2_group_budget() / L.slot_bytes;
+    size_t g = ep::l2_group_budget() / L.touched_bytes;
     if (g < 1) g = 1;
     if (g > (size_t)batch) g = (size_t)batch;
     return L.meta_bytes + g * L.slot_bytes;
