@@ -104,32 +104,37 @@ class GroupingModule:
         return attn_mask, rel_pos_idx
 
     def _prepare_grouping(self, coords):
-        group_id = self._get_group_id(coords)
-        idx_merge = torch.argsort(group_id, stable=True)
-        group_id = group_id[idx_merge].contiguous()
-        exact_win_sz = torch.unique_consecutive(group_id, return_counts=True)[1].tolist()
+        # The index bookkeeping runs on the host in numpy (the coordinates are a few KB; one small D2H copy instead of a
+        # chain of tiny device ops and a .tolist() sync), the DP in native code; only the final index / mask tensors go
+        # back to the device, where the two (nG, GS, GS) tables are built.
+        dev = coords.device
+        ch = coords[0].detach().cpu().numpy().astype(np.int64)                       # (N_vis, 2)
+        g = (ch + (self.window_size - self.shift_size) % self.window_size) // self.window_size
+        group_id = g[:, 0] * ch.shape[0] + g[:, 1]                                    # :366 (the multiplier is N_vis, as in the reference)
+        idx_merge = np.argsort(group_id, kind="stable")
+        gid_sorted = group_id[idx_merge]
+        change = np.flatnonzero(np.diff(gid_sorted)) + 1
+        starts = np.concatenate([[0], change, [gid_sorted.shape[0]]]).astype(np.int64)
+        exact_win_sz = np.diff(starts).tolist()
         self.group_size = min(self.window_size ** 2, max(exact_win_sz))
-        num_ele_group, grouped_idx = group_windows(self.group_size, exact_win_sz)        # native DP
-        # window w holds idx_merge[start[w] : start[w] + exact_win_sz[w]]: build the padded shuffle in one pass on the host
-        starts = np.concatenate([[0], np.cumsum(exact_win_sz)]).astype(np.int64)
+        num_ele_group, grouped_idx = group_windows(self.group_size, exact_win_sz)     # native DP
         GS, nG = self.group_size, len(num_ele_group)
         src = np.full(nG * GS, -1, np.int64)                  # position in idx_merge of every slot, -1 = padding
-        for g, gidx in enumerate(grouped_idx):
-            at = g * GS
+        for gi, gidx in enumerate(grouped_idx):
+            at = gi * GS
             for w in gidx:
                 n = exact_win_sz[w]
                 src[at:at + n] = np.arange(starts[w], starts[w] + n)
                 at += n
-        src_t = torch.from_numpy(src).to(coords.device)
-        pad = src_t < 0
-        safe = src_t.clamp(min=0)
-        idx_shuffle = torch.where(pad, torch.full_like(src_t, -1), idx_merge[safe])
-        amask = torch.where(pad, torch.full_like(src_t, -1), group_id[safe]).reshape(nG, GS)
-        self.idx_unshuffle = torch.argsort(idx_shuffle, stable=True)[-sum(num_ele_group):]
-        idx_shuffle = torch.where(pad, torch.zeros_like(idx_shuffle), idx_shuffle)   # index_select does not permit negative index
-        self.idx_shuffle = idx_shuffle
-        attn_mask = self._get_attn_mask(amask)
-        coords_shuffled = coords[0][self.idx_shuffle].reshape(-1, self.group_size, 2)
+        pad = src < 0
+        idx_shuffle = np.where(pad, -1, idx_merge[np.maximum(src, 0)])
+        amask = np.where(pad, -1, gid_sorted[np.maximum(src, 0)]).reshape(nG, GS)
+        idx_unshuffle = np.argsort(idx_shuffle, kind="stable")[-sum(num_ele_group):]
+        idx_shuffle = np.where(pad, 0, idx_shuffle)           # index_select does not permit negative index
+        self.idx_shuffle = torch.from_numpy(idx_shuffle).to(dev)
+        self.idx_unshuffle = torch.from_numpy(np.ascontiguousarray(idx_unshuffle)).to(dev)
+        attn_mask = self._get_attn_mask(torch.from_numpy(amask).to(dev))
+        coords_shuffled = torch.from_numpy(ch[idx_shuffle].reshape(-1, GS, 2)).to(dev)
         rel_pos_idx = self._get_rel_pos_idx(coords_shuffled)
         rel_pos_mask = torch.ones_like(rel_pos_idx).masked_fill_(attn_mask.bool(), 0)
         return attn_mask, rel_pos_idx * rel_pos_mask

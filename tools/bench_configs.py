@@ -151,7 +151,65 @@ def c5():
     report("C5 Swin apply_mask (512,3136,96)->(512,768,96)", ms, B * 2 * 4 * 768 * 96, B, "samples", launches=2)
 
 
+def f_rows():
+    """SURVEY.md §8(f) "next" rows that are built: f1 view augmentation, f3 decoder un-shuffle + fused patch loss, f4 Swin grouping."""
+    from types import SimpleNamespace
+    from eventpretrain_b200.view_augment import ViewChoice
+    B, C, H, W = 256, 5, 480, 640
+    x = torch.randn(B, C, H, W, device=dev)
+    rng = np.random.default_rng(7)
+    choices = []
+    for _ in range(B):
+        cw, ch = int(rng.integers(500, 640)), int(rng.integers(380, 480))
+        choices.append(ViewChoice(int(rng.integers(0, W - cw + 1)), int(rng.integers(0, H - ch + 1)), cw, ch, bool(rng.integers(0, 2)),
+                                  bool(rng.integers(0, 2)), bool(rng.integers(0, 2))))
+    touched = sum(c.crop_w * c.crop_h for c in choices) * C * 4
+    for mode in ("nearest", "bilinear"):
+        ms = timeit(lambda: ep.apply_views(x, choices, (224, 224), mode), reps=20)
+        report(f"f1 evg_augment batch (256,5,480,640) -> crop -> {mode} 224x224 -> flips (one launch)", ms,
+               (touched if mode != "nearest" else B * C * 224 * 224 * 4) + B * C * 224 * 224 * 4, B, "samples", launches=1)
+    fr = torch.randn(B, 1, H, W, device=dev)
+    ms = timeit(lambda: ep.apply_views(fr, choices, (224, 224), "bicubic"), reps=20)
+    report("f1 frame_augment batch (256,1,480,640) -> crop -> bicubic 224x224 -> flip/negate", ms,
+           touched // C + B * 224 * 224 * 4, B, "samples", launches=1)
+    Bm, L, K, D = 128, 196, 49, 256
+    emb = torch.randn(Bm, K, D, device=dev)
+    mt = torch.randn(1, 1, D, device=dev)
+    pos = torch.randn(1, L, D, device=dev)
+    ids_restore = torch.argsort(torch.rand(Bm, L, device=dev), 1)
+    ms = timeit(lambda: ep.unshuffle_tokens(emb, mt, ids_restore, pos))
+    report("f3 decoder un-shuffle (128,49,256) + mask token + pos -> (128,196,256)", ms, Bm * 4 * (K * D + L * D) + 4 * L * D, Bm, "samples", launches=1)
+    pred = torch.randn(Bm, L, 256, device=dev)
+    sub = torch.randn(Bm, 1, 224, 224, device=dev)
+    ms = timeit(lambda: ep.target_patch_loss(pred, sub, 16))
+    report("f3 fused target (patchify + norm_pix) + per-patch MSE (128,196,256)", ms, Bm * 4 * (224 * 224 + L * 256 + L), Bm, "samples", launches=1)
+    # f4: grouping plan of a fresh mask (host DP in native code + torch index ops), then the cached call
+    keep = 24
+    m = torch.zeros(49)
+    m[torch.randperm(49)[:49 - keep]] = 1
+    mm = m.reshape(7, 7)[:, None, :, None].expand(7, 8, 7, 8).reshape(-1).bool()
+    ii, jj = torch.meshgrid(torch.arange(56), torch.arange(56), indexing="ij")
+    coords = torch.stack([ii, jj], -1).reshape(1, -1, 2)[:, ~mm].to(dev)
+    t0 = time.perf_counter()
+    for i in range(20):
+        ep.GroupingModule._cache.clear()
+        ep.GroupingModule(7, 3).prepare(coords, coords.shape[1])
+    torch.cuda.synchronize()
+    fresh = (time.perf_counter() - t0) / 20 * 1e3
+    t0 = time.perf_counter()
+    for i in range(200):
+        ep.GroupingModule(7, 3).prepare(coords, coords.shape[1])
+    cached = (time.perf_counter() - t0) / 200 * 1e3
+    wt = [24] * 48 + [12] * 16
+    t0 = time.perf_counter()
+    for i in range(200):
+        ep.group_windows(49, wt)
+    dp = (time.perf_counter() - t0) / 200 * 1e3
+    print(json.dumps({"config": "f4 Swin GroupingModule.prepare, 1536 visible tokens, window 7 shift 3 (host wall time)",
+                      "ms_fresh_mask": fresh, "ms_cached_mask": cached, "ms_native_group_windows_64_windows": dp}), flush=True)
+
+
 if __name__ == "__main__":
-    for f in (c1, c3, c4, c5):
+    for f in (c1, c3, c4, c5, f_rows):
         f()
         torch.cuda.empty_cache()
