@@ -529,7 +529,7 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
                        aligned16(ev->t) && aligned16(ev->p);
     if ((canon || compact) && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
         // Route + banded shared-memory sweep (ep_binning_banded.cu), on request.  Measured on B200 it is
-        // 4-8 % faster than the global-RED kernels when the events are spread evenly over the sensor and 15-20 % slower
+        // on par with the global-RED kernels when the events are spread evenly over the sensor and ~30 % slower
         // when they sit on edges and hot pixels, so the global-RED kernels, which do not care, stay the default.
         if ((prm->flags & EP_BIN_FORCE_BANDED) || (banded_auto() && banded_worthwhile(ev, prm))) {
             rc = run_banded_canon(st, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count);
