@@ -191,7 +191,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "Gevents/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Gevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -201,8 +201,6 @@ def run_ours(args):
     from eventpretrain_b200 import _lib
     from eventpretrain_b200.dist import init_from_env
 
-    # stdout carries exactly one JSON line: NCCL's banner / debug output (printed at WARN level and above) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU port)")
@@ -450,13 +448,32 @@ def run_ours(args):
                            "cache": f"inputs ({host_gb:.1f} GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"shard-by-sample x{world}, no data-path collective", "method": args.method},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner, for one)
+    # is sent to stderr by pointing fd 1 at fd 2 for the lifetime of the process; emit() writes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
