@@ -1,23 +1,24 @@
-// Stage 1, fast path — route + banded shared-memory sweep (sm_100a).
+// Stage 1, second path (opt-in, method "banded") — route + banded shared-memory sweep (sm_100a).
 //
 // Same arithmetic and outputs as ep_binning.cu (events_to_voxel_grid.py:4-61, events_to_image.py:6-62), bit for bit,
-// but no global atomics and no accumulator round trip through L2:
+// but no global atomics and no accumulator round trip through L2.  Measured on B200 it matches the global-RED kernels on
+// evenly spread events and is ~30 % slower on edge-concentrated ones, which is why it is not the default.
 //
 //   route  (k_route)   one pass over the events of a sample group.  A CTA takes a chunk of 4096 consecutive events of one
-//                      sample: pass A histograms them by spatial band (shared-memory RED), a scan turns the histogram
-//                      into cursors, pass B computes per event (cell, interval k, r = rn(d * 2^24), polarity) — integer
+//                      sample: pass A histograms them by band (shared-memory RED), a scan turns the histogram into
+//                      cursors, pass B computes per event (cell, interval k, r = rn(d * 2^24), polarity) — integer
 //                      fixed-point time arithmetic for tick stamps (ticks_to_v) — and claims a slot with one returning
 //                      ATOMS; the chunk goes back to global memory sorted by band, coalesced, as 8-byte records
-//                      {cell, r | k << 25 | negative << 31}, plus one (begin, end) entry per band.  The record buffer
-//                      of a group is sized to stay L2-resident.
-//   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks and own the band's cells for a window of up to 6 voxel
-//                      planes in shared memory: int32 Q24 planes + one count word per cell.  A warp takes the band's run
-//                      of one chunk at a time (the next run's rows already in flight); per record: two fire-and-forget
-//                      ATOMS.ADD on the planes k and k + 1 (p * (2^24 - r), p * r) and one on the count word
-//                      (n_pos | n_neg << 16).  The flush converts
-//                      the planes to fp32 (one rounding from the exact integer), adds the fused voxel.sum(0) plane and
-//                      the polarity count frame, and writes every output element exactly once with 16-byte streaming
-//                      stores.
+//                      {cell in band, r | k << 25 | negative << 31}, plus one (begin, end) entry per band.  The record
+//                      buffer of a group is sized to stay L2-resident.
+//   bands              are row-cyclic (band b owns rows b, b + nb, ...): dense image regions are dealt out over all bands.
+//   sweep  (k_sweep)   persistent CTAs take (sample, band) tasks from an atomic counter and own the band's cells for a
+//                      window of up to 6 voxel planes in shared memory: int32 Q24 planes + one count word per cell.  A
+//                      warp takes the band's run of one chunk at a time (the next run's rows already in flight); per
+//                      record: one returning ATOMS on the count word (n_pos | n_neg << 16) and two fire-and-forget
+//                      ATOMS.ADD on the planes k and k + 1 (p * (2^24 - r), p * r).  The flush converts the planes to
+//                      fp32 (one rounding from the exact integer), adds the fused voxel.sum(0) plane and the polarity
+//                      count frame, and writes every output element exactly once with 16-byte streaming stores.
 //   Routes run on the caller's stream and sweeps on a side stream, so the route of group g + 1 fills the SMs the sweep
 //   of group g leaves idle.
 //
@@ -487,7 +488,9 @@ cudaError_t launch_route(cudaStream_t st, const RouteSrc& src, const BandArgs& g
 // ---- sweep ------------------------------------------------------------------------------------------------
 struct Window { int q0, q1; };   // voxel planes [q0, q1) held in shared memory
 
-// mode 0: int32 planes + count word (fast); mode 1: hi/lo split planes (exact for any count); mode 2: count word only
+// Rare passes of a task, written for clarity rather than speed (the steady state is accumulate_fast below):
+// mode 1: hi/lo split planes (exact for any count); mode 2: count word only (count frame of a multi-window task).
+// (mode 0, int32 planes + count word without the dense-cell side table, is kept for reference and unused.)
 template <int MODE, int THREADS>
 __device__ __forceinline__ unsigned accumulate(const BandArgs& g, Window w, bool count_all, bool filter, int band,
                                                int64_t band_base, int ch0, int nch, uint32_t* s_run, uint16_t* s_kk,
@@ -745,10 +748,6 @@ __device__ __forceinline__ int64_t out_offset(const BandArgs& g, int band, int c
     const uint32_t q = __umulhi((uint32_t)c, g.w_magic) >> g.w_shift;
     return (int64_t)(q * (uint32_t)g.nb + (uint32_t)band) * g.bin.W + ((uint32_t)c - q * (uint32_t)g.bin.W);
 }
-
-template <int VEC> struct VecF;
-template <> struct VecF<4> { typedef float4 type; typedef uint4 utype; };
-template <> struct VecF<1> { typedef float type; typedef uint32_t utype; };
 
 template <int VEC>
 __device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
@@ -1019,7 +1018,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_sweep(BandArgs g, int n_tasks, i
 
 // ---- host side ----------------------------------------------------------------------------------------------
 struct BandPlan {
-    int nb, cpb, P, chunk, route_threads;
+    int nb, cpb, P, chunk;
     uint32_t w_magic, w_shift, nb_magic, nb_shift;
     int slot_words;
     size_t sweep_smem;
@@ -1091,7 +1090,6 @@ bool plan_bands(const ep_bin_params* p, int batch, int64_t n_events, BandPlan* b
     bp->slot_words = words_per_cell * bp->cpb;
     bp->sweep_smem = (size_t)bp->slot_words * 4 + table_bytes;
     bp->chunk = 4096;
-    bp->route_threads = 256;
     return true;
 }
 
