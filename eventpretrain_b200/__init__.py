@@ -16,6 +16,7 @@ from .masking import (block_mask_expand, convvit_keep_masks, gather_tokens, len_
                       mask_from_noise, patch_density, random_masking, swin_apply_mask, unshuffle_tokens)
 from .pipeline import MaskedInputPipeline  # noqa: F401
 from .swin_grouping import GroupingModule, group_windows, knapsack, patch_merging_order  # noqa: F401
+from .readers import pack_soa, read_ddd17_memmap, read_nimagenet_npz  # noqa: F401
 from .reshape import (diffmap_frames, frame2emb, patchify_gather, reconstruct_loss, target_normpix,  # noqa: F401
                       target_patch_loss)
 
