@@ -364,6 +364,11 @@ int ep_patchify_gather(void* stream, const float* x, const int64_t* ids_keep, in
     if (rows > 0x7fffffffLL) return EP_EUNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = (patch % 4 == 0) && (width % 4 == 0) && ep::aligned16(x) && ep::aligned16(out);
+    if (order == EP_ORDER_CPQ && !ep::patch_tma_disabled()) {
+        // TMA form (csrc/ep_patch_tma.cu): box load of the (p, p, C) patch, bulk store of the finished row
+        const int rc = ep::patchify_gather_tma(st, x, ids_keep, batch, channels, height, width, patch, K, out);
+        if (rc == EP_OK) { EP_LAUNCH_CHECK(); return EP_OK; }
+    }
     if (order == EP_ORDER_CPQ) {
         if (vec) ep::k_patchify_gather<EP_ORDER_CPQ, true><<<(unsigned)rows, 128, 0, st>>>(x, ids_keep, channels, height, width, patch, K, out);
         else ep::k_patchify_gather<EP_ORDER_CPQ, false><<<(unsigned)rows, 128, 0, st>>>(x, ids_keep, channels, height, width, patch, K, out);

@@ -100,6 +100,28 @@ def test_patchify_gather_commutes_with_patch_embed(ep):
     assert torch.equal(patches, torch.gather(unf, 1, ik[..., None].repeat(1, 1, unf.shape[-1])))
 
 
+def test_patchify_gather_tma_form_is_identical():
+    """EP_PATCH_TMA=1 routes the (c,ph,pw) gather through the TMA box-load / bulk-store kernel (csrc/ep_patch_tma.cu);
+    the switch is read once per process, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, eventpretrain_b200 as ep\n"
+        "torch.manual_seed(1)\n"
+        "for (B, C, H, W, p, K) in [(3, 5, 224, 224, 16, 49), (2, 1, 64, 96, 8, 10), (5, 3, 32, 32, 4, 64), (130, 2, 64, 64, 16, 5)]:\n"
+        "    x = torch.randn(B, C, H, W, device='cuda'); L = (H // p) * (W // p)\n"
+        "    ids = torch.stack([torch.randperm(L, device='cuda')[:K] for _ in range(B)]) if K < L else None\n"
+        "    unf = torch.nn.functional.unfold(x, p, stride=p).permute(0, 2, 1)\n"
+        "    ref = unf if ids is None else torch.gather(unf, 1, ids[..., None].repeat(1, 1, unf.shape[-1]))\n"
+        "    assert torch.equal(ep.patchify_gather(x, p, ids, 'cpq'), ref), (B, C, H, W, p, K)\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EP_PATCH_TMA="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_convvit_masks(ep, golden_stage3):
     c = golden_stage3["convvit_masks"]
     _, m, _ = ep.mask_from_noise(cu(c["noise"]), 49)
