@@ -226,6 +226,76 @@ __global__ void __launch_bounds__(256) k_patch_target(const float* __restrict__ 
     }
 }
 
+// Single-channel frames (the reference's sub_frame target, pr_ef_imagenet_dataset.py:167-173) with p in {8,16,32}: (ph,pw,c)
+// order is then plain row-major inside the patch, so a warp moves its patch as 16-byte vectors held in registers — no
+// staging, no index divisions; mean / unbiased variance are the same two-pass reductions as above.
+template <int P, bool LOSS>
+__global__ void __launch_bounds__(256) k_patch_target_c1(const float* __restrict__ frame, const float* __restrict__ pred,
+                                                         int64_t patches, int H, int W, int norm_pix, float eps,
+                                                         float* __restrict__ out) {
+    constexpr int P4 = P / 4, NV = P * P4, V = (NV + 31) / 32, n = P * P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= patches) return;
+    const int gw = W / P, L = (H / P) * gw;
+    const int64_t b = row / L;
+    const int l = (int)(row % L);
+    const float* base = frame + b * (int64_t)H * W + (int64_t)((l / gw) * P) * W + (l % gw) * P;
+    float4 v[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int f = lane + 32 * j;
+        v[j] = (NV % 32 == 0 || f < NV) ? ld_stream(reinterpret_cast<const float4*>(base + (int64_t)(f / P4) * W) + (f % P4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 pr[V];
+    if (LOSS) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int f = lane + 32 * j;
+            pr[j] = (NV % 32 == 0 || f < NV) ? ld_stream(reinterpret_cast<const float4*>(pred + row * n) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float mean = 0.f, sd = 1.f;
+    if (norm_pix) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        sum = warp_reduce(sum, [](float a, float c) { return a + c; });
+        mean = sum / (float)n;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (NV % 32 == 0 || lane + 32 * j < NV) {
+                const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+                ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+        }
+        ss = warp_reduce(ss, [](float a, float c) { return a + c; });
+        sd = sqrtf(ss / (float)(n - 1) + eps);          // torch.var default: unbiased; (var + 1e-6) ** .5
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+            v[j] = make_float4((v[j].x - mean) / sd, (v[j].y - mean) / sd, (v[j].z - mean) / sd, (v[j].w - mean) / sd);
+    }
+    if (LOSS) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (NV % 32 == 0 || lane + 32 * j < NV) {
+                const float d0 = pr[j].x - v[j].x, d1 = pr[j].y - v[j].y, d2 = pr[j].z - v[j].z, d3 = pr[j].w - v[j].w;
+                acc += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+        }
+        acc = warp_reduce(acc, [](float a, float c) { return a + c; });
+        if (lane == 0) out[row] = acc / (float)n;
+    } else {
+        float4* o = reinterpret_cast<float4*>(out + row * n);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+            if (NV % 32 == 0 || lane + 32 * j < NV) st_stream(o + lane + 32 * j, v[j]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ConvViT block masks   model/backbone/convvit.py:129-130,142-143
 // ---------------------------------------------------------------------------------------------------
@@ -390,6 +460,16 @@ static int launch_patch_target(void* stream, bool loss, const float* frame, cons
     const int64_t patches = (int64_t)batch * (height / patch) * (width / patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned blocks = (unsigned)ep::ceil_div64(patches, warps);
+    if (channels == 1 && (patch == 8 || patch == 16 || patch == 32) && width % 4 == 0 && ep::aligned16(frame) && ep::aligned16(out) &&
+        (!loss || ep::aligned16(pred))) {
+#define EP_TARGET_C1(P)                                                                                                            \
+    if (loss) ep::k_patch_target_c1<P, true><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, out); \
+    else ep::k_patch_target_c1<P, false><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, out)
+        if (patch == 8) { EP_TARGET_C1(8); } else if (patch == 16) { EP_TARGET_C1(16); } else { EP_TARGET_C1(32); }
+#undef EP_TARGET_C1
+        EP_LAUNCH_CHECK();
+        return EP_OK;
+    }
     if (loss) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(ep::k_patch_target<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ep::k_patch_target<true><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, out);

@@ -2,7 +2,8 @@
 
 At ViT-S/16 sizes every stage-3 kernel runs for a few microseconds, so a Python call per kernel is launch-bound.
 `MaskedInputPipeline` captures mask -> visible-patch gather -> patchified normalised target into a CUDA graph over
-static buffers; `run()` is a single graph launch.
+static buffers; `run()` is a single graph launch.  The target depends only on the frame, so it is captured on a forked
+stream: in the graph it is a parallel branch beside mask -> gather, and the step costs the longer branch, not the sum.
 """
 import torch
 
@@ -23,12 +24,17 @@ class MaskedInputPipeline:
         self.sub_frame = torch.zeros(batch, target_channels, H, W, device=dev)
         self.out = None
         self.graph = None
+        self._side = torch.cuda.Stream(device=dev)
         self._warm(dev)
 
     def _body(self):
+        main = torch.cuda.current_stream(self.x.device)
+        self._side.wait_stream(main)                       # fork
+        with torch.cuda.stream(self._side):
+            target = target_normpix(self.sub_frame, self.patch, self.norm)
         ids_keep, mask, ids_restore = mask_from_noise(self.noise, self.keep)
         patches = patchify_gather(self.x, self.patch, ids_keep, self.order)
-        target = target_normpix(self.sub_frame, self.patch, self.norm)
+        main.wait_stream(self._side)                       # join
         return {"ids_keep": ids_keep, "mask": mask, "ids_restore": ids_restore, "visible_patches": patches, "target": target}
 
     def _warm(self, dev):

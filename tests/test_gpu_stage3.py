@@ -168,6 +168,22 @@ def test_target(ep, golden_stage3, p, L):
     np.testing.assert_allclose(ep.target_patch_loss(pr, f, p, True).cpu().numpy()[sel], ref[sel], rtol=2e-5)
 
 
+@pytest.mark.parametrize("C,p,H,W", [(1, 8, 64, 96), (1, 16, 224, 224), (1, 32, 224, 224), (1, 4, 32, 48), (3, 8, 64, 64), (1, 16, 64, 80), (2, 16, 32, 32)])
+def test_target_vector_and_staged_kernels_agree_with_torch(ep, C, p, H, W):
+    """Single-channel p in {8,16,32} takes the register/float4 kernel, everything else the staged one; both against the
+    reference formulation (utils/reshape.py:15-22, pr_hub_model.py:126-131) in torch."""
+    torch.manual_seed(7)
+    frame = torch.randn(5, C, H, W, device="cuda") * 3 + 1
+    gh, gw = H // p, W // p
+    emb = torch.einsum("bchpwq->bhwpqc", frame.reshape(5, C, gh, p, gw, p)).reshape(5, gh * gw, p * p * C)
+    assert torch.equal(ep.target_normpix(frame, p, False), emb)
+    ref = (emb - emb.mean(-1, keepdim=True)) / (emb.var(-1, keepdim=True) + 1e-6) ** .5
+    got = ep.target_normpix(frame, p, True)
+    assert torch.all((got - ref).abs() <= 1e-5 * ref.abs() + 1e-6)
+    pred = torch.randn_like(ref)
+    torch.testing.assert_close(ep.target_patch_loss(pred, frame, p, True), ((pred - ref) ** 2).mean(-1), rtol=2e-5, atol=1e-6)
+
+
 def test_frame2emb_multichannel(ep, golden_stage3):
     c = golden_stage3["frame2emb_c3"]
     assert np.array_equal(ep.frame2emb(8, cu(hash_uniform((2, 3, 64, 64), 3700))).cpu().numpy(), c["emb"])
