@@ -226,48 +226,54 @@ __device__ __forceinline__ void finalize_voxel_block(const BinArgs& a, float* __
     float sum[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { a_prev[v] = 0; sum[v] = 0.f; }
-    unsigned long long* acc = a.vox_acc + (int64_t)slot * B * HW + pix;
+    unsigned long long* acc = a.vox_acc + (int64_t)slot * B * HW + pix;      // walks plane by plane
     float* o = out_voxel + (int64_t)b * B * HW + pix;
+    uint32_t ovf = 0;
     for (int k0 = 0; k0 < B; k0 += kFinChunk) {
         unsigned long long w[kFinChunk][VEC];
+        {
+            const unsigned long long* src = acc;
 #pragma unroll
-        for (int j = 0; j < kFinChunk; ++j) {
-            const int k = k0 + j;
-            if (k < n_planes) {
-                if (VEC == 2) {
-                    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(acc + (int64_t)k * HW);
-                    w[j][0] = q.x; w[j][VEC - 1] = q.y;
+            for (int j = 0; j < kFinChunk; ++j, src += HW) {
+                if (k0 + j < n_planes) {
+                    if (VEC == 2) {
+                        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(src);
+                        w[j][0] = q.x; w[j][VEC - 1] = q.y;
+                    } else {
+                        w[j][0] = *src;
+                    }
                 } else {
-                    w[j][0] = acc[(int64_t)k * HW];
-                }
-            } else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) w[j][v] = 0ull;
+                    for (int v = 0; v < VEC; ++v) w[j][v] = 0ull;
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < kFinChunk; ++j) {
-            const int k = k0 + j;
-            if (k >= B) break;
-            if (k < n_planes && (w[j][0] | w[j][VEC - 1]) != 0ull) {   // sparse grids: most words are still zero
-                if (VEC == 2) *reinterpret_cast<ulonglong2*>(acc + (int64_t)k * HW) = make_ulonglong2(0ull, 0ull);
-                else acc[(int64_t)k * HW] = 0ull;
+        for (int j = 0; j < kFinChunk; ++j, acc += HW, o += HW) {
+            if (k0 + j >= B) break;
+            if ((w[j][0] | w[j][VEC - 1]) != 0ull) {   // sparse grids: most words are still zero (planes past n_planes read as zero)
+                if (VEC == 2) *reinterpret_cast<ulonglong2*>(acc) = make_ulonglong2(0ull, 0ull);
+                else *acc = 0ull;
             }
             float r[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const long long A = ((long long)(w[j][v] << (64 - kABits))) >> (64 - kABits);
-                const long long C = ((long long)(w[j][v] - (unsigned long long)A)) >> kABits;
-                if ((C >= (1ll << 18) || C < -(1ll << 18)) && a.bad_count) atomicOr(a.bad_count, 0x80000000u);
-                const long long val = C * (1ll << kQ) - A + a_prev[v];
+                // w = C * 2^44 + A with A the signed low 44 bits: the low words of w and A coincide, so C comes from the high words alone
+                const uint32_t w_lo = (uint32_t)w[j][v], w_hi = (uint32_t)(w[j][v] >> 32);
+                const int32_t a_hi = (int32_t)(w_hi << (64 - kABits)) >> (64 - kABits);
+                const int32_t C = (int32_t)(w_hi - (uint32_t)a_hi) >> (kABits - 32);
+                ovf |= (uint32_t)(C + (1 << 18)) >> 19;                          // |C| >= 2^18: reported once per thread below
+                const long long A = (long long)(((unsigned long long)(uint32_t)a_hi << 32) | w_lo);
+                const long long val = ((long long)C << kQ) - A + a_prev[v];
                 a_prev[v] = A;
                 r[v] = __ll2float_rn(val) * (1.0f / 16777216.0f);
                 sum[v] += r[v];    // voxel.sum(dim=0): sequential fp32 over bins
             }
-            if (VEC == 2) st_stream(reinterpret_cast<float2*>(o + (int64_t)k * HW), make_float2(r[0], r[VEC - 1]));
-            else st_stream(o + (int64_t)k * HW, r[0]);
+            if (VEC == 2) st_stream(reinterpret_cast<float2*>(o), make_float2(r[0], r[VEC - 1]));
+            else st_stream(o, r[0]);
         }
     }
+    if (ovf && a.bad_count) atomicOr(a.bad_count, 0x80000000u);
     if (out_sum) {
         float* s = out_sum + (int64_t)b * HW + pix;
         if (VEC == 2) st_stream(reinterpret_cast<float2*>(s), make_float2(sum[0], sum[VEC - 1]));
