@@ -302,8 +302,11 @@ __device__ __forceinline__ void finalize_count_block(const BinArgs& a, float* __
 // (An experiment that ran the finalize of group g-1 as interleaved CTAs of the scatter launch of group g, with
 // ping-pong accumulator slots, did not help: 3.12 ms vs 3.05 ms per step — both halves are limited by the same L2,
 // see DESIGN.md §3.  The two stay separate launches.)
+#ifndef EP_SCATTER_MINB
+#define EP_SCATTER_MINB 4      // 64 registers
+#endif
 template <class Loader>
-__global__ void __launch_bounds__(kThreads) k_scatter(Loader ld, BinArgs a) {
+__global__ void __launch_bounds__(kThreads, EP_SCATTER_MINB) k_scatter(Loader ld, BinArgs a) {
     scatter_tiles<Loader>(ld, a, blockIdx.x, gridDim.x);
 }
 
