@@ -14,6 +14,7 @@ EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64, EP_U32 = range(1, 
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
 EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_BANDED = 1, 2
+EP_EINVAL, EP_EWORKSPACE, EP_EUNSUPPORTED, EP_EALIGN = -1, -2, -3, -4
 EP_RESIZE_NEAREST, EP_RESIZE_BILINEAR, EP_RESIZE_BICUBIC = 0, 1, 2
 
 c_void_p, c_int, c_int64, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
@@ -74,6 +75,10 @@ SIGNATURES = {
     "ep_target_patch_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                      c_void_p]),
     "ep_swin_group_windows_host": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ep_collate_aos_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int]),
+    "ep_pack_transport_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int]),
     "ep_mask_from_noise": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ep_patch_density": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ep_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

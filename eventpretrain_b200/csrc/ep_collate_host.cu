@@ -1,0 +1,196 @@
+// SURVEY.md §8 row f2 — the host side of the ragged collate, as native multi-threaded code (no device work).
+//
+// The reference bins every sample on the CPU inside its DataLoader workers (e.g. pr_n_imagenet_dataset.py:85-87) and ships
+// dense tensors.  Here the workers ship raw events; the collate step turns the per-sample (N,4) x,y,t,p arrays of the
+// reference's event format into the canonical SoA batch, and the canonical batch into the packed transport layouts of
+// include/eventpretrain_b200.h (ep_events_soa.t_base) that cross PCIe at 4-5 B/event.  Both steps stream tens of bytes per
+// event; numpy does them at ~0.1 Gevents/s, a GPU bins 13 Gevents/s end to end, so they are threaded C++ here.
+#include <atomic>
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "ep_common.cuh"
+
+namespace ep {
+namespace {
+
+int pick_threads(int threads, int64_t work_items) {
+    int n = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 256) n = 256;
+    if ((int64_t)n > work_items) n = work_items > 0 ? (int)work_items : 1;
+    return n;
+}
+
+// run fn(item) for item in [0, n_items) on `threads` threads, dynamically scheduled in runs of `grain`
+template <class Fn>
+void parallel_for(int64_t n_items, int64_t grain, int threads, Fn fn) {
+    if (n_items <= 0) return;
+    const int nt = pick_threads(threads, (n_items + grain - 1) / grain);
+    if (nt == 1) {
+        for (int64_t i = 0; i < n_items; ++i) fn(i);
+        return;
+    }
+    std::atomic<int64_t> next(0);
+    auto body = [&]() {
+        for (;;) {
+            const int64_t lo = next.fetch_add(grain, std::memory_order_relaxed);
+            if (lo >= n_items) break;
+            const int64_t hi = lo + grain < n_items ? lo + grain : n_items;
+            for (int64_t i = lo; i < hi; ++i) fn(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    pool.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) pool.emplace_back(body);
+    body();
+    for (auto& th : pool) th.join();
+}
+
+// last sample b with offsets[b] <= i < offsets[b + 1] (empty samples skipped); offsets[0] == 0, i < offsets[B]
+int owner_of(const int64_t* off, int B, int64_t i) {
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <class T>
+bool collate_sample(const T* s, int64_t n, double t_scale, uint16_t* x, uint16_t* y, int64_t* t, uint8_t* p) {
+    bool ok = true;
+    for (int64_t i = 0; i < n; ++i) {
+        const double fx = (double)s[4 * i], fy = (double)s[4 * i + 1], ft = (double)s[4 * i + 2], fp = (double)s[4 * i + 3];
+        const bool in_range = fx >= 0.0 && fx <= 65535.0 && fy >= 0.0 && fy <= 65535.0;      // (also false for NaN)
+        const uint16_t ux = in_range ? (uint16_t)fx : 0, uy = in_range ? (uint16_t)fy : 0;
+        ok &= in_range && (double)ux == fx && (double)uy == fy && (fp == 0.0 || fp == 1.0);
+        // rint() by the 1.5 * 2^52 trick (round-to-nearest-even, exact for |v| < 2^51): no libm call in the loop
+        const double v = ft * t_scale;
+        const double ticks = (v + 6755399441055744.0) - 6755399441055744.0;
+        ok &= std::fabs(v) < 2251799813685248.0;
+        x[i] = ux; y[i] = uy; p[i] = (uint8_t)(fp != 0.0);
+        t[i] = (int64_t)ticks;
+    }
+    return ok;
+}
+
+}  // namespace
+}  // namespace ep
+
+extern "C" {
+
+int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale, uint16_t* x,
+                        uint16_t* y, int64_t* t, uint8_t* p, int64_t* offsets, int threads) {
+    using namespace ep;
+    if (!samples || !counts || !x || !y || !t || !p || !offsets || batch <= 0) return EP_EINVAL;
+    if (dtype != EP_F64 && dtype != EP_F32) return EP_EINVAL;
+    if (!(t_scale > 0.0)) return EP_EINVAL;
+    offsets[0] = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (counts[b] < 0 || (counts[b] > 0 && !samples[b])) return EP_EINVAL;
+        offsets[b + 1] = offsets[b] + counts[b];
+    }
+    // work items = (sample, 64K-event piece) so that a few long samples still spread over all threads
+    constexpr int64_t kPiece = 1 << 16;
+    std::vector<int64_t> first_piece((size_t)batch + 1, 0);
+    for (int b = 0; b < batch; ++b) first_piece[b + 1] = first_piece[b] + (counts[b] + kPiece - 1) / kPiece;
+    std::atomic<int> bad(0);
+    parallel_for(first_piece[batch], 1, threads, [&](int64_t item) {
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (first_piece[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int64_t i0 = (item - first_piece[b]) * kPiece;
+        const int64_t n = counts[b] - i0 < kPiece ? counts[b] - i0 : kPiece;
+        const int64_t o = offsets[b] + i0;
+        const bool ok = dtype == EP_F64
+            ? collate_sample(static_cast<const double*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o)
+            : collate_sample(static_cast<const float*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o);
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+    });
+    return bad.load() ? EP_EUNSUPPORTED : EP_OK;
+}
+
+int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, const int64_t* offsets,
+                           int batch, int nbytes, uint32_t* w, uint8_t* tick_low, uint32_t* blk_base, int64_t* t_base,
+                           int threads) {
+    using namespace ep;
+    if (!x || !y || !t || !p || !offsets || !w || !blk_base || !t_base || batch <= 0) return EP_EINVAL;
+    if (nbytes != 4 && nbytes != 5) return EP_EINVAL;
+    if (nbytes == 5 && !tick_low) return EP_EINVAL;
+    if (offsets[0] != 0) return EP_EINVAL;
+    for (int b = 0; b < batch; ++b)
+        if (offsets[b + 1] < offsets[b]) return EP_EINVAL;
+    const int64_t n = offsets[batch];
+    const int64_t K = nbytes == 5 ? 1024 : 256;
+    const int tick_bits = nbytes == 5 ? 17 : 9;
+    const int64_t n_blocks = (n + K - 1) / K;
+    // per-sample base = smallest stamp (0 for an empty sample); partial minima per (sample, piece), then combined
+    constexpr int64_t kPiece = 1 << 16;
+    std::vector<int64_t> first_piece((size_t)batch + 1, 0);
+    for (int b = 0; b < batch; ++b) first_piece[b + 1] = first_piece[b] + (offsets[b + 1] - offsets[b] + kPiece - 1) / kPiece;
+    std::vector<int64_t> part((size_t)first_piece[batch], 0);
+    parallel_for(first_piece[batch], 1, threads, [&](int64_t item) {
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (first_piece[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int64_t i0 = offsets[lo] + (item - first_piece[lo]) * kPiece;
+        const int64_t i1 = i0 + kPiece < offsets[lo + 1] ? i0 + kPiece : offsets[lo + 1];
+        int64_t m = t[i0];
+        for (int64_t i = i0 + 1; i < i1; ++i) m = t[i] < m ? t[i] : m;
+        part[(size_t)item] = m;
+    });
+    for (int b = 0; b < batch; ++b) {
+        int64_t m = 0;
+        for (int64_t q = first_piece[b]; q < first_piece[b + 1]; ++q) m = (q == first_piece[b] || part[(size_t)q] < m) ? part[(size_t)q] : m;
+        t_base[b] = m;
+    }
+    std::atomic<int> bad(0);
+    parallel_for(n_blocks, 64, threads, [&](int64_t g) {
+        const int64_t i0 = g * K, i1 = i0 + K < n ? i0 + K : n;
+        int b = owner_of(offsets, batch, i0);
+        while (offsets[b + 1] <= i0) ++b;      // (owner_of lands on the last sample starting at or before i0: never empty, kept as a guard)
+        // tick offset of the block: smallest relative stamp among the events of the sample that owns the block's first slot
+        const int64_t own_end = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
+        int64_t m = t[i0];
+        for (int64_t i = i0 + 1; i < own_end; ++i) m = t[i] < m ? t[i] : m;
+        m -= t_base[b];
+        bool ok = m >= 0 && m < ((int64_t)1 << 32);
+        const int64_t add_own = ok ? m : 0;
+        blk_base[g] = (uint32_t)add_own;
+        // one branch-free run per sample inside the block (a sample that starts here counts from its own base)
+        uint64_t viol = 0;
+        for (int64_t lo = i0; lo < i1;) {
+            while (lo >= offsets[b + 1]) ++b;
+            const int64_t hi = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
+            const int64_t sub = t_base[b] + (offsets[b] / K == g ? 0 : add_own);
+            if (nbytes == 5) {
+                for (int64_t i = lo; i < hi; ++i) {
+                    const uint64_t ticks = (uint64_t)(t[i] - sub);
+                    const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
+                    viol |= (ticks >> tick_bits) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
+                    w[i] = xi | (yi << 11) | (pi << 22) | ((tk >> 8) << 23);
+                    tick_low[i] = (uint8_t)(tk & 0xffu);
+                }
+            } else {
+                for (int64_t i = lo; i < hi; ++i) {
+                    const uint64_t ticks = (uint64_t)(t[i] - sub);
+                    const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
+                    viol |= (ticks >> tick_bits) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
+                    w[i] = xi | (yi << 11) | (pi << 22) | (tk << 23);
+                }
+            }
+            lo = hi;
+        }
+        if (!ok || viol) bad.store(1, std::memory_order_relaxed);
+    });
+    return bad.load() ? EP_EUNSUPPORTED : EP_OK;
+}
+
+}  // extern "C"

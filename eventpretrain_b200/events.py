@@ -115,7 +115,7 @@ class RaggedEvents:
                 continue
         return self
 
-    def packed(self, nbytes=5):
+    def packed(self, nbytes=5, native=True, threads=0):
         """Host-side repack into a packed transport layout (include/eventpretrain_b200.h, ep_events_soa.t_base): one
         uint32 x | y << 11 | polarity << 22 | tick bits << 23 per event; `ticks` count from the sample's base inside the
         block of the arrays where the sample starts and from base + a per-block offset afterwards.
@@ -123,7 +123,9 @@ class RaggedEvents:
           nbytes=4: blocks of 256 events, 9-bit ticks in the word (dense streams)
         Needs int64 tick stamps, p in {0,1}, x,y < 2048 and a block's stamps (of one sample) within the tick range (raises
         ValueError otherwise: use the next wider layout, see transport()).  Binning results are bit-identical to the int64
-        layout; H2D traffic drops from 13 to 5 or 4 B/event."""
+        layout; H2D traffic drops from 13 to 5 or 4 B/event.  Host-resident batches are packed by the library's threaded
+        `ep_pack_transport_host` (native=True; `threads` <= 0: all cores) straight into pinned buffers; native=False is the
+        numpy statement of the same rule (what the tests compare it with)."""
         if nbytes not in (4, 5):
             raise ValueError("packed layouts have 4 or 5 bytes per event")
         if self.t_base is not None and self.y is None:
@@ -135,6 +137,8 @@ class RaggedEvents:
         if int(self.offsets_host[0]) != 0:
             raise ValueError("packed() needs a whole batch (offsets[0] == 0): the block offsets are tied to array positions")
         off = self.offsets_host
+        if native and not self.x.is_cuda:
+            return self._packed_native(nbytes, threads)
         x = self.x.cpu().numpy().astype(np.uint32)
         y = self.y.cpu().numpy().astype(np.uint32)
         t = self.t.cpu().numpy()
@@ -179,6 +183,22 @@ class RaggedEvents:
             w = x | (y << np.uint32(11)) | (p << np.uint32(22)) | (tk << np.uint32(23))
             tl = None
         return RaggedEvents(cv(w), None, tl, cv(blk), self.offsets, off, self.t_div, cv(base))
+
+    def _packed_native(self, nbytes, threads):
+        n, B, K = int(self.offsets_host[-1]), self.batch, (1024 if nbytes == 5 else 256)
+        pin = self.x.is_pinned() and torch.cuda.is_available()
+        mk = lambda size, dt: torch.empty(size, dtype=dt, pin_memory=pin)
+        w, blk, base = mk(n, torch.uint32), mk((n + K - 1) // K, torch.uint32), mk(B, torch.int64)
+        tl = mk(n, torch.uint8) if nbytes == 5 else None
+        off = np.ascontiguousarray(self.offsets_host, np.int64)
+        x, y, t, p = (a.contiguous() for a in (self.x, self.y, self.t, self.p))
+        rc = _lib.load().ep_pack_transport_host(x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(), off.ctypes.data, B, nbytes,
+                                                w.data_ptr(), ptr(tl), blk.data_ptr(), base.data_ptr(), int(threads))
+        if rc == _lib.EP_EUNSUPPORTED:
+            raise ValueError(f"batch does not fit the {nbytes} B/event packed layout (x, y < 2048, p in {{0,1}}, "
+                             f"{K}-event blocks within 2^{17 if nbytes == 5 else 9} ticks)")
+        _lib.check(rc, "ep_pack_transport_host")
+        return RaggedEvents(w, None, tl, blk, self.offsets, self.offsets_host, self.t_div, base)
 
     def unpack_host(self):
         """Decode a packed() batch back to (x, y, t_ticks, p) numpy arrays (tests / debugging)."""
@@ -252,6 +272,34 @@ def pack_events(samples, t_div=1.0, canonical=True, pin=True):
         p = np.ascontiguousarray(ev[:, 3])
     t = np.ascontiguousarray(ev[:, 2])
     return from_soa(x, y, t, p, offsets, t_div=t_div, pin=pin)
+
+
+def collate_events(samples, ticks_per_unit=1.0e6, pin=True, threads=0):
+    """The collate step as native threaded code (`ep_collate_aos_host`): per-sample (N,4) x,y,t,p arrays (float64 or float32,
+    the reference's event format) -> canonical ragged batch with uint16 coordinates, uint8 polarity and int64 tick stamps
+    `rint(t * ticks_per_unit)` (t_div = ticks_per_unit, so stamps in seconds at the default become microsecond ticks),
+    written straight into pinned buffers.  Raises ValueError for batches the canonical layout cannot hold (fractional or
+    out-of-range coordinates, polarity outside {0,1}): those go through pack_events(canonical=False)."""
+    B = len(samples)
+    if B == 0:
+        raise ValueError("empty batch")
+    dt = np.asarray(samples[0]).dtype
+    if dt not in (np.float64, np.float32):
+        dt = np.dtype(np.float64)
+    arrs = [np.ascontiguousarray(s, dt).reshape(-1, 4) for s in samples]
+    counts = np.array([a.shape[0] for a in arrs], np.int64)
+    n = int(counts.sum())
+    pin = pin and torch.cuda.is_available()
+    mk = lambda size, d: torch.empty(size, dtype=d, pin_memory=pin)
+    x, y, t, p, off = mk(n, torch.uint16), mk(n, torch.uint16), mk(n, torch.int64), mk(n, torch.uint8), mk(B + 1, torch.int64)
+    ptrs = (ctypes.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    rc = _lib.load().ep_collate_aos_host(ptrs, counts.ctypes.data, B, _lib.EP_F64 if dt == np.float64 else _lib.EP_F32,
+                                         float(ticks_per_unit), x.data_ptr(), y.data_ptr(), t.data_ptr(), p.data_ptr(),
+                                         off.data_ptr(), int(threads))
+    if rc == _lib.EP_EUNSUPPORTED:
+        raise ValueError("canonical collate needs integer coordinates in [0, 65535] and polarity in {0, 1}")
+    _lib.check(rc, "ep_collate_aos_host")
+    return RaggedEvents(x, y, t, p, off, offsets_host=off.numpy().copy(), t_div=float(ticks_per_unit))
 
 
 def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):

@@ -289,6 +289,24 @@ EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask
 EP_API int ep_swin_group_windows_host(int group_size, const int* num_ele_win, int n_win, int* num_ele_group, int* group_first,
                                       int* grouped_idx, int* n_groups);
 
+/* Ragged collate, HOST functions, multi-threaded (threads <= 0: all hardware threads), no device work.
+ * The reference's DataLoader workers hand over per-sample (N,4) arrays with columns x, y, t, p (float64, or float32 for
+ * DDD17 / DVS128-Gesture: pr_n_imagenet_dataset.py:52-54, ft_ddd17_dataset.py:96-97); the collate step replaces the
+ * per-sample CPU binning there (e.g. pr_n_imagenet_dataset.py:85-87).
+ *
+ * ep_collate_aos_host: B sample pointers + counts -> canonical SoA batch (x, y uint16; t int64 ticks = rint(t * t_scale);
+ *   p uint8) and offsets[B + 1].  dtype = EP_F64 or EP_F32.  EP_EUNSUPPORTED when a coordinate is not an integer in
+ *   [0, 65535] or a polarity is not 0 / 1 (such batches keep the generic layout); the outputs are then unspecified.
+ * ep_pack_transport_host: canonical SoA batch (offsets[0] == 0) -> packed transport layout of ep_events_soa.t_base:
+ *   nbytes = 5: w[n] + tick_low[n], blk_base[ceil(n / 1024)], t_base[B];  nbytes = 4: w[n], blk_base[ceil(n / 256)], t_base[B]
+ *   (tick_low may be NULL).  EP_EUNSUPPORTED when the batch does not fit the layout (x or y >= 2048, polarity > 1, a
+ *   block spanning more ticks than its field, stamps far out of order): the caller takes the next wider layout. */
+EP_API int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale,
+                               uint16_t* x, uint16_t* y, int64_t* t, uint8_t* p, int64_t* offsets, int threads);
+EP_API int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p,
+                                  const int64_t* offsets, int batch, int nbytes, uint32_t* w, uint8_t* tick_low,
+                                  uint32_t* blk_base, int64_t* t_base, int threads);
+
 #ifdef __cplusplus
 }
 #endif

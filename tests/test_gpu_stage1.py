@@ -104,6 +104,61 @@ def test_ragged_batch_vs_oracle(ep):
     assert torch.equal(o2["voxel"], out["voxel"][3:])
 
 
+def test_group_chain_orderings(ep, monkeypatch):
+    """The group loop is a chain of dependent launches (scatter -> finalize voxel -> finalize count -> next scatter) over
+    shared accumulator slots.  One sample per group (EP_L2_GROUP_MB=1), empty samples in between (their groups launch no
+    scatter), voxel + count + sum: every grouping must give the tensors of the single-group call bit for bit."""
+    rng = np.random.default_rng(5)
+    H, W, bins = 96, 128, 7
+    counts = [3000, 0, 0, 9000, 1, 0, 20000, 512, 0]
+    xs, ys, ts, ps = [], [], [], []
+    for n in counts:
+        xs.append(rng.integers(0, W, n)); ys.append(rng.integers(0, H, n)); ps.append(rng.integers(0, 2, n))
+        ts.append(np.sort(rng.integers(0, 50000, n)).astype(np.int64))
+    off = np.cumsum([0] + counts)
+    ev = ep.from_soa(np.concatenate(xs).astype(np.uint16), np.concatenate(ys).astype(np.uint16), np.concatenate(ts),
+                     np.concatenate(ps).astype(np.uint8), off, t_div=1e6).to("cuda")
+    kw = dict(num_bins=bins, count_channels=2, voxel_sum=True, check=True)
+    ref = {k: v.clone() for k, v in ep.bin_events(ev, (H, W), **kw).items()}
+    monkeypatch.setenv("EP_L2_GROUP_MB", "1")
+    for rep in range(3):                                  # repeated: the slots must come back zeroed every time
+        got = ep.bin_events(ev, (H, W), **kw)
+        for k in ref:
+            assert torch.equal(got[k], ref[k]), (k, rep)
+    got = ep.bin_events(ev, (H, W), num_bins=0, count_channels=3, check=True)        # count-only chain
+    assert torch.equal(got["count"][:, 0], ref["count"][:, 0]) and torch.equal(got["count"][:, 2], ref["count"][:, 1])
+
+
+def test_bin_events_in_cuda_graph(ep):
+    """The whole binning call (memset + dependent-launch chain) can be captured into a CUDA graph and replayed on new data."""
+    rng = np.random.default_rng(9)
+    H, W, bins, n = 64, 96, 5, 40000
+    def make(seed):
+        r = np.random.default_rng(seed)
+        off = np.array([0, n // 4, n // 4, n])
+        t = np.concatenate([np.sort(r.integers(0, 90000, c)) for c in np.diff(off)]).astype(np.int64)
+        return ep.from_soa(r.integers(0, W, n).astype(np.uint16), r.integers(0, H, n).astype(np.uint16), t,
+                           r.integers(0, 2, n).astype(np.uint8), off, t_div=1e6)
+    static = make(1).to("cuda")
+    out = ep.bin_events(static, (H, W), num_bins=bins, count_channels=2, voxel_sum=True)         # warm-up: workspace, outputs
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ep.bin_events(static, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ep.bin_events(static, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, out=out)
+    for seed in (2, 3):
+        fresh = make(seed).to("cuda")
+        for name in ("x", "y", "t", "p"):
+            getattr(static, name).copy_(getattr(fresh, name))
+        g.replay()
+        ref = ep.bin_events(fresh, (H, W), num_bins=bins, count_channels=2, voxel_sum=True)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), (k, seed)
+
+
 def test_generic_layouts_vs_oracle(ep, golden_stage1):
     """Non-canonical SoA dtype tags (float coords, fp32 time, int8 polarity) take the scalar-load kernel."""
     from oracle import events as oe

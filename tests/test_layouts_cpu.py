@@ -62,3 +62,70 @@ def test_packed_mildly_unsorted_and_limits():
         wide.packed()
     with pytest.raises(ValueError):
         ev.shard(1, 2).packed()                       # block offsets are tied to array positions: whole batches only
+
+
+def _same(a, b):
+    for name in ("x", "y", "t", "p", "t_base"):
+        u, v = getattr(a, name), getattr(b, name)
+        assert (u is None) == (v is None), name
+        assert u is None or (u.dtype == v.dtype and torch.equal(u, v)), name
+
+
+@pytest.mark.parametrize("threads", [1, 3, 0])
+def test_native_packer_equals_the_numpy_rule(threads):
+    """ep_pack_transport_host (threaded C++) against the numpy statement of the layout rule, word for word: ragged batches with
+    empty samples, samples starting exactly on block boundaries, mild disorder, both widths."""
+    rng = np.random.default_rng(11)
+    for counts, span in (([3000, 0, 1, 5003, 1024, 2047, 9999, 0, 2], 50_000), ([1024, 1024, 0, 512, 512, 70000], 30_000),
+                         ([256, 0, 0, 256, 1, 255, 300000], 300), ([5], 3)):
+        ev = _batch(rng, counts, span=span)
+        t = ev.t.numpy().copy()
+        if len(t) > 300:
+            t[100:200] = t[100:200][::-1]
+        ev = ep.from_soa(ev.x.numpy(), ev.y.numpy(), t, ev.p.numpy(), ev.offsets_host, t_div=1e6, pin=False)
+        for nbytes in (4, 5):
+            try:
+                ref = ev.packed(nbytes, native=False)
+            except ValueError:
+                with pytest.raises(ValueError):
+                    ev.packed(nbytes, native=True, threads=threads)
+                continue
+            _same(ev.packed(nbytes, native=True, threads=threads), ref)
+
+
+def test_native_packer_refuses_what_the_layout_cannot_hold():
+    one = lambda x, p, t: ep.from_soa(np.array([x], np.uint16), np.array([0], np.uint16), np.array(t, np.int64).reshape(-1)[:1],
+                                      np.array([p], np.uint8), np.array([0, 1]), pin=False)
+    for bad in (one(2048, 1, [5]), one(3, 2, [5])):
+        for nbytes in (4, 5):
+            with pytest.raises(ValueError):
+                bad.packed(nbytes)
+    rng = np.random.default_rng(3)
+    far = _batch(rng, [4000], span=2_000_000_000_000)       # a block's offset would not fit 32 bits
+    with pytest.raises(ValueError):
+        far.packed(5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_native_collate_equals_pack_events(dtype):
+    """ep_collate_aos_host: the reference's per-sample (N,4) x,y,t,p arrays -> canonical SoA with integer tick stamps."""
+    rng = np.random.default_rng(21)
+    samples = []
+    for n in (1000, 0, 1, 70000, 65536, 3):
+        t_us = np.sort(rng.integers(0, 250_000, n))
+        t = t_us / 1e6 if dtype == np.float64 else t_us.astype(np.float32)       # seconds (N-ImageNet) / raw ticks as fp32 (DDD17)
+        samples.append(np.stack([rng.integers(0, 640, n), rng.integers(0, 480, n), t, rng.integers(0, 2, n)], 1).astype(dtype))
+    scale = 1e6 if dtype == np.float64 else 1.0
+    for threads in (1, 0):
+        ev = ep.collate_events(samples, scale, pin=False, threads=threads)
+        ref = ep.pack_events([np.column_stack([s[:, 0], s[:, 1], np.rint(s[:, 2].astype(np.float64) * scale), s[:, 3]]) for s in samples],
+                             t_div=scale, pin=False)
+        assert ev.t.dtype == torch.int64 and ev.t_div == scale
+        assert torch.equal(ev.x, ref.x) and torch.equal(ev.y, ref.y) and torch.equal(ev.p, ref.p)
+        assert np.array_equal(ev.t.numpy(), ref.t.numpy().astype(np.int64)) and np.array_equal(ev.offsets_host, ref.offsets_host)
+    with pytest.raises(ValueError):
+        ep.collate_events([np.array([[0.5, 1, 0, 1]], dtype)], scale, pin=False)           # fractional coordinate (after erase_and_add_events)
+    with pytest.raises(ValueError):
+        ep.collate_events([np.array([[1, 1, 0, -1]], dtype)], scale, pin=False)            # polarity -1: generic layout
+    with pytest.raises(ValueError):
+        ep.collate_events([np.array([[70000, 1, 0, 1]], dtype)], scale, pin=False)
