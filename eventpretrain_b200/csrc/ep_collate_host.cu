@@ -119,10 +119,11 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
                            int batch, int nbytes, uint32_t* w, uint8_t* tick_low, uint32_t* blk_base, int64_t* t_base,
                            int threads) {
     using namespace ep;
-    if (!x || !y || !t || !p || !offsets || !w || !blk_base || !t_base || batch <= 0) return EP_EINVAL;
-    if (nbytes != 4 && nbytes != 5) return EP_EINVAL;
+    if (!t || !p || !offsets || !w || !t_base || batch <= 0) return EP_EINVAL;
+    if (nbytes != 4 && nbytes != 5 && nbytes != 8) return EP_EINVAL;
+    if (nbytes != 8 && (!x || !y || !blk_base)) return EP_EINVAL;
     if (nbytes == 5 && !tick_low) return EP_EINVAL;
-    if (offsets[0] != 0) return EP_EINVAL;
+    if (nbytes != 8 ? offsets[0] != 0 : offsets[0] < 0) return EP_EINVAL;      // block offsets are tied to array positions
     for (int b = 0; b < batch; ++b)
         if (offsets[b + 1] < offsets[b]) return EP_EINVAL;
     const int64_t n = offsets[batch];
@@ -152,6 +153,27 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
         t_base[b] = m;
     }
     std::atomic<int> bad(0);
+    if (nbytes == 8) {      // compact layout: x, y stay as they are; one word = ticks since the sample's base | polarity << 31
+        parallel_for(first_piece[batch], 1, threads, [&](int64_t item) {
+            int lo = 0, hi = batch;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (first_piece[mid] <= item) lo = mid; else hi = mid;
+            }
+            const int64_t i0 = offsets[lo] + (item - first_piece[lo]) * kPiece;
+            const int64_t i1 = i0 + kPiece < offsets[lo + 1] ? i0 + kPiece : offsets[lo + 1];
+            const int64_t base = t_base[lo];
+            uint64_t viol = 0;
+            for (int64_t i = i0; i < i1; ++i) {
+                const uint64_t rel = (uint64_t)(t[i] - base);
+                const uint32_t pi = p[i];
+                viol |= (rel >> 31) | (uint64_t)(pi >> 1);
+                w[i] = (uint32_t)rel | (pi << 31);
+            }
+            if (viol) bad.store(1, std::memory_order_relaxed);
+        });
+        return bad.load() ? EP_EUNSUPPORTED : EP_OK;
+    }
     parallel_for(n_blocks, 64, threads, [&](int64_t g) {
         const int64_t i0 = g * K, i1 = i0 + K < n ? i0 + K : n;
         int b = owner_of(offsets, batch, i0);

@@ -64,15 +64,29 @@ class RaggedEvents:
     def pin_memory(self):
         return self._map(lambda a: a.pin_memory())
 
-    def compact(self):
+    def compact(self, native=True, threads=0):
         """Host-side repack into the 8 B/event transport layout: u16 x,y + u32 (ticks relative to the sample's first
         stamp | polarity << 31).  Needs int64 tick stamps, p in {0,1} and < 2^31 ticks between a sample's smallest and
-        largest stamp.  Binning results are bit-identical to the int64 layout; H2D traffic drops from 13 to 8 B/event."""
+        largest stamp.  Binning results are bit-identical to the int64 layout; H2D traffic drops from 13 to 8 B/event.
+        Host-resident batches go through the library's threaded `ep_pack_transport_host`; native=False is the numpy
+        statement of the same rule."""
         if self.t_base is not None:
             return self
         if self.t.dtype != torch.int64 or self.p.dtype != torch.uint8 or self.x.dtype != torch.uint16:
             raise TypeError("compact() needs the canonical u16 / int64-tick / u8 layout")
         off = self.offsets_host
+        if native and not self.x.is_cuda:
+            pin = self.x.is_pinned() and torch.cuda.is_available()
+            rel = torch.empty(self.t.shape[0], dtype=torch.uint32, pin_memory=pin)
+            base = torch.empty(self.batch, dtype=torch.int64, pin_memory=pin)
+            o = np.ascontiguousarray(off, np.int64)
+            t, p = self.t.contiguous(), self.p.contiguous()
+            rc = _lib.load().ep_pack_transport_host(None, None, t.data_ptr(), p.data_ptr(), o.ctypes.data, self.batch, 8,
+                                                    rel.data_ptr(), None, None, base.data_ptr(), int(threads))
+            if rc == _lib.EP_EUNSUPPORTED:
+                raise ValueError("compact() needs p in {0,1} and fewer than 2^31 ticks between a sample's smallest and largest stamp")
+            _lib.check(rc, "ep_pack_transport_host")
+            return RaggedEvents(self.x, self.y, rel, None, self.offsets, off, self.t_div, base)
         t = self.t.cpu().numpy()
         p = self.p.cpu().numpy()
         B = self.batch
@@ -85,6 +99,8 @@ class RaggedEvents:
                 d = t[lo:hi] - base[b]
                 if d.max() >= (1 << 31):
                     raise ValueError("sample spans more than 2^31 ticks")
+                if p[lo:hi].max() > 1:
+                    raise ValueError("compact() needs polarity in {0, 1}")
                 rel[lo:hi] = d.astype(np.uint32)
         rel |= p.astype(np.uint32) << np.uint32(31)
         mk = (lambda a: a.pin_memory()) if (self.x.is_pinned() or self.x.is_cuda) and torch.cuda.is_available() else (lambda a: a)

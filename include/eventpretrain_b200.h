@@ -299,7 +299,8 @@ EP_API int ep_swin_group_windows_host(int group_size, const int* num_ele_win, in
  *   [0, 65535] or a polarity is not 0 / 1 (such batches keep the generic layout); the outputs are then unspecified.
  * ep_pack_transport_host: canonical SoA batch (offsets[0] == 0) -> packed transport layout of ep_events_soa.t_base:
  *   nbytes = 5: w[n] + tick_low[n], blk_base[ceil(n / 1024)], t_base[B];  nbytes = 4: w[n], blk_base[ceil(n / 256)], t_base[B]
- *   (tick_low may be NULL).  EP_EUNSUPPORTED when the batch does not fit the layout (x or y >= 2048, polarity > 1, a
+ *   (tick_low may be NULL);  nbytes = 8: compact layout, w[i] = ticks since t_base[b] | polarity << 31 at the events' own
+ *   array positions (x, y, tick_low, blk_base unused and may be NULL; offsets[0] >= 0).  EP_EUNSUPPORTED when the batch does not fit the layout (x or y >= 2048, polarity > 1, a
  *   block spanning more ticks than its field, stamps far out of order): the caller takes the next wider layout. */
 EP_API int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale,
                                uint16_t* x, uint16_t* y, int64_t* t, uint8_t* p, int64_t* offsets, int threads);

@@ -129,3 +129,19 @@ def test_native_collate_equals_pack_events(dtype):
         ep.collate_events([np.array([[1, 1, 0, -1]], dtype)], scale, pin=False)            # polarity -1: generic layout
     with pytest.raises(ValueError):
         ep.collate_events([np.array([[70000, 1, 0, 1]], dtype)], scale, pin=False)
+
+
+def test_native_compact_equals_the_numpy_rule():
+    rng = np.random.default_rng(31)
+    ev = _batch(rng, [3000, 0, 1, 70000, 2], span=2_000_000_000)
+    a, b = ev.compact(native=True, threads=3), ev.compact(native=False)
+    _same(a, b)
+    assert a.x is ev.x and a.p is None and a.t.dtype == torch.uint32
+    sh = ev.shard(1, 2)                                   # offsets[0] > 0: positions of the full arrays
+    c, d = sh.compact(native=True), sh.compact(native=False)
+    lo, hi = int(sh.offsets_host[0]), int(sh.offsets_host[-1])
+    assert torch.equal(c.t[lo:hi], d.t[lo:hi]) and torch.equal(c.t_base, d.t_base)
+    far = _batch(rng, [10], span=1 << 40)
+    for native in (True, False):
+        with pytest.raises(ValueError):
+            far.compact(native=native)
