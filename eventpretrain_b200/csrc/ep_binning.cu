@@ -347,7 +347,7 @@ SlotLayout slot_layout(const ep_bin_params* p, int B) {
 size_t l2_group_budget() {
     // accumulator bytes a group touches, kept L2-resident: measured on B200 with the bench workload (5 samples = 49 MB -> 97.2,
     // 6 = 59 MB -> 99.1, 7 = 69 MB -> 93.1, 8 = 79 MB -> 86.5 Gev/s; 64 rather than 60 lets two 15-bin 640x440 samples
-    // (63 MB) share a group: C4 0.83 -> 0.77 ms)
+    // (63 MB) share a group: C4 0.81-0.83 -> 0.77-0.83 ms, C5 1.33 -> 1.28 ms)
     const char* e = getenv("EP_L2_GROUP_MB");
     long mb = e ? atol(e) : 64;
     if (mb < 1) mb = 1;

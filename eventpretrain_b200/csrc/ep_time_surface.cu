@@ -87,20 +87,28 @@ __global__ void __launch_bounds__(256) k_ts_scatter(TsArgs a, int64_t n_quads) {
     if (nbad && a.bad) atomicAdd(a.bad, nbad);
 }
 
+// One CTA row per sample of the group (blockIdx.y): the reference time is fetched once per CTA, and each thread turns two
+// adjacent keys (one 16-byte load) into two fp32 decays.  (The first version derived the sample from a flat 64-bit index and
+// re-read / re-divided the reference stamp in every thread: ~1300 issue slots per warp, 0.3 TB/s.)
 __global__ void __launch_bounds__(256) k_ts_finish(TsArgs a, double tau, const double* t_ref_opt, float* __restrict__ out) {
-    const int64_t HW = (int64_t)a.H * a.W;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // cell of the group
-    if (idx >= (int64_t)(a.g1 - a.g0) * 2 * HW) return;
-    const int b = a.g0 + (int)(idx / (2 * HW));
-    const unsigned long long k = a.keys[idx];
-    a.keys[idx] = 0ull;
-    float r = 0.f;
-    if (k) {
-        const int64_t hi = a.offsets[b + 1];
-        const double t_ref = t_ref_opt ? t_ref_opt[b] : ts_time(a, hi - 1);      // default: the sample's last row
-        r = (float)exp(-(t_ref - key_f64(k)) / tau);
+    __shared__ double s_ref;
+    const int slot = blockIdx.y, b = a.g0 + slot;
+    const int64_t cells = 2 * (int64_t)a.H * a.W;                              // even: pairs never straddle a sample
+    if (threadIdx.x == 0) {
+        const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
+        s_ref = t_ref_opt ? t_ref_opt[b] : (hi > lo ? ts_time(a, hi - 1) : 0.0);   // default: the sample's last row
     }
-    st_stream(out + (int64_t)a.g0 * 2 * HW + idx, r);
+    __syncthreads();
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (c >= cells) return;
+    unsigned long long* kp = a.keys + (int64_t)slot * cells + c;
+    const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(kp);
+    if (k.x | k.y) *reinterpret_cast<ulonglong2*>(kp) = make_ulonglong2(0ull, 0ull);
+    const double t_ref = s_ref;
+    float2 r;
+    r.x = k.x ? (float)exp(-(t_ref - key_f64(k.x)) / tau) : 0.f;
+    r.y = k.y ? (float)exp(-(t_ref - key_f64(k.y)) / tau) : 0.f;
+    st_stream(reinterpret_cast<float2*>(out + (int64_t)b * cells + c), r);
 }
 
 constexpr size_t kTsGroupBytes = (size_t)64 << 20;      // key slots kept in flight: L2-resident, like the binning accumulators
@@ -151,8 +159,8 @@ int ep_time_surface(void* stream, const ep_events_soa* ev, int height, int width
             else k_ts_scatter<false><<<grid, 256, 0, st>>>(a, n_quads);
             EP_LAUNCH_CHECK();
         }
-        const int64_t cells = (int64_t)(a.g1 - a.g0) * 2 * height * width;
-        k_ts_finish<<<(unsigned)ceil_div64(cells, 256), 256, 0, st>>>(a, tau, t_ref, out);
+        const dim3 fin_grid((unsigned)ceil_div64((int64_t)height * width, 256), (unsigned)(a.g1 - a.g0));      // 2 cells per thread
+        k_ts_finish<<<fin_grid, 256, 0, st>>>(a, tau, t_ref, out);
         EP_LAUNCH_CHECK();
     }
     return EP_OK;
