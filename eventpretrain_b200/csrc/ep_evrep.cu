@@ -4,9 +4,9 @@
 // The reference sorts all events with np.lexsort((t, y, x)) and accumulates, per pixel and in that
 // order, the differences between consecutive sorted timestamps (the first event of a pixel is
 // differenced against the last event of the previous non-empty pixel in x-major order).  Here:
-//   1. histogram per pixel in x-major order q = x*H + y        (E_C, E_I: integer REDs)
-//   2. per-sample exclusive scan over q                        (one CTA per sample, shuffle scans)
-//   3. counting-sort scatter of the timestamps into per-pixel segments
+//   1. histogram per pixel in x-major order q = x*H + y        (E_C and E_I share one 64-bit word: one RED per event)
+//   2. per-sample exclusive scan over q                        (chunk sums -> scan of the sums -> chunk scans)
+//   3. counting-sort scatter of the timestamps into per-pixel segments (cursors start at the segment starts)
 //   4. each pixel's (short) segment is sorted by t in place    (one thread per pixel)
 //   5. one thread per pixel replays numpy's accumulation exactly: fp32 accumulators updated as
 //      (float)((double)acc + d) and the fp64 statistics of :117-120 — bit-exact with the reference.
@@ -29,10 +29,11 @@ struct RepArgs {
     EvDesc ev;
     int H, W;
     int64_t begin, end;
-    int32_t* cnt;      // [B][HW]  indexed by q = x*H + y
-    int32_t* pol;      // [B][HW]
-    int32_t* start;    // [B][HW]  exclusive scan of cnt (relative to offsets[b])
-    int32_t* cursor;   // [B][HW]
+    unsigned long long* cp;   // [B][HW]  indexed by q = x*H + y: count * 2^32 + net polarity (signed sum, two's complement)
+    int32_t* start;    // [B][HW]  exclusive scan of the counts (relative to offsets[b])
+    int32_t* cursor;   // [B][HW]  next free slot of the pixel's segment (initialised to start by the scan)
+    int32_t* sums;     // [B][n_chunks]  scan scratch
+    int n_chunks;
     double* sorted_t;  // [n_total] indexed by absolute event slot - offsets[0]
     unsigned int* bad;
 };
@@ -45,6 +46,9 @@ __device__ __forceinline__ int find_sample(const int64_t* off, int B, int64_t i)
     }
     return lo;
 }
+
+__device__ __forceinline__ int pol_of(unsigned long long w) { return (int)(uint32_t)w; }
+__device__ __forceinline__ int cnt_of(unsigned long long w) { return (int)((long long)(w - (unsigned long long)(long long)pol_of(w)) >> 32); }
 
 // returns q (x-major pixel index) or -1 when the reference would raise IndexError
 __device__ __forceinline__ int64_t pixel_q(const RepArgs& a, int64_t i) {
@@ -64,37 +68,85 @@ __global__ void __launch_bounds__(256) k_evrep_hist(RepArgs a) {
     const double p = load_as_double(a.ev.p, a.ev.p_dtype, i);
     if (q < 0 || !(p == 1.0 || p == 0.0 || p == -1.0)) { if (a.bad) atomicAdd(a.bad, 1u); return; }
     const int64_t HW = (int64_t)a.H * a.W;
-    atomicAdd(a.cnt + b * HW + q, 1);
-    atomicAdd(a.pol + b * HW + q, p == 1.0 ? 1 : -1);          // :97,100-101
+    const long long delta = (1ll << 32) + (p == 1.0 ? 1 : -1);      // E_C += 1, E_I += +-1 (:97,100-101) in one RED
+    atomicAdd(a.cp + b * HW + q, (unsigned long long)delta);
 }
 
-__global__ void __launch_bounds__(1024) k_evrep_scan(RepArgs a) {
+// ---- exclusive scan of the per-pixel counts, per sample, over chunks of 4096 pixels (1024 threads x 4 consecutive) ----
+constexpr int kScanThreads = 1024, kScanPer = 4, kScanChunk = kScanThreads * kScanPer;
+
+// block-wide exclusive scan of one value per thread; returns the thread's prefix, total in `total`
+__device__ __forceinline__ int block_excl_scan(int v, int& total) {
     __shared__ int s_warp[32];
-    __shared__ int s_base, s_total;
-    const int b = blockIdx.x;
-    const int64_t HW = (int64_t)a.H * a.W;
+    __shared__ int s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int32_t* c = a.cnt + b * HW;
-    int32_t* s = a.start + b * HW;
+    const int incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp[lane];
+        const int ws = warp_incl_scan(w, lane);
+        s_warp[lane] = ws - w;
+        if (lane == 31) s_total = ws;
+    }
+    __syncthreads();
+    const int r = s_warp[warp] + incl - v;
+    total = s_total;
+    __syncthreads();            // s_warp / s_total may be reused by the caller's next round
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_evrep_chunk_sums(RepArgs a) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int64_t HW = (int64_t)a.H * a.W;
+    const unsigned long long* w = a.cp + b * HW;
+    const int64_t i0 = (int64_t)c * kScanChunk + threadIdx.x * kScanPer;
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j)
+        if (i0 + j < HW) v += cnt_of(w[i0 + j]);
+    int total;
+    block_excl_scan(v, total);
+    if (threadIdx.x == 0) a.sums[b * a.n_chunks + c] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_evrep_scan_sums(RepArgs a) {
+    __shared__ int s_base;
+    int32_t* s = a.sums + blockIdx.x * a.n_chunks;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int64_t st = 0; st < HW; st += blockDim.x) {
-        const int64_t i = st + threadIdx.x;
-        const int v = i < HW ? c[i] : 0;
-        const int incl = warp_incl_scan(v, lane);
-        if (lane == 31) s_warp[warp] = incl;
+    for (int st = 0; st < a.n_chunks; st += kScanThreads) {
+        const int i = st + threadIdx.x;
+        const int v = i < a.n_chunks ? s[i] : 0;
+        int total;
+        const int pre = block_excl_scan(v, total);
+        if (i < a.n_chunks) s[i] = s_base + pre;
         __syncthreads();
-        if (warp == 0) {
-            const int w = s_warp[lane];
-            const int ws = warp_incl_scan(w, lane);
-            s_warp[lane] = ws - w;
-            if (lane == 31) s_total = ws;
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_evrep_chunk_scan(RepArgs a) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int64_t HW = (int64_t)a.H * a.W;
+    const unsigned long long* w = a.cp + b * HW;
+    const int64_t i0 = (int64_t)c * kScanChunk + threadIdx.x * kScanPer;
+    int n[kScanPer], v = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) {
+        n[j] = i0 + j < HW ? cnt_of(w[i0 + j]) : 0;
+        v += n[j];
+    }
+    int total;
+    int run = a.sums[b * a.n_chunks + c] + block_excl_scan(v, total);
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) {
+        if (i0 + j < HW) {
+            a.start[b * HW + i0 + j] = run;
+            a.cursor[b * HW + i0 + j] = run;
         }
-        __syncthreads();
-        if (i < HW) s[i] = s_base + s_warp[warp] + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += s_total;
-        __syncthreads();
+        run += n[j];
     }
 }
 
@@ -108,7 +160,7 @@ __global__ void __launch_bounds__(256) k_evrep_scatter(RepArgs a) {
     const int64_t HW = (int64_t)a.H * a.W;
     double t = load_as_double(a.ev.t, a.ev.t_dtype, i);
     if (a.ev.t_div != 1.0) t = t / a.ev.t_div;
-    const int slot = a.start[b * HW + q] + atomicAdd(a.cursor + b * HW + q, 1);
+    const int slot = atomicAdd(a.cursor + b * HW + q, 1);
     a.sorted_t[a.ev.offsets[b] - a.begin + slot] = t;
 }
 
@@ -153,7 +205,7 @@ __global__ void __launch_bounds__(256) k_evrep_sort(RepArgs a) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)a.ev.B * HW) return;
     const int b = (int)(idx / HW);
-    const int n = a.cnt[idx];
+    const int n = cnt_of(a.cp[idx]);
     if (n > 1) sort_segment(a.sorted_t + (a.ev.offsets[b] - a.begin) + a.start[idx], n);
 }
 
@@ -165,7 +217,8 @@ __global__ void __launch_bounds__(256) k_evrep_finish(RepArgs a, double* __restr
     const int64_t pix = idx % HW;
     const int y = (int)(pix / a.W), x = (int)(pix % a.W);
     const int64_t qi = b * HW + (int64_t)x * a.H + y;
-    const int n = a.cnt[qi];
+    const unsigned long long cw = a.cp[qi];
+    const int n = cnt_of(cw);
     float tsum = 0.f, tsq = 0.f;
     if (n > 0) {
         const int64_t lo = (a.ev.offsets[b] - a.begin) + a.start[qi];
@@ -187,16 +240,18 @@ __global__ void __launch_bounds__(256) k_evrep_finish(RepArgs a, double* __restr
     if (et > 1000.0) et = 1000.0;                                             // :120
     double* o = out + (int64_t)b * 3 * HW + pix;
     o[0] = (double)n;
-    o[HW] = (double)a.pol[qi];
+    o[HW] = (double)pol_of(cw);
     o[2 * HW] = et;
 }
 
-struct RepLayout { size_t cnt, pol, start, cursor, sorted, total; };
+struct RepLayout { size_t cp, start, cursor, sums, sorted, total; int n_chunks; };
 
 RepLayout rep_layout(int B, int H, int W, int64_t n_total) {
     RepLayout L;
     const size_t plane = align_up(sizeof(int32_t) * (size_t)B * H * W, 256);
-    L.cnt = 0; L.pol = plane; L.start = 2 * plane; L.cursor = 3 * plane; L.sorted = 4 * plane;
+    L.n_chunks = (int)ceil_div64((int64_t)H * W, kScanChunk);
+    L.cp = 0; L.start = 2 * plane; L.cursor = 3 * plane; L.sums = 4 * plane;
+    L.sorted = L.sums + align_up(sizeof(int32_t) * (size_t)B * L.n_chunks, 256);
     L.total = L.sorted + align_up(sizeof(double) * (size_t)(n_total > 0 ? n_total : 1), 256);
     return L;
 }
@@ -220,6 +275,7 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
     if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype) || !(ev->t_div != 0.0))
         return EP_EINVAL;
     const int B = ev->batch;
+    if (B > 65535) return EP_EUNSUPPORTED;                       // samples ride blockIdx.y in the scan
     const int64_t begin = ev->offsets_host[0], end = ev->offsets_host[B];
     if (end < begin) return EP_EINVAL;
     for (int b = 0; b < B; ++b)
@@ -233,13 +289,14 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
     RepArgs a;
     a.ev = EvDesc{ev->x, ev->y, ev->t, ev->p, ev->xy_dtype, ev->t_dtype, ev->p_dtype, ev->t_div, ev->offsets, B};
     a.H = height; a.W = width; a.begin = begin; a.end = end;
-    a.cnt = reinterpret_cast<int32_t*>(ws + L.cnt);
-    a.pol = reinterpret_cast<int32_t*>(ws + L.pol);
+    a.cp = reinterpret_cast<unsigned long long*>(ws + L.cp);
     a.start = reinterpret_cast<int32_t*>(ws + L.start);
     a.cursor = reinterpret_cast<int32_t*>(ws + L.cursor);
+    a.sums = reinterpret_cast<int32_t*>(ws + L.sums);
+    a.n_chunks = L.n_chunks;
     a.sorted_t = reinterpret_cast<double*>(ws + L.sorted);
     a.bad = bad_count;
-    cudaError_t ce = cudaMemsetAsync(ws, 0, L.sorted, st);
+    cudaError_t ce = cudaMemsetAsync(ws, 0, L.start, st);      // the count / polarity words; start and cursor are written by the scan
     if (ce != cudaSuccess) return (int)ce;
     const int64_t n = end - begin;
     const int64_t cells = (int64_t)B * height * width;
@@ -247,7 +304,12 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
         k_evrep_hist<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a);
         EP_LAUNCH_CHECK();
     }
-    k_evrep_scan<<<B, 1024, 0, st>>>(a);
+    const dim3 scan_grid((unsigned)L.n_chunks, (unsigned)B);
+    k_evrep_chunk_sums<<<scan_grid, kScanThreads, 0, st>>>(a);
+    EP_LAUNCH_CHECK();
+    k_evrep_scan_sums<<<B, kScanThreads, 0, st>>>(a);
+    EP_LAUNCH_CHECK();
+    k_evrep_chunk_scan<<<scan_grid, kScanThreads, 0, st>>>(a);
     EP_LAUNCH_CHECK();
     if (n > 0) {
         k_evrep_scatter<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a);

@@ -243,6 +243,30 @@ def test_evrep_batch(ep):
         assert np.array_equal(out[b], oe.evrep(p[0], p[1], p[2], p[3], (W, H))), b
 
 
+def test_evrep_multi_chunk_scan(ep):
+    """Grids larger than one 4096-pixel scan chunk, an empty sample in the middle, unsorted stamps, a hot pixel: bit-exact."""
+    from oracle import events as oe
+    rng = np.random.default_rng(19)
+    H, W = 100, 131                                              # 13100 pixels: 4 chunks, the last one partial
+    counts = [20000, 0, 7, 40000]
+    parts = []
+    for n in counts:
+        parts.append((rng.integers(0, W, n).astype(np.int16), rng.integers(0, H, n).astype(np.int16),
+                      rng.permutation(np.sort(rng.uniform(0, 9e4, n))) if n == 7 else np.sort(rng.uniform(0, 9e4, n)),
+                      rng.integers(0, 2, n).astype(np.float64)))
+    parts[3][0][500:900] = 130
+    parts[3][1][500:900] = 99                                    # hot pixel in the last (partial) chunk
+    off = np.cumsum([0] + counts)
+    ev = ep.from_soa(*(np.concatenate([p[i] for p in parts]) for i in range(4)), off).to("cuda")
+    for rep in range(2):                                         # the workspace is reused: second call must not see stale words
+        out = ep.evrep(ev, (H, W), check=True).cpu().numpy()
+        for b, p in enumerate(parts):
+            if len(p[0]) == 0:
+                assert not out[b][:2].any()
+                continue
+            assert np.array_equal(out[b], oe.evrep(p[0], p[1], p[2], p[3], (W, H))), (b, rep)
+
+
 def _random_batch(ep, rng, counts, H, W, t_span=50_000, hot=None, unsorted=False):
     xs, ys, ts, ps = [], [], [], []
     for n in counts:
