@@ -202,20 +202,20 @@ __device__ void sort_segment(double* s, int n) {
 
 __global__ void __launch_bounds__(256) k_evrep_sort(RepArgs a) {
     const int64_t HW = (int64_t)a.H * a.W;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.ev.B * HW) return;
-    const int b = (int)(idx / HW);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // pixel of sample blockIdx.y, x-major
+    if (q >= HW) return;
+    const int b = blockIdx.y;
+    const int64_t idx = b * HW + q;
     const int n = cnt_of(a.cp[idx]);
     if (n > 1) sort_segment(a.sorted_t + (a.ev.offsets[b] - a.begin) + a.start[idx], n);
 }
 
 __global__ void __launch_bounds__(256) k_evrep_finish(RepArgs a, double* __restrict__ out) {
     const int64_t HW = (int64_t)a.H * a.W;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // b*HW + y*W + x  (output order)
-    if (idx >= (int64_t)a.ev.B * HW) return;
-    const int b = (int)(idx / HW);
-    const int64_t pix = idx % HW;
-    const int y = (int)(pix / a.W), x = (int)(pix % a.W);
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // y*W + x of sample blockIdx.y (output order)
+    if (pix >= HW) return;
+    const int b = blockIdx.y;
+    const int y = (int)((uint32_t)pix / (uint32_t)a.W), x = (int)((uint32_t)pix - (uint32_t)y * (uint32_t)a.W);
     const int64_t qi = b * HW + (int64_t)x * a.H + y;
     const unsigned long long cw = a.cp[qi];
     const int n = cnt_of(cw);
@@ -299,7 +299,8 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
     cudaError_t ce = cudaMemsetAsync(ws, 0, L.start, st);      // the count / polarity words; start and cursor are written by the scan
     if (ce != cudaSuccess) return (int)ce;
     const int64_t n = end - begin;
-    const int64_t cells = (int64_t)B * height * width;
+    if ((int64_t)height * width > 0x7fffffffLL) return EP_EUNSUPPORTED;
+    const dim3 cell_grid((unsigned)ceil_div64((int64_t)height * width, 256), (unsigned)B);      // one thread per pixel, samples on y
     if (n > 0) {
         k_evrep_hist<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a);
         EP_LAUNCH_CHECK();
@@ -314,10 +315,10 @@ int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, doubl
     if (n > 0) {
         k_evrep_scatter<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a);
         EP_LAUNCH_CHECK();
-        k_evrep_sort<<<(unsigned)ceil_div64(cells, 256), 256, 0, st>>>(a);
+        k_evrep_sort<<<cell_grid, 256, 0, st>>>(a);
         EP_LAUNCH_CHECK();
     }
-    k_evrep_finish<<<(unsigned)ceil_div64(cells, 256), 256, 0, st>>>(a, out);
+    k_evrep_finish<<<cell_grid, 256, 0, st>>>(a, out);
     EP_LAUNCH_CHECK();
     return EP_OK;
 }

@@ -136,14 +136,35 @@ __global__ void __launch_bounds__(256) k_hot_apply(float* __restrict__ hist, int
 }
 
 // ---- frame-side difference map (self-defined formula; sign flip = view_augment.py:60-63)
+// Samples ride blockIdx.y (the negate flag is per sample: no per-element division); VEC: 16-byte loads and stores.
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_diffmap(const float* __restrict__ f0, const float* __restrict__ f1,
-                                                 float* __restrict__ out, int64_t n, int64_t per_sample, int mode,
+                                                 float* __restrict__ out, int64_t n_samples, int64_t per_sample, int mode,
                                                  float eps, const uint8_t* __restrict__ negate) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float a = ld_stream(f0 + i), b = ld_stream(f1 + i);
-        float d = mode == 1 ? __fsub_rn(logf(b + eps), logf(a + eps)) : __fsub_rn(b, a);
-        if (negate && negate[i / per_sample]) d = -d;
-        st_stream(out + i, d);
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (VEC ? 4 : 1);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * (VEC ? 4 : 1);
+    for (int64_t s = blockIdx.y; s < n_samples; s += gridDim.y) {
+        const bool neg = negate && negate[s];
+        const int64_t base = s * per_sample;
+        for (int64_t i = first; i < per_sample; i += stride) {
+            if (VEC) {
+                const float4 a = ld_stream(reinterpret_cast<const float4*>(f0 + base + i));
+                const float4 b = ld_stream(reinterpret_cast<const float4*>(f1 + base + i));
+                float4 d;
+                if (mode == 1) {
+                    d.x = __fsub_rn(logf(b.x + eps), logf(a.x + eps)); d.y = __fsub_rn(logf(b.y + eps), logf(a.y + eps));
+                    d.z = __fsub_rn(logf(b.z + eps), logf(a.z + eps)); d.w = __fsub_rn(logf(b.w + eps), logf(a.w + eps));
+                } else {
+                    d.x = __fsub_rn(b.x, a.x); d.y = __fsub_rn(b.y, a.y); d.z = __fsub_rn(b.z, a.z); d.w = __fsub_rn(b.w, a.w);
+                }
+                if (neg) { d.x = -d.x; d.y = -d.y; d.z = -d.z; d.w = -d.w; }
+                st_stream(reinterpret_cast<float4*>(out + base + i), d);
+            } else {
+                const float a = ld_stream(f0 + base + i), b = ld_stream(f1 + base + i);
+                float d = mode == 1 ? __fsub_rn(logf(b + eps), logf(a + eps)) : __fsub_rn(b, a);
+                st_stream(out + base + i, neg ? -d : d);
+            }
+        }
     }
 }
 
@@ -245,9 +266,15 @@ int ep_mem_hotpixel(void* stream, float* hist, int batch, int height, int width,
 int ep_diffmap_frames(void* stream, const float* f0, const float* f1, float* out, int64_t n, int64_t per_sample,
                       int mode, float eps, const uint8_t* negate) {
     if (!f0 || !f1 || !out || n <= 0 || per_sample <= 0 || (mode != 0 && mode != 1)) return EP_EINVAL;
-    int64_t blocks = ep::ceil_div64(n, 256 * 4);
-    if (blocks > ep::kNumSMs * 16) blocks = ep::kNumSMs * 16;
-    ep::k_diffmap<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f0, f1, out, n, per_sample, mode, eps, negate);
+    if (n % per_sample) return EP_EINVAL;
+    const int64_t n_samples = n / per_sample;
+    const bool vec = per_sample % 4 == 0 && ep::aligned16(f0) && ep::aligned16(f1) && ep::aligned16(out);
+    int64_t bx = ep::ceil_div64(per_sample, 256 * (vec ? 4 : 1));
+    if (bx > ep::kNumSMs * 16) bx = ep::kNumSMs * 16;
+    const dim3 grid((unsigned)bx, (unsigned)(n_samples < 65535 ? n_samples : 65535));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec) ep::k_diffmap<true><<<grid, 256, 0, st>>>(f0, f1, out, n_samples, per_sample, mode, eps, negate);
+    else ep::k_diffmap<false><<<grid, 256, 0, st>>>(f0, f1, out, n_samples, per_sample, mode, eps, negate);
     EP_LAUNCH_CHECK();
     return EP_OK;
 }

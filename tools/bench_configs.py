@@ -156,6 +156,14 @@ def f_rows():
     from types import SimpleNamespace
     from eventpretrain_b200.view_augment import ViewChoice
     B, C, H, W = 256, 5, 480, 640
+    # a8: frame-side difference map at the C2 batch (two frames in, one map out; SURVEY 8(d): 4*H*W*(inputs+1) bytes per sample)
+    f0 = torch.rand(B, 1, H, W, device=dev) + 0.1
+    f1 = torch.rand(B, 1, H, W, device=dev) + 0.1
+    flips = [int(i % 2) for i in range(B)]
+    for mode in ("linear", "log"):
+        ms = timeit(lambda: ep.diffmap_frames(f0, f1, mode, negate=flips), reps=20)
+        report(f"a8 diff-map target from frames (256,1,480,640), {mode}, per-sample sign flip", ms, B * 4 * H * W * 3, B, "samples", launches=1)
+    del f0, f1
     x = torch.randn(B, C, H, W, device=dev)
     rng = np.random.default_rng(7)
     choices = []
