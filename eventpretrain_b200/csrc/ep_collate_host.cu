@@ -12,6 +12,13 @@
 
 #include "ep_common.cuh"
 
+// The streaming loops below are compiled twice on x86-64 (AVX2 and baseline) and picked at load time by the CPU.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define EP_HOST_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define EP_HOST_CLONES
+#endif
+
 namespace ep {
 namespace {
 
@@ -58,22 +65,70 @@ int owner_of(const int64_t* off, int B, int64_t i) {
     return lo;
 }
 
-template <class T>
-bool collate_sample(const T* s, int64_t n, double t_scale, uint16_t* x, uint16_t* y, int64_t* t, uint8_t* p) {
-    bool ok = true;
-    for (int64_t i = 0; i < n; ++i) {
-        const double fx = (double)s[4 * i], fy = (double)s[4 * i + 1], ft = (double)s[4 * i + 2], fp = (double)s[4 * i + 3];
-        const bool in_range = fx >= 0.0 && fx <= 65535.0 && fy >= 0.0 && fy <= 65535.0;      // (also false for NaN)
-        const uint16_t ux = in_range ? (uint16_t)fx : 0, uy = in_range ? (uint16_t)fy : 0;
-        ok &= in_range && (double)ux == fx && (double)uy == fy && (fp == 0.0 || fp == 1.0);
-        // rint() by the 1.5 * 2^52 trick (round-to-nearest-even, exact for |v| < 2^51): no libm call in the loop
-        const double v = ft * t_scale;
-        const double ticks = (v + 6755399441055744.0) - 6755399441055744.0;
-        ok &= std::fabs(v) < 2251799813685248.0;
-        x[i] = ux; y[i] = uy; p[i] = (uint8_t)(fp != 0.0);
-        t[i] = (int64_t)ticks;
+#define EP_DEFINE_COLLATE(NAME, T) \
+EP_HOST_CLONES bool NAME(const T* s, int64_t n, double t_scale, uint16_t* x, uint16_t* y, int64_t* t, uint8_t* p) { \
+    bool ok = true; \
+    for (int64_t i = 0; i < n; ++i) { \
+        const double fx = (double)s[4 * i], fy = (double)s[4 * i + 1], ft = (double)s[4 * i + 2], fp = (double)s[4 * i + 3]; \
+        const bool in_range = fx >= 0.0 && fx <= 65535.0 && fy >= 0.0 && fy <= 65535.0; \
+        const uint16_t ux = in_range ? (uint16_t)fx : 0, uy = in_range ? (uint16_t)fy : 0; \
+        ok &= in_range && (double)ux == fx && (double)uy == fy && (fp == 0.0 || fp == 1.0); \
+ \
+        const double v = ft * t_scale; \
+        const double ticks = (v + 6755399441055744.0) - 6755399441055744.0; \
+        ok &= std::fabs(v) < 2251799813685248.0; \
+        x[i] = ux; y[i] = uy; p[i] = (uint8_t)(fp != 0.0); \
+        t[i] = (int64_t)ticks; \
+    } \
+    return ok; \
+}
+EP_DEFINE_COLLATE(collate_f64, double)
+EP_DEFINE_COLLATE(collate_f32, float)
+#undef EP_DEFINE_COLLATE
+
+// rint() above is the 1.5 * 2^52 trick (round-to-nearest-even, exact for |v| < 2^51): no libm call in the loop.
+
+EP_HOST_CLONES int64_t min_run(const int64_t* t, int64_t i0, int64_t i1) {
+    int64_t m = t[i0];
+    for (int64_t i = i0 + 1; i < i1; ++i) m = t[i] < m ? t[i] : m;
+    return m;
+}
+
+// one branch-free run of events of one sample inside a block; returns the OR of all range violations
+EP_HOST_CLONES uint64_t pack_run5(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, int64_t lo, int64_t hi,
+                                  int64_t sub, uint32_t* w, uint8_t* tick_low) {
+    uint64_t viol = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t ticks = (uint64_t)(t[i] - sub);
+        const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
+        viol |= (ticks >> 17) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
+        w[i] = xi | (yi << 11) | (pi << 22) | ((tk >> 8) << 23);
+        tick_low[i] = (uint8_t)(tk & 0xffu);
     }
-    return ok;
+    return viol;
+}
+
+EP_HOST_CLONES uint64_t pack_run4(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p, int64_t lo, int64_t hi,
+                                  int64_t sub, uint32_t* w) {
+    uint64_t viol = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t ticks = (uint64_t)(t[i] - sub);
+        const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
+        viol |= (ticks >> 9) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
+        w[i] = xi | (yi << 11) | (pi << 22) | (tk << 23);
+    }
+    return viol;
+}
+
+EP_HOST_CLONES uint64_t pack_run8(const int64_t* t, const uint8_t* p, int64_t lo, int64_t hi, int64_t base, uint32_t* w) {
+    uint64_t viol = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t rel = (uint64_t)(t[i] - base);
+        const uint32_t pi = p[i];
+        viol |= (rel >> 31) | (uint64_t)(pi >> 1);
+        w[i] = (uint32_t)rel | (pi << 31);
+    }
+    return viol;
 }
 
 }  // namespace
@@ -108,8 +163,8 @@ int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int b
         const int64_t n = counts[b] - i0 < kPiece ? counts[b] - i0 : kPiece;
         const int64_t o = offsets[b] + i0;
         const bool ok = dtype == EP_F64
-            ? collate_sample(static_cast<const double*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o)
-            : collate_sample(static_cast<const float*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o);
+            ? collate_f64(static_cast<const double*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o)
+            : collate_f32(static_cast<const float*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o);
         if (!ok) bad.store(1, std::memory_order_relaxed);
     });
     return bad.load() ? EP_EUNSUPPORTED : EP_OK;
@@ -143,9 +198,7 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
         }
         const int64_t i0 = offsets[lo] + (item - first_piece[lo]) * kPiece;
         const int64_t i1 = i0 + kPiece < offsets[lo + 1] ? i0 + kPiece : offsets[lo + 1];
-        int64_t m = t[i0];
-        for (int64_t i = i0 + 1; i < i1; ++i) m = t[i] < m ? t[i] : m;
-        part[(size_t)item] = m;
+        part[(size_t)item] = min_run(t, i0, i1);
     });
     for (int b = 0; b < batch; ++b) {
         int64_t m = 0;
@@ -162,15 +215,7 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
             }
             const int64_t i0 = offsets[lo] + (item - first_piece[lo]) * kPiece;
             const int64_t i1 = i0 + kPiece < offsets[lo + 1] ? i0 + kPiece : offsets[lo + 1];
-            const int64_t base = t_base[lo];
-            uint64_t viol = 0;
-            for (int64_t i = i0; i < i1; ++i) {
-                const uint64_t rel = (uint64_t)(t[i] - base);
-                const uint32_t pi = p[i];
-                viol |= (rel >> 31) | (uint64_t)(pi >> 1);
-                w[i] = (uint32_t)rel | (pi << 31);
-            }
-            if (viol) bad.store(1, std::memory_order_relaxed);
+            if (pack_run8(t, p, i0, i1, t_base[lo], w)) bad.store(1, std::memory_order_relaxed);
         });
         return bad.load() ? EP_EUNSUPPORTED : EP_OK;
     }
@@ -180,9 +225,7 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
         while (offsets[b + 1] <= i0) ++b;      // (owner_of lands on the last sample starting at or before i0: never empty, kept as a guard)
         // tick offset of the block: smallest relative stamp among the events of the sample that owns the block's first slot
         const int64_t own_end = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
-        int64_t m = t[i0];
-        for (int64_t i = i0 + 1; i < own_end; ++i) m = t[i] < m ? t[i] : m;
-        m -= t_base[b];
+        int64_t m = min_run(t, i0, own_end) - t_base[b];
         bool ok = m >= 0 && m < ((int64_t)1 << 32);
         const int64_t add_own = ok ? m : 0;
         blk_base[g] = (uint32_t)add_own;
@@ -192,22 +235,7 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
             while (lo >= offsets[b + 1]) ++b;
             const int64_t hi = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
             const int64_t sub = t_base[b] + (offsets[b] / K == g ? 0 : add_own);
-            if (nbytes == 5) {
-                for (int64_t i = lo; i < hi; ++i) {
-                    const uint64_t ticks = (uint64_t)(t[i] - sub);
-                    const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
-                    viol |= (ticks >> tick_bits) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
-                    w[i] = xi | (yi << 11) | (pi << 22) | ((tk >> 8) << 23);
-                    tick_low[i] = (uint8_t)(tk & 0xffu);
-                }
-            } else {
-                for (int64_t i = lo; i < hi; ++i) {
-                    const uint64_t ticks = (uint64_t)(t[i] - sub);
-                    const uint32_t xi = x[i], yi = y[i], pi = p[i], tk = (uint32_t)ticks;
-                    viol |= (ticks >> tick_bits) | (uint64_t)((xi | yi) >> 11) | (uint64_t)(pi >> 1);
-                    w[i] = xi | (yi << 11) | (pi << 22) | (tk << 23);
-                }
-            }
+            viol |= nbytes == 5 ? pack_run5(x, y, t, p, lo, hi, sub, w, tick_low) : pack_run4(x, y, t, p, lo, hi, sub, w);
             lo = hi;
         }
         if (!ok || viol) bad.store(1, std::memory_order_relaxed);
