@@ -139,7 +139,7 @@ extern "C" {
 int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale, uint16_t* x,
                         uint16_t* y, int64_t* t, uint8_t* p, int64_t* offsets, int threads) {
     using namespace ep;
-    if (!samples || !counts || !x || !y || !t || !p || !offsets || batch <= 0) return EP_EINVAL;
+    if (!samples || !counts || !offsets || batch <= 0) return EP_EINVAL;
     if (dtype != EP_F64 && dtype != EP_F32) return EP_EINVAL;
     if (!(t_scale > 0.0)) return EP_EINVAL;
     offsets[0] = 0;
@@ -147,6 +147,8 @@ int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int b
         if (counts[b] < 0 || (counts[b] > 0 && !samples[b])) return EP_EINVAL;
         offsets[b + 1] = offsets[b] + counts[b];
     }
+    if (offsets[batch] == 0) return EP_OK;                      // a batch of empty samples: nothing to write
+    if (!x || !y || !t || !p) return EP_EINVAL;
     // work items = (sample, 64K-event piece) so that a few long samples still spread over all threads
     constexpr int64_t kPiece = 1 << 16;
     std::vector<int64_t> first_piece((size_t)batch + 1, 0);
@@ -174,13 +176,18 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
                            int batch, int nbytes, uint32_t* w, uint8_t* tick_low, uint32_t* blk_base, int64_t* t_base,
                            int threads) {
     using namespace ep;
-    if (!t || !p || !offsets || !w || !t_base || batch <= 0) return EP_EINVAL;
+    if (!offsets || !t_base || batch <= 0) return EP_EINVAL;
     if (nbytes != 4 && nbytes != 5 && nbytes != 8) return EP_EINVAL;
-    if (nbytes != 8 && (!x || !y || !blk_base)) return EP_EINVAL;
-    if (nbytes == 5 && !tick_low) return EP_EINVAL;
     if (nbytes != 8 ? offsets[0] != 0 : offsets[0] < 0) return EP_EINVAL;      // block offsets are tied to array positions
     for (int b = 0; b < batch; ++b)
         if (offsets[b + 1] < offsets[b]) return EP_EINVAL;
+    if (offsets[batch] == offsets[0]) {                          // a batch of empty samples: only the bases exist
+        for (int b = 0; b < batch; ++b) t_base[b] = 0;
+        return EP_OK;
+    }
+    if (!t || !p || !w) return EP_EINVAL;
+    if (nbytes != 8 && (!x || !y || !blk_base)) return EP_EINVAL;
+    if (nbytes == 5 && !tick_low) return EP_EINVAL;
     const int64_t n = offsets[batch];
     const int64_t K = nbytes == 5 ? 1024 : 256;
     const int tick_bits = nbytes == 5 ? 17 : 9;

@@ -145,3 +145,13 @@ def test_native_compact_equals_the_numpy_rule():
     for native in (True, False):
         with pytest.raises(ValueError):
             far.compact(native=native)
+
+
+def test_host_packers_accept_batches_of_empty_samples():
+    ev = ep.from_soa(np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(0, np.int64), np.zeros(0, np.uint8), np.array([0, 0, 0]),
+                     t_div=1e6, pin=False)
+    for make in (lambda: ev.packed(5), lambda: ev.packed(4), ev.compact, lambda: ev.packed(5, native=False), lambda: ev.compact(native=False)):
+        r = make()
+        assert r.batch == 2 and r.num_events == 0 and r.t_base.tolist() == [0, 0]
+    c = ep.collate_events([np.zeros((0, 4)), np.zeros((0, 4))], pin=False)
+    assert c.batch == 2 and c.num_events == 0 and c.offsets_host.tolist() == [0, 0, 0]
