@@ -7,6 +7,10 @@
 // event; numpy does them at ~0.1 Gevents/s, a GPU bins 13 Gevents/s end to end, so they are threaded C++ here.
 #include <atomic>
 #include <cmath>
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#include <immintrin.h>
+#define EP_HOST_AVX2 1
+#endif
 #include <thread>
 #include <vector>
 
@@ -86,6 +90,46 @@ EP_DEFINE_COLLATE(collate_f64, double)
 EP_DEFINE_COLLATE(collate_f32, float)
 #undef EP_DEFINE_COLLATE
 
+#ifdef EP_HOST_AVX2
+// float64 rows, four events per step: 4x4 transpose of the (x, y, t, p) rows, the same checks and the same rint trick as the
+// scalar loop (the integer stamp is read off the mantissa of v + 1.5 * 2^52, exact for |v| < 2^51); tail in scalar code.
+__attribute__((target("avx2"))) bool collate_f64_avx2(const double* s, int64_t n, double t_scale, uint16_t* x, uint16_t* y, int64_t* t,
+                                                      uint8_t* p) {
+    const __m256d zero = _mm256_setzero_pd(), one = _mm256_set1_pd(1.0), top = _mm256_set1_pd(65535.0);
+    const __m256d scale = _mm256_set1_pd(t_scale), magic = _mm256_set1_pd(6755399441055744.0), lim = _mm256_set1_pd(2251799813685248.0);
+    const __m256d absmask = _mm256_castsi256_pd(_mm256_set1_epi64x(0x7fffffffffffffffLL));
+    const __m256i magic_bits = _mm256_castpd_si256(magic);
+    __m256d ok = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m256d r0 = _mm256_loadu_pd(s + 4 * i), r1 = _mm256_loadu_pd(s + 4 * i + 4);
+        const __m256d r2 = _mm256_loadu_pd(s + 4 * i + 8), r3 = _mm256_loadu_pd(s + 4 * i + 12);
+        const __m256d a = _mm256_unpacklo_pd(r0, r1), b = _mm256_unpackhi_pd(r0, r1);      // [x0 x1 t0 t1], [y0 y1 p0 p1]
+        const __m256d c = _mm256_unpacklo_pd(r2, r3), d = _mm256_unpackhi_pd(r2, r3);
+        const __m256d X = _mm256_permute2f128_pd(a, c, 0x20), T = _mm256_permute2f128_pd(a, c, 0x31);
+        const __m256d Y = _mm256_permute2f128_pd(b, d, 0x20), P = _mm256_permute2f128_pd(b, d, 0x31);
+        const __m128i xi = _mm256_cvttpd_epi32(X), yi = _mm256_cvttpd_epi32(Y);
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(X, zero, _CMP_GE_OQ), _mm256_cmp_pd(X, top, _CMP_LE_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(Y, zero, _CMP_GE_OQ), _mm256_cmp_pd(Y, top, _CMP_LE_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtepi32_pd(xi), X, _CMP_EQ_OQ), _mm256_cmp_pd(_mm256_cvtepi32_pd(yi), Y, _CMP_EQ_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_or_pd(_mm256_cmp_pd(P, zero, _CMP_EQ_OQ), _mm256_cmp_pd(P, one, _CMP_EQ_OQ)));
+        const __m256d v = _mm256_mul_pd(T, scale);
+        ok = _mm256_and_pd(ok, _mm256_cmp_pd(_mm256_and_pd(v, absmask), lim, _CMP_LT_OQ));
+        const __m256i ticks = _mm256_sub_epi64(_mm256_castpd_si256(_mm256_add_pd(v, magic)), magic_bits);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(t + i), ticks);
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(x + i), _mm_packus_epi32(xi, xi));
+        _mm_storel_epi64(reinterpret_cast<__m128i*>(y + i), _mm_packus_epi32(yi, yi));
+        const __m128i pi = _mm256_cvttpd_epi32(P);
+        const __m128i p16 = _mm_packus_epi32(pi, pi);
+        const int p4 = _mm_cvtsi128_si32(_mm_packus_epi16(p16, p16));
+        __builtin_memcpy(p + i, &p4, 4);
+    }
+    bool all = _mm256_movemask_pd(ok) == 0xf;
+    if (i < n) all &= collate_f64(s + 4 * i, n - i, t_scale, x + i, y + i, t + i, p + i);
+    return all;
+}
+#endif
+
 // rint() above is the 1.5 * 2^52 trick (round-to-nearest-even, exact for |v| < 2^51): no libm call in the loop.
 
 EP_HOST_CLONES int64_t min_run(const int64_t* t, int64_t i0, int64_t i1) {
@@ -164,6 +208,14 @@ int ep_collate_aos_host(const void* const* samples, const int64_t* counts, int b
         const int64_t i0 = (item - first_piece[b]) * kPiece;
         const int64_t n = counts[b] - i0 < kPiece ? counts[b] - i0 : kPiece;
         const int64_t o = offsets[b] + i0;
+#ifdef EP_HOST_AVX2
+        static const bool have_avx2 = __builtin_cpu_supports("avx2");
+        if (dtype == EP_F64 && have_avx2) {
+            if (!collate_f64_avx2(static_cast<const double*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o))
+                bad.store(1, std::memory_order_relaxed);
+            return;
+        }
+#endif
         const bool ok = dtype == EP_F64
             ? collate_f64(static_cast<const double*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o)
             : collate_f32(static_cast<const float*>(samples[b]) + 4 * i0, n, t_scale, x + o, y + o, t + o, p + o);

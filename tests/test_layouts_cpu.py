@@ -155,3 +155,15 @@ def test_host_packers_accept_batches_of_empty_samples():
         assert r.batch == 2 and r.num_events == 0 and r.t_base.tolist() == [0, 0]
     c = ep.collate_events([np.zeros((0, 4)), np.zeros((0, 4))], pin=False)
     assert c.batch == 2 and c.num_events == 0 and c.offsets_host.tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_native_collate_rejections_inside_vector_groups(dtype):
+    """Violations anywhere in a sample (not only in the scalar tail of the 4-wide AVX2 loop) are reported."""
+    base = np.stack([np.arange(13) % 7, np.arange(13) % 5, np.arange(13) * 1e-6, np.arange(13) % 2], 1).astype(dtype)
+    assert ep.collate_events([base], 1e6, pin=False).num_events == 13
+    for row, col, val in ((2, 0, 0.5), (5, 1, -1.0), (6, 0, 65536.0), (1, 3, 2.0), (9, 3, -1.0), (3, 1, np.nan), (12, 0, 1.25)):
+        bad = base.copy()
+        bad[row, col] = val
+        with pytest.raises(ValueError):
+            ep.collate_events([base, bad], 1e6, pin=False)
