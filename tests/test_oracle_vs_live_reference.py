@@ -73,3 +73,51 @@ def test_evrep(ref, seed):
     want = ref.evrep(xs.copy(), ys.copy(), ts.copy(), ps.copy(), resolution=(W, H))
     got = oe.evrep(xs, ys, ts, ps, (W, H))
     assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.fixture(scope="module")
+def ref_models():
+    """The reference's model-side modules (timm is absent from the image: the 3-symbol stub of tests/golden/make_golden.py)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    saved = list(sys.path)
+    try:
+        return make_golden._import_reference()
+    finally:
+        sys.path[:] = saved
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_masking_and_target(ref_models, seed):
+    """random_masking (random / density / anti-density), frame2emb and the norm_pix target of reconstruct_loss."""
+    import torch
+    from oracle import stage3_np as s3
+    rng = np.random.default_rng(3000 + seed)
+    p = [16, 8, 32][seed % 3]
+    g = int(rng.integers(2, 8))
+    B, C, S = int(rng.integers(1, 5)), int(rng.integers(1, 6)), g * p
+    L = g * g
+    ratio = [0.75, 0.5, 0.9][seed % 3]
+    strategy = ["random", "density", "anti-density"][seed % 3 if seed < 6 else 0]
+    x = torch.from_numpy(rng.standard_normal((B, C, S, S)).astype(np.float32))
+    fake = SimpleNamespace(num_patches=L, mask_ratio=ratio, patch_size=p, args=SimpleNamespace(masking_strategy=strategy))
+    torch.manual_seed(seed)
+    ik, m, ir = ref_models.vit.ViT.random_masking(fake, x)                # model/backbone/vit.py:66-105, unbound
+    if strategy == "random":
+        torch.manual_seed(seed)
+        noise = torch.rand(B, L).numpy()
+    else:
+        noise = s3.patch_density(x.numpy(), p) * (1.0 if strategy == "density" else -1.0)
+        want = torch.nn.AvgPool2d(p, p)(abs(torch.sum(x, dim=1))).flatten(1).numpy() * (1.0 if strategy == "density" else -1.0)
+        assert np.array_equal(noise, want)
+    keep = s3.len_keep(L, ratio)
+    gk, gm, gr = s3.mask_from_noise(noise, keep)
+    clean = ~s3.rows_with_ties(noise)                                     # unstable argsort: parity is defined on tie-free rows
+    assert np.array_equal(gk[clean], ik.numpy()[clean]) and np.array_equal(gm[clean], m.numpy()[clean])
+    assert np.array_equal(gr[clean], ir.numpy()[clean])
+    frame = torch.from_numpy(rng.standard_normal((B, 1, S, S)).astype(np.float32))
+    emb = ref_models.reshape.frame2emb(p, frame)
+    assert np.array_equal(s3.target_normpix(frame.numpy(), p, False), emb.numpy())
+    tgt = (emb - emb.mean(dim=-1, keepdim=True)) / (emb.var(dim=-1, keepdim=True) + 1.0e-6) ** .5    # pr_hub_model.py:129-131
+    got = s3.target_normpix(frame.numpy(), p, True)
+    assert np.all(np.abs(got - tgt.numpy()) <= 1e-5 * np.abs(tgt.numpy()) + 1e-6)
