@@ -122,9 +122,9 @@ class RaggedEvents:
         """Events per tick-offset block of a packed() batch: 1024 (5 B/event form) or 256 (4 B/event form)."""
         return 1024 if self.t is not None else 256
 
-    def transport(self):
+    def transport(self, threads=0):
         """Densest lossless transport layout this batch fits: packed 4 B/event, else packed 5 B/event, else compact 8 B/event."""
-        for make in (lambda: self.packed(4), lambda: self.packed(5), self.compact):
+        for make in (lambda: self.packed(4, threads=threads), lambda: self.packed(5, threads=threads), lambda: self.compact(threads=threads)):
             try:
                 return make()
             except ValueError:
@@ -316,6 +316,37 @@ def collate_events(samples, ticks_per_unit=1.0e6, pin=True, threads=0):
         raise ValueError("canonical collate needs integer coordinates in [0, 65535] and polarity in {0, 1}")
     _lib.check(rc, "ep_collate_aos_host")
     return RaggedEvents(x, y, t, p, off, offsets_host=off.numpy().copy(), t_div=float(ticks_per_unit))
+
+
+class EventCollator:
+    """`collate_fn` for a torch DataLoader whose dataset returns the raw event window instead of binning it
+    (the reference bins per sample on the CPU inside `__getitem__`, e.g.
+    pr_n_imagenet_dataset.py:85-87).  Each item is a dict; `events_key` holds the reference-format (N,4) x,y,t,p array.
+    The events of the batch become one RaggedEvents (native threaded collate; the densest transport layout that fits when
+    layout="transport", the canonical 13 B/event layout when layout="canonical"); batches the canonical layout cannot
+    hold (fractional coordinates after erase_and_add_events, polarity -1) fall back to the generic layout.  Every other key
+    goes through torch's default_collate.  Workers return unpinned buffers; `DataLoader(pin_memory=True)` pins the batch
+    through `RaggedEvents.pin_memory()`.  threads=1 suits many worker processes; 0 uses every core of one."""
+
+    def __init__(self, events_key="events", ticks_per_unit=1.0e6, layout="transport", threads=1):
+        if layout not in ("transport", "canonical"):
+            raise ValueError("layout is 'transport' or 'canonical'")
+        self.events_key, self.ticks_per_unit, self.layout, self.threads = events_key, float(ticks_per_unit), layout, int(threads)
+
+    def __call__(self, batch):
+        from torch.utils.data import default_collate
+        key = self.events_key
+        samples = [item[key] for item in batch]
+        rest = [{k: v for k, v in item.items() if k != key} for item in batch]
+        out = default_collate(rest) if rest and rest[0] else {}
+        try:
+            ev = collate_events(samples, self.ticks_per_unit, pin=False, threads=self.threads)
+            if self.layout == "transport":
+                ev = ev.transport(threads=self.threads)
+        except ValueError:
+            ev = pack_events(samples, canonical=False, pin=False)
+        out[key] = ev
+        return out
 
 
 def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
