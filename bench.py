@@ -38,6 +38,7 @@ H, W, BINS = 480, 640, 5
 BATCH, MEAN_EVENTS = 256, 1_000_000
 WORKLOAD = "N-ImageNet-shaped ragged batch 256 x ~1M events, 640x480 -> 5-bin voxel grid + voxel.sum(0) diff-map target (sensor-res)"
 BYTES_PER_EVENT = 13
+WINDOW_US = 300_000      # stamps uniform in [0, 0.3 s)
 
 
 def counts_for(rank, batch=BATCH, mean=MEAN_EVENTS):
@@ -50,9 +51,9 @@ def algorithmic_bytes(n_events, batch):
     return BYTES_PER_EVENT * n_events + 4 * (BINS + 1) * H * W * batch
 
 
-def make_batch_gpu(rank, device, skewed=False, batch=BATCH, mean=MEAN_EVENTS):
+def make_batch_gpu(rank, device, skewed=False, batch=BATCH, mean=MEAN_EVENTS, window_us=WINDOW_US):
     """Synthetic streams generated on the device: uniform pixels (or the skewed mix: 70 % on 64 line segments,
-    0.1 % on 32 hot pixels), time-sorted int64 microsecond stamps in a 50 ms window, p in {0,1}."""
+    0.1 % on 32 hot pixels), time-sorted int64 microsecond stamps in a 0.3 s window, p in {0,1}."""
     import torch
     import eventpretrain_b200 as ep
     counts = counts_for(rank, batch, mean)
@@ -83,7 +84,7 @@ def make_batch_gpu(rank, device, skewed=False, batch=BATCH, mean=MEAN_EVENTS):
     t = torch.empty(n, dtype=torch.int64, device=device)
     for b in range(batch):
         lo, hi = int(off[b]), int(off[b + 1])
-        t[lo:hi] = torch.sort(torch.randint(0, 50_000, (hi - lo,), device=device, generator=g)).values
+        t[lo:hi] = torch.sort(torch.randint(0, window_us, (hi - lo,), device=device, generator=g)).values
     ev = ep.RaggedEvents(x.to(torch.uint16), y.to(torch.uint16), t, p, torch.from_numpy(off).to(device), off, t_div=1e6)
     return ev
 

@@ -34,6 +34,11 @@ int run_banded_canon(cudaStream_t st, const ep_events_soa* ev, const ep_bin_para
 size_t banded_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
 bool banded_worthwhile(const ep_events_soa* ev, const ep_bin_params* p);
 
+// finalize-free shared-memory path (ep_binning_tiled.cu): 4 B/event packed layout, voxel grid (+ sum plane)
+int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                      void* ws, size_t ws_bytes, unsigned int* bad);
+size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
+
 namespace {
 
 // ---- scatter ----------------------------------------------------------------------------------------
@@ -532,6 +537,8 @@ size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_p
     if (!(prm->flags & EP_BIN_FORCE_GLOBAL) && ev->offsets_host) {
         const size_t b = ep::banded_workspace_bytes(ev, prm);
         if (b > need) need = b;
+        const size_t t = ep::tiled_workspace_bytes(ev, prm);
+        if (t > need) need = t;
     }
     return need;
 }
@@ -560,6 +567,14 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
         if (ev->y != nullptr || (!ev->p && n_events > 0) || ev->p_dtype != EP_U32 || !ev->t_base || prm->time_f32) return EP_EINVAL;
         if (!aligned16(ev->x) || !aligned16(ev->t)) return EP_EALIGN;
         if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
+        if (!five && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
+            // default: route + two-plane shared-memory sweep, no global accumulators (ep_binning_tiled.cu); shapes, workspaces or
+            // outputs it does not take (count frames, > 64 row tiles) fall through to the global-RED kernels
+            rc = run_tiled_packed4(st, ev, prm, out_voxel, out_voxel_sum, workspace, workspace_bytes, bad_count);
+            if (rc != EP_EUNSUPPORTED || (prm->flags & EP_BIN_FORCE_TILED)) return rc;
+        } else if (prm->flags & EP_BIN_FORCE_TILED) {
+            return EP_EUNSUPPORTED;
+        }
         if (five) {
             SoaPackedLoader<true> ld{static_cast<const uint32_t*>(ev->x), static_cast<const uint8_t*>(ev->t),
                                      static_cast<const uint32_t*>(ev->p), ev->t_base, ev->t_div};
@@ -570,6 +585,7 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
         return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
                            workspace_bytes, bad_count);
     }
+    if (prm->flags & EP_BIN_FORCE_TILED) return EP_EUNSUPPORTED;
     const bool compact = ev->t_dtype == EP_U32;
     if (compact) {
         // compact transport layout: u16 x,y + u32 (relative ticks | polarity << 31) + per-sample int64 base

@@ -1,0 +1,850 @@
+// Stage 1, default fast path — finalize-free, shared-memory-privatised voxel binning (sm_100a).
+//
+// Replaces events_to_voxel_grid (dataset/dataset_utils/events_to_voxel_grid.py:4-61), the fused events_reshape scale
+// (dataset/augmentation/events_augment.py:22-26; the reference's own pre-training order "rescale to 224x224, then bin",
+// dataset/pretrain/pr_n_imagenet_dataset.py:85-87) and voxel.sum(0) (dataset/pretrain/pr_ef_imagenet_dataset.py:192-193)
+// for a ragged batch in the 4 B/event packed transport layout.  Same integers as the global-RED path of ep_binning.cu
+// (Q24 fixed-point weights, one rounding per output element), so the two are bit-identical; that path stays as the
+// general one (any layout, count frames, fp64 stamps, grids whose rows do not fit a tile).
+//
+// Design:
+//   * route (k_route): one CTA per 8192-event chunk of one sample.  Each event becomes a 4-byte record
+//         [ polarity as a signed 2-bit field (+1 / -1):2 | cell-in-tile:14 | ticks relative to the chunk:16 ]
+//     and the chunk's records are bucketed by row tile (a tile = `rows` full rows of the output grid, at most 12800 cells)
+//     with one returning shared-memory atomic per event for the rank, staged in shared memory and written back coalesced.
+//     Coordinates go through shared-memory look-up tables (fp64 scale and truncation of events_reshape, tile id, row base),
+//     out-of-grid events land in a trash bucket that is counted into bad_count and never read.  No weights are computed
+//     here: a record stays 4 bytes, so the route moves 4 B in + 4 B out per event.  The next task's event words are
+//     requested before the current task's records are copied out.
+//   * sweep (k_sweep): persistent CTAs, two per SM; a task is (sample, tile).  Two adjacent output planes of the tile
+//     live in shared memory as int32 Q24 sums (100 KB).  The task walks the temporal intervals k = 0 .. bins-1: the events
+//     of interval k (found through the per-chunk interval range the route wrote; contiguous for time-sorted streams, any
+//     order is handled) add 2^24 - r to plane k and r to plane k + 1 with two shared-memory atomics, then plane k is
+//     converted to fp32 (one rounding), written to the output with 16-byte streaming stores, added into the voxel.sum(0)
+//     plane (sequential fp32 over bins, like the reference's sum), and its buffer is re-zeroed to become plane k + 2.
+//     The runs (chunk, tile) of a phase are cut into items of at most 128 records that the warps draw from a shared
+//     counter, with the next item's records in flight while the current one is accumulated.
+//     Every record is read once; there are no global accumulators, no memset and no finalize pass.
+//   * exactness under any distribution: the int32 plane words may wrap (more than 127 same-polarity events on one cell
+//     within one interval pair).  Every atomic returns the old value; a wrap is detected when it happens and logged as a
+//     +-2^32 correction in a small spill list that the flush applies in 64-bit arithmetic.  Integer adds commute, so the
+//     result does not depend on the order of events, warps or CTAs: bit-reproducible.
+//   * generality: chunks whose stamps span 2^16 ticks or more keep block-relative ticks in the record ("wide" format),
+//     and samples without integer-time constants (deltaT == 0, last row before the first) use the fp64 expression; both
+//     take an out-of-line slow path in the sweep.
+#include "ep_binning_common.cuh"
+
+namespace ep {
+
+namespace {
+
+constexpr int kChunkShift = 13;
+constexpr int kChunk = 1 << kChunkShift;      // events per route task = 32 tick blocks of the 4 B layout
+constexpr int kTickBlockShift = 8;            // 256-event tick blocks (SoaPackedLoader<false>)
+constexpr int kMaxTiles = 64;
+constexpr int kTileCells = 12800;             // cells of a plane tile: two live planes = 100 KB -> two sweep CTAs per SM
+constexpr int kRouteThreads = 512;
+constexpr int kRouteEv = kChunk / kRouteThreads;   // 16 events per thread, as 4 quads
+constexpr int kSweepThreads = 512;
+constexpr int kTabCap = kSweepThreads;        // chunks of one sample whose run table is resident (one per thread)
+constexpr int kItemCap = 384;                 // items (<= 128 records each, 8-byte descriptors) listed per round of a phase
+constexpr int kItemRecs = 128;
+constexpr int kSpillCap = 128;
+
+constexpr uint32_t kChunkFast = 1u;           // integer-tick sample, narrow records, every v of the chunk fits 32 bits
+constexpr uint32_t kChunkNarrow = 2u;         // records carry chunk-relative ticks (else: tick block + block-relative ticks)
+
+struct __align__(16) ChunkMeta {
+    int64_t cbase;        // ticks: smallest block base of the task minus the sample's first-row ticks
+    uint32_t pos0;        // position (in the record array) of the task's first record
+    uint8_t klo, khi;     // temporal intervals the task's events can fall in (conservative)
+    uint8_t flags, pad;
+};
+static_assert(sizeof(ChunkMeta) == 16, "ChunkMeta layout");
+
+struct __align__(16) TaskDesc {
+    int64_t c0;           // first array position of the chunk
+    int b;                // sample
+    uint32_t lohi;        // slots [lo, hi) of the chunk that belong to the sample: lo | hi << 16
+};
+
+struct TiledArgs {
+    const uint32_t* w;          // packed words
+    const uint32_t* blk_base;   // tick offset per 256-event block
+    const int64_t* offsets;     // device, B+1
+    int64_t n_total;            // offsets_host[B]: vector loads stay below it
+    int64_t rec_pos0;           // array position of rec[0] (multiple of kChunk)
+    int B, H, W, num_bins;
+    int NT, rows;               // row tiles per plane, rows per tile
+    int off_stride;             // NT + 2 bucket offsets per task
+    double sx, sy;
+    int scaled;
+    int n_tasks;                // route tasks (sample, chunk)
+    SampleMeta* meta;
+    int* first_task;            // B+1
+    TaskDesc* desc;             // n_tasks
+    ChunkMeta* cmeta;           // n_tasks
+    uint16_t* coff;             // n_tasks x off_stride: bucket starts relative to pos0; [NT] = first dropped, [NT+1] = records
+    uint32_t* crel;             // n_tasks x 32: block base minus the task's smallest (wide records)
+    uint32_t* rec;              // routed records, indexed by array position - rec_pos0
+    unsigned int* counters;     // [0] sweep task counter
+    unsigned int* bad_count;
+    float* out_voxel;
+    float* out_sum;
+};
+
+__device__ __forceinline__ void pdl_wait_t() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger_t() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- setup: route tasks per sample ---------------------------------------------------------------------------------
+// task c of sample b covers the part of array chunk (offsets[b] >> 13) + c that belongs to the sample
+__global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < a.B; b0 += 1024) {
+        const int b = b0 + tid;
+        int n = 0;
+        int64_t lo = 0, hi = 0;
+        if (b < a.B) {
+            lo = a.offsets[b]; hi = a.offsets[b + 1];
+            if (hi > lo) n = (int)(((hi - 1) >> kChunkShift) - (lo >> kChunkShift)) + 1;
+        }
+        const int incl = warp_incl_scan(n, lane);
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int v = s_warp[lane];
+            const int s = warp_incl_scan(v, lane);
+            s_warp[lane] = s - v;
+        }
+        __syncthreads();
+        const int first = s_carry + s_warp[wid] + incl - n;
+        if (b < a.B) {
+            a.first_task[b] = first;
+            for (int c = 0; c < n; ++c) {
+                const int64_t c0 = ((lo >> kChunkShift) + c) << kChunkShift;
+                const uint32_t s_lo = (uint32_t)((lo > c0 ? lo : c0) - c0);
+                const uint32_t s_hi = (uint32_t)((hi < c0 + kChunk ? hi : c0 + kChunk) - c0);
+                TaskDesc d;
+                d.c0 = c0; d.b = b; d.lohi = s_lo | (s_hi << 16);
+                a.desc[first + c] = d;
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = first + n;
+        __syncthreads();
+    }
+    if (tid == 0) a.first_task[a.B] = s_carry;
+}
+
+// ---- route ---------------------------------------------------------------------------------------------------------
+// dynamic shared memory: lut_y[2048] u32 | lut_x[2048] u32 | stage[8192] u32 | cnt[kMaxTiles + 2] | off[kMaxTiles + 2]
+constexpr size_t kRouteSmem = 2048 * 4 + 2048 * 4 + (size_t)kChunk * 4 + 2 * (kMaxTiles + 2) * 4 + 64;
+
+// polarity bit of the packed word -> signed 2-bit field of the record: 1 -> 01 (+1), 0 -> 11 (-1)
+__device__ __forceinline__ uint32_t pol2(uint32_t word) { return 3u - ((word >> 21) & 2u); }
+
+__device__ __forceinline__ void route_load(const TiledArgs& a, const TaskDesc& d, int tid, uint32_t (&wv)[kRouteEv]) {
+    const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
+    if (slot_lo == 0 && slot_hi == kChunk && d.c0 + kChunk <= a.n_total) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = ld_stream(reinterpret_cast<const uint4*>(a.w + d.c0) + q * kRouteThreads + tid);
+            wv[q * 4 + 0] = v.x; wv[q * 4 + 1] = v.y; wv[q * 4 + 2] = v.z; wv[q * 4 + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int slot0 = (q * kRouteThreads + tid) * 4;
+            const int64_t pos = d.c0 + slot0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wv[q * 4 + e] = 0;
+            if (slot0 + 4 > slot_lo && slot0 < slot_hi) {
+                if (pos + 4 <= a.n_total) {
+                    const uint4 v = ld_stream(reinterpret_cast<const uint4*>(a.w + pos));
+                    wv[q * 4 + 0] = v.x; wv[q * 4 + 1] = v.y; wv[q * 4 + 2] = v.z; wv[q * 4 + 3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (pos + e < a.n_total) wv[q * 4 + e] = a.w[pos + e];
+                }
+            }
+        }
+    }
+}
+
+// tick-block bases of a task (warp 0, lane = block of the chunk) -> s_rel[32], chunk metadata
+__device__ __forceinline__ void route_bases(const TiledArgs& a, const TaskDesc& d, int task, int lane, uint32_t* s_rel, uint32_t* s_fmt) {
+    const int64_t lo_b = a.offsets[d.b];
+    const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
+    const int64_t blk_id = (d.c0 >> kTickBlockShift) + lane;
+    const bool used = (lane << kTickBlockShift) < slot_hi && ((lane + 1) << kTickBlockShift) > slot_lo;
+    const uint32_t base = (used && blk_id != (lo_b >> kTickBlockShift)) ? __ldg(a.blk_base + blk_id) : 0u;
+    uint32_t mn = used ? base : 0xffffffffu, mx = used ? base : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const uint32_t rel = used ? base - mn : 0u;
+    const bool narrow = (mx - mn) < 65536u - 512u;
+    s_rel[lane] = narrow ? (rel << 16) : ((uint32_t)lane << 16);      // per-quad addend of the record's high half
+    a.crel[(size_t)task * 32 + lane] = rel;
+    if (lane == 0) {
+        *s_fmt = narrow ? 16u : 21u;                                   // shift of the 9 tick bits inside the record
+        const SampleMeta m = a.meta[d.b];
+        const int64_t cbase = (int64_t)mn - m.t0_ticks;
+        const int64_t dt_hi = cbase + (int64_t)(mx - mn) + 511;
+        const bool int_time = (m.flags & kFlagIntTime) != 0;
+        int klo = 0, khi = a.num_bins - 1;
+        bool fast = false;
+        if (int_time) {
+            uint32_t v;
+            const uint32_t v_end = (uint32_t)a.num_bins << kQ;
+            if (cbase > 0 && ticks_to_v(cbase, m.tmul, m.tshift, m.thalf, v_end, v)) klo = (int)(v >> kQ);
+            else if (cbase >= (1ll << 32)) klo = a.num_bins - 1;
+            if (dt_hi >= 0 && ticks_to_v(dt_hi, m.tmul, m.tshift, m.thalf, v_end, v)) khi = (int)(v >> kQ);
+            else if (dt_hi < 0) khi = 0;
+            if (narrow && cbase >= 0 && dt_hi < (1ll << 32)) {
+                // every v of the chunk fits 32 bits: the sweep's fast path then needs no range test beyond the interval's
+                const uint64_t q = (uint64_t)dt_hi * m.tmul + m.thalf;
+                fast = ((q >> 32) >> m.tshift) == 0;
+            }
+        }
+        ChunkMeta cm;
+        cm.cbase = cbase;
+        cm.pos0 = (uint32_t)(d.c0 + slot_lo - a.rec_pos0);
+        cm.klo = (uint8_t)klo; cm.khi = (uint8_t)khi;
+        cm.flags = (uint8_t)((fast ? kChunkFast : 0u) | (narrow ? kChunkNarrow : 0u));
+        cm.pad = 0;
+        a.cmeta[task] = cm;
+    }
+}
+
+__global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* lut_y = reinterpret_cast<uint32_t*>(smem_raw);                    // tile << 16 | (row in tile) * W
+    uint32_t* lut_x = lut_y + 2048;                                             // scaled x
+    uint32_t* stage = lut_x + 2048;
+    uint32_t* s_cnt = stage + kChunk;                                           // tile << 16 | events so far
+    uint32_t* s_off = s_cnt + (kMaxTiles + 2);                                  // bucket start - (tile << 16)
+    __shared__ uint32_t s_rel[2][32];
+    __shared__ uint32_t s_fmt[2];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int NT = a.NT, NB = NT + 1;          // bucket NT = trash (coordinates outside the grid)
+    pdl_trigger_t();
+    // events_reshape: x * (input_w / sensor_w) in fp64, truncated by the .long() of the binning call
+    for (int i = tid; i < 2048; i += kRouteThreads) {
+        const long long yy = a.scaled ? __double2ll_rz(__dmul_rn((double)i, a.sy)) : (long long)i;
+        const long long xx = a.scaled ? __double2ll_rz(__dmul_rn((double)i, a.sx)) : (long long)i;
+        uint32_t ly = (uint32_t)NT << 16;
+        if (yy < a.H) {
+            const uint32_t t = (uint32_t)(yy / a.rows);
+            // cells of the last (possibly shorter) tile are kept at the END of the plane, so that one compare against the
+            // full tile size catches every index that leaves the tile or the grid
+            const uint32_t bias = ((int)t == NT - 1) ? (uint32_t)(a.rows * a.W - (a.H - (NT - 1) * a.rows) * a.W) : 0u;
+            ly = (t << 16) | ((uint32_t)((yy % a.rows) * a.W) + bias);
+        }
+        lut_y[i] = ly;
+        lut_x[i] = (uint32_t)(xx < 4095 ? xx : 4095);                 // anything >= W is redone exactly in the cold path
+    }
+    if (tid < kMaxTiles + 2) s_cnt[tid] = (uint32_t)tid << 16;
+    pdl_wait_t();          // the workspace (headers, records) may still be read by the previous call's sweep
+
+    int task = blockIdx.x;
+    if (task >= a.n_tasks) return;
+    TaskDesc d = a.desc[task];
+    uint32_t wv[kRouteEv];
+    route_load(a, d, tid, wv);
+    if (tid < 32) route_bases(a, d, task, lane, s_rel[0], &s_fmt[0]);
+    int buf = 0;
+    __syncthreads();
+
+    const uint32_t tc = (uint32_t)(a.rows * a.W);                       // cells of a full tile
+    const uint32_t last_bias = tc - (uint32_t)((a.H - (NT - 1) * a.rows) * a.W);   // the last tile's cells sit at the end of the plane
+    for (;;) {
+        const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
+        const bool full = slot_lo == 0 && slot_hi == kChunk;
+        const uint32_t fmt = s_fmt[buf];
+        // ---- pass 1: record and bucket of every event of the thread (branch-free), then the ranks ----
+        uint32_t rt[kRouteEv];      // tile, then tile << 16 | rank; 0xffffffff = not an event of this task
+        bool fix = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t add = s_rel[buf][q * 8 + (tid >> 6)];      // block of slot s = s >> 8 = q * 8 + (tid >> 6)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t word = wv[q * 4 + e];
+                const uint32_t ly = lut_y[(word >> 11) & 0x7ffu];
+                const uint32_t xx = a.scaled ? lut_x[word & 0x7ffu] : (word & 0x7ffu);
+                const uint32_t cell = (ly & 0xffffu) + xx;
+                // x + y * W has no bound on x alone in the reference (events_to_voxel_grid.py:46): an x >= W stays correct while
+                // the sum stays inside the tile; anything that leaves it is redone exactly below (rare)
+                fix |= cell >= tc;
+                rt[q * 4 + e] = ly >> 16;
+                wv[q * 4 + e] = pol2(word) + (cell << 2) + ((word >> 23) << fmt) + add;
+            }
+        }
+        if (fix) {
+            // cold: redo the thread's 16 events from the source words with the reference's own index arithmetic
+#pragma unroll 1
+            for (int i = 0; i < kRouteEv; ++i) {
+                const int q = i >> 2, e = i & 3;
+                const int64_t pos = d.c0 + (q * kRouteThreads + tid) * 4 + e;
+                const uint32_t word = pos < a.n_total ? a.w[pos] : 0u;
+                const uint32_t x0 = word & 0x7ffu, y0 = (word >> 11) & 0x7ffu;
+                const int64_t xs = a.scaled ? __double2ll_rz(__dmul_rn((double)x0, a.sx)) : (int64_t)x0;
+                const int64_t ys = a.scaled ? __double2ll_rz(__dmul_rn((double)y0, a.sy)) : (int64_t)y0;
+                uint32_t tile = (uint32_t)NT, cell = 0;
+                if (ys < a.H + 65536 && xs < (1ll << 40)) {
+                    const int64_t flat = ys * a.W + xs;
+                    if (flat < (int64_t)a.H * a.W) {
+                        const uint32_t y2 = (uint32_t)(flat / a.W);
+                        tile = y2 / (uint32_t)a.rows;
+                        cell = (y2 % (uint32_t)a.rows) * (uint32_t)a.W + (uint32_t)(flat - (int64_t)y2 * a.W);
+                        if ((int)tile == NT - 1) cell += last_bias;
+                    }
+                }
+                const uint32_t addq = s_rel[buf][q * 8 + (tid >> 6)];
+                const uint32_t rec = pol2(word) + (cell << 2) + ((word >> 23) << fmt) + addq;
+                // (static indexing: the arrays stay in registers)
+#pragma unroll
+                for (int j = 0; j < kRouteEv; ++j) if (j == i) { wv[j] = rec; rt[j] = tile; }
+            }
+        }
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < kRouteEv; ++i) rt[i] = atomicAdd(&s_cnt[rt[i]], 1u);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRouteEv; ++i) {
+                const int sl = ((i >> 2) * kRouteThreads + tid) * 4 + (i & 3);
+                rt[i] = (sl >= slot_lo && sl < slot_hi) ? atomicAdd(&s_cnt[rt[i]], 1u) : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        // ---- bucket starts (warp 0): exclusive scan of the NB <= 65 bucket sizes ----
+        if (tid < 32) {
+            uint32_t c[3], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { const int t = lane * 3 + j; c[j] = (t < NB) ? (s_cnt[t] & 0xffffu) : 0u; sum += c[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+            uint32_t run = incl - sum;
+            uint16_t* co = a.coff + (size_t)task * a.off_stride;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int t = lane * 3 + j;
+                if (t <= NB) { s_off[t] = run - ((uint32_t)t << 16); co[t] = (uint16_t)run; }
+                run += c[j];
+            }
+            if (lane == 0 && a.bad_count) {
+                const uint32_t nbad = s_cnt[NT] & 0xffffu;
+                if (nbad) atomicAdd(a.bad_count, nbad);
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: records to their bucket slots ----
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < kRouteEv; ++i) stage[s_off[rt[i] >> 16] + rt[i]] = wv[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRouteEv; ++i)
+                if (rt[i] != 0xffffffffu) stage[s_off[rt[i] >> 16] + rt[i]] = wv[i];
+        }
+        // ---- the next task's words are requested now and land while this task's records are copied out ----
+        const int next = task + gridDim.x;
+        const bool more = next < a.n_tasks;
+        TaskDesc dn = d;
+        if (more) {
+            dn = a.desc[next];
+            route_load(a, dn, tid, wv);
+            if (tid < 32) route_bases(a, dn, next, lane, s_rel[buf ^ 1], &s_fmt[buf ^ 1]);
+        }
+        __syncthreads();
+        // ---- coalesced copy-out; bucket counters reset for the next task ----
+        if (tid < kMaxTiles + 2) s_cnt[tid] = (uint32_t)tid << 16;
+        const int n = slot_hi - slot_lo;
+        const int64_t p0 = d.c0 + slot_lo - a.rec_pos0;
+        uint32_t* dst = a.rec + p0;
+        if ((p0 & 3) == 0) {
+            const int n4 = n >> 2;
+            for (int i = tid; i < n4; i += kRouteThreads)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(stage)[i];
+            for (int i = (n4 << 2) + tid; i < n; i += kRouteThreads) dst[i] = stage[i];
+        } else {
+            for (int i = tid; i < n; i += kRouteThreads) dst[i] = stage[i];
+        }
+        if (!more) break;
+        task = next; d = dn; buf ^= 1;
+        __syncthreads();
+    }
+}
+
+// ---- sweep ---------------------------------------------------------------------------------------------------------
+// dynamic shared memory: planes[2][tile_cells] int32 | t_q[kTabCap] u64 | items[kItemCap] uint2 | spill[kSpillCap] int2 |
+//                        t_pos[kTabCap] u32 | t_len[kTabCap] u16 | t_kr[kTabCap] u16
+__host__ __device__ inline size_t sweep_smem_bytes(int tile_cells) {
+    return (size_t)2 * tile_cells * 4 + (size_t)kTabCap * (8 + 4 + 2 + 2) + (size_t)kItemCap * 8 + kSpillCap * 8 + 16;
+}
+
+// a wrapped int32 plane word: add a +-2^32 correction for (cell, plane) to the spill list.  Entries start as {-1, 0}
+// (reset per task); a slot's key is published after its first correction went in with an atomic, so concurrent wraps of
+// the same word either find the entry or open a duplicate, and the flush sums every entry that matches.
+__device__ __noinline__ void note_wrap(int old, int w, uint32_t key, int2* spill, int* n_spill, unsigned int* bad) {
+    const uint32_t nw = (uint32_t)old + (uint32_t)w;
+    if ((int)(((uint32_t)old ^ nw) & ((uint32_t)w ^ nw)) >= 0) return;
+    const int d = w > 0 ? 1 : -1;
+    int n = *reinterpret_cast<volatile int*>(n_spill);
+    if (n > kSpillCap) n = kSpillCap;
+    for (int i = 0; i < n; ++i)
+        if (reinterpret_cast<volatile int2*>(spill)[i].x == (int)key) { atomicAdd(&spill[i].y, d); return; }
+    const int i = atomicAdd(n_spill, 1);
+    if (i < kSpillCap) {
+        atomicAdd(&spill[i].y, d);
+        __threadfence_block();
+        reinterpret_cast<volatile int2*>(spill)[i].x = (int)key;
+    } else if (bad) {
+        atomicOr(bad, 0x80000000u);
+    }
+}
+
+struct SweepCtx {
+    uint32_t pl0s, pl1s;  // shared-memory addresses of plane k (left node of interval k) and plane k+1 (right node)
+    int2* spill;
+    int* n_spill;
+    unsigned int* bad;
+    uint32_t kbase;       // k << 24
+    int k;
+};
+
+// returning shared-memory atomic add on a 32-bit shared address
+__device__ __forceinline__ int atoms_add(uint32_t saddr, int w) {
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(w) : "memory");
+    return old;
+}
+__device__ __forceinline__ int atoms_inc(uint32_t saddr) {       // plain atom: keeps the compiler's warp-aggregation rewrite out
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(saddr) : "memory");
+    return old;
+}
+__device__ __forceinline__ int sgn2(uint32_t rec) {              // signed 2-bit polarity field
+    int r;
+    asm("bfe.s32 %0, %1, 0, 2;" : "=r"(r) : "r"(rec));
+    return r;
+}
+__device__ __forceinline__ bool near_wrap(int old) { return (uint32_t)old + 0x7f000000u >= 0xfe000000u; }
+
+// general time arithmetic of one record (samples without the integer-tick constants, chunks whose dt leaves [0, 2^32)):
+// the same expressions as voxel_weights() for the tick layouts
+__device__ __forceinline__ bool v_general(int64_t dt, const SampleMeta& m, int num_bins, uint32_t& v) {
+    if (m.flags & kFlagIntTime) return ticks_to_v(dt, m.tmul, m.tshift, m.thalf, (uint32_t)num_bins << kQ, v);
+    const double ts = (double)dt * m.scale_raw;
+    const double tis = floor(ts);
+    if (!(tis >= 0.0 && tis < (double)num_bins)) return false;
+    const float d = (float)(ts - tis);
+    v = ((uint32_t)(int)tis << kQ) + (uint32_t)__float2int_rn(d * 16777216.0f);
+    return true;
+}
+
+// slow path of one record: wide records and / or general time arithmetic
+__device__ __noinline__ void sweep_record_slow(const ChunkMeta* cmp, const uint32_t* crel, int num_bins, SweepCtx c,
+                                               const SampleMeta* mp, uint32_t r, bool has_right) {
+    const SampleMeta m = *mp;
+    const ChunkMeta cm = *cmp;
+    int64_t dt = cm.cbase;
+    if (cm.flags & kChunkNarrow) dt += (int64_t)(r >> 16);
+    else dt += (int64_t)crel[(r >> 16) & 31u] + (int64_t)(r >> 21);
+    uint32_t v = 0;
+    if (!v_general(dt, m, num_bins, v)) return;
+    const uint32_t u = v - c.kbase;
+    if (u >= (1u << kQ)) return;
+    const int sgn = sgn2(r);
+    const uint32_t boff = r & 0xfffcu;
+    const int wr = (int)u * sgn, wl = (sgn << kQ) - wr;
+    const int old0 = atoms_add(c.pl0s + boff, wl);
+    if (near_wrap(old0)) note_wrap(old0, wl, (boff >> 2) | ((uint32_t)c.k << 16), c.spill, c.n_spill, c.bad);
+    if (has_right) {
+        const int old1 = atoms_add(c.pl1s + boff, wr);
+        if (near_wrap(old1)) note_wrap(old1, wr, (boff >> 2) | ((uint32_t)(c.k + 1) << 16), c.spill, c.n_spill, c.bad);
+    }
+}
+
+template <bool VEC, bool FIRST, bool LAST, bool SUM>
+__device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so,
+                                              const int2* spill, int n_spill, int key0) {
+    constexpr float kInv = 1.0f / 16777216.0f;
+    if (VEC) {
+        for (int i = threadIdx.x * 4; i < ncell; i += kSweepThreads * 4) {
+            const int4 q = *reinterpret_cast<const int4*>(pl + i);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (SUM && !FIRST) s = __ldcg(reinterpret_cast<const float4*>(so + i));
+            *reinterpret_cast<int4*>(pl + i) = make_int4(0, 0, 0, 0);
+            float4 f = make_float4(__int2float_rn(q.x) * kInv, __int2float_rn(q.y) * kInv, __int2float_rn(q.z) * kInv,
+                                   __int2float_rn(q.w) * kInv);
+            if (n_spill) {
+                const int qi[4] = {q.x, q.y, q.z, q.w};
+                float* fp = reinterpret_cast<float*>(&f);
+                for (int j = 0; j < 4; ++j) {
+                    const int key = (key0 + i + j) | (k << 16);
+                    long long hi = 0;
+                    for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
+                    if (hi) fp[j] = __ll2float_rn((hi << 32) + (long long)qi[j]) * kInv;
+                }
+            }
+            st_stream(reinterpret_cast<float4*>(o + i), f);
+            if (SUM) {
+                s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;       // voxel.sum(dim=0): sequential fp32 over bins
+                if (LAST) st_stream(reinterpret_cast<float4*>(so + i), s);
+                else __stcg(reinterpret_cast<float4*>(so + i), s);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < ncell; i += kSweepThreads) {
+            const int q = pl[i];
+            float s = 0.f;
+            if (SUM && !FIRST) s = __ldcg(so + i);
+            pl[i] = 0;
+            float f = __int2float_rn(q) * kInv;
+            if (n_spill) {
+                const int key = (key0 + i) | (k << 16);
+                long long hi = 0;
+                for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
+                if (hi) f = __ll2float_rn((hi << 32) + (long long)q) * kInv;
+            }
+            st_stream(o + i, f);
+            if (SUM) {
+                s += f;
+                if (LAST) st_stream(so + i, s); else __stcg(so + i, s);
+            }
+        }
+    }
+}
+
+// pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys)
+template <bool VEC>
+__device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, const int2* spill, int n_spill,
+                                            int key0) {
+    const bool first = k == 0, last = k == num_bins - 1;
+    if (!so) flush_plane_t<VEC, false, false, false>(pl, ncell, k, o, so, spill, n_spill, key0);
+    else if (first && last) flush_plane_t<VEC, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0);
+    else if (first) flush_plane_t<VEC, true, false, true>(pl, ncell, k, o, so, spill, n_spill, key0);
+    else if (last) flush_plane_t<VEC, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0);
+    else flush_plane_t<VEC, false, false, true>(pl, ncell, k, o, so, spill, n_spill, key0);
+}
+
+// the warps of the CTA draw items (<= 128 records of one run: .x = first record, .y = chunk slot | (records - 1) << 9 |
+// slow << 16) from a shared counter; the records of the next item are in flight while the current one is accumulated.
+// Fast path per record: v = (Q + ticks * tmul) >> tshift, two predicated returning atomics, no branch; the returned values
+// of the item's 8 atomics are screened together for words that came near the int32 range (rare -> exact check, spill list).
+template <bool HAS_RIGHT>
+__device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& c, const SampleMeta* mp, uint32_t tmul, uint32_t tshift,
+                                            int task0, const unsigned long long* t_q, const uint2* items, int n_items,
+                                            uint32_t s_next_addr, int lane) {
+    auto draw = [&]() -> int {
+        int it = 0;
+        if (lane == 0) it = atoms_inc(s_next_addr);
+        return __shfl_sync(0xffffffffu, it, 0);
+    };
+    uint2 dn = make_uint2(0u, 0u);
+    uint32_t rn0 = 0, rn1 = 0, rn2 = 0, rn3 = 0;
+    auto load = [&](int it) {
+        dn = items[it];
+        const uint32_t cnt = ((dn.y >> 9) & 127u) + 1u;
+        const uint32_t* p = a.rec + dn.x + lane;
+        // lanes past the end of the item get a harmless record of their own (cell = lane): its weights are forced to 0 below
+        rn0 = ((uint32_t)lane < cnt) ? ld_stream(p) : (uint32_t)lane << 2;
+        rn1 = ((uint32_t)lane + 32u < cnt) ? ld_stream(p + 32) : (uint32_t)lane << 2;
+        rn2 = ((uint32_t)lane + 64u < cnt) ? ld_stream(p + 64) : (uint32_t)lane << 2;
+        rn3 = ((uint32_t)lane + 96u < cnt) ? ld_stream(p + 96) : (uint32_t)lane << 2;
+    };
+    int it = draw();
+    if (it < n_items) load(it);
+    while (it < n_items) {
+        const uint2 d = dn;
+        const uint32_t r[4] = {rn0, rn1, rn2, rn3};
+        it = draw();
+        if (it < n_items) load(it);
+        const uint32_t slot = d.y & 511u;
+        const uint32_t cnt = ((d.y >> 9) & 127u) + 1u;
+        if (!(d.y >> 16)) {
+            const uint64_t Q = t_q[slot];                                    // cbase * tmul + thalf
+            int o0[4], o1[4];
+            uint32_t u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t q = (uint64_t)(r[j] >> 16) * tmul + Q;
+                const uint32_t v = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), tshift);
+                u[j] = v - c.kbase;
+                // events of other intervals (chunks straddle interval boundaries) and lanes past the end add zero: no branch
+                const bool ok = (uint32_t)lane + 32u * j < cnt && u[j] < (1u << kQ);
+                const int sgn = ok ? sgn2(r[j]) : 0;
+                const uint32_t boff = r[j] & 0xfffcu;                        // cell * 4
+                const int wr = (int)u[j] * sgn, wl = (sgn << kQ) - wr;
+                o0[j] = atoms_add(c.pl0s + boff, wl);
+                o1[j] = HAS_RIGHT ? atoms_add(c.pl1s + boff, wr) : 0;
+            }
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m = max(m, (uint32_t)o0[j] + 0x7f000000u);
+                if (HAS_RIGHT) m = max(m, (uint32_t)o1[j] + 0x7f000000u);
+            }
+            if (m >= 0xfe000000u) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = (uint32_t)lane + 32u * j < cnt && u[j] < (1u << kQ);
+                    const int sgn = ok ? sgn2(r[j]) : 0;
+                    const uint32_t cell = (r[j] & 0xfffcu) >> 2;
+                    const int wr = (int)u[j] * sgn, wl = (sgn << kQ) - wr;
+                    if (near_wrap(o0[j])) note_wrap(o0[j], wl, cell | ((uint32_t)c.k << 16), c.spill, c.n_spill, c.bad);
+                    if (HAS_RIGHT && near_wrap(o1[j])) note_wrap(o1[j], wr, cell | ((uint32_t)(c.k + 1) << 16), c.spill, c.n_spill, c.bad);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((uint32_t)lane + 32u * j < cnt)
+                    sweep_record_slow(a.cmeta + task0 + slot, a.crel + (size_t)(task0 + slot) * 32, a.num_bins, c, mp, r[j], HAS_RIGHT);
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile_cells = a.rows * a.W;
+    int* plane0 = reinterpret_cast<int*>(smem_raw);
+    int* plane1 = plane0 + tile_cells;
+    unsigned long long* t_q = reinterpret_cast<unsigned long long*>(plane1 + tile_cells);
+    uint2* s_items = reinterpret_cast<uint2*>(t_q + kTabCap);
+    int2* s_spill = reinterpret_cast<int2*>(s_items + kItemCap);
+    uint32_t* t_pos = reinterpret_cast<uint32_t*>(s_spill + kSpillCap);
+    uint16_t* t_len = reinterpret_cast<uint16_t*>(t_pos + kTabCap);
+    uint16_t* t_kr = t_len + kTabCap;
+    __shared__ int s_task, s_nitems, s_next, s_nspill;
+    __shared__ SampleMeta s_meta;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    pdl_trigger_t();
+    for (int i = tid; i < 2 * tile_cells; i += kSweepThreads) plane0[i] = 0;
+    pdl_wait_t();          // records and headers of the route
+    const int n_sweep = a.B * a.NT;
+    const int64_t HW = (int64_t)a.H * a.W;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_task = (int)atomicAdd(a.counters, 1u); s_nspill = 0; }
+        if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= n_sweep) break;
+        const int b = task / a.NT, tile = task - b * a.NT;
+        const int first = a.first_task[b], nch = a.first_task[b + 1] - first;
+        if (tid == 0) s_meta = a.meta[b];
+        const int row0 = tile * a.rows;
+        const int nrows = (a.H - row0 < a.rows) ? a.H - row0 : a.rows;
+        const int ncell = nrows * a.W;
+        const int cell0 = tile_cells - ncell;              // a shorter last tile sits at the end of the plane (k_route's lut_y)
+        const bool resident = nch <= kTabCap;
+        __syncthreads();
+        const uint32_t tmul = s_meta.tmul, tshift = s_meta.tshift, thalf = s_meta.thalf;
+
+        for (int k = 0; k < a.num_bins; ++k) {
+            SweepCtx c;
+            int* pl0 = (k & 1) ? plane1 : plane0;
+            c.pl0s = (uint32_t)__cvta_generic_to_shared(pl0);
+            c.pl1s = (uint32_t)__cvta_generic_to_shared((k & 1) ? plane0 : plane1);
+            c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
+            c.kbase = (uint32_t)k << kQ; c.k = k;
+            const bool has_right = k + 1 < a.num_bins;
+            for (int c_round = 0; c_round < nch; c_round += kTabCap) {
+                const int ci = c_round + tid;
+                if (!resident || k == 0) {
+                    // run table of the round: one chunk per thread
+                    if (ci < nch) {
+                        const ChunkMeta cm = a.cmeta[first + ci];
+                        const uint16_t* co = a.coff + (size_t)(first + ci) * a.off_stride + tile;
+                        const uint32_t o0 = co[0], o1 = co[1];
+                        t_pos[tid] = cm.pos0 + o0;
+                        t_q[tid] = (unsigned long long)(uint32_t)cm.cbase * tmul + thalf;
+                        t_len[tid] = (uint16_t)((o1 - o0) | ((cm.flags & kChunkFast) ? 0u : 0x8000u));
+                        t_kr[tid] = (uint16_t)(cm.klo | (cm.khi << 8));
+                    } else {
+                        t_len[tid] = 0; t_kr[tid] = 0xff;       // klo = 255: never qualifies
+                    }
+                    __syncthreads();
+                }
+                // items of this phase: runs whose chunk can hold events of interval k, cut into pieces of 128 records
+                int remaining = 0, cursor = 0;
+                {
+                    const uint32_t kr = t_kr[tid];
+                    const int len = t_len[tid] & 0x7fff;
+                    if ((int)(kr & 0xffu) <= k && k <= (int)(kr >> 8)) remaining = (len + kItemRecs - 1) / kItemRecs;
+                }
+                for (;;) {
+                    if (tid == 0) { s_nitems = 0; s_next = 0; }
+                    __syncthreads();
+                    if (remaining) {
+                        const int base = atomicAdd(&s_nitems, remaining);
+                        int take = kItemCap - base;
+                        take = take < 0 ? 0 : (take > remaining ? remaining : take);
+                        const uint32_t lenf = t_len[tid], len = lenf & 0x7fffu, pos = t_pos[tid];
+                        for (int j = 0; j < take; ++j) {
+                            const uint32_t start = (uint32_t)(cursor + j) * kItemRecs;
+                            const uint32_t cnt = len - start < (uint32_t)kItemRecs ? len - start : (uint32_t)kItemRecs;
+                            s_items[base + j] = make_uint2(pos + start, (uint32_t)tid | ((cnt - 1u) << 9) | ((lenf >> 15) << 16));
+                        }
+                        cursor += take; remaining -= take;
+                    }
+                    const int any_left = __syncthreads_or(remaining > 0);
+                    const int n_items = s_nitems < kItemCap ? s_nitems : kItemCap;
+                    const uint32_t next_addr = (uint32_t)__cvta_generic_to_shared(&s_next);
+                    if (has_right) sweep_items<true>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, next_addr, lane);
+                    else sweep_items<false>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, next_addr, lane);
+                    __syncthreads();
+                    if (!any_left) break;
+                }
+            }
+            // plane k is complete: fp32 out (+ running voxel.sum(0)), buffer re-zeroed -> plane k + 2
+            const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
+            float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
+            float* so = a.out_sum ? a.out_sum + (int64_t)b * HW + (int64_t)row0 * a.W : nullptr;
+            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0);
+            __syncthreads();
+        }
+    }
+}
+
+struct TiledPlan {
+    int NT, rows, n_tasks;
+    int64_t rec_pos0, n_rec;
+    size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_rec, total;
+};
+
+bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) {
+    if (ev->xy_dtype != EP_U32 || ev->t_dtype != 0 || ev->t != nullptr) return false;      // 4 B packed layout only
+    if (p->count_channels != 0 || p->num_bins < 1 || p->num_bins > 64 || p->time_f32) return false;
+    if (!ev->offsets_host || ev->batch <= 0) return false;
+    const int H = p->height, W = p->width;
+    if (W > kTileCells || W > 65535 || H > 65535) return false;
+    int rows = kTileCells / W;
+    if (rows > H) rows = H;
+    int NT = (H + rows - 1) / rows;
+    if (NT > kMaxTiles) return false;
+    rows = (H + NT - 1) / NT;
+    NT = (H + rows - 1) / rows;
+    pl.NT = NT; pl.rows = rows;
+    const int B = ev->batch;
+    int64_t tasks = 0;
+    for (int b = 0; b < B; ++b) {
+        const int64_t lo = ev->offsets_host[b], hi = ev->offsets_host[b + 1];
+        if (hi > lo) tasks += ((hi - 1) >> kChunkShift) - (lo >> kChunkShift) + 1;
+    }
+    if (tasks > (1ll << 30) || (int64_t)B * NT > (1ll << 30)) return false;
+    pl.n_tasks = (int)tasks;
+    pl.rec_pos0 = (ev->offsets_host[0] >> kChunkShift) << kChunkShift;
+    pl.n_rec = ev->offsets_host[B] - pl.rec_pos0;
+    if (pl.n_rec >= (1ll << 32)) return false;                  // ChunkMeta::pos0 is 32 bits
+    const size_t nt = (size_t)(tasks ? tasks : 1);
+    size_t o = 0;
+    pl.off_meta = o; o += align_up(sizeof(SampleMeta) * (size_t)B, 256);
+    pl.off_first = o; o += align_up(sizeof(int) * ((size_t)B + 1), 256);
+    pl.off_desc = o; o += align_up(sizeof(TaskDesc) * nt, 256);
+    pl.off_cmeta = o; o += align_up(sizeof(ChunkMeta) * nt, 256);
+    pl.off_coff = o; o += align_up(sizeof(uint16_t) * nt * (size_t)(NT + 2), 256);
+    pl.off_crel = o; o += align_up(sizeof(uint32_t) * nt * 32, 256);
+    pl.off_counters = o; o += 256;
+    pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
+    pl.total = o;
+    return true;
+}
+
+}  // namespace
+
+size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p) {
+    TiledPlan pl;
+    return tiled_plan(ev, p, pl) ? pl.total : 0;
+}
+
+// Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
+int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                      void* ws, size_t ws_bytes, unsigned int* bad) {
+    TiledPlan pl;
+    if (!tiled_plan(ev, p, pl)) return EP_EUNSUPPORTED;
+    if (!ws || ws_bytes < pl.total) return EP_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(ws) & 255u) return EP_EALIGN;
+    if (!out_voxel) return EP_EINVAL;
+    if (!aligned16(ev->x)) return EP_EALIGN;
+    const int B = ev->batch;
+    char* base = static_cast<char*>(ws);
+    TiledArgs a;
+    a.w = static_cast<const uint32_t*>(ev->x);
+    a.blk_base = static_cast<const uint32_t*>(ev->p);
+    a.offsets = ev->offsets;
+    a.n_total = ev->offsets_host[B];
+    a.rec_pos0 = pl.rec_pos0;
+    a.B = B; a.H = p->height; a.W = p->width; a.num_bins = p->num_bins;
+    a.NT = pl.NT; a.rows = pl.rows; a.off_stride = pl.NT + 2;
+    a.sx = p->scale_x; a.sy = p->scale_y; a.scaled = (p->scale_x != 1.0 || p->scale_y != 1.0);
+    a.n_tasks = pl.n_tasks;
+    a.meta = reinterpret_cast<SampleMeta*>(base + pl.off_meta);
+    a.first_task = reinterpret_cast<int*>(base + pl.off_first);
+    a.desc = reinterpret_cast<TaskDesc*>(base + pl.off_desc);
+    a.cmeta = reinterpret_cast<ChunkMeta*>(base + pl.off_cmeta);
+    a.coff = reinterpret_cast<uint16_t*>(base + pl.off_coff);
+    a.crel = reinterpret_cast<uint32_t*>(base + pl.off_crel);
+    a.counters = reinterpret_cast<unsigned int*>(base + pl.off_counters);
+    a.rec = reinterpret_cast<uint32_t*>(base + pl.off_rec);
+    a.bad_count = bad;
+    a.out_voxel = out_voxel;
+    a.out_sum = out_sum;
+
+    // per-sample first / last stamps and integer-time constants: the same kernel as the global path
+    SoaPackedLoader<false> ld{a.w, nullptr, a.blk_base, ev->t_base, ev->t_div};
+    BinArgs ba = {};
+    ba.offsets = ev->offsets; ba.num_bins = p->num_bins; ba.meta = a.meta;
+    profile_begin(st, kProfOther);
+    k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
+    EP_LAUNCH_CHECK();
+    k_tiled_setup<<<1, 1024, 0, st>>>(a);
+    EP_LAUNCH_CHECK();
+    cudaError_t ce = cudaMemsetAsync(a.counters, 0, 256, st);
+    if (ce != cudaSuccess) return (int)ce;
+    profile_end(st);
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
+        cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        attr_done = true;
+    }
+    if (pl.n_tasks > 0) {
+        const int grid = pl.n_tasks < 2 * kNumSMs ? pl.n_tasks : 2 * kNumSMs;
+        profile_begin(st, kProfScatter);
+        k_route<<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        profile_end(st);
+        EP_LAUNCH_CHECK();
+    }
+    {
+        const int64_t n_sweep = (int64_t)B * pl.NT;
+        const int grid = n_sweep < 2 * kNumSMs ? (int)n_sweep : 2 * kNumSMs;
+        const size_t smem = sweep_smem_bytes(pl.rows * p->width);
+        const bool vec = (p->width % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
+        profile_begin(st, kProfFinalize);
+        if (vec) k_sweep<true><<<grid, kSweepThreads, smem, st>>>(a);
+        else k_sweep<false><<<grid, kSweepThreads, smem, st>>>(a);
+        profile_end(st);
+        EP_LAUNCH_CHECK();
+    }
+    return EP_OK;
+}
+
+}  // namespace ep

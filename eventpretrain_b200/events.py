@@ -359,7 +359,8 @@ def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
     return RaggedEvents(*tens, offsets_host=off, t_div=t_div)
 
 
-_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "banded": _lib.EP_BIN_FORCE_BANDED}
+_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "banded": _lib.EP_BIN_FORCE_BANDED,
+           "tiled": _lib.EP_BIN_FORCE_TILED}
 
 
 def _bin_params(size, num_bins, count_channels, scale, time_f32, method=None):

@@ -123,6 +123,8 @@ typedef struct ep_bin_params {
 } ep_bin_params;
 #define EP_BIN_FORCE_GLOBAL 1    /* packed-u64 global RED + finalize (any layout, any size) */
 #define EP_BIN_FORCE_BANDED 2    /* banded shared-memory sweep (canonical SoA layout only) */
+#define EP_BIN_FORCE_TILED 4     /* route + two-plane shared-memory sweep, no global accumulators (4 B packed layout, voxel grid
+                                    and sum plane only; EP_EUNSUPPORTED otherwise).  The default for what it takes. */
 
 /* Scratch for ep_bin_events*: per-sample accumulator slots.  Returns the recommended size (enough
  * slots to keep one group of samples L2-resident); any size >= the minimum (one slot + per-sample

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--skewed", action="store_true")
     ap.add_argument("--compact", action="store_true")
     ap.add_argument("--packed", action="store_true")
+    ap.add_argument("--packed4", action="store_true")
+    ap.add_argument("--size", default="", help="HxW output grid with the fused events_reshape scale, e.g. 224x224")
     ap.add_argument("--bins", type=int, default=bench.BINS)
     ap.add_argument("--count", type=int, default=0)
     args = ap.parse_args()
@@ -41,11 +43,18 @@ def main():
     if args.packed:
         host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
         ev = host.packed().to(dev)
+    if args.packed4:
+        host = ep.RaggedEvents(ev.x.cpu(), ev.y.cpu(), ev.t.cpu(), ev.p.cpu(), ev.offsets.cpu(), ev.offsets_host, ev.t_div)
+        ev = host.packed(4).to(dev)
     n = ev.num_events
     H, W = bench.H, bench.W
+    scale = (1.0, 1.0)
+    if args.size:
+        H, W = (int(v) for v in args.size.split("x"))
+        scale = (W / bench.W, H / bench.H)
     results = {}
     for m in args.methods.split(","):
-        kw = dict(num_bins=args.bins, voxel_sum=True, count_channels=args.count, method=m)
+        kw = dict(num_bins=args.bins, voxel_sum=True, count_channels=args.count, method=m, scale=scale)
         out = ep.bin_events(ev, (H, W), check=True, **kw)
         for _ in range(2):
             ep.bin_events(ev, (H, W), out=out, **kw)
