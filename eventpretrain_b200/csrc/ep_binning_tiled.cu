@@ -429,11 +429,6 @@ __device__ __forceinline__ int atoms_add(uint32_t saddr, int w) {
     asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(w) : "memory");
     return old;
 }
-__device__ __forceinline__ int atoms_inc(uint32_t saddr) {       // plain atom: keeps the compiler's warp-aggregation rewrite out
-    int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(saddr) : "memory");
-    return old;
-}
 __device__ __forceinline__ int sgn2(uint32_t rec) {              // signed 2-bit polarity field
     int r;
     asm("bfe.s32 %0, %1, 0, 2;" : "=r"(r) : "r"(rec));
@@ -476,52 +471,89 @@ __device__ __noinline__ void sweep_record_slow(const ChunkMeta* cmp, const uint3
     }
 }
 
+// One plane of the tile: int32 Q24 words -> fp32 output (one rounding), running voxel.sum(0) in the output buffer itself
+// (read back through L2, the same thread wrote it in the previous phase), plane words re-zeroed.  The loop is cut into
+// groups of kFlushUnroll vectors whose shared-memory and L2 loads are all issued before the first use: a thread owns at
+// most 7 vectors of a 12800-cell tile, and one dependent L2 round trip per vector was the longest stall of the sweep.
+constexpr int kFlushUnroll = 4;
+
 template <bool VEC, bool FIRST, bool LAST, bool SUM>
 __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so,
                                               const int2* spill, int n_spill, int key0) {
     constexpr float kInv = 1.0f / 16777216.0f;
     if (VEC) {
-        for (int i = threadIdx.x * 4; i < ncell; i += kSweepThreads * 4) {
-            const int4 q = *reinterpret_cast<const int4*>(pl + i);
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (SUM && !FIRST) s = __ldcg(reinterpret_cast<const float4*>(so + i));
-            *reinterpret_cast<int4*>(pl + i) = make_int4(0, 0, 0, 0);
-            float4 f = make_float4(__int2float_rn(q.x) * kInv, __int2float_rn(q.y) * kInv, __int2float_rn(q.z) * kInv,
-                                   __int2float_rn(q.w) * kInv);
-            if (n_spill) {
-                const int qi[4] = {q.x, q.y, q.z, q.w};
-                float* fp = reinterpret_cast<float*>(&f);
-                for (int j = 0; j < 4; ++j) {
-                    const int key = (key0 + i + j) | (k << 16);
-                    long long hi = 0;
-                    for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
-                    if (hi) fp[j] = __ll2float_rn((hi << 32) + (long long)qi[j]) * kInv;
+        constexpr int kStep = kSweepThreads * 4;
+        for (int i0 = threadIdx.x * 4; i0 < ncell; i0 += kStep * kFlushUnroll) {
+            int4 q[kFlushUnroll];
+            float4 s[kFlushUnroll];
+#pragma unroll
+            for (int u = 0; u < kFlushUnroll; ++u) {
+                const int i = i0 + u * kStep;
+                q[u] = make_int4(0, 0, 0, 0);
+                s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < ncell) {
+                    q[u] = *reinterpret_cast<const int4*>(pl + i);
+                    if (SUM && !FIRST) s[u] = __ldcg(reinterpret_cast<const float4*>(so + i));
                 }
             }
-            st_stream(reinterpret_cast<float4*>(o + i), f);
-            if (SUM) {
-                s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;       // voxel.sum(dim=0): sequential fp32 over bins
-                if (LAST) st_stream(reinterpret_cast<float4*>(so + i), s);
-                else __stcg(reinterpret_cast<float4*>(so + i), s);
+#pragma unroll
+            for (int u = 0; u < kFlushUnroll; ++u) {
+                const int i = i0 + u * kStep;
+                if (i < ncell) {
+                    *reinterpret_cast<int4*>(pl + i) = make_int4(0, 0, 0, 0);
+                    float4 f = make_float4(__int2float_rn(q[u].x) * kInv, __int2float_rn(q[u].y) * kInv,
+                                           __int2float_rn(q[u].z) * kInv, __int2float_rn(q[u].w) * kInv);
+                    if (n_spill) {
+                        const int qi[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                        float* fp = reinterpret_cast<float*>(&f);
+                        for (int j = 0; j < 4; ++j) {
+                            const int key = (key0 + i + j) | (k << 16);
+                            long long hi = 0;
+                            for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
+                            if (hi) fp[j] = __ll2float_rn((hi << 32) + (long long)qi[j]) * kInv;
+                        }
+                    }
+                    st_stream(reinterpret_cast<float4*>(o + i), f);
+                    if (SUM) {
+                        float4 t = s[u];
+                        t.x += f.x; t.y += f.y; t.z += f.z; t.w += f.w;      // voxel.sum(dim=0): sequential fp32 over bins
+                        if (LAST) st_stream(reinterpret_cast<float4*>(so + i), t);
+                        else __stcg(reinterpret_cast<float4*>(so + i), t);
+                    }
+                }
             }
         }
     } else {
-        for (int i = threadIdx.x; i < ncell; i += kSweepThreads) {
-            const int q = pl[i];
-            float s = 0.f;
-            if (SUM && !FIRST) s = __ldcg(so + i);
-            pl[i] = 0;
-            float f = __int2float_rn(q) * kInv;
-            if (n_spill) {
-                const int key = (key0 + i) | (k << 16);
-                long long hi = 0;
-                for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
-                if (hi) f = __ll2float_rn((hi << 32) + (long long)q) * kInv;
+        for (int i0 = threadIdx.x; i0 < ncell; i0 += kSweepThreads * kFlushUnroll) {
+            int q[kFlushUnroll];
+            float s[kFlushUnroll];
+#pragma unroll
+            for (int u = 0; u < kFlushUnroll; ++u) {
+                const int i = i0 + u * kSweepThreads;
+                q[u] = 0; s[u] = 0.f;
+                if (i < ncell) {
+                    q[u] = pl[i];
+                    if (SUM && !FIRST) s[u] = __ldcg(so + i);
+                }
             }
-            st_stream(o + i, f);
-            if (SUM) {
-                s += f;
-                if (LAST) st_stream(so + i, s); else __stcg(so + i, s);
+#pragma unroll
+            for (int u = 0; u < kFlushUnroll; ++u) {
+                const int i = i0 + u * kSweepThreads;
+                if (i < ncell) {
+                    pl[i] = 0;
+                    float f = __int2float_rn(q[u]) * kInv;
+                    if (n_spill) {
+                        const int key = (key0 + i) | (k << 16);
+                        long long hi = 0;
+                        for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
+                        if (hi) f = __ll2float_rn((hi << 32) + (long long)q[u]) * kInv;
+                    }
+                    st_stream(o + i, f);
+                    if (SUM) {
+                        const float t = s[u] + f;
+                        if (LAST) st_stream(so + i, t); else __stcg(so + i, t);
+                    }
+                }
             }
         }
     }
@@ -539,41 +571,46 @@ __device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_b
     else flush_plane_t<VEC, false, false, true>(pl, ncell, k, o, so, spill, n_spill, key0);
 }
 
-// the warps of the CTA draw items (<= 128 records of one run: .x = first record, .y = chunk slot | (records - 1) << 9 |
-// slow << 16) from a shared counter; the records of the next item are in flight while the current one is accumulated.
-// Fast path per record: v = (Q + ticks * tmul) >> tshift, two predicated returning atomics, no branch; the returned values
-// of the item's 8 atomics are screened together for words that came near the int32 range (rare -> exact check, spill list).
+struct ItemRegs {
+    uint2 d;             // .x = first record, .y = chunk slot | (records - 1) << 9 | slow << 16
+    uint32_t r0, r1, r2, r3;
+};
+
+// The items (<= 128 records of one run) of a phase are dealt to the warps round-robin (they cost the same but for run
+// tails, and a shared counter would put an atomic and a shuffle on every item); the records of the next two items are in
+// flight while the current one is accumulated.
+// Fast path per record: v = (Q + ticks * tmul) >> tshift, two returning atomics, no branch (events of other intervals and
+// lanes past the end add zero); the returned values of the item's 8 atomics are screened together for words that came
+// near the int32 range (rare -> exact check, spill list).
 template <bool HAS_RIGHT>
 __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& c, const SampleMeta* mp, uint32_t tmul, uint32_t tshift,
                                             int task0, const unsigned long long* t_q, const uint2* items, int n_items,
-                                            uint32_t s_next_addr, int lane) {
-    auto draw = [&]() -> int {
-        int it = 0;
-        if (lane == 0) it = atoms_inc(s_next_addr);
-        return __shfl_sync(0xffffffffu, it, 0);
-    };
-    uint2 dn = make_uint2(0u, 0u);
-    uint32_t rn0 = 0, rn1 = 0, rn2 = 0, rn3 = 0;
-    auto load = [&](int it) {
-        dn = items[it];
-        const uint32_t cnt = ((dn.y >> 9) & 127u) + 1u;
-        const uint32_t* p = a.rec + dn.x + lane;
+                                            int wid, int lane) {
+    constexpr int kWarps = kSweepThreads / 32;
+    auto load = [&](int it, ItemRegs& g) {
+        g.d = items[it];
+        const uint32_t cnt = ((g.d.y >> 9) & 127u) + 1u;
+        const uint32_t* p = a.rec + g.d.x + lane;
         // lanes past the end of the item get a harmless record of their own (cell = lane): its weights are forced to 0 below
-        rn0 = ((uint32_t)lane < cnt) ? ld_stream(p) : (uint32_t)lane << 2;
-        rn1 = ((uint32_t)lane + 32u < cnt) ? ld_stream(p + 32) : (uint32_t)lane << 2;
-        rn2 = ((uint32_t)lane + 64u < cnt) ? ld_stream(p + 64) : (uint32_t)lane << 2;
-        rn3 = ((uint32_t)lane + 96u < cnt) ? ld_stream(p + 96) : (uint32_t)lane << 2;
+        g.r0 = ((uint32_t)lane < cnt) ? ld_stream(p) : (uint32_t)lane << 2;
+        g.r1 = ((uint32_t)lane + 32u < cnt) ? ld_stream(p + 32) : (uint32_t)lane << 2;
+        g.r2 = ((uint32_t)lane + 64u < cnt) ? ld_stream(p + 64) : (uint32_t)lane << 2;
+        g.r3 = ((uint32_t)lane + 96u < cnt) ? ld_stream(p + 96) : (uint32_t)lane << 2;
     };
-    int it = draw();
-    if (it < n_items) load(it);
-    while (it < n_items) {
-        const uint2 d = dn;
-        const uint32_t r[4] = {rn0, rn1, rn2, rn3};
-        it = draw();
-        if (it < n_items) load(it);
-        const uint32_t slot = d.y & 511u;
-        const uint32_t cnt = ((d.y >> 9) & 127u) + 1u;
-        if (!(d.y >> 16)) {
+    ItemRegs n1, n2;
+    n1.d = n2.d = make_uint2(0u, 0u);
+    n1.r0 = n1.r1 = n1.r2 = n1.r3 = n2.r0 = n2.r1 = n2.r2 = n2.r3 = 0u;
+    int it = wid;
+    if (it < n_items) load(it, n1);
+    if (it + kWarps < n_items) load(it + kWarps, n2);
+    for (; it < n_items; it += kWarps) {
+        const ItemRegs cur = n1;
+        n1 = n2;
+        if (it + 2 * kWarps < n_items) load(it + 2 * kWarps, n2);
+        const uint32_t r[4] = {cur.r0, cur.r1, cur.r2, cur.r3};
+        const uint32_t slot = cur.d.y & 511u;
+        const uint32_t cnt = ((cur.d.y >> 9) & 127u) + 1u;
+        if (!(cur.d.y >> 16)) {
             const uint64_t Q = t_q[slot];                                    // cbase * tmul + thalf
             int o0[4], o1[4];
             uint32_t u[4];
@@ -582,7 +619,6 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
                 const uint64_t q = (uint64_t)(r[j] >> 16) * tmul + Q;
                 const uint32_t v = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), tshift);
                 u[j] = v - c.kbase;
-                // events of other intervals (chunks straddle interval boundaries) and lanes past the end add zero: no branch
                 const bool ok = (uint32_t)lane + 32u * j < cnt && u[j] < (1u << kQ);
                 const int sgn = ok ? sgn2(r[j]) : 0;
                 const uint32_t boff = r[j] & 0xfffcu;                        // cell * 4
@@ -628,7 +664,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
     uint32_t* t_pos = reinterpret_cast<uint32_t*>(s_spill + kSpillCap);
     uint16_t* t_len = reinterpret_cast<uint16_t*>(t_pos + kTabCap);
     uint16_t* t_kr = t_len + kTabCap;
-    __shared__ int s_task, s_nitems, s_next, s_nspill;
+    __shared__ int s_task, s_nitems, s_nspill;
     __shared__ SampleMeta s_meta;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -689,7 +725,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
                     if ((int)(kr & 0xffu) <= k && k <= (int)(kr >> 8)) remaining = (len + kItemRecs - 1) / kItemRecs;
                 }
                 for (;;) {
-                    if (tid == 0) { s_nitems = 0; s_next = 0; }
+                    if (tid == 0) s_nitems = 0;
                     __syncthreads();
                     if (remaining) {
                         const int base = atomicAdd(&s_nitems, remaining);
@@ -705,9 +741,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
                     }
                     const int any_left = __syncthreads_or(remaining > 0);
                     const int n_items = s_nitems < kItemCap ? s_nitems : kItemCap;
-                    const uint32_t next_addr = (uint32_t)__cvta_generic_to_shared(&s_next);
-                    if (has_right) sweep_items<true>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, next_addr, lane);
-                    else sweep_items<false>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, next_addr, lane);
+                    if (has_right) sweep_items<true>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, tid >> 5, lane);
+                    else sweep_items<false>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, tid >> 5, lane);
                     __syncthreads();
                     if (!any_left) break;
                 }
