@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libeventpretrain_b200.so")
 EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64, EP_U32 = range(1, 10)
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
-EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_BANDED, EP_BIN_FORCE_TILED = 1, 2, 4
+EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_TILED = 1, 4
 EP_EINVAL, EP_EWORKSPACE, EP_EUNSUPPORTED, EP_EALIGN = -1, -2, -3, -4
 EP_RESIZE_NEAREST, EP_RESIZE_BILINEAR, EP_RESIZE_BICUBIC = 0, 1, 2
 
@@ -59,6 +59,10 @@ SIGNATURES = {
     "ep_bin_events_workspace_bytes_for": (c_size_t, [P(EventsSoa), P(BinParams)]),
     "ep_bin_events": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
+    "ep_bin_events_stats": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p, c_void_p]),
+    "ep_plane_statistics_workspace_bytes": (c_size_t, [c_int]),
+    "ep_plane_statistics": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t]),
     "ep_bin_events_aos": (c_int, [c_void_p, P(EventsAos), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
     "ep_normalise_workspace_bytes": (c_size_t, [c_int, c_int]),

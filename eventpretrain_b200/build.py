@@ -18,10 +18,6 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--ex
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=true"]
 
 
-if os.environ.get("EP_PHASE_TIMING"):
-    FLAGS.append("-DEP_PHASE_TIMING")      # tools only: per-phase cycle counters in the banded kernels
-
-
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

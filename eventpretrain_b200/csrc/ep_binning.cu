@@ -28,15 +28,11 @@
 
 namespace ep {
 
-// banded shared-memory sweep (ep_binning_banded.cu); returns EP_EUNSUPPORTED when the shape does not qualify
-int run_banded_canon(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                     float* out_count, void* ws, size_t ws_bytes, unsigned int* bad);
-size_t banded_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
-bool banded_worthwhile(const ep_events_soa* ev, const ep_bin_params* p);
-
 // finalize-free shared-memory path (ep_binning_tiled.cu): 4 B/event packed layout, voxel grid (+ sum plane)
 int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                      void* ws, size_t ws_bytes, unsigned int* bad);
+                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats);
+// one-pass channel statistics of a (B,C,H,W) tensor (ep_misc.cu): the paths that do not produce them as a by-product
+int plane_statistics(cudaStream_t st, const float* x, int batch, int channels, int64_t hw, double* out, void* ws, size_t ws_bytes);
 size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p);
 
 namespace {
@@ -385,11 +381,6 @@ bool persist_l2_enabled() {
     return e ? atoi(e) != 0 : false;
 }
 
-bool banded_auto() {       // EP_BIN_AUTO_BANDED=1: let method "auto" pick the banded path for large canonical batches
-    const char* e = getenv("EP_BIN_AUTO_BANDED");
-    return e ? atoi(e) != 0 : false;
-}
-
 int scatter_ctas_per_sm() {
     const char* e = getenv("EP_SCATTER_CTAS_PER_SM");
     int v = e ? atoi(e) : 8;
@@ -535,8 +526,6 @@ size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_p
     if (!ev || ep::check_params(prm) != EP_OK || ev->batch <= 0) return 0;
     size_t need = ep_bin_events_workspace_bytes(prm, ev->batch, nullptr);
     if (!(prm->flags & EP_BIN_FORCE_GLOBAL) && ev->offsets_host) {
-        const size_t b = ep::banded_workspace_bytes(ev, prm);
-        if (b > need) need = b;
         const size_t t = ep::tiled_workspace_bytes(ev, prm);
         if (t > need) need = t;
     }
@@ -546,6 +535,32 @@ size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_p
 int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* prm, float* out_voxel,
                   float* out_voxel_sum, float* out_count, void* workspace, size_t workspace_bytes,
                   unsigned int* bad_count) {
+    return ep_bin_events_stats(stream, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count, nullptr);
+}
+
+static int bin_events_any(void* stream, const ep_events_soa* ev, const ep_bin_params* prm, float* out_voxel,
+                          float* out_voxel_sum, float* out_count, void* workspace, size_t workspace_bytes,
+                          unsigned int* bad_count, double* out_stats, bool* stats_done);
+
+int ep_bin_events_stats(void* stream, const ep_events_soa* ev, const ep_bin_params* prm, float* out_voxel,
+                        float* out_voxel_sum, float* out_count, void* workspace, size_t workspace_bytes,
+                        unsigned int* bad_count, double* out_stats) {
+    bool done = false;
+    int rc = bin_events_any(stream, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count, out_stats, &done);
+    if (rc != EP_OK || !out_stats || done) return rc;
+    if (!prm->num_bins || !out_voxel) return EP_EINVAL;
+    // kernels without the fused side output: one extra native pass over the finished planes
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t hw = (int64_t)prm->height * prm->width;
+    rc = ep::plane_statistics(st, out_voxel, ev->batch, prm->num_bins, hw, out_stats, workspace, workspace_bytes);
+    if (rc == EP_OK && out_voxel_sum)
+        rc = ep::plane_statistics(st, out_voxel_sum, ev->batch, 1, hw, out_stats + 4 * prm->num_bins, workspace, workspace_bytes);
+    return rc;
+}
+
+static int bin_events_any(void* stream, const ep_events_soa* ev, const ep_bin_params* prm, float* out_voxel,
+                          float* out_voxel_sum, float* out_count, void* workspace, size_t workspace_bytes,
+                          unsigned int* bad_count, double* out_stats, bool* stats_done) {
     using namespace ep;
     int rc = check_params(prm);
     if (rc != EP_OK) return rc;
@@ -566,11 +581,11 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
         if ((!five && (ev->t_dtype != 0 || ev->t)) || (five && !ev->t && n_events > 0)) return EP_EINVAL;
         if (ev->y != nullptr || (!ev->p && n_events > 0) || ev->p_dtype != EP_U32 || !ev->t_base || prm->time_f32) return EP_EINVAL;
         if (!aligned16(ev->x) || !aligned16(ev->t)) return EP_EALIGN;
-        if (prm->flags & EP_BIN_FORCE_BANDED) return EP_EUNSUPPORTED;
         if (!five && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
             // default: route + two-plane shared-memory sweep, no global accumulators (ep_binning_tiled.cu); shapes, workspaces or
             // outputs it does not take (count frames, > 64 row tiles) fall through to the global-RED kernels
-            rc = run_tiled_packed4(st, ev, prm, out_voxel, out_voxel_sum, workspace, workspace_bytes, bad_count);
+            rc = run_tiled_packed4(st, ev, prm, out_voxel, out_voxel_sum, workspace, workspace_bytes, bad_count, out_stats);
+            if (rc == EP_OK) *stats_done = true;
             if (rc != EP_EUNSUPPORTED || (prm->flags & EP_BIN_FORCE_TILED)) return rc;
         } else if (prm->flags & EP_BIN_FORCE_TILED) {
             return EP_EUNSUPPORTED;
@@ -595,17 +610,6 @@ int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* pr
     const bool canon = !compact && ev->xy_dtype == EP_U16 && ev->p_dtype == EP_U8 && !prm->time_f32 &&
                        (ev->t_dtype == EP_I64 || ev->t_dtype == EP_F64) && aligned16(ev->x) && aligned16(ev->y) &&
                        aligned16(ev->t) && aligned16(ev->p);
-    if ((canon || compact) && !(prm->flags & EP_BIN_FORCE_GLOBAL)) {
-        // Route + banded shared-memory sweep (ep_binning_banded.cu), on request.  Measured on B200 it is
-        // on par with the global-RED kernels when the events are spread evenly over the sensor and ~30 % slower
-        // when they sit on edges and hot pixels, so the global-RED kernels, which do not care, stay the default.
-        if ((prm->flags & EP_BIN_FORCE_BANDED) || (banded_auto() && banded_worthwhile(ev, prm))) {
-            rc = run_banded_canon(st, ev, prm, out_voxel, out_voxel_sum, out_count, workspace, workspace_bytes, bad_count);
-            if (rc == EP_OK || (rc != EP_EUNSUPPORTED && rc != EP_EWORKSPACE) || (prm->flags & EP_BIN_FORCE_BANDED)) return rc;
-        }
-    } else if (prm->flags & EP_BIN_FORCE_BANDED) {
-        return EP_EUNSUPPORTED;
-    }
     if (compact) {
         SoaCompactLoader ld{static_cast<const uint16_t*>(ev->x), static_cast<const uint16_t*>(ev->y),
                             static_cast<const uint32_t*>(ev->t), ev->t_base, ev->t_div};

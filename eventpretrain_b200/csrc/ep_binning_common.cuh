@@ -1,4 +1,4 @@
-// Shared pieces of the binning kernels (v1 global-RED path and the banded shared-memory sweep):
+// Shared pieces of the binning kernels (global-RED path and the tiled shared-memory path):
 // constants, per-sample metadata, argument block, event loaders.
 #pragma once
 #include <math.h>

@@ -91,6 +91,7 @@ struct TiledArgs {
     unsigned int* bad_count;
     float* out_voxel;
     float* out_sum;
+    double* stats_part;         // (B * NT) x (num_bins + 1) x 3 partial statistics, or null
 };
 
 __device__ __forceinline__ void pdl_wait_t() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -477,9 +478,16 @@ __device__ __noinline__ void sweep_record_slow(const ChunkMeta* cmp, const uint3
 // most 7 vectors of a 12800-cell tile, and one dependent L2 round trip per vector was the longest stall of the sweep.
 constexpr int kFlushUnroll = 4;
 
-template <bool VEC, bool FIRST, bool LAST, bool SUM>
+// Per-thread partial statistics of the values a thread writes (fixed element order => reproducible)
+struct StatAcc {
+    float s1, s2, mx;
+    __device__ __forceinline__ void init() { s1 = 0.f; s2 = 0.f; mx = -INFINITY; }
+    __device__ __forceinline__ void add(float v) { s1 += v; s2 = fmaf(v, v, s2); mx = fmaxf(mx, v); }
+};
+
+template <bool VEC, bool FIRST, bool LAST, bool SUM, bool STATS>
 __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so,
-                                              const int2* spill, int n_spill, int key0) {
+                                              const int2* spill, int n_spill, int key0, StatAcc& sa, StatAcc& ss) {
     constexpr float kInv = 1.0f / 16777216.0f;
     if (VEC) {
         constexpr int kStep = kSweepThreads * 4;
@@ -514,11 +522,13 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
                         }
                     }
                     st_stream(reinterpret_cast<float4*>(o + i), f);
+                    if (STATS) { sa.add(f.x); sa.add(f.y); sa.add(f.z); sa.add(f.w); }
                     if (SUM) {
                         float4 t = s[u];
                         t.x += f.x; t.y += f.y; t.z += f.z; t.w += f.w;      // voxel.sum(dim=0): sequential fp32 over bins
                         if (LAST) st_stream(reinterpret_cast<float4*>(so + i), t);
                         else __stcg(reinterpret_cast<float4*>(so + i), t);
+                        if (STATS && LAST) { ss.add(t.x); ss.add(t.y); ss.add(t.z); ss.add(t.w); }
                     }
                 }
             }
@@ -549,9 +559,11 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
                         if (hi) f = __ll2float_rn((hi << 32) + (long long)q[u]) * kInv;
                     }
                     st_stream(o + i, f);
+                    if (STATS) sa.add(f);
                     if (SUM) {
                         const float t = s[u] + f;
                         if (LAST) st_stream(so + i, t); else __stcg(so + i, t);
+                        if (STATS && LAST) ss.add(t);
                     }
                 }
             }
@@ -559,16 +571,50 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
     }
 }
 
-// pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys)
+// fixed-order block reduction of the per-thread statistics -> part[0..2] = (sum, sum of squares, max) as fp64
+__device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part, double (*s_red)[3]) {
+    double d1 = (double)a.s1, d2 = (double)a.s2;
+    float mx = a.mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_red[wid][0] = d1; s_red[wid][1] = d2; s_red[wid][2] = (double)mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0, tm = -INFINITY;
+        for (int w = 0; w < kSweepThreads / 32; ++w) { t1 += s_red[w][0]; t2 += s_red[w][1]; tm = fmax(tm, s_red[w][2]); }
+        part[0] = t1; part[1] = t2; part[2] = tm;
+    }
+    __syncthreads();
+}
+
+// pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys).
+// stats_part (or null): per-(task, channel) partial statistics of the written values, channel num_bins = the sum plane.
 template <bool VEC>
 __device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, const int2* spill, int n_spill,
-                                            int key0) {
+                                            int key0, double* stats_part, double (*s_red)[3]) {
     const bool first = k == 0, last = k == num_bins - 1;
-    if (!so) flush_plane_t<VEC, false, false, false>(pl, ncell, k, o, so, spill, n_spill, key0);
-    else if (first && last) flush_plane_t<VEC, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0);
-    else if (first) flush_plane_t<VEC, true, false, true>(pl, ncell, k, o, so, spill, n_spill, key0);
-    else if (last) flush_plane_t<VEC, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0);
-    else flush_plane_t<VEC, false, false, true>(pl, ncell, k, o, so, spill, n_spill, key0);
+    StatAcc sa, ss;
+    sa.init(); ss.init();
+    if (stats_part) {
+        if (!so) flush_plane_t<VEC, false, false, false, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (first && last) flush_plane_t<VEC, true, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (first) flush_plane_t<VEC, true, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (last) flush_plane_t<VEC, false, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else flush_plane_t<VEC, false, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        stat_reduce_store(sa, stats_part + (size_t)k * 3, s_red);
+        if (so && last) stat_reduce_store(ss, stats_part + (size_t)num_bins * 3, s_red);
+    } else {
+        if (!so) flush_plane_t<VEC, false, false, false, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (first && last) flush_plane_t<VEC, true, true, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (first) flush_plane_t<VEC, true, false, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else if (last) flush_plane_t<VEC, false, true, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        else flush_plane_t<VEC, false, false, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+    }
 }
 
 struct ItemRegs {
@@ -666,6 +712,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
     uint16_t* t_kr = t_len + kTabCap;
     __shared__ int s_task, s_nitems, s_nspill;
     __shared__ SampleMeta s_meta;
+    __shared__ double s_red[kSweepThreads / 32][3];
 
     const int tid = threadIdx.x, lane = tid & 31;
     pdl_trigger_t();
@@ -751,7 +798,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
             const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
             float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
             float* so = a.out_sum ? a.out_sum + (int64_t)b * HW + (int64_t)row0 * a.W : nullptr;
-            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0);
+            double* sp = a.stats_part ? a.stats_part + (size_t)task * (a.num_bins + 1) * 3 : nullptr;
+            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0, sp, s_red);
             __syncthreads();
         }
     }
@@ -760,7 +808,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
 struct TiledPlan {
     int NT, rows, n_tasks;
     int64_t rec_pos0, n_rec;
-    size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_rec, total;
+    size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_rec, total;
 };
 
 bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) {
@@ -796,6 +844,7 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_coff = o; o += align_up(sizeof(uint16_t) * nt * (size_t)(NT + 2), 256);
     pl.off_crel = o; o += align_up(sizeof(uint32_t) * nt * 32, 256);
     pl.off_counters = o; o += 256;
+    pl.off_stats = o; o += align_up(sizeof(double) * 3 * (size_t)B * NT * (size_t)(p->num_bins + 1), 256);
     pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
     pl.total = o;
     return true;
@@ -809,8 +858,27 @@ size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p) {
 }
 
 // Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
+// channel statistics from the sweep's per-(task, channel) partials, in a fixed order: out[c] = (count, sum, sum of squares, max)
+__global__ void __launch_bounds__(256) k_stats_reduce(const double* __restrict__ part, int n_parts, int n_ch, double count,
+                                                      double* __restrict__ out) {
+    __shared__ double s1[256], s2[256], sm[256];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    double a1 = 0.0, a2 = 0.0, am = -INFINITY;
+    for (int i = tid; i < n_parts; i += 256) {
+        const double* q = part + ((size_t)i * n_ch + c) * 3;
+        a1 += q[0]; a2 += q[1]; am = fmax(am, q[2]);
+    }
+    s1[tid] = a1; s2[tid] = a2; sm[tid] = am;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { s1[tid] += s1[tid + o]; s2[tid] += s2[tid + o]; sm[tid] = fmax(sm[tid], sm[tid + o]); }
+        __syncthreads();
+    }
+    if (tid == 0) { out[c * 4 + 0] = count; out[c * 4 + 1] = s1[0]; out[c * 4 + 2] = s2[0]; out[c * 4 + 3] = sm[0]; }
+}
+
 int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                      void* ws, size_t ws_bytes, unsigned int* bad) {
+                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
     TiledPlan pl;
     if (!tiled_plan(ev, p, pl)) return EP_EUNSUPPORTED;
     if (!ws || ws_bytes < pl.total) return EP_EUNSUPPORTED;
@@ -840,6 +908,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     a.bad_count = bad;
     a.out_voxel = out_voxel;
     a.out_sum = out_sum;
+    a.stats_part = out_stats ? reinterpret_cast<double*>(base + pl.off_stats) : nullptr;
 
     // per-sample first / last stamps and integer-time constants: the same kernel as the global path
     SoaPackedLoader<false> ld{a.w, nullptr, a.blk_base, ev->t_base, ev->t_div};
@@ -876,6 +945,13 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
         profile_begin(st, kProfFinalize);
         if (vec) k_sweep<true><<<grid, kSweepThreads, smem, st>>>(a);
         else k_sweep<false><<<grid, kSweepThreads, smem, st>>>(a);
+        profile_end(st);
+        EP_LAUNCH_CHECK();
+    }
+    if (out_stats) {
+        const int n_ch = p->num_bins + 1;
+        profile_begin(st, kProfOther);
+        k_stats_reduce<<<out_sum ? n_ch : p->num_bins, 256, 0, st>>>(a.stats_part, B * pl.NT, n_ch, (double)B * p->height * p->width, out_stats);
         profile_end(st);
         EP_LAUNCH_CHECK();
     }

@@ -171,6 +171,60 @@ __global__ void __launch_bounds__(256) k_diffmap(const float* __restrict__ f0, c
 }  // namespace
 }  // namespace ep
 
+
+namespace ep {
+namespace {
+constexpr int kPlaneStatBlocks = 2 * kNumSMs;
+
+// per-channel (sum, sum of squares, max) of a (B,C,H,W) f32 tensor: fixed partition and fixed reduction order, fp64 partials
+__global__ void __launch_bounds__(256) k_plane_stats_partial(const float* __restrict__ x, int batch, int channels, int64_t hw,
+                                                             double* __restrict__ part) {
+    __shared__ double s1[256], s2[256], sm[256];
+    const int c = blockIdx.y, tid = threadIdx.x;
+    const int64_t per = (int64_t)batch * hw;
+    double a1 = 0.0, a2 = 0.0, am = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < per; i += (int64_t)gridDim.x * 256) {
+        const int64_t b = i / hw, r = i - b * hw;
+        const double v = (double)x[((int64_t)b * channels + c) * hw + r];
+        a1 += v; a2 += v * v; am = fmax(am, v);
+    }
+    s1[tid] = a1; s2[tid] = a2; sm[tid] = am;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { s1[tid] += s1[tid + o]; s2[tid] += s2[tid + o]; sm[tid] = fmax(sm[tid], sm[tid + o]); }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* q = part + ((size_t)c * gridDim.x + blockIdx.x) * 3;
+        q[0] = s1[0]; q[1] = s2[0]; q[2] = sm[0];
+    }
+}
+
+__global__ void k_plane_stats_final(const double* __restrict__ part, int n_blocks, double count, double* __restrict__ out) {
+    const int c = blockIdx.x;
+    if (threadIdx.x) return;
+    double a1 = 0.0, a2 = 0.0, am = -INFINITY;
+    for (int i = 0; i < n_blocks; ++i) {
+        const double* q = part + ((size_t)c * n_blocks + i) * 3;
+        a1 += q[0]; a2 += q[1]; am = fmax(am, q[2]);
+    }
+    out[c * 4 + 0] = count; out[c * 4 + 1] = a1; out[c * 4 + 2] = a2; out[c * 4 + 3] = am;
+}
+}  // namespace
+
+// out (channels,4) f64 = (count, sum, sum of squares, max) per channel; ws: 3 * channels * kPlaneStatBlocks doubles
+int plane_statistics(cudaStream_t st, const float* x, int batch, int channels, int64_t hw, double* out, void* ws, size_t ws_bytes) {
+    if (!x || !out || batch <= 0 || channels <= 0 || hw <= 0) return EP_EINVAL;
+    if (!ws || ws_bytes < sizeof(double) * 3 * (size_t)channels * kPlaneStatBlocks) return EP_EWORKSPACE;
+    double* part = static_cast<double*>(ws);
+    k_plane_stats_partial<<<dim3(kPlaneStatBlocks, channels), 256, 0, st>>>(x, batch, channels, hw, part);
+    EP_LAUNCH_CHECK();
+    k_plane_stats_final<<<channels, 32, 0, st>>>(part, kPlaneStatBlocks, (double)batch * (double)hw, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+}  // namespace ep
+
 extern "C" {
 
 int ep_abi_version(void) { return EP_ABI_VERSION; }
@@ -277,6 +331,13 @@ int ep_diffmap_frames(void* stream, const float* f0, const float* f1, float* out
     else ep::k_diffmap<false><<<grid, 256, 0, st>>>(f0, f1, out, n_samples, per_sample, mode, eps, negate);
     EP_LAUNCH_CHECK();
     return EP_OK;
+}
+
+size_t ep_plane_statistics_workspace_bytes(int channels) { return sizeof(double) * 3 * (size_t)(channels > 0 ? channels : 1) * ep::kPlaneStatBlocks; }
+
+int ep_plane_statistics(void* stream, const float* x, int batch, int channels, int height, int width, double* out, void* workspace,
+                        size_t workspace_bytes) {
+    return ep::plane_statistics(static_cast<cudaStream_t>(stream), x, batch, channels, (int64_t)height * width, out, workspace, workspace_bytes);
 }
 
 }  // extern "C"

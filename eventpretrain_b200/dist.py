@@ -50,13 +50,24 @@ def balance_by_events(counts, world):
     return [sorted(p) for p in parts]
 
 
-def local_statistics(x):
-    """Per-channel (count, sum, sum of squares, max) of a (B,C,H,W) tensor as fp64: shape (C,4)."""
-    xd = x.double()
-    C = x.shape[1]
-    flat = xd.transpose(0, 1).reshape(C, -1)
-    cnt = torch.full((C,), float(flat.shape[1]), dtype=torch.float64, device=x.device)
-    return torch.stack([cnt, flat.sum(1), (flat * flat).sum(1), flat.amax(1)], dim=1)
+def plane_statistics(x):
+    """Per-channel (count, sum, sum of squares, max) of a CUDA (B,C,H,W) float32 tensor as fp64, shape (C,4): one native pass
+    with a fixed reduction order (ep_plane_statistics).  ep.bin_events(..., stats=True) returns the same table for the voxel
+    grid as a by-product of the binning kernels; this entry is for tensors produced elsewhere (count frames, targets)."""
+    import ctypes  # noqa: F401
+    from ._runtime import lib, require_cuda, stream_ptr, workspace
+    from . import _lib
+    require_cuda(x)
+    if x.dim() != 4 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("plane_statistics needs a contiguous float32 (B,C,H,W) tensor")
+    B, C, H, W = x.shape
+    L = lib()
+    out = torch.empty((C, 4), dtype=torch.float64, device=x.device)
+    ws = workspace(L.ep_plane_statistics_workspace_bytes(C), x.device, "stats")
+    with torch.cuda.device(x.device):
+        rc = L.ep_plane_statistics(stream_ptr(x.device), x.data_ptr(), B, C, H, W, out.data_ptr(), ws.data_ptr(), ws.numel())
+    _lib.check(rc, "ep_plane_statistics")
+    return out
 
 
 def allreduce_statistics(stats, group=None, async_op=False):

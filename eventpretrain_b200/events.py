@@ -359,8 +359,7 @@ def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
     return RaggedEvents(*tens, offsets_host=off, t_div=t_div)
 
 
-_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "banded": _lib.EP_BIN_FORCE_BANDED,
-           "tiled": _lib.EP_BIN_FORCE_TILED}
+_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "tiled": _lib.EP_BIN_FORCE_TILED}
 
 
 def _bin_params(size, num_bins, count_channels, scale, time_f32, method=None):
@@ -387,14 +386,17 @@ def _raise_bad(bad):
 
 
 def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_sum=False, time_f32=False,
-               check=False, out=None, method=None):
+               check=False, out=None, method=None, stats=False):
     """Batched events -> tensors: voxel grid (B,num_bins,H,W), optional voxel.sum(0) plane (B,1,H,W) and/or
     polarity count frame (B,count_channels,H,W); one C-ABI call (ep_bin_events).
 
     Returns a dict with the keys that were requested: 'voxel', 'voxel_sum', 'count'.
+    stats=True adds 'stats': (num_bins + 1, 4) fp64 rows (element count, sum, sum of squares, max) per voxel channel and, in
+    the last row, of the sum plane (valid when voxel_sum) — the table dist.allreduce_statistics reduces over the ranks; on
+    the tiled path it is a by-product of the kernel that writes the planes.
     check=True synchronises and raises for events the reference would have raised on.
-    method: None/"auto" (the global-RED kernels), "global", "banded" (route + shared-memory sweep; canonical and
-    compact layouts only) — same results bit for bit.
+    method: None/"auto" (the tiled shared-memory kernels for the 4 B/event packed layout without count frames, else the
+    global-RED kernels), "global", "tiled" — same results bit for bit.
     """
     require_cuda(ev.x)
     dev = ev.device
@@ -412,10 +414,15 @@ def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_s
     nbytes = L.ep_bin_events_workspace_bytes_for(ctypes.byref(desc), ctypes.byref(prm))
     ws = workspace(nbytes, dev, "bin")
     bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    if stats:
+        if not num_bins:
+            raise ValueError("stats=True needs a voxel grid")
+        if "stats" not in out:
+            out["stats"] = torch.zeros((num_bins + 1, 4), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        rc = L.ep_bin_events(stream_ptr(dev), ctypes.byref(desc), ctypes.byref(prm), ptr(out.get("voxel")),
-                             ptr(out.get("voxel_sum")) if voxel_sum else 0, ptr(out.get("count")), ws.data_ptr(),
-                             ws.numel(), ptr(bad))
+        rc = L.ep_bin_events_stats(stream_ptr(dev), ctypes.byref(desc), ctypes.byref(prm), ptr(out.get("voxel")),
+                                   ptr(out.get("voxel_sum")) if voxel_sum else 0, ptr(out.get("count")), ws.data_ptr(),
+                                   ws.numel(), ptr(bad), ptr(out.get("stats")) if stats else 0)
     _lib.check(rc, "ep_bin_events")
     if check:
         _raise_bad(bad)

@@ -119,10 +119,9 @@ typedef struct ep_bin_params {
     double scale_x, scale_y;     /* events_reshape fused (dataset/augmentation/events_augment.py:22-26):
                                     x*scale_x, y*scale_y in fp64, then truncation; 1.0 = none */
     int time_f32;                /* 1 = do the time arithmetic in fp32 (what torch does for float32 event arrays) */
-    int flags;                   /* 0 = choose; EP_BIN_FORCE_GLOBAL / EP_BIN_FORCE_BANDED pin the kernel family */
+    int flags;                   /* 0 = choose; EP_BIN_FORCE_GLOBAL / EP_BIN_FORCE_TILED pin the kernel family */
 } ep_bin_params;
 #define EP_BIN_FORCE_GLOBAL 1    /* packed-u64 global RED + finalize (any layout, any size) */
-#define EP_BIN_FORCE_BANDED 2    /* banded shared-memory sweep (canonical SoA layout only) */
 #define EP_BIN_FORCE_TILED 4     /* route + two-plane shared-memory sweep, no global accumulators (4 B packed layout, voxel grid
                                     and sum plane only; EP_EUNSUPPORTED otherwise).  The default for what it takes. */
 
@@ -130,8 +129,8 @@ typedef struct ep_bin_params {
  * slots to keep one group of samples L2-resident); any size >= the minimum (one slot + per-sample
  * metadata), returned through *min_bytes when non-NULL, works. */
 EP_API size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch, size_t* min_bytes);
-/* Same, knowing the batch (reads offsets_host only): also covers the routed-record buffer of the banded
- * fast path, which is chosen when the layout is canonical and the workspace is large enough. */
+/* Same, knowing the batch (reads offsets_host only): also covers the routed-record buffer of the tiled
+ * path, which is taken when the layout is the 4 B packed one and the workspace is large enough. */
 EP_API size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_params* prm);
 
 /* Replaces, for a whole ragged batch in one call:
@@ -145,6 +144,20 @@ EP_API size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const e
 EP_API int ep_bin_events(void* stream, const ep_events_soa* ev, const ep_bin_params* prm,
                   float* out_voxel, float* out_voxel_sum, float* out_count,
                   void* workspace, size_t workspace_bytes, unsigned int* bad_count);
+
+/* ep_bin_events plus the batch statistics that feed the path's one collective (north_star: "small all-reduce of
+ * dataset-level normalisation statistics"; the reference's analogue is misc.all_reduce_mean, utils/misc.py:406-414):
+ * out_stats (num_bins + 1, 4) f64 = per voxel channel, then for the sum plane when out_voxel_sum is given,
+ * (element count, sum, sum of squares, max) over the batch.  On the tiled path they are by-products of the pass that
+ * writes the planes (block-reduced in a fixed order: reproducible); other paths add one native pass.  NULL = none. */
+EP_API int ep_bin_events_stats(void* stream, const ep_events_soa* ev, const ep_bin_params* prm,
+                        float* out_voxel, float* out_voxel_sum, float* out_count,
+                        void* workspace, size_t workspace_bytes, unsigned int* bad_count, double* out_stats);
+
+/* The same statistics for any (B,C,H,W) f32 tensor: out (C,4) f64, one pass, fixed reduction order. */
+EP_API size_t ep_plane_statistics_workspace_bytes(int channels);
+EP_API int ep_plane_statistics(void* stream, const float* x, int batch, int channels, int height, int width, double* out,
+                        void* workspace, size_t workspace_bytes);
 
 /* Same, for one (N,4) array exactly as the reference functions receive it. */
 EP_API int ep_bin_events_aos(void* stream, const ep_events_aos* ev, const ep_bin_params* prm,

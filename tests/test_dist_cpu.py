@@ -10,6 +10,12 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 
+def _table(x):
+    """(C,4) fp64 table (count, sum, sum of squares, max) of a CPU tensor: what the GPU kernels hand to the all-reduce."""
+    xd = x.double().transpose(0, 1).reshape(x.shape[1], -1)
+    return torch.stack([torch.full((x.shape[1],), float(xd.shape[1]), dtype=torch.float64), xd.sum(1), (xd * xd).sum(1), xd.amax(1)], 1)
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0")
@@ -28,12 +34,12 @@ def _worker(rank, world, port, q):
     # statistics: each rank holds its shard of a (B,C,H,W) tensor; the reduced result must equal the global one
     g = torch.Generator().manual_seed(1)
     full = torch.randn(len(counts), 3, 8, 8, generator=g)
-    stats = epd.local_statistics(full[lo:hi])
+    stats = _table(full[lo:hi])
     stats, _ = epd.allreduce_statistics(stats)
-    ref = epd.local_statistics(full)
+    ref = _table(full)
     fin, fin_ref = epd.finalize_statistics(stats), epd.finalize_statistics(ref)
     ok = all(torch.allclose(fin[k], fin_ref[k], rtol=1e-12, atol=1e-12) for k in fin)
-    finish, works = epd.allreduce_statistics(epd.local_statistics(full[lo:hi]), async_op=True)
+    finish, works = epd.allreduce_statistics(_table(full[lo:hi]), async_op=True)
     for wk in works:
         wk.wait()
     ok = ok and torch.allclose(finish(), ref, rtol=1e-12)

@@ -286,66 +286,6 @@ def _random_batch(ep, rng, counts, H, W, t_span=50_000, hot=None, unsorted=False
     return ev.to("cuda"), samples
 
 
-@pytest.mark.parametrize("H,W,bins", [(224, 224, 5), (480, 640, 5), (44, 64, 15), (65, 87, 9)])
-def test_banded_equals_global_and_oracle(ep, H, W, bins):
-    """The banded shared-memory sweep and the global-RED kernels are the same integer arithmetic: identical bits;
-    both within tolerance of the oracle.  Ragged batch with an empty sample, a 1-event sample and a hot pixel
-    (2000 same-polarity events on one cell: exercises the spill table beyond the 127 admitted events)."""
-    from oracle import events as oe
-    rng = np.random.default_rng(H * 1000 + bins)
-    counts = [30000, 0, 1, 70001, 4099, 12288]
-    ev, samples = _random_batch(ep, rng, counts, H, W, hot=2000)
-    kw = dict(num_bins=bins, count_channels=2, voxel_sum=True, check=True)
-    a = ep.bin_events(ev, (H, W), method="global", **kw)
-    b = ep.bin_events(ev, (H, W), method="banded", **kw)
-    for key in ("voxel", "voxel_sum", "count"):
-        assert torch.equal(a[key], b[key]), key
-    for i, s in enumerate(samples):
-        if len(s) == 0:
-            assert not b["voxel"][i].any() and not b["count"][i].any()
-            continue
-        assert close(b["voxel"][i].cpu().numpy(), oe.voxel_grid(s, bins, (H, W))), i
-        assert np.array_equal(b["count"][i].cpu().numpy(), oe.count_frame(s, (H, W), 2)), i
-    # shard with offsets[0] > 0, count-only and voxel-only variants, fused scale
-    sh = ev.shard(1, 2)
-    c = ep.bin_events(sh, (H, W), num_bins=bins, method="banded", check=True)
-    assert torch.equal(c["voxel"], a["voxel"][3:])
-    d = ep.bin_events(ev, (H, W), count_channels=3, method="banded", check=True)
-    assert torch.equal(d["count"][:, 0], a["count"][:, 0]) and torch.equal(d["count"][:, 2], a["count"][:, 1])
-    assert not d["count"][:, 1].any()
-    sc = (0.5, 0.75)
-    e1 = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, scale=sc, method="global", check=True)
-    e2 = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, scale=sc, method="banded", check=True)
-    assert torch.equal(e1["voxel"], e2["voxel"]) and torch.equal(e1["count"], e2["count"])
-
-
-def test_banded_unsorted_and_out_of_window(ep):
-    """Unsorted stamps: first/last rows are not min/max, so some events fall outside the bins (dropped from the voxel
-    grid, still counted in the count frame); chunks then span several intervals."""
-    from oracle import events as oe
-    rng = np.random.default_rng(31)
-    H, W, bins = 48, 64, 5
-    ev, samples = _random_batch(ep, rng, [20000, 9000], H, W, unsorted=True)
-    a = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, method="global", check=True)
-    b = ep.bin_events(ev, (H, W), num_bins=bins, count_channels=2, voxel_sum=True, method="banded", check=True)
-    for key in ("voxel", "voxel_sum", "count"):
-        assert torch.equal(a[key], b[key]), key
-    for i, s in enumerate(samples):
-        assert close(b["voxel"][i].cpu().numpy(), oe.voxel_grid(s, bins, (H, W)))
-        assert np.array_equal(b["count"][i].cpu().numpy(), oe.count_frame(s, (H, W), 2))
-
-
-def test_banded_bad_events_raise(ep):
-    rng = np.random.default_rng(3)
-    ev, _ = _random_batch(ep, rng, [5000] * 40, 48, 64)
-    ev.x[17] = 64 + 63 * 64          # flat index far outside the 48x64 grid
-    ev.y[17] = 47
-    with pytest.raises(IndexError):
-        ep.bin_events(ev, (48, 64), num_bins=5, method="banded", check=True)
-    with pytest.raises(IndexError):
-        ep.bin_events(ev, (48, 64), num_bins=5, check=True)
-
-
 def test_time_surface_self_oracle(ep):
     """No reference routine exists: checked against the numpy self-oracle."""
     from oracle import stage3_np as s3
@@ -414,7 +354,7 @@ def test_full_size_properties(ep):
     """BASELINE configs[1] sizes (640x480, ~1M events/sample, 5 bins; 24 samples here to keep the suite short): size-independent
     properties instead of an oracle pass — conservation (every in-window event adds p in total, so the grid sums to the
     sample's net polarity and voxel.sum(0) to the same), run-to-run bit identity, identical bits across the resident layouts
-    and both kernel families, shards equal to the rows of the whole batch."""
+    and both kernel families (the 4 B transport layout takes the tiled shared-memory path by default), shards equal to the rows of the whole batch."""
     import bench
     dev = torch.device("cuda", 0)
     ev = bench.make_batch_gpu(0, dev, batch=24)
@@ -432,8 +372,8 @@ def test_full_size_properties(ep):
     b2 = ep.bin_events(ev, (H, W), num_bins=bins, voxel_sum=True, count_channels=2)
     for key in ("voxel", "voxel_sum", "count"):
         assert torch.equal(a[key], b2[key]), key
-    for other, method in ((host.transport().to(dev), None), (host.packed(5).to(dev), None), (host.compact().to(dev), None),
-                          (host.compact().to(dev), "banded"), (ev, "banded")):
+    for other, method in ((host.transport().to(dev), None), (host.transport().to(dev), "global"), (host.packed(5).to(dev), None),
+                          (host.compact().to(dev), None)):
         o = ep.bin_events(other, (H, W), num_bins=bins, voxel_sum=True, count_channels=2, check=True, method=method)
         for key in ("voxel", "voxel_sum", "count"):
             assert torch.equal(a[key], o[key]), (key, method)

@@ -221,3 +221,30 @@ def test_config_sizes_vs_oracle(ep, H, W, bins, n, B):
     assert torch.equal(a["voxel"], out["voxel"]) and torch.equal(a["voxel_sum"], out["voxel_sum"])
     for i in range(min(B, 4)):
         assert close(out["voxel"][i].cpu().numpy(), oe.voxel_grid(samples[i], bins, (H, W))), i
+
+
+def test_fused_statistics(ep):
+    """(count, sum, sum of squares, max) per channel: by-product of the tiled kernels, one native pass elsewhere; both equal
+    the fp64 statistics of the tensors they describe and are bit-reproducible run to run."""
+    from eventpretrain_b200 import dist as epd
+    rng = np.random.default_rng(77)
+    H, W, bins = 96, 128, 5
+    ev, _ = dense_batch(ep, rng, [20000, 0, 30000, 511, 9000], H, W, hot=300)
+    p4 = ev.packed(4).to("cuda")
+
+    def table(x):
+        xd = x.double().transpose(0, 1).reshape(x.shape[1], -1)
+        return torch.stack([torch.full((x.shape[1],), float(xd.shape[1]), dtype=torch.float64, device=x.device), xd.sum(1),
+                            (xd * xd).sum(1), xd.amax(1)], 1)
+
+    for method in ("tiled", "global"):
+        o = ep.bin_events(p4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method=method)
+        ref = torch.cat([table(o["voxel"]), table(o["voxel_sum"])], 0)
+        assert torch.allclose(o["stats"], ref, rtol=1e-6, atol=1e-6), method
+        assert torch.equal(o["stats"][:, 0], ref[:, 0]) and torch.equal(o["stats"][:, 3], ref[:, 3]), method
+        again = ep.bin_events(p4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method=method)
+        assert torch.equal(again["stats"], o["stats"]), method
+    x = torch.randn(7, 3, 33, 50, device="cuda")
+    assert torch.allclose(epd.plane_statistics(x), table(x), rtol=1e-12, atol=1e-9)
+    fin = epd.finalize_statistics(epd.plane_statistics(x))
+    assert torch.allclose(fin["mean"], x.double().mean((0, 2, 3)), atol=1e-12)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Quick timing / cross-check of the binning paths on a slice of the bench workload (development tool).
 
-    python tools/quick_bin.py [--batch 64] [--steps 5] [--methods banded,global] [--check] [--skewed] [--compact]
+    python tools/quick_bin.py [--batch 64] [--steps 5] [--methods tiled,global] [--check] [--skewed] [--compact]
 
 Prints per method: ms/step, Gevents/s and the library's per-kernel device times (pass 1 = route | scatter,
 pass 2 = sweep | finalize).  --check compares the methods bit for bit.
@@ -22,7 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--methods", default="banded,global")
+    ap.add_argument("--methods", default="tiled,global")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--skewed", action="store_true")
     ap.add_argument("--compact", action="store_true")
