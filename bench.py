@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""Benchmark of the EventPretrain input hot path on B200 (contract: see the task statement / DESIGN.md §6).
+"""Benchmark of the EventPretrain input hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload at every N (weak scaling: the same per-GPU batch on each rank): BASELINE.json configs[1] —
-an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), binned at sensor
-resolution into a 5-bin voxel grid plus the event-side difference-map target voxel.sum(0).  The batch is resident in
-the layout the collate step ships over PCIe: the densest lossless transport layout the stream fits
-(RaggedEvents.transport(): here 4 B/event, one u32 x | y << 11 | p << 22 | ticks << 23 with 9-bit ticks relative to a base
-per 256 events; results bit-identical to the 13 B/event canonical SoA, whose number is reported under "extra").  A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
+an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), time-sorted microsecond stamps
+uniform in a 0.3 s window, binned at sensor resolution into a 5-bin voxel grid plus the event-side
+difference-map target voxel.sum(0), plus the per-channel batch statistics that feed the path's one collective.  The batch is
+resident in the layout the collate step ships over PCIe: the densest lossless transport layout the stream fits
+(RaggedEvents.transport(): here 4 B/event; results bit-identical to the 13 B/event canonical SoA, whose number is under "extra").
+A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
 
   value     events/s with the batch already resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same metric through the public API from pinned HOST buffers: H2D of the SoA batch (in slices, so the
-            copy of slice i+1 overlaps the binning of slice i) and a D2H read of the per-sample checksum of the result
-            are inside the timed region
-  roofline  binning kernels (scatter + finalize): algorithmic bytes / their summed device time (CUDA events
-            recorded by the library around each launch: ep_profile_*), against the measured HBM copy peak
+  roofline  SURVEY 8(d) algorithmic bytes of a step / the device time of the step — the same quotient at every N —
+            against the measured HBM copy peak; frac_actual_layout_bytes = the same with the bytes the kernels really have
+            to move in the resident layout; traffic = DRAM bytes per step from the committed ncu capture (profiles/)
+  e2e       the same metric through the public API from pinned HOST buffers in the transport layout: H2D of the batch in
+            slices (copy of slice i+1 overlaps the binning of slice i) and a D2H read of a per-sample checksum inside the
+            timed region; the tensors themselves stay on the device, where the encoder consumes them.  Sub-entries:
+            from_reference_format = the whole host side too, starting from the reference's own per-sample (N,4) float64 arrays
+            (threaded collate + pack of slice i+1 overlapping H2D + binning of slice i; bounded sample, rate-normalised);
+            h2d_only = the same buffers copied with no kernels (the ceiling the interconnect sets at this N)
   cpu_baseline  the oracle C port of the reference routine on the host cores, bounded sample, rank 0 / N=1 only
+  extra.configs  BASELINE.json configs[0], [2], [3], [4] at their own sizes (per-GPU share at N > 1), each with
+            throughput, SURVEY 8(d) bytes, roofline fraction and a parity check against the oracle
 
 --impl reference times that CPU port alone (the reference is pure Python and /root/reference does not exist
 on the GPU box; its arithmetic is restated in oracle/ep_oracle.c and pinned bit-exact to the reference).
@@ -28,6 +35,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -41,50 +49,58 @@ BYTES_PER_EVENT = 13
 WINDOW_US = 300_000      # stamps uniform in [0, 0.3 s)
 
 
-def counts_for(rank, batch=BATCH, mean=MEAN_EVENTS):
+def counts_for(rank, batch=BATCH, mean=MEAN_EVENTS, spread=0.2):
     rng = np.random.default_rng(2000 + rank)
-    return np.round(mean * rng.uniform(0.8, 1.2, batch)).astype(np.int64)
+    return np.maximum(1, np.round(mean * rng.uniform(1 - spread, 1 + spread, batch))).astype(np.int64)
 
 
-def algorithmic_bytes(n_events, batch):
-    # SURVEY.md §8(d): 13 B/event read once + every output element written once (voxel bins + the sum plane)
-    return BYTES_PER_EVENT * n_events + 4 * (BINS + 1) * H * W * batch
+def algorithmic_bytes(n_events, batch, h=H, w=W, planes=BINS + 1):
+    # SURVEY.md 8(d): 13 B/event read once + every output element written once (voxel bins + the sum plane)
+    return BYTES_PER_EVENT * n_events + 4 * planes * h * w * batch
 
 
-def make_batch_gpu(rank, device, skewed=False, batch=BATCH, mean=MEAN_EVENTS, window_us=WINDOW_US):
+def make_batch_gpu(rank, device, skewed=False, batch=BATCH, mean=MEAN_EVENTS, window_us=WINDOW_US, size=(H, W), spread=0.2,
+                   bursty=False, seed=2000):
     """Synthetic streams generated on the device: uniform pixels (or the skewed mix: 70 % on 64 line segments,
-    0.1 % on 32 hot pixels), time-sorted int64 microsecond stamps in a 0.3 s window, p in {0,1}."""
+    0.1 % on 32 hot pixels), time-sorted int64 microsecond stamps uniform in a window (0.3 s) or bursty
+    (90 % of the events inside ten 3 ms bursts, the rest spread over the window), p in {0,1}."""
     import torch
     import eventpretrain_b200 as ep
-    counts = counts_for(rank, batch, mean)
+    h, w = size
+    counts = counts_for(rank + seed - 2000, batch, mean, spread)
     off = np.zeros(batch + 1, np.int64)
     np.cumsum(counts, out=off[1:])
     n = int(off[-1])
-    g = torch.Generator(device=device).manual_seed(2000 + rank)
-    x = torch.randint(0, W, (n,), device=device, generator=g, dtype=torch.int32)
-    y = torch.randint(0, H, (n,), device=device, generator=g, dtype=torch.int32)
+    g = torch.Generator(device=device).manual_seed(seed + rank)
+    x = torch.randint(0, w, (n,), device=device, generator=g, dtype=torch.int32)
+    y = torch.randint(0, h, (n,), device=device, generator=g, dtype=torch.int32)
     if skewed:
         u = torch.rand(n, device=device, generator=g)
         seg = torch.randint(0, 64, (n,), device=device, generator=g)
         gs = torch.Generator(device=device).manual_seed(99)
-        ends = torch.rand(64, 4, device=device, generator=gs) * torch.tensor([W - 1, H - 1, W - 1, H - 1], device=device)
+        ends = torch.rand(64, 4, device=device, generator=gs) * torch.tensor([w - 1, h - 1, w - 1, h - 1], device=device)
         a = torch.rand(n, device=device, generator=g)
         lx = ends[seg, 0] + a * (ends[seg, 2] - ends[seg, 0]) + 1.5 * torch.randn(n, device=device, generator=g)
         ly = ends[seg, 1] + a * (ends[seg, 3] - ends[seg, 1]) + 1.5 * torch.randn(n, device=device, generator=g)
         on_line = u < 0.7
-        x = torch.where(on_line, lx.round().clamp_(0, W - 1).int(), x)
-        y = torch.where(on_line, ly.round().clamp_(0, H - 1).int(), y)
+        x = torch.where(on_line, lx.round().clamp_(0, w - 1).int(), x)
+        y = torch.where(on_line, ly.round().clamp_(0, h - 1).int(), y)
         hot = torch.randint(0, 32, (n,), device=device, generator=g)
-        hp = torch.randint(0, W * H, (32,), device=device, generator=gs)
+        hp = torch.randint(0, w * h, (32,), device=device, generator=gs)
         is_hot = u > 0.999
-        x = torch.where(is_hot, (hp[hot] % W).int(), x)
-        y = torch.where(is_hot, (hp[hot] // W).int(), y)
+        x = torch.where(is_hot, (hp[hot] % w).int(), x)
+        y = torch.where(is_hot, (hp[hot] // w).int(), y)
         del u, seg, a, lx, ly, hot
     p = torch.randint(0, 2, (n,), device=device, generator=g, dtype=torch.uint8)
     t = torch.empty(n, dtype=torch.int64, device=device)
     for b in range(batch):
         lo, hi = int(off[b]), int(off[b + 1])
-        t[lo:hi] = torch.sort(torch.randint(0, window_us, (hi - lo,), device=device, generator=g)).values
+        tt = torch.randint(0, window_us, (hi - lo,), device=device, generator=g)
+        if bursty:
+            k = torch.randint(0, 10, (hi - lo,), device=device, generator=g)
+            inside = torch.rand(hi - lo, device=device, generator=g) < 0.9
+            tt = torch.where(inside, k * (window_us // 10) + tt % 3000, tt)
+        t[lo:hi] = torch.sort(tt).values
     ev = ep.RaggedEvents(x.to(torch.uint16), y.to(torch.uint16), t, p, torch.from_numpy(off).to(device), off, t_div=1e6)
     return ev
 
@@ -132,10 +148,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_step():
-    """dram bytes of the binning kernels from the committed ncu --set full capture, or None."""
+def ncu_traffic():
+    """DRAM bytes per step of the headline layout from the committed ncu capture (--cache-control none), or None."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["dram_bytes_per_step"]
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         return None
 
@@ -143,8 +159,9 @@ def ncu_traffic_per_step():
 def aos_sample(ev_host_soa, off, b):
     lo, hi = int(off[b]), int(off[b + 1])
     x, y, t, p = ev_host_soa
-    return np.stack([x[lo:hi].astype(np.float64), y[lo:hi].astype(np.float64), t[lo:hi].astype(np.float64) / 1e6,
-                     p[lo:hi].astype(np.float64)], 1)
+    out = np.empty((hi - lo, 4), np.float64)
+    out[:, 0] = x[lo:hi]; out[:, 1] = y[lo:hi]; out[:, 2] = t[lo:hi]; out[:, 2] /= 1e6; out[:, 3] = p[lo:hi]
+    return out
 
 
 def cpu_port_setup(n_samples, rank=0):
@@ -156,7 +173,7 @@ def cpu_port_setup(n_samples, rank=0):
     for n in counts:
         n = int(n)
         samples.append(np.stack([rng.integers(0, W, n), rng.integers(0, H, n),
-                                 np.sort(rng.integers(0, 50_000, n)) / 1e6, rng.integers(0, 2, n)], 1).astype(np.float64))
+                                 np.sort(rng.integers(0, WINDOW_US, n)) / 1e6, rng.integers(0, 2, n)], 1).astype(np.float64))
     off = np.cumsum([0] + [len(s) for s in samples]).astype(np.int64)
     return np.ascontiguousarray(np.concatenate(samples, 0)), off
 
@@ -195,11 +212,26 @@ def run_reference(args):
     emit(line)
 
 
+def close(a, b, rel=1e-5, abs_=1e-6):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return bool(np.all(np.abs(a - b) <= rel * np.abs(b) + abs_))
+
+
+def layout_name_of(host):
+    bpe = host.nbytes() / max(host.num_events, 1)
+    name = ("canonical SoA: x,y u16 | t i64 ticks | p u8" if host.t_base is None else
+            "compact SoA: x,y u16 | u32 ticks relative to the sample | polarity << 31" if host.y is not None else
+            "packed SoA: u32 x | y << 11 | p << 22 | ticks << 23 (9-bit ticks relative to a base per 256 events)" if host.t is None else
+            "packed SoA: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 + u8 ticks & 0xff (ticks relative to a base per 1024 events)")
+    return f"{name} ({bpe:.2f} B/event)", bpe
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import eventpretrain_b200 as ep
     from eventpretrain_b200 import _lib
+    from eventpretrain_b200 import dist as epd
     from eventpretrain_b200.dist import init_from_env
 
     rank, world, local = init_from_env()
@@ -208,36 +240,62 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     L = ep.load_library()
+    cores = os.cpu_count() or 1
+    host_threads = max(1, cores // world)            # host-side work of this rank (collate / pack)
+    peak, peak_src = measured_peak()
+
+    def timed_ms(fn, steps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(steps):
+            fn()
+        s1.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) / steps
+
+    def allmax(v):
+        t_ = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    def allsum(v):
+        t_ = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.SUM)
+        return float(t_.item())
+
+    def to_host(e):
+        return ep.RaggedEvents(e.x.cpu(), e.y.cpu(), e.t.cpu(), e.p.cpu(), e.offsets.cpu(), e.offsets_host, e.t_div)
 
     ev13 = make_batch_gpu(rank, dev)
     n_events = ev13.num_events
-    host13 = ep.RaggedEvents(ev13.x.cpu(), ev13.y.cpu(), ev13.t.cpu(), ev13.p.cpu(), ev13.offsets.cpu(), ev13.offsets_host, ev13.t_div)
-    # resident copy in the transport layout: the densest lossless one the stream fits (4 B/event here; the opt-in
-    # banded path takes the 8 B/event one)
-    host = (host13.compact() if args.method == "banded" else host13.transport()).pin_memory()
+    host13 = to_host(ev13)
+    host = host13.transport(threads=host_threads).pin_memory()
     ev = host.to(dev)
-    bpe = host.nbytes() / max(n_events, 1)
+    layout_name, bpe = layout_name_of(host)
+    layout_name += "; the lossless transport layout, results bit-identical to the 13 B/event canonical SoA"
     host_gb = host.nbytes() / 1e9
-    layout_name = ("compact SoA: x,y u16 | u32 ticks relative to the sample | polarity << 31" if host.y is not None else
-                   "packed SoA: u32 x | y << 11 | p << 22 | ticks << 23 (9-bit ticks relative to a base per 256 events)" if host.t is None else
-                   "packed SoA: u32 x | y << 11 | p << 22 | ticks >> 8 << 23 + u8 ticks & 0xff (ticks relative to a base per 1024 events)")
-    layout_name += f" ({bpe:.2f} B/event, the lossless transport layout; results bit-identical to the 13 B/event canonical SoA)"
     torch.cuda.synchronize()
     out = {"voxel": torch.empty((BATCH, BINS, H, W), dtype=torch.float32, device=dev),
-           "voxel_sum": torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev)}
-    stats_src = torch.tensor([n_events, BATCH], dtype=torch.int64, device=dev)
-    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+           "voxel_sum": torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev),
+           "stats": torch.zeros((BINS + 1, 4), dtype=torch.float64, device=dev)}
+    reduced = torch.zeros((BINS + 1, 4), dtype=torch.float64, device=dev)
     side = torch.cuda.Stream(device=dev)
 
     def step(comm=True):
-        ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method)
+        # the hot path: events -> voxel grid + voxel.sum(0) + batch statistics, one C-ABI call
+        ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method, stats=True)
         if world > 1 and comm:
-            # the path's only collective: a small all-reduce of batch statistics (events binned, samples), issued
-            # on a side stream so it never gates the binning kernels
+            # the path's only collective: the small all-reduce of the normalisation statistics the kernels just produced
+            # (SUM of count / sum / sum of squares, MAX of max), on a side stream so that it never gates the next binning call
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                stats.copy_(stats_src)
-                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+                reduced.copy_(out["stats"])
+                epd.allreduce_statistics(reduced)
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,207 +327,402 @@ def run_ours(args):
         step(comm=False)          # time-based loop: no collectives here (iteration counts differ between ranks)
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    total_events = n_events
-    if world > 1:
-        te = torch.tensor([n_events], dtype=torch.int64, device=dev)
-        dist.all_reduce(te, op=dist.ReduceOp.SUM)
-        total_events = int(te.item())
+    ms_total = allmax(ms_total)
+    total_events = int(allsum(n_events))
     value = total_events * args.steps / (ms_total * 1e-3) / 1e9
+    ms_step = ms_total / args.steps
 
-    # ---- roofline of the binning kernels: per-launch device time from the library's own CUDA events ----------
+    # all-reduce overlap: the same K steps without the collective (N > 1)
+    ms_no_comm = None
+    if world > 1:
+        barrier()
+        ms_no_comm = allmax(timed_ms(lambda: step(comm=False), args.steps, warm=1))
+
+    # ---- roofline: the same quotient at every N: algorithmic bytes of one rank's step / device time of the step ----
     L.ep_profile_enable(1)
     for _ in range(args.steps):
-        step()
+        step(comm=False)
     prof = _lib.ProfileStats()
     L.ep_profile_read(prof)
     L.ep_profile_enable(0)
-    scatter_ms, finalize_ms = prof.ms[0] / args.steps, prof.ms[1] / args.steps
-    peak, peak_src = measured_peak()
+    route_ms, sweep_ms, other_ms = (prof.ms[i] / args.steps for i in range(3))
     alg = algorithmic_bytes(n_events, BATCH)
-    # the step IS the binning call: its device time (CUDA events around the K timed steps, above) is the kernels' time;
-    # the per-kernel figures come from the library's own events around each launch
-    kernel_ms = ms_total / args.steps if world == 1 else scatter_ms + finalize_ms
-    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    actual = host.nbytes() + 4 * (BINS + 1) * H * W * BATCH
+    achieved = alg / (ms_step * 1e-3) / 1e9
+    traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_step(), "peak_source": peak_src,
-                "frac_of_8TBs_spec": achieved / 8000.0,
-                "kernels": {"pass1_ms_per_step (k_scatter | k_route)": scatter_ms,
-                            "pass2_ms_per_step (k_finalize_voxel | k_sweep)": finalize_ms,
-                            "pass1_launches_per_step": prof.launches[0] // args.steps,
-                            "pass1_Gevents_per_s": n_events / (scatter_ms * 1e-3) / 1e9},
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_step"),
+                "traffic_source": None if traffic is None else traffic.get("how"),
+                "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
+                "frac_actual_layout_bytes": actual / (ms_step * 1e-3) / 1e9 / peak,
+                "actual_layout_bytes_per_step": actual,
+                "denominator": "device time of the whole step (CUDA events around the K timed steps), the same rule at every N",
+                "kernels": {"k_route_ms_per_step": route_ms, "k_sweep_ms_per_step": sweep_ms, "setup_and_statistics_ms_per_step": other_ms,
+                            "note": "each kernel timed alone with CUDA events around its launch (library instrumentation, profiling run "
+                                    "after the timed region); they run back to back, their sum is the step"},
                 "algorithmic_bytes_per_step": alg,
                 "algorithmic_bytes_rule": f"SURVEY.md 8(d): 13 B/event canonical record + 4 B per output element, whatever the resident layout ({bpe:.1f} B/event here)"}
 
-    # ---- the same step on the canonical 13 B/event layout, with the banded path, and on the skewed distribution
-    # (contention evidence: 70 % of events on 64 segments + hot pixels), same sizes
     extra = {}
+    if ms_no_comm is not None:
+        extra["allreduce_overlap"] = {"ms_per_step_with_allreduce": ms_step, "ms_per_step_without": ms_no_comm,
+                                      "note": "(6,4) fp64 statistics table, NCCL all-reduce SUM + MAX on a side stream"}
 
-    def timed(evx, method):
-        for _ in range(3):
-            ep.bin_events(evx, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=method)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(args.steps):
-            ep.bin_events(evx, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=method)
-        s1.record()
-        torch.cuda.synchronize()
-        return evx.num_events * args.steps / (s0.elapsed_time(s1) * 1e-3) / 1e9
+    def gev(evx, method, size=(H, W), scale=(1.0, 1.0), o=None):
+        o = out if o is None else o
+        ms = timed_ms(lambda: ep.bin_events(evx, size, num_bins=BINS, voxel_sum=True, out=o, method=method, scale=scale), args.steps)
+        return evx.num_events / (ms * 1e-3) / 1e9, ms
 
+    # ---- the same batch in the other layouts / kernel family, on the skewed and on a bursty stream, and binned the way the
+    #      reference's own pre-training does it (events_reshape to 224x224 fused, pr_n_imagenet_dataset.py:85-87) ----
     if world == 1:
-        extra["canonical_13B_layout_Gevents_per_s"] = timed(ev13, args.method)
-        ev8 = host13.compact().to(dev)
-        extra["compact_8B_layout_Gevents_per_s"] = timed(ev8, args.method)
-        extra["banded_path_8B_layout_Gevents_per_s"] = timed(ev8, "banded")
+        lay = {}
+        lay["packed_4B_tiled_path_Gevents_per_s (headline, without the statistics)"] = gev(ev, args.method)[0]
+        lay["packed_4B_global_RED_path_Gevents_per_s"] = gev(ev, "global")[0]
+        lay["canonical_13B_layout_Gevents_per_s (global-RED path)"] = gev(ev13, args.method)[0]
+        ev8 = host13.compact(threads=host_threads).to(dev)
+        lay["compact_8B_layout_Gevents_per_s (global-RED path)"] = gev(ev8, args.method)[0]
         del ev8
-        del ev13
-        torch.cuda.empty_cache()
+        extra["layouts"] = lay
+        o224 = {"voxel": torch.empty((BATCH, BINS, 224, 224), dtype=torch.float32, device=dev),
+                "voxel_sum": torch.empty((BATCH, 1, 224, 224), dtype=torch.float32, device=dev)}
+        g224, ms224 = gev(ev, args.method, (224, 224), (224 / W, 224 / H), o224)
+        alg224 = algorithmic_bytes(n_events, BATCH, 224, 224)
+        extra["reference_res_224"] = {"what": "the reference's pre-training order: events_reshape 640x480 -> 224x224 fused, then the voxel grid "
+                                              "+ voxel.sum(0) (dataset/pretrain/pr_n_imagenet_dataset.py:85-87)",
+                                      "Gevents_per_s": g224, "ms_per_step": ms224, "algorithmic_bytes_per_step": alg224,
+                                      "roofline_frac": alg224 / (ms224 * 1e-3) / 1e9 / peak,
+                                      "global_RED_path_Gevents_per_s": gev(ev, "global", (224, 224), (224 / W, 224 / H), o224)[0]}
+        del o224
+    del ev13
+    torch.cuda.empty_cache()
+    if world == 1:
         sk13 = make_batch_gpu(rank, dev, skewed=True)
-        skh = ep.RaggedEvents(sk13.x.cpu(), sk13.y.cpu(), sk13.t.cpu(), sk13.p.cpu(), sk13.offsets.cpu(), sk13.offsets_host, sk13.t_div)
+        skh = to_host(sk13)
         del sk13
-        sk = skh.transport().to(dev)
-        extra["skewed_distribution_Gevents_per_s"] = timed(sk, args.method)
-        del sk
-        sk = skh.compact().to(dev)
-        extra["skewed_distribution_banded_path_8B_layout_Gevents_per_s"] = timed(sk, "banded")
-        del sk, skh
+        skt = skh.transport(threads=host_threads)
+        sk = skt.to(dev)
+        extra["skewed_distribution"] = {"what": "70 % of the events on 64 line segments, 0.1 % on 32 hot pixels", "layout": layout_name_of(skt)[0],
+                                        "Gevents_per_s": gev(sk, args.method)[0]}
+        del sk, skh, skt
         torch.cuda.empty_cache()
-    else:
-        del ev13
+        bu13 = make_batch_gpu(rank, dev, bursty=True, batch=64)
+        buh = to_host(bu13)
+        del bu13
+        but = buh.transport(threads=host_threads)
+        bu = but.to(dev)
+        o64 = {"voxel": out["voxel"][:64], "voxel_sum": out["voxel_sum"][:64]}
+        extra["bursty_stream"] = {"what": "64 samples; 90 % of each sample's events inside ten 3 ms bursts, the rest spread over 0.3 s "
+                                          "(quiet stretches of ~0.4 Mevents/s: a 256-event block then spans more than 2^9 ticks)",
+                                  "layout_chosen_by_transport": layout_name_of(but)[0], "Gevents_per_s": gev(bu, args.method, o=o64)[0]}
+        del bu, buh, but
+        torch.cuda.empty_cache()
 
-    # ---- pretrain input pipeline (configs[2] per-GPU share: ViT-S/16 @224, 75 % mask, B=128): one CUDA graph ----------
-    pipe = ep.MaskedInputPipeline(128, BINS, (224, 224), 16, 0.75, dev)
-    pipe.x.normal_(); pipe.sub_frame.normal_()
-    for _ in range(3):
-        pipe.run()
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(50):
-        pipe.run()
-    p1.record()
-    torch.cuda.synchronize()
-    extra["pretrain_input_samples_per_s_per_gpu"] = 128 * 50 / (p0.elapsed_time(p1) * 1e-3)
-    extra["pretrain_input_config"] = "ViT-S/16 @224, C=5, 75 % random mask, B=128/GPU: mask + visible-patch gather + norm_pix target (CUDA graph, 3 kernels)"
-    del pipe
-
-    # ---- e2e: pinned host SoA -> H2D -> bin -> D2H of the per-sample checksum, all inside the timed region ----
-    # host buffers are what the collate step hands over: the ragged SoA batch in pinned memory, in the densest lossless
-    # transport layout that fits (RaggedEvents.transport()).  The batch crosses PCIe in E2E_SLICES slices of consecutive samples: the copy of slice i+1
-    # (copy stream) overlaps the binning of slice i (compute stream); two device staging sets, guarded by events.
+    # ---- e2e: pinned host transport buffers -> H2D -> bin -> D2H of the per-sample checksum, all inside the timed region ----
+    # The batch crosses PCIe in E2E_SLICES slices of consecutive samples: the copy of slice i+1 (copy stream) overlaps the binning
+    # of slice i (compute stream); two device staging sets, guarded by events.
     del ev
     torch.cuda.empty_cache()
     E2E_SLICES = 8
     bounds = [(BATCH * i) // E2E_SLICES for i in range(E2E_SLICES + 1)]
     # every slice is packed on its own (the collate step would produce them like this): block offsets start at 0
-    slices = [host13.take(bounds[i], bounds[i + 1]).transport().pin_memory() for i in range(E2E_SLICES)]
+    slices = [host13.take(bounds[i], bounds[i + 1]).transport(threads=host_threads).pin_memory() for i in range(E2E_SLICES)]
     if any((sl.t is None) != (slices[0].t is None) or (sl.y is None) != (slices[0].y is None) for sl in slices):
         slices = [host13.take(bounds[i], bounds[i + 1]).packed(5).pin_memory() for i in range(E2E_SLICES)]
     h2d = sum(sl.nbytes() for sl in slices)
     fields = tuple(f for f in ("x", "y", "t", "p", "offsets", "t_base") if getattr(slices[0], f) is not None)
-    stage = [{f: torch.empty(max(getattr(sl, f).numel() for sl in slices), dtype=getattr(slices[0], f).dtype, device=dev)
+    stage = [{f: torch.empty(int(1.05 * max(getattr(sl, f).numel() for sl in slices)) + 64, dtype=getattr(slices[0], f).dtype, device=dev)
               for f in fields} for _ in range(2)]
     copy_stream, comp_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(E2E_SLICES)]
     binned = [torch.cuda.Event() for _ in range(E2E_SLICES)]
-    e2e_method = args.method if args.method != "banded" else "auto"
 
-    def e2e_step():
-        for i, sl in enumerate(slices):
-            st_ = stage[i % 2]
-            with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(binned[i - 2])                 # the staging set is free again
-                view = {}
-                for f in fields:
-                    src = getattr(sl, f)
-                    view[f] = st_[f][:src.numel()]
-                    view[f].copy_(src, non_blocking=True)
-                copied[i].record(copy_stream)
-            with torch.cuda.stream(comp_stream):
-                comp_stream.wait_event(copied[i])
+    def upload(i, sl, kernels=True):
+        st_ = stage[i % 2]
+        with torch.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(binned[i - 2])                 # the staging set is free again
+            view = {}
+            for f in fields:
+                src = getattr(sl, f)
+                view[f] = st_[f][:src.numel()]
+                view[f].copy_(src, non_blocking=True)
+            copied[i].record(copy_stream)
+        with torch.cuda.stream(comp_stream):
+            comp_stream.wait_event(copied[i])
+            if kernels:
                 d = ep.RaggedEvents(view["x"], view.get("y"), view.get("t"), view.get("p"), view["offsets"], sl.offsets_host, sl.t_div,
                                     view["t_base"])
                 o = {"voxel": out["voxel"][bounds[i]:bounds[i + 1]], "voxel_sum": out["voxel_sum"][bounds[i]:bounds[i + 1]]}
-                ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=o, method=e2e_method)
-                binned[i].record(comp_stream)
+                ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=o, method=args.method)
+            binned[i].record(comp_stream)
+
+    def e2e_step(kernels=True):
+        for i, sl in enumerate(slices):
+            upload(i, sl, kernels)
         with torch.cuda.stream(comp_stream):
-            chk_ = out["voxel_sum"].sum(dim=(1, 2, 3)).cpu()          # (B,) fp32: sum of polarities per sample (synchronises)
+            chk_ = out["voxel_sum"].sum(dim=(1, 2, 3)).cpu() if kernels else None   # (B,) fp32 per-sample checksum (synchronises)
+        if not kernels:
+            comp_stream.synchronize()
         return chk_
 
-    for _ in range(2):
-        chk = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        chk = e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e = {"value": total_events * args.steps / float(tm.item()) / 1e9, "unit": "Gevents/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * float(tm.item()) / args.steps,
+    def wall(fn, steps):
+        r_ = None
+        for _ in range(2):
+            fn()
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(steps):
+            r_ = fn()
+        barrier()
+        return allmax(time.perf_counter() - t0_) / steps, r_
+
+    e2e_s, chk = wall(e2e_step, args.steps)
+    h2d_s, _ = wall(lambda: e2e_step(kernels=False), args.steps)
+    e2e = {"value": total_events / e2e_s / 1e9, "unit": "Gevents/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(chk.numel() * chk.element_size()), "ms_per_step": 1e3 * e2e_s,
            "host_layout": "pinned " + layout_name + "; include/eventpretrain_b200.h",
-           "pipelining": f"{E2E_SLICES} slices of consecutive samples; H2D of slice i+1 overlaps the binning of slice i"}
+           "pipelining": f"{E2E_SLICES} slices of consecutive samples; H2D of slice i+1 overlaps the binning of slice i",
+           "outputs": "the voxel grids and sum planes (1.9 GB per step and GPU) stay on the device, where the encoder consumes them "
+                      "(the reference's trainer moves them there, pr_trainer.py:27-28); the D2H read is a per-sample checksum of the result",
+           "h2d_only": {"Gevents_per_s": total_events / h2d_s / 1e9, "ms_per_step": 1e3 * h2d_s, "GBps_all_ranks": world * h2d / h2d_s / 1e9,
+                        "what": "the same pinned buffers copied with no kernels: the ceiling the host interconnect sets at this N"},
+           "frac_of_h2d_only_ceiling": h2d_s / e2e_s}
+
+    # ---- e2e from the reference's own input format: per-sample (N,4) float64 arrays -> threaded collate + pack (slice i+1 on
+    #      worker threads) -> H2D -> bin; bounded sample (REF_SAMPLES of the batch), rate-normalised ----
+    REF_SAMPLES, REF_SLICE = 64, 8
+    hx, hy, ht, hp = (a.numpy() for a in (host13.x, host13.y, host13.t, host13.p))
+    off13 = host13.offsets_host
+    aos = [aos_sample((hx, hy, ht, hp), off13, b) for b in range(REF_SAMPLES)]
+    n_ref = int(off13[REF_SAMPLES] - off13[0])
+    ref_bounds = list(range(0, REF_SAMPLES + 1, REF_SLICE))
+    n_ref_slices = len(ref_bounds) - 1
+
+    def host_side(i):
+        hb = ep.collate_events(aos[ref_bounds[i]:ref_bounds[i + 1]], 1e6, pin=True, threads=host_threads)
+        return hb.transport(threads=host_threads)
+
+    pool = ThreadPoolExecutor(max_workers=2)
+
+    def ref_step():
+        futs = [pool.submit(host_side, 0)]
+        if n_ref_slices > 1:
+            futs.append(pool.submit(host_side, 1))
+        for i in range(n_ref_slices):
+            sl = futs[i].result()
+            if i + 2 < n_ref_slices:
+                futs.append(pool.submit(host_side, i + 2))
+            d = sl.to(dev, non_blocking=True)
+            o = {"voxel": out["voxel"][ref_bounds[i]:ref_bounds[i + 1]], "voxel_sum": out["voxel_sum"][ref_bounds[i]:ref_bounds[i + 1]]}
+            ep.bin_events(d, (H, W), num_bins=BINS, voxel_sum=True, out=o, method=args.method)
+        return out["voxel_sum"][:REF_SAMPLES].sum(dim=(1, 2, 3)).cpu()
+
+    try:
+        ref_s, _ = wall(ref_step, max(2, args.steps // 3))
+        t0 = time.perf_counter()
+        for i in range(n_ref_slices):
+            host_side(i)
+        host_only_s = time.perf_counter() - t0
+        e2e["from_reference_format"] = {
+            "Gevents_per_s": world * n_ref / ref_s / 1e9, "ms_per_sample_step": 1e3 * ref_s,
+            "what": "per-sample (N,4) float64 x,y,t,p arrays (the reference's event format, 32 B/event) -> ep.collate_events -> "
+                    "RaggedEvents.transport() -> H2D -> ep.bin_events; host work of slice i+1 / i+2 on worker threads while slice i is "
+                    "copied and binned",
+            "sample": f"first {REF_SAMPLES} of {BATCH} samples per rank ({n_ref} events), slices of {REF_SLICE}, rate-normalised",
+            "host_threads_per_rank": host_threads, "host_side_alone_Gevents_per_s": world * n_ref / host_only_s / 1e9,
+            "note": "bounded by the host: 32 B/event of float64 rows have to be read from host memory before anything is shipped"}
+    except Exception as e:      # a side measurement: never at the expense of the result line
+        e2e["from_reference_format"] = {"error": repr(e)}
+    pool.shutdown()
+    del aos
 
     # ---- CPU baseline beside it (rank 0, N=1): oracle port on the host cores, bounded sample + parity check ----
     cpu = None
     if rank == 0 and world == 1:
         from oracle import events as oe
         oe.build()
-        threads = os.cpu_count() or 1
-        n_s = min(BATCH, max(8, min(threads, 64)))
-        hx, hy, ht, hp = (a.numpy() for a in (host13.x, host13.y, host13.t, host13.p))
-        off = host13.offsets_host
-        aos = np.ascontiguousarray(np.concatenate([aos_sample((hx, hy, ht, hp), off, b) for b in range(n_s)], 0))
-        soff = (off[: n_s + 1] - off[0]).astype(np.int64)
+        e2e_step()                                   # the whole batch again (the reference-format leg rewrote the first samples)
+        n_s = min(BATCH, max(8, min(cores, 64)))
+        pick = [int(v) for v in np.linspace(0, BATCH - 1, n_s).round()]          # spread over the whole batch
+        sam = [aos_sample((hx, hy, ht, hp), off13, b) for b in pick]
+        aos_cat = np.ascontiguousarray(np.concatenate(sam, 0))
+        soff = np.cumsum([0] + [len(s) for s in sam]).astype(np.int64)
         t0 = time.perf_counter()
-        ref = oe.voxel_grid_batch(aos, soff, BINS, (H, W), num_threads=threads)
+        ref = oe.voxel_grid_batch(aos_cat, soff, BINS, (H, W), num_threads=cores)
         ref_sum = ref.sum(axis=1, keepdims=True)
         cpu_s = time.perf_counter() - t0
-        got = out["voxel"][:n_s].cpu().numpy()
+        idx = torch.tensor(pick, device=dev)
+        got = out["voxel"][idx].cpu().numpy()
         err = np.abs(got - ref)
-        ok = bool(np.all(err <= 1e-5 * np.abs(ref) + 1e-6))
-        sum_ok = bool(np.all(np.abs(out["voxel_sum"][:n_s].cpu().numpy() - ref_sum) <= 1e-5 * np.abs(ref_sum) + 2e-6))
-        sample = f"first {n_s} of {BATCH} samples ({int(soff[-1])} events), one pass"
-        cpu = {"value": int(soff[-1]) / cpu_s / 1e9, "unit": "Gevents/s", "cores": threads, "kind": "port", "sample": sample,
+        ok = close(got, ref)
+        sum_ok = close(out["voxel_sum"][idx].cpu().numpy(), ref_sum, 1e-5, 2e-6)
+        sample = f"{n_s} of {BATCH} samples spread over the batch ({int(soff[-1])} events), one pass"
+        cpu = {"value": int(soff[-1]) / cpu_s / 1e9, "unit": "Gevents/s", "cores": cores, "kind": "port", "sample": sample,
                "parity_vs_port": {"voxel_within_1e-5rel_1e-6abs": ok, "voxel_sum_ok": sum_ok, "max_abs_err": float(err.max())}}
+        del ref, ref_sum, got, err, aos_cat, sam
+    del hx, hy, ht, hp, host13, slices, stage
+    out.clear()
+    torch.cuda.empty_cache()
 
-        # host side of the collate: reference-format (N,4) float64 samples -> canonical SoA -> transport layout,
-        # native threaded code writing into pinned buffers; second call timed (the first one sizes torch's pinned pool)
-        try:
-            samples = [aos[soff[b]:soff[b + 1]] for b in range(n_s)]
-            ep.collate_events(samples, 1e6).transport()
-            t0 = time.perf_counter()
-            hb = ep.collate_events(samples, 1e6)
-            t1 = time.perf_counter()
-            hpk = hb.transport()
-            t2 = time.perf_counter()
-            n_c = int(soff[-1])
-            extra["host_collate"] = {"collate_Gevents_per_s": n_c / (t1 - t0) / 1e9, "pack_transport_Gevents_per_s": n_c / (t2 - t1) / 1e9,
-                                     "threads": threads, "sample": sample, "bytes_per_event_out": float(hpk.nbytes()) / max(n_c, 1),
-                                     "matches_resident_batch": bool(torch.equal(hb.t, host13.t[:n_c]) and torch.equal(hb.x, host13.x[:n_c]))}
-        except Exception as e:      # a side measurement: never at the expense of the result line
-            extra["host_collate"] = {"error": repr(e)}
+    # ---- the other BASELINE configs at their own sizes (per-GPU share), each with bytes, roofline fraction and a parity check ----
+    try:
+        extra["configs"] = run_configs(ep, torch, dev, rank, world, peak, allmax, allsum, timed_ms)
+    except Exception as e:
+        extra["configs"] = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": "events_binned_per_s", "value": value, "unit": "Gevents/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "integer-tick time arithmetic, Q24 fixed-point int64 accumulate -> f32",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "integer-tick time arithmetic, Q24 fixed-point int32/int64 accumulate -> f32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": layout_name,
+                           "stamps": "time-sorted int64 microseconds, uniform in a 0.3 s window per sample (SURVEY.md 8d)",
                            "cache": f"inputs ({host_gb:.1f} GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
-                           "parallelism": f"shard-by-sample x{world}, no data-path collective", "method": args.method},
+                           "parallelism": f"shard-by-sample x{world}, no data-path collective; one (6,4) fp64 statistics all-reduce per step on a side stream",
+                           "method": args.method, "step": "ep_bin_events_stats: voxel grid + voxel.sum(0) + per-channel batch statistics"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_configs(ep, torch, dev, rank, world, peak, allmax, allsum, timed_ms):
+    """BASELINE.json configs[0], [2], [3], [4] (C1, C3, C4, C5), per-GPU share, weak scaling.  Values are whole-job
+    (all ranks); ms is the slowest rank's; parity = rank 0's tensors against the CPU oracle on a bounded sample."""
+    from oracle import events as oe
+    from oracle import stage3_np as s3
+    if rank == 0:
+        oe.build()
+    res = {}
+
+    def entry(name, ms, alg_bytes, units, unit, parity, **kw):
+        ms = allmax(ms)
+        tot = allsum(units)
+        e = {"ms": ms, unit + "_per_s": tot / (ms * 1e-3), "algorithmic_bytes_per_gpu": int(alg_bytes),
+             "roofline_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "parity": parity}
+        e.update(kw)
+        res[name] = e
+
+    def sample_aos(evh, b):
+        lo, hi = int(evh.offsets_host[b]), int(evh.offsets_host[b + 1])
+        return np.stack([evh.x[lo:hi].numpy(), evh.y[lo:hi].numpy(), evh.t[lo:hi].numpy() / 1e6, evh.p[lo:hi].numpy()], 1).astype(np.float64)
+
+    def host_of(e):
+        return ep.RaggedEvents(e.x.cpu(), e.y.cpu(), e.t.cpu(), e.p.cpu(), e.offsets.cpu(), e.offsets_host, e.t_div)
+
+    # ---- C1: single N-Caltech101-shaped sample, 2-ch count frame + 5-bin voxel grid, one fused call ----
+    h, w, n = 180, 240, 200_000
+    e1 = make_batch_gpu(rank, dev, batch=1, mean=n, size=(h, w), spread=0.0, seed=1001)
+    o = {}
+    ms = timed_ms(lambda: ep.bin_events(e1, (h, w), num_bins=5, count_channels=2, out=o), 50)
+    par = None
+    if rank == 0:
+        s = sample_aos(host_of(e1), 0)
+        par = bool(close(o["voxel"][0].cpu().numpy(), oe.voxel_grid(s, 5, (h, w))) and
+                   np.array_equal(o["count"][0].cpu().numpy(), oe.count_frame(s, (h, w), 2)))
+    entry("C1 single 240x180 sample, 200k events -> 2-ch count frame + 5-bin voxel grid (one call)", ms, 13 * n + 4 * 7 * h * w, n, "events", par,
+          note="3.8 MB of work: latency-bound by construction (SURVEY 8d); the CPU port takes ~3.4 ms for the same sample on one core")
+    del e1, o
+
+    # ---- C3: masked-modelling input pipeline, ViT-S/16 @224, 75 % mask, B = 128 per GPU (1024 over 8) ----
+    B, C, Lp, K, p = 128, 5, 196, 49, 16
+    pipe = ep.MaskedInputPipeline(B, C, (224, 224), p, 0.75, dev)
+    g = torch.Generator(device=dev).manual_seed(3000 + rank)
+    pipe.x.copy_(torch.randn(pipe.x.shape, device=dev, generator=g))
+    pipe.sub_frame.copy_(torch.randn(pipe.sub_frame.shape, device=dev, generator=g))
+    ms = timed_ms(lambda: pipe.run(), 50)
+    alg = B * (4 * Lp + 8 * K + 12 * Lp + 2 * 4 * K * C * p * p + 2 * 4 * 224 * 224)
+    par = None
+    if rank == 0:
+        r = pipe.run(draw_noise=False)
+        noise = pipe.noise[:4].cpu().numpy()
+        rk, rm, rr = s3.mask_from_noise(noise, K)
+        xs = pipe.x[:4].cpu().numpy()
+        par = bool(np.array_equal(r["ids_keep"][:4].cpu().numpy(), rk) and np.array_equal(r["mask"][:4].cpu().numpy(), rm) and
+                   np.array_equal(r["ids_restore"][:4].cpu().numpy(), rr) and
+                   np.array_equal(r["visible_patches"][:4].cpu().numpy(), s3.patchify_gather(xs, p, rk, "cpq")) and
+                   close(r["target"][:4].cpu().numpy(), s3.target_normpix(pipe.sub_frame[:4].cpu().numpy(), p), 1e-5, 1e-5))
+    entry("C3 pretraining input pipeline: ViT-S/16 @224, C=5, 75 % random mask, B=128 per GPU: noise + mask + visible-patch gather + "
+          "norm_pix target (one CUDA graph)", ms, alg, B, "samples", par, launches_per_step=3)
+    del pipe
+
+    # ---- C4: DSEC-shaped, 640x440 after the crop, 15 bins, ~2M events per sample, B = 32 per GPU; voxel grid + EvRep ----
+    h, w, bins, Bc = 440, 640, 15, 32
+    e4 = make_batch_gpu(rank, dev, batch=Bc, mean=2_000_000, size=(h, w), spread=0.1, seed=4000, window_us=100_000)
+    h4 = host_of(e4)
+    h4t = h4.transport()
+    t4 = h4t.to(dev)
+    o = {"voxel": torch.empty((Bc, bins, h, w), dtype=torch.float32, device=dev)}
+    ms = timed_ms(lambda: ep.bin_events(t4, (h, w), num_bins=bins, out=o), 5)
+    par = bool(close(o["voxel"][1].cpu().numpy(), oe.voxel_grid(sample_aos(h4, 1), bins, (h, w)))) if rank == 0 else None
+    entry("C4 DSEC-shaped B=32 per GPU, 640x440, 15 bins, ~2M events/sample: voxel grid", ms, 13 * e4.num_events + 4 * bins * h * w * Bc,
+          e4.num_events, "events", par, layout=layout_name_of(h4t)[0])
+    del o, t4, h4t
+    keep = {}
+
+    def do_evrep():
+        keep["ev"] = ep.evrep(e4, (h, w))
+    ms = timed_ms(do_evrep, 3, warm=1)
+    par = None
+    if rank == 0:
+        s = sample_aos(h4, 1)
+        # stamp value = ticks / t_div on both sides (the same fp64 quotient)
+        par = bool(np.array_equal(keep["ev"][1].cpu().numpy(), oe.evrep(s[:, 0], s[:, 1], s[:, 2], s[:, 3], (w, h)), equal_nan=True))
+    entry("C4 EvRep (3,440,640) f64, the pinned stand-in for the time surface (events_to_image.py:77-125)", ms,
+          13 * e4.num_events + 12 * h * w * Bc, e4.num_events, "events", par)
+    keep.clear()
+    ms = timed_ms(lambda: ep.time_surface(e4, (h, w), tau=0.03), 5)
+    entry("C4 exponential time surface (2,440,640) [parity unpinned: no reference routine, SURVEY F5]", ms,
+          13 * e4.num_events + 8 * h * w * Bc, e4.num_events, "events", None)
+    del e4, h4
+    torch.cuda.empty_cache()
+
+    # ---- C5: MVSEC-shaped, 346x260, 9 bins, B = 512 per GPU: paired output (org grid + bilinear 224x224), block-mask variants ----
+    h, w, bins, Bc = 260, 346, 9, 512
+    e5 = make_batch_gpu(rank, dev, batch=Bc, mean=100_000, size=(h, w), spread=0.5, seed=5000, window_us=50_000)
+    h5 = host_of(e5)
+    h5t = h5.transport()
+    t5 = h5t.to(dev)
+    o = {"voxel": torch.empty((Bc, bins, h, w), dtype=torch.float32, device=dev)}
+    from eventpretrain_b200.view_augment import ViewChoice
+    full = [ViewChoice(0, 0, w, h, False, False, False)] * Bc
+    paired = {}
+
+    def do_paired():
+        ep.bin_events(t5, (h, w), num_bins=bins, out=o)
+        paired["resized"] = ep.apply_views(o["voxel"], full, (224, 224), "bilinear")      # ft_mvsec_dataset.py:229-239
+    ms = timed_ms(do_paired, 5)
+    par = None
+    if rank == 0:
+        import torch.nn.functional as F
+        ok_v = close(o["voxel"][3].cpu().numpy(), oe.voxel_grid(sample_aos(h5, 3), bins, (h, w)))
+        ref_r = F.interpolate(o["voxel"][:8], size=(224, 224), mode="bilinear")
+        par = bool(ok_v and torch.allclose(paired["resized"][:8], ref_r, rtol=1e-5, atol=1e-6))
+    entry("C5 MVSEC-shaped B=512 per GPU, 346x260, 9 bins, ~100k events/sample: paired output = org voxel grid + bilinear 224x224 copy",
+          ms, 13 * e5.num_events + 4 * bins * Bc * (h * w + 224 * 224), e5.num_events, "events", par,
+          samples_per_s=allsum(Bc) / (allmax(ms) * 1e-3), layout=layout_name_of(h5t)[0])
+    del o, paired, t5, e5, h5, h5t
+    mask = (torch.rand(Bc, 196, device=dev) < 0.75).float()
+    ms = timed_ms(lambda: ep.convvit_keep_masks(mask), 50)
+    par = None
+    if rank == 0:
+        m1, m2 = ep.convvit_keep_masks(mask)
+        r1, r2 = s3.block_mask_expand(mask.cpu().numpy(), 14, 4), s3.block_mask_expand(mask.cpu().numpy(), 14, 2)
+        par = bool(np.array_equal(m1.cpu().numpy(), r1) and np.array_equal(m2.cpu().numpy(), r2))
+    entry("C5 ConvViT block masks (512,196) -> (512,1,56,56), (512,1,28,28)", ms, Bc * 4 * (196 + 56 * 56 + 28 * 28), Bc, "samples", par)
+    xs = torch.randn(Bc, 3136, 96, device=dev)
+    m49 = torch.zeros(Bc, 49, device=dev)
+    m49[:, torch.randperm(49, device=dev)[:37]] = 1
+    ms = timed_ms(lambda: ep.swin_apply_mask(xs, m49, (56, 56), n_vis=12 * 64), 20)
+    par = None
+    if rank == 0:
+        got = ep.swin_apply_mask(xs, m49, (56, 56), n_vis=12 * 64)
+        rx, rc = s3.swin_apply_mask(xs[:2].cpu().numpy(), m49[:1].cpu().numpy() > 0, (56, 56))[:2]
+        par = bool(np.array_equal(got[0][:2].cpu().numpy(), rx) and np.array_equal(got[1].cpu().numpy().reshape(rc.shape), rc))
+    entry("C5 Swin apply_mask (512,3136,96) -> (512,768,96) + coords", ms, Bc * 2 * 4 * 768 * 96, Bc, "samples", par)
+    return res
 
 
 _RESULT_FD = None
@@ -497,7 +750,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--method", default="auto", choices=["auto", "global", "banded"], help="binning kernel family")
+    ap.add_argument("--method", default="auto", choices=["auto", "global", "tiled"], help="binning kernel family")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,7 +91,7 @@ struct TiledArgs {
     unsigned int* bad_count;
     float* out_voxel;
     float* out_sum;
-    double* stats_part;         // (B * NT) x (num_bins + 1) x 3 partial statistics, or null
+    double* stats_part;         // (B * NT) x (num_bins + 1) x warps x 3 partial statistics, or null
 };
 
 __device__ __forceinline__ void pdl_wait_t() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
 }
 
 // ---- route ---------------------------------------------------------------------------------------------------------
-// dynamic shared memory: lut_y[2048] u32 | lut_x[2048] u32 | stage[8192] u32 | cnt[kMaxTiles + 2] | off[kMaxTiles + 2]
-constexpr size_t kRouteSmem = 2048 * 4 + 2048 * 4 + (size_t)kChunk * 4 + 2 * (kMaxTiles + 2) * 4 + 64;
+// dynamic shared memory: lut_y[2048] u32 | lut_x[2048] u32 | stage[2][8192] u32 | cnt[2][kMaxTiles + 2] | off[warps][kMaxTiles + 4]
+constexpr size_t kRouteSmem = 2048 * 4 + 2048 * 4 + (size_t)2 * kChunk * 4 + 2 * (kMaxTiles + 2) * 4 +
+                              (size_t)(kRouteThreads / 32) * (kMaxTiles + 4) * 4 + 64;
 
 // polarity bit of the packed word -> signed 2-bit field of the record: 1 -> 01 (+1), 0 -> 11 (-1)
 __device__ __forceinline__ uint32_t pol2(uint32_t word) { return 3u - ((word >> 21) & 2u); }
@@ -176,13 +177,28 @@ __device__ __forceinline__ void route_load(const TiledArgs& a, const TaskDesc& d
     }
 }
 
-// tick-block bases of a task (warp 0, lane = block of the chunk) -> s_rel[32], chunk metadata
-__device__ __forceinline__ void route_bases(const TiledArgs& a, const TaskDesc& d, int task, int lane, uint32_t* s_rel, uint32_t* s_fmt) {
-    const int64_t lo_b = a.offsets[d.b];
+// Tick-block bases of a task (one warp, lane = block of the chunk) -> s_rel[32], chunk metadata.  Split into the loads
+// (issued one phase early, so that the global-memory latency hides behind the bucket ranking) and the arithmetic.
+struct BasesRegs {
+    int64_t lo_b, t0_ticks;
+    uint32_t base, tmul, tshift, thalf, flags;
+};
+
+__device__ __forceinline__ void bases_load(const TiledArgs& a, const TaskDesc& d, int lane, BasesRegs& r) {
+    const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
+    const bool used = (lane << kTickBlockShift) < slot_hi && ((lane + 1) << kTickBlockShift) > slot_lo;
+    r.lo_b = __ldg(a.offsets + d.b);
+    r.base = used ? __ldg(a.blk_base + (d.c0 >> kTickBlockShift) + lane) : 0u;
+    const SampleMeta* m = a.meta + d.b;          // written by k_sample_meta of this call: plain loads
+    r.t0_ticks = m->t0_ticks; r.tmul = m->tmul; r.tshift = m->tshift; r.thalf = m->thalf; r.flags = m->flags;
+}
+
+__device__ __forceinline__ void bases_finish(const TiledArgs& a, const TaskDesc& d, int task, int lane, const BasesRegs& r,
+                                             uint32_t* s_rel, uint32_t* s_fmt) {
     const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
     const int64_t blk_id = (d.c0 >> kTickBlockShift) + lane;
     const bool used = (lane << kTickBlockShift) < slot_hi && ((lane + 1) << kTickBlockShift) > slot_lo;
-    const uint32_t base = (used && blk_id != (lo_b >> kTickBlockShift)) ? __ldg(a.blk_base + blk_id) : 0u;
+    const uint32_t base = (used && blk_id != (r.lo_b >> kTickBlockShift)) ? r.base : 0u;
     uint32_t mn = used ? base : 0xffffffffu, mx = used ? base : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -195,23 +211,22 @@ __device__ __forceinline__ void route_bases(const TiledArgs& a, const TaskDesc& 
     a.crel[(size_t)task * 32 + lane] = rel;
     if (lane == 0) {
         *s_fmt = narrow ? 16u : 21u;                                   // shift of the 9 tick bits inside the record
-        const SampleMeta m = a.meta[d.b];
-        const int64_t cbase = (int64_t)mn - m.t0_ticks;
+        const int64_t cbase = (int64_t)mn - r.t0_ticks;
         const int64_t dt_hi = cbase + (int64_t)(mx - mn) + 511;
-        const bool int_time = (m.flags & kFlagIntTime) != 0;
+        const bool int_time = (r.flags & kFlagIntTime) != 0;
         int klo = 0, khi = a.num_bins - 1;
         bool fast = false;
         if (int_time) {
             uint32_t v;
             const uint32_t v_end = (uint32_t)a.num_bins << kQ;
-            if (cbase > 0 && ticks_to_v(cbase, m.tmul, m.tshift, m.thalf, v_end, v)) klo = (int)(v >> kQ);
+            if (cbase > 0 && ticks_to_v(cbase, r.tmul, r.tshift, r.thalf, v_end, v)) klo = (int)(v >> kQ);
             else if (cbase >= (1ll << 32)) klo = a.num_bins - 1;
-            if (dt_hi >= 0 && ticks_to_v(dt_hi, m.tmul, m.tshift, m.thalf, v_end, v)) khi = (int)(v >> kQ);
+            if (dt_hi >= 0 && ticks_to_v(dt_hi, r.tmul, r.tshift, r.thalf, v_end, v)) khi = (int)(v >> kQ);
             else if (dt_hi < 0) khi = 0;
             if (narrow && cbase >= 0 && dt_hi < (1ll << 32)) {
                 // every v of the chunk fits 32 bits: the sweep's fast path then needs no range test beyond the interval's
-                const uint64_t q = (uint64_t)dt_hi * m.tmul + m.thalf;
-                fast = ((q >> 32) >> m.tshift) == 0;
+                const uint64_t q = (uint64_t)dt_hi * r.tmul + r.thalf;
+                fast = ((q >> 32) >> r.tshift) == 0;
             }
         }
         ChunkMeta cm;
@@ -224,18 +239,26 @@ __device__ __forceinline__ void route_bases(const TiledArgs& a, const TaskDesc& 
     }
 }
 
+// Two barriers per chunk: [rank the events into buckets] B1 [every warp scans the bucket sizes for itself; records to their
+// slots of this chunk's stage buffer] B2 [coalesced copy-out].  Stage buffer, bucket counters and tick-base tables are double
+// buffered, so the copy-out of chunk i runs under the ranking of chunk i + 1; the next chunk's descriptor is fetched at the
+// top of the iteration, its tick-block bases and sample constants between the barriers (by warp 1, while warp 0 also writes
+// the chunk's run table), and its event words as soon as this chunk's are consumed.
+constexpr int kRouteWarps = kRouteThreads / 32;
+constexpr int kOffStride = kMaxTiles + 4;
 __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* lut_y = reinterpret_cast<uint32_t*>(smem_raw);                    // tile << 16 | (row in tile) * W
     uint32_t* lut_x = lut_y + 2048;                                             // scaled x
-    uint32_t* stage = lut_x + 2048;
-    uint32_t* s_cnt = stage + kChunk;                                           // tile << 16 | events so far
-    uint32_t* s_off = s_cnt + (kMaxTiles + 2);                                  // bucket start - (tile << 16)
+    uint32_t* stage0 = lut_x + 2048;                                            // 2 x kChunk records
+    uint32_t* s_cnt0 = stage0 + 2 * kChunk;                                     // 2 x (kMaxTiles + 2): tile << 16 | events so far
+    uint32_t* s_off0 = s_cnt0 + 2 * (kMaxTiles + 2);                            // per warp: bucket start - (tile << 16)
     __shared__ uint32_t s_rel[2][32];
     __shared__ uint32_t s_fmt[2];
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NT = a.NT, NB = NT + 1;          // bucket NT = trash (coordinates outside the grid)
+    uint32_t* s_off = s_off0 + wid * kOffStride;
     pdl_trigger_t();
     // events_reshape: x * (input_w / sensor_w) in fp64, truncated by the .long() of the binning call
     for (int i = tid; i < 2048; i += kRouteThreads) {
@@ -252,7 +275,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
         lut_y[i] = ly;
         lut_x[i] = (uint32_t)(xx < 4095 ? xx : 4095);                 // anything >= W is redone exactly in the cold path
     }
-    if (tid < kMaxTiles + 2) s_cnt[tid] = (uint32_t)tid << 16;
+    if (tid < 2 * (kMaxTiles + 2)) s_cnt0[tid] = (uint32_t)(tid % (kMaxTiles + 2)) << 16;
     pdl_wait_t();          // the workspace (headers, records) may still be read by the previous call's sweep
 
     int task = blockIdx.x;
@@ -260,7 +283,11 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     TaskDesc d = a.desc[task];
     uint32_t wv[kRouteEv];
     route_load(a, d, tid, wv);
-    if (tid < 32) route_bases(a, d, task, lane, s_rel[0], &s_fmt[0]);
+    if (wid == 1) {
+        BasesRegs br;
+        bases_load(a, d, lane, br);
+        bases_finish(a, d, task, lane, br, s_rel[0], &s_fmt[0]);
+    }
     int buf = 0;
     __syncthreads();
 
@@ -269,6 +296,12 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     for (;;) {
         const int slot_lo = (int)(d.lohi & 0xffffu), slot_hi = (int)(d.lohi >> 16);
         const bool full = slot_lo == 0 && slot_hi == kChunk;
+        const int next = task + gridDim.x;
+        const bool more = next < a.n_tasks;
+        TaskDesc dn = d;
+        if (more) dn = a.desc[next];                                    // consumed after the ranking
+        uint32_t* stage = stage0 + buf * kChunk;
+        uint32_t* s_cnt = s_cnt0 + buf * (kMaxTiles + 2);
         const uint32_t fmt = s_fmt[buf];
         // ---- pass 1: record and bucket of every event of the thread (branch-free), then the ranks ----
         uint32_t rt[kRouteEv];      // tile, then tile << 16 | rank; 0xffffffff = not an event of this task
@@ -326,9 +359,9 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
                 rt[i] = (sl >= slot_lo && sl < slot_hi) ? atomicAdd(&s_cnt[rt[i]], 1u) : 0xffffffffu;
             }
         }
-        __syncthreads();
-        // ---- bucket starts (warp 0): exclusive scan of the NB <= 65 bucket sizes ----
-        if (tid < 32) {
+        __syncthreads();                                                // B1: the bucket sizes are final
+        // ---- bucket starts: every warp scans the NB <= 65 bucket sizes for itself (no serial section, no barrier) ----
+        {
             uint32_t c[3], sum = 0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) { const int t = lane * 3 + j; c[j] = (t < NB) ? (s_cnt[t] & 0xffffu) : 0u; sum += c[j]; }
@@ -340,15 +373,22 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int t = lane * 3 + j;
-                if (t <= NB) { s_off[t] = run - ((uint32_t)t << 16); co[t] = (uint16_t)run; }
+                if (t <= NB) { s_off[t] = run - ((uint32_t)t << 16); if (wid == 0) co[t] = (uint16_t)run; }
                 run += c[j];
             }
-            if (lane == 0 && a.bad_count) {
+            if (tid == 0 && a.bad_count) {
                 const uint32_t nbad = s_cnt[NT] & 0xffffu;
                 if (nbad) atomicAdd(a.bad_count, nbad);
             }
         }
-        __syncthreads();
+        BasesRegs br;
+        if (wid == 1 && more) bases_load(a, dn, lane, br);
+        // the other counter set was last read by the scans of the previous chunk (all warps are past them): reset for the next
+        if (wid == 2 || wid == 3 || wid == 4) {
+            const int t = tid - 64;
+            if (t < kMaxTiles + 2) s_cnt0[(buf ^ 1) * (kMaxTiles + 2) + t] = (uint32_t)t << 16;
+        }
+        __syncwarp();
         // ---- pass 2: records to their bucket slots ----
         if (full) {
 #pragma unroll
@@ -359,17 +399,12 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
                 if (rt[i] != 0xffffffffu) stage[s_off[rt[i] >> 16] + rt[i]] = wv[i];
         }
         // ---- the next task's words are requested now and land while this task's records are copied out ----
-        const int next = task + gridDim.x;
-        const bool more = next < a.n_tasks;
-        TaskDesc dn = d;
         if (more) {
-            dn = a.desc[next];
             route_load(a, dn, tid, wv);
-            if (tid < 32) route_bases(a, dn, next, lane, s_rel[buf ^ 1], &s_fmt[buf ^ 1]);
+            if (wid == 1) bases_finish(a, dn, next, lane, br, s_rel[buf ^ 1], &s_fmt[buf ^ 1]);
         }
-        __syncthreads();
-        // ---- coalesced copy-out; bucket counters reset for the next task ----
-        if (tid < kMaxTiles + 2) s_cnt[tid] = (uint32_t)tid << 16;
+        __syncthreads();                                                // B2: the stage buffer is complete
+        // ---- coalesced copy-out (no barrier behind it: this buffer is written again two chunks later, past B1 of the next) ----
         const int n = slot_hi - slot_lo;
         const int64_t p0 = d.c0 + slot_lo - a.rec_pos0;
         uint32_t* dst = a.rec + p0;
@@ -383,7 +418,6 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
         }
         if (!more) break;
         task = next; d = dn; buf ^= 1;
-        __syncthreads();
     }
 }
 
@@ -477,6 +511,8 @@ __device__ __noinline__ void sweep_record_slow(const ChunkMeta* cmp, const uint3
 // groups of kFlushUnroll vectors whose shared-memory and L2 loads are all issued before the first use: a thread owns at
 // most 7 vectors of a 12800-cell tile, and one dependent L2 round trip per vector was the longest stall of the sweep.
 constexpr int kFlushUnroll = 4;
+constexpr int kStatSlices = 32;                          // CTAs per channel of the statistics reduction
+constexpr int kStatSlot = (kSweepThreads / 32) * 3;      // doubles per (task, channel): one (sum, sum of squares, max) per warp
 
 // Per-thread partial statistics of the values a thread writes (fixed element order => reproducible)
 struct StatAcc {
@@ -571,8 +607,9 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
     }
 }
 
-// fixed-order block reduction of the per-thread statistics -> part[0..2] = (sum, sum of squares, max) as fp64
-__device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part, double (*s_red)[3]) {
+// per-warp reduction of the per-thread statistics (fixed shuffle tree) -> part[warp][0..2] = (sum, sum of squares, max) as
+// fp64; no barrier: every (task, channel, warp) slot is written exactly once and k_stats_reduce adds them in a fixed order
+__device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part) {
     double d1 = (double)a.s1, d2 = (double)a.s2;
     float mx = a.mx;
 #pragma unroll
@@ -581,22 +618,17 @@ __device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part, doubl
         d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { s_red[wid][0] = d1; s_red[wid][1] = d2; s_red[wid][2] = (double)mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t1 = 0.0, t2 = 0.0, tm = -INFINITY;
-        for (int w = 0; w < kSweepThreads / 32; ++w) { t1 += s_red[w][0]; t2 += s_red[w][1]; tm = fmax(tm, s_red[w][2]); }
-        part[0] = t1; part[1] = t2; part[2] = tm;
+    if ((threadIdx.x & 31) == 0) {
+        double* q = part + (threadIdx.x >> 5) * 3;
+        q[0] = d1; q[1] = d2; q[2] = (double)mx;
     }
-    __syncthreads();
 }
 
 // pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys).
-// stats_part (or null): per-(task, channel) partial statistics of the written values, channel num_bins = the sum plane.
+// stats_part (or null): per-(task, channel, warp) partial statistics of the written values, channel num_bins = the sum plane.
 template <bool VEC>
 __device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, const int2* spill, int n_spill,
-                                            int key0, double* stats_part, double (*s_red)[3]) {
+                                            int key0, double* stats_part) {
     const bool first = k == 0, last = k == num_bins - 1;
     StatAcc sa, ss;
     sa.init(); ss.init();
@@ -606,8 +638,8 @@ __device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_b
         else if (first) flush_plane_t<VEC, true, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
         else if (last) flush_plane_t<VEC, false, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
         else flush_plane_t<VEC, false, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        stat_reduce_store(sa, stats_part + (size_t)k * 3, s_red);
-        if (so && last) stat_reduce_store(ss, stats_part + (size_t)num_bins * 3, s_red);
+        stat_reduce_store(sa, stats_part + (size_t)k * kStatSlot);
+        if (so && last) stat_reduce_store(ss, stats_part + (size_t)num_bins * kStatSlot);
     } else {
         if (!so) flush_plane_t<VEC, false, false, false, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
         else if (first && last) flush_plane_t<VEC, true, true, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
@@ -698,6 +730,8 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool VEC>
 __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -712,20 +746,19 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
     uint16_t* t_kr = t_len + kTabCap;
     __shared__ int s_task, s_nitems, s_nspill;
     __shared__ SampleMeta s_meta;
-    __shared__ double s_red[kSweepThreads / 32][3];
 
     const int tid = threadIdx.x, lane = tid & 31;
     pdl_trigger_t();
     for (int i = tid; i < 2 * tile_cells; i += kSweepThreads) plane0[i] = 0;
+    if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
+    if (tid == 0) { s_nspill = 0; s_nitems = 0; }
     pdl_wait_t();          // records and headers of the route
     const int n_sweep = a.B * a.NT;
     const int64_t HW = (int64_t)a.H * a.W;
+    if (tid == 0) s_task = (int)atomicAdd(a.counters, 1u);
+    __syncthreads();
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { s_task = (int)atomicAdd(a.counters, 1u); s_nspill = 0; }
-        if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
-        __syncthreads();
         const int task = s_task;
         if (task >= n_sweep) break;
         const int b = task / a.NT, tile = task - b * a.NT;
@@ -736,7 +769,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
         const int ncell = nrows * a.W;
         const int cell0 = tile_cells - ncell;              // a shorter last tile sits at the end of the plane (k_route's lut_y)
         const bool resident = nch <= kTabCap;
-        __syncthreads();
+        __syncthreads();       // s_task is read by everyone before the last phase overwrites it
         const uint32_t tmul = s_meta.tmul, tshift = s_meta.tshift, thalf = s_meta.thalf;
 
         for (int k = 0; k < a.num_bins; ++k) {
@@ -747,6 +780,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
             c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
             c.kbase = (uint32_t)k << kQ; c.k = k;
             const bool has_right = k + 1 < a.num_bins;
+            // last phase: the next task is drawn now, its number is looked at after the accumulation
+            int next_task = 0;
+            if (!has_right && tid == kSweepThreads - 1) next_task = (int)atomicAdd(a.counters, 1u);
             for (int c_round = 0; c_round < nch; c_round += kTabCap) {
                 const int ci = c_round + tid;
                 if (!resident || k == 0) {
@@ -772,8 +808,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
                     if ((int)(kr & 0xffu) <= k && k <= (int)(kr >> 8)) remaining = (len + kItemRecs - 1) / kItemRecs;
                 }
                 for (;;) {
-                    if (tid == 0) s_nitems = 0;
-                    __syncthreads();
+                    // s_nitems is 0 here (reset behind the barrier that follows the accumulation)
                     if (remaining) {
                         const int base = atomicAdd(&s_nitems, remaining);
                         int take = kItemCap - base;
@@ -791,15 +826,49 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
                     if (has_right) sweep_items<true>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, tid >> 5, lane);
                     else sweep_items<false>(a, c, &s_meta, tmul, tshift, first + c_round, t_q, s_items, n_items, tid >> 5, lane);
                     __syncthreads();
+                    if (tid == 0) s_nitems = 0;
                     if (!any_left) break;
+                    __syncthreads();       // rare: more items than the list holds
+                }
+                if (!resident) __syncthreads();       // the next round rewrites the run table and the item counter
+            }
+            // The records of the next phase are requested into L2 now and arrive under the flush: the runs of the chunks that
+            // can hold events of interval k + 1 (those that also fed interval k were just read).
+            if (resident && has_right) {
+                const uint32_t kr = t_kr[tid];
+                if ((int)(kr & 0xffu) == k + 1) {
+                    const uint32_t* p = a.rec + t_pos[tid];
+                    const int len = t_len[tid] & 0x7fff;
+                    for (int i = 0; i < len; i += 32) prefetch_l2(p + i);
+                }
+            }
+            // Last phase: publish the next task and request its run-table sources (chunk headers, bucket offsets) into L2.
+            if (!has_right && tid == kSweepThreads - 1) {
+                const int nt = next_task;
+                s_task = nt;
+                if (nt < n_sweep) {
+                    const int nb = nt / a.NT, ntile = nt - nb * a.NT;
+                    const int nf = a.first_task[nb], nn = a.first_task[nb + 1] - nf;
+                    const char* cmp = reinterpret_cast<const char*>(a.cmeta + nf);
+                    for (int i = 0; i < nn * (int)sizeof(ChunkMeta); i += 128) prefetch_l2(cmp + i);
+                    const char* cop = reinterpret_cast<const char*>(a.coff + (size_t)nf * a.off_stride + ntile);
+                    const int span = nn * a.off_stride * 2;
+                    for (int i = 0; i < span; i += 128) prefetch_l2(cop + i);
+                    prefetch_l2(a.meta + nb);
                 }
             }
             // plane k is complete: fp32 out (+ running voxel.sum(0)), buffer re-zeroed -> plane k + 2
             const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
             float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
             float* so = a.out_sum ? a.out_sum + (int64_t)b * HW + (int64_t)row0 * a.W : nullptr;
-            double* sp = a.stats_part ? a.stats_part + (size_t)task * (a.num_bins + 1) * 3 : nullptr;
-            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0, sp, s_red);
+            double* sp = a.stats_part ? a.stats_part + (size_t)task * (a.num_bins + 1) * kStatSlot : nullptr;
+            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0, sp);
+            if (!has_right && n_spill) {
+                // the spill list is per task
+                __syncthreads();
+                if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
+                if (tid == 0) s_nspill = 0;
+            }
             __syncthreads();
         }
     }
@@ -808,7 +877,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
 struct TiledPlan {
     int NT, rows, n_tasks;
     int64_t rec_pos0, n_rec;
-    size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_rec, total;
+    size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_stats2, off_rec, total;
 };
 
 bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) {
@@ -844,7 +913,8 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_coff = o; o += align_up(sizeof(uint16_t) * nt * (size_t)(NT + 2), 256);
     pl.off_crel = o; o += align_up(sizeof(uint32_t) * nt * 32, 256);
     pl.off_counters = o; o += 256;
-    pl.off_stats = o; o += align_up(sizeof(double) * 3 * (size_t)B * NT * (size_t)(p->num_bins + 1), 256);
+    pl.off_stats = o; o += align_up(sizeof(double) * kStatSlot * (size_t)B * NT * (size_t)(p->num_bins + 1), 256);
+    pl.off_stats2 = o; o += align_up(sizeof(double) * 3 * kStatSlices * (size_t)(p->num_bins + 1), 256);
     pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
     pl.total = o;
     return true;
@@ -857,15 +927,19 @@ size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p) {
     return tiled_plan(ev, p, pl) ? pl.total : 0;
 }
 
-// Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
-// channel statistics from the sweep's per-(task, channel) partials, in a fixed order: out[c] = (count, sum, sum of squares, max)
-__global__ void __launch_bounds__(256) k_stats_reduce(const double* __restrict__ part, int n_parts, int n_ch, double count,
-                                                      double* __restrict__ out) {
+// Channel statistics from the sweep's per-(task, channel, warp) partials, in a fixed order (bit-reproducible):
+// k_stats_slices: CTA (channel c, slice s) adds the partials of its contiguous share of the tasks -> part2[c][s][0..2];
+// k_stats_final: out[c] = (count, sum, sum of squares, max) from the kStatSlices slice sums.
+__global__ void __launch_bounds__(256) k_stats_slices(const double* __restrict__ part, int n_tasks, int n_ch, double* __restrict__ part2) {
     __shared__ double s1[256], s2[256], sm[256];
-    const int c = blockIdx.x, tid = threadIdx.x;
+    constexpr int kWarps = kSweepThreads / 32;
+    const int c = blockIdx.x, sl = blockIdx.y, tid = threadIdx.x;
+    const int per = (n_tasks + kStatSlices - 1) / kStatSlices;
+    const int t0 = sl * per, t1 = (t0 + per < n_tasks) ? t0 + per : n_tasks;
     double a1 = 0.0, a2 = 0.0, am = -INFINITY;
-    for (int i = tid; i < n_parts; i += 256) {
-        const double* q = part + ((size_t)i * n_ch + c) * 3;
+    for (int i = t0 * kWarps + tid; i < t1 * kWarps; i += 256) {
+        const int task = i / kWarps, w = i - task * kWarps;
+        const double* q = part + ((size_t)task * n_ch + c) * kStatSlot + w * 3;
         a1 += q[0]; a2 += q[1]; am = fmax(am, q[2]);
     }
     s1[tid] = a1; s2[tid] = a2; sm[tid] = am;
@@ -874,9 +948,26 @@ __global__ void __launch_bounds__(256) k_stats_reduce(const double* __restrict__
         if (tid < o) { s1[tid] += s1[tid + o]; s2[tid] += s2[tid + o]; sm[tid] = fmax(sm[tid], sm[tid + o]); }
         __syncthreads();
     }
-    if (tid == 0) { out[c * 4 + 0] = count; out[c * 4 + 1] = s1[0]; out[c * 4 + 2] = s2[0]; out[c * 4 + 3] = sm[0]; }
+    if (tid == 0) {
+        double* q = part2 + ((size_t)c * kStatSlices + sl) * 3;
+        q[0] = s1[0]; q[1] = s2[0]; q[2] = sm[0];
+    }
 }
 
+__global__ void __launch_bounds__(32) k_stats_final(const double* __restrict__ part2, double count, double* __restrict__ out) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const double* q = part2 + ((size_t)c * kStatSlices + lane) * 3;
+    double a1 = q[0], a2 = q[1], am = q[2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+    }
+    if (lane == 0) { out[c * 4 + 0] = count; out[c * 4 + 1] = a1; out[c * 4 + 2] = a2; out[c * 4 + 3] = am; }
+}
+
+// Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
 int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
                       void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
     TiledPlan pl;
@@ -951,7 +1042,11 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     if (out_stats) {
         const int n_ch = p->num_bins + 1;
         profile_begin(st, kProfOther);
-        k_stats_reduce<<<out_sum ? n_ch : p->num_bins, 256, 0, st>>>(a.stats_part, B * pl.NT, n_ch, (double)B * p->height * p->width, out_stats);
+        double* part2 = reinterpret_cast<double*>(base + pl.off_stats2);
+        const int n_out = out_sum ? n_ch : p->num_bins;
+        k_stats_slices<<<dim3((unsigned)n_out, kStatSlices), 256, 0, st>>>(a.stats_part, B * pl.NT, n_ch, part2);
+        EP_LAUNCH_CHECK();
+        k_stats_final<<<n_out, 32, 0, st>>>(part2, (double)B * p->height * p->width, out_stats);
         profile_end(st);
         EP_LAUNCH_CHECK();
     }

@@ -366,6 +366,44 @@ __global__ void __launch_bounds__(256) k_swin_gather(const float* __restrict__ x
     for (int i = lane; i < C / 4; i += 32) o[i] = ld_stream(s + i);
 }
 
+// ---- Swin stage outputs back to dense grids, and the per-sample re-gather (model/backbone/swin.py:212-238) ----
+// dense[b, c, cell] = x[b, n, c] for the visible token n that sits on cell = h * G + w, 0 elsewhere:
+//   _emb = zeros(B, G*G, C); _emb[:, coords[0,:,0]*G + coords[0,:,1], :] = x; _emb.reshape(B,G,G,C).permute(0,3,1,2)   (swin.py:221-225)
+// One CTA per (sample, 32-channel slab, 32-cell strip): the inverse map cell -> token is built per CTA from the coordinates
+// (batch-shared, a few KB), tokens are read as rows, transposed through shared memory and written as channel rows.
+__global__ void __launch_bounds__(256) k_swin_scatter_dense(const float* __restrict__ x, const int64_t* __restrict__ coords, int n_vis,
+                                                            int G, int C, float* __restrict__ out) {
+    __shared__ int s_tok[32];
+    __shared__ float s_tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, cell0 = blockIdx.x * 32;
+    const int cells = G * G;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x < 32) s_tok[threadIdx.x] = -1;
+    __syncthreads();
+    for (int n = threadIdx.x; n < n_vis; n += 256) {
+        const int cell = (int)(coords[2 * n] * G + coords[2 * n + 1]);
+        if (cell >= cell0 && cell < cell0 + 32) s_tok[cell - cell0] = n;       // last writer wins like the indexed assignment; coords are unique
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {            // r = cell of the strip, tx = channel of the slab: coalesced token rows
+        const int tok = s_tok[r];
+        s_tile[r][tx] = (tok >= 0 && c0 + tx < C) ? x[((int64_t)b * n_vis + tok) * C + c0 + tx] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {            // r = channel of the slab, tx = cell: coalesced channel rows
+        if (c0 + r < C && cell0 + tx < cells) out[((int64_t)b * C + c0 + r) * cells + cell0 + tx] = s_tile[tx][r];
+    }
+}
+
+// out[b, k, d] = feat[b, d, ids[b, k]]: stage_output_decode(...).flatten(2).permute(0,2,1) gathered by ids_keep   (swin.py:226-228)
+__global__ void __launch_bounds__(256) k_gather_tokens_nchw(const float* __restrict__ feat, const int64_t* __restrict__ ids, int L, int K,
+                                                            int D, float* __restrict__ out) {
+    const int b = blockIdx.y, k = blockIdx.x;
+    int64_t src = ids[(int64_t)b * K + k];
+    if (src < 0 || src >= L) src = 0;
+    for (int d = threadIdx.x; d < D; d += 256) out[((int64_t)b * K + k) * D + d] = feat[((int64_t)b * D + d) * L + src];
+}
+
 }  // namespace
 }  // namespace ep
 
@@ -515,6 +553,23 @@ int ep_swin_apply_mask(void* stream, const float* x, const float* mask_row, int 
         ep::k_swin_gather<<<(unsigned)ep::ceil_div64(rows, 8), 256, 0, st>>>(x, coords, n_vis_out, batch, N, Wt, C, n_vis_max, x_vis);
         EP_LAUNCH_CHECK();
     }
+    return EP_OK;
+}
+
+int ep_swin_scatter_dense(void* stream, const float* x, const int64_t* coords, int batch, int n_vis, int grid, int C, float* out) {
+    if (!x || !coords || !out || batch <= 0 || n_vis < 0 || grid <= 0 || C <= 0) return EP_EINVAL;
+    if (batch > 65535) return EP_EUNSUPPORTED;
+    const dim3 g((unsigned)((grid * grid + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)batch);
+    ep::k_swin_scatter_dense<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, coords, n_vis, grid, C, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_gather_tokens_nchw(void* stream, const float* feat, const int64_t* ids_keep, int batch, int L, int K, int D, float* out) {
+    if (!feat || !ids_keep || !out || batch <= 0 || L <= 0 || K <= 0 || D <= 0) return EP_EINVAL;
+    if (batch > 65535) return EP_EUNSUPPORTED;
+    ep::k_gather_tokens_nchw<<<dim3((unsigned)K, (unsigned)batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, ids_keep, L, K, D, out);
+    EP_LAUNCH_CHECK();
     return EP_OK;
 }
 

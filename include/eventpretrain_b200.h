@@ -290,6 +290,17 @@ EP_API int ep_swin_apply_mask(void* stream, const float* x, const float* mask_ro
                        int rep, int C, int n_vis_max, float* x_vis, int64_t* coords, uint8_t* vis_mask,
                        int* n_vis_out);
 
+/* Swin stage outputs, the consumers of the visibility mask   model/backbone/swin.py:212-238
+ * ep_swin_scatter_dense: x (B,n_vis,C) f32 tokens of the visible cells, coords (n_vis,2) i64 (h,w) (batch-shared, from
+ *   ep_swin_apply_mask or a PatchMerging stage) -> out (B,C,G,G) f32, zero where no token sits: the
+ *   `_emb = zeros(B,G*G,C); _emb[:, h*G+w, :] = x; reshape; permute(0,3,1,2)` of :221-225 in one pass.
+ * ep_gather_tokens_nchw: feat (B,D,L) f32 (a conv output (B,D,Gh,Gw) as it lies in memory) and the per-sample
+ *   ids_keep (B,K) i64 -> out (B,K,D) = feat.flatten(2).permute(0,2,1) gathered along the tokens (:226-228). */
+EP_API int ep_swin_scatter_dense(void* stream, const float* x, const int64_t* coords, int batch, int n_vis, int grid, int C,
+                          float* out);
+EP_API int ep_gather_tokens_nchw(void* stream, const float* feat, const int64_t* ids_keep, int batch, int L, int K, int D,
+                          float* out);
+
 /* decoder un-shuffle   model/pretrain/pr_rec_decoder.py:56-62
  * out[b,l,:] = (ids_restore[b,l] < K ? emb[b, ids_restore[b,l], :] : mask_token[:]) + pos_embed[l,:]. */
 EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask_token, const float* pos_embed,

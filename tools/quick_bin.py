@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--size", default="", help="HxW output grid with the fused events_reshape scale, e.g. 224x224")
     ap.add_argument("--bins", type=int, default=bench.BINS)
     ap.add_argument("--count", type=int, default=0)
+    ap.add_argument("--stats", action="store_true", help="ep_bin_events_stats: batch statistics as a by-product of the sweep")
     args = ap.parse_args()
     import eventpretrain_b200 as ep
     from eventpretrain_b200 import _lib
@@ -54,7 +55,7 @@ def main():
         scale = (W / bench.W, H / bench.H)
     results = {}
     for m in args.methods.split(","):
-        kw = dict(num_bins=args.bins, voxel_sum=True, count_channels=args.count, method=m, scale=scale)
+        kw = dict(num_bins=args.bins, voxel_sum=True, count_channels=args.count, method=m, scale=scale, stats=args.stats)
         out = ep.bin_events(ev, (H, W), check=True, **kw)
         for _ in range(2):
             ep.bin_events(ev, (H, W), out=out, **kw)
