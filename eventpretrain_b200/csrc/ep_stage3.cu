@@ -178,11 +178,15 @@ template <bool LOSS>
 __global__ void __launch_bounds__(256) k_patch_target(const float* __restrict__ frame,
                                                       const float* __restrict__ pred, int64_t patches, int C,
                                                       int H, int W, int p, int norm_pix, float eps,
-                                                      float* __restrict__ out) {
+                                                      const float* __restrict__ mask, float* __restrict__ out) {
     extern __shared__ float s_patch[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= patches) return;
+    if (LOSS && mask && mask[row] == 0.0f) {            // a patch the loss discards (mask * loss, pr_hub_model.py:139): not even read
+        if (lane == 0) out[row] = 0.0f;
+        return;
+    }
     const int gw = W / p, L = (H / p) * gw;
     const int64_t b = row / L;
     const int l = (int)(row % L);
@@ -191,35 +195,37 @@ __global__ void __launch_bounds__(256) k_patch_target(const float* __restrict__ 
     const float* base = frame + b * C * HW + (int64_t)(py * p) * W + px * p;
     const int n = C * p * p;
     float* sp = s_patch + (int64_t)warp * n;
-    float sum = 0.f;
+    // the three reductions run in fp64 (a few dozen adds per lane): mean, variance and loss then carry one fp32 rounding each,
+    // which keeps the per-patch loss within 1e-5 of the reference's whatever its summation order
+    double sum = 0.0;
     for (int e = lane; e < n; e += 32) {
         const int c = e % C, q = (e / C) % p, r = e / (C * p);
         const float v = ld_stream(base + c * HW + (int64_t)r * W + q);
         sp[e] = v;
-        sum += v;
+        sum += (double)v;
     }
     float mean = 0.f, sd = 1.f;
     if (norm_pix) {
-        sum = warp_reduce(sum, [](float a, float c) { return a + c; });
-        mean = sum / (float)n;
-        float ss = 0.f;
+        sum = warp_reduce(sum, [](double a, double c) { return a + c; });
+        mean = (float)(sum / (double)n);
+        double ss = 0.0;
         __syncwarp();
-        for (int e = lane; e < n; e += 32) { const float d = sp[e] - mean; ss += d * d; }
-        ss = warp_reduce(ss, [](float a, float c) { return a + c; });
-        const float var = ss / (float)(n - 1);          // torch.var default: unbiased
+        for (int e = lane; e < n; e += 32) { const float d = sp[e] - mean; ss += (double)d * (double)d; }
+        ss = warp_reduce(ss, [](double a, double c) { return a + c; });
+        const float var = (float)(ss / (double)(n - 1));          // torch.var default: unbiased
         sd = sqrtf(var + eps);                          // (var + 1e-6) ** .5
     }
     __syncwarp();
     if (LOSS) {
         const float* pr = pred + row * n;
-        float acc = 0.f;
+        double acc = 0.0;
         for (int e = lane; e < n; e += 32) {
             const float t = norm_pix ? (sp[e] - mean) / sd : sp[e];
             const float d = ld_stream(pr + e) - t;
-            acc += d * d;
+            acc += (double)d * (double)d;
         }
-        acc = warp_reduce(acc, [](float a, float c) { return a + c; });
-        if (lane == 0) out[row] = acc / (float)n;
+        acc = warp_reduce(acc, [](double a, double c) { return a + c; });
+        if (lane == 0) out[row] = (float)(acc / (double)n);
     } else {
         float* o = out + row * n;
         for (int e = lane; e < n; e += 32) st_stream(o + e, norm_pix ? (sp[e] - mean) / sd : sp[e]);
@@ -232,11 +238,15 @@ __global__ void __launch_bounds__(256) k_patch_target(const float* __restrict__ 
 template <int P, bool LOSS>
 __global__ void __launch_bounds__(256) k_patch_target_c1(const float* __restrict__ frame, const float* __restrict__ pred,
                                                          int64_t patches, int H, int W, int norm_pix, float eps,
-                                                         float* __restrict__ out) {
+                                                         const float* __restrict__ mask, float* __restrict__ out) {
     constexpr int P4 = P / 4, NV = P * P4, V = (NV + 31) / 32, n = P * P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= patches) return;
+    if (LOSS && mask && mask[row] == 0.0f) {            // a patch the loss discards: not even read
+        if (lane == 0) out[row] = 0.0f;
+        return;
+    }
     const int gw = W / P, L = (H / P) * gw;
     const int64_t b = row / L;
     const int l = (int)(row % L);
@@ -258,36 +268,37 @@ __global__ void __launch_bounds__(256) k_patch_target_c1(const float* __restrict
     }
     float mean = 0.f, sd = 1.f;
     if (norm_pix) {
-        float sum = 0.f;
+        // fp64 reductions, as in k_patch_target
+        double sum = 0.0;
 #pragma unroll
-        for (int j = 0; j < V; ++j) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-        sum = warp_reduce(sum, [](float a, float c) { return a + c; });
-        mean = sum / (float)n;
-        float ss = 0.f;
+        for (int j = 0; j < V; ++j) sum += ((double)v[j].x + (double)v[j].y) + ((double)v[j].z + (double)v[j].w);
+        sum = warp_reduce(sum, [](double a, double c) { return a + c; });
+        mean = (float)(sum / (double)n);
+        double ss = 0.0;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             if (NV % 32 == 0 || lane + 32 * j < NV) {
-                const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+                const double d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
                 ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
             }
         }
-        ss = warp_reduce(ss, [](float a, float c) { return a + c; });
-        sd = sqrtf(ss / (float)(n - 1) + eps);          // torch.var default: unbiased; (var + 1e-6) ** .5
+        ss = warp_reduce(ss, [](double a, double c) { return a + c; });
+        sd = sqrtf((float)(ss / (double)(n - 1)) + eps);          // torch.var default: unbiased; (var + 1e-6) ** .5
 #pragma unroll
         for (int j = 0; j < V; ++j)
             v[j] = make_float4((v[j].x - mean) / sd, (v[j].y - mean) / sd, (v[j].z - mean) / sd, (v[j].w - mean) / sd);
     }
     if (LOSS) {
-        float acc = 0.f;
+        double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             if (NV % 32 == 0 || lane + 32 * j < NV) {
-                const float d0 = pr[j].x - v[j].x, d1 = pr[j].y - v[j].y, d2 = pr[j].z - v[j].z, d3 = pr[j].w - v[j].w;
+                const double d0 = pr[j].x - v[j].x, d1 = pr[j].y - v[j].y, d2 = pr[j].z - v[j].z, d3 = pr[j].w - v[j].w;
                 acc += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
             }
         }
-        acc = warp_reduce(acc, [](float a, float c) { return a + c; });
-        if (lane == 0) out[row] = acc / (float)n;
+        acc = warp_reduce(acc, [](double a, double c) { return a + c; });
+        if (lane == 0) out[row] = (float)(acc / (double)n);
     } else {
         float4* o = reinterpret_cast<float4*>(out + row * n);
 #pragma unroll
@@ -404,6 +415,24 @@ __global__ void __launch_bounds__(256) k_gather_tokens_nchw(const float* __restr
     for (int d = threadIdx.x; d < D; d += 256) out[((int64_t)b * K + k) * D + d] = feat[((int64_t)b * D + d) * L + src];
 }
 
+// ConvViT feature fusion (convvit.py:137-140, 151-154, 166-167): the two stage decoders' outputs, still (B,D,14,14) as the
+// convolutions leave them, gathered by ids_keep and added to the transformer stage's tokens in one pass:
+//   out[b,k,:] = (feat1[b,:,ids[b,k]] + feat2[b,:,ids[b,k]]) + emb3[b,k,:]        (the reference's left-to-right sum)
+// without the two flatten(2).permute(0,2,1) copies, the two gathers and the two adds.
+__global__ void __launch_bounds__(256) k_gather_sum_nchw(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                         const float* __restrict__ e3, const int64_t* __restrict__ ids, int L, int K, int D,
+                                                         float* __restrict__ out) {
+    const int b = blockIdx.y, k = blockIdx.x;
+    int64_t src = ids[(int64_t)b * K + k];
+    if (src < 0 || src >= L) src = 0;
+    for (int d = threadIdx.x; d < D; d += 256) {
+        const int64_t fi = ((int64_t)b * D + d) * L + src, oi = ((int64_t)b * K + k) * D + d;
+        float v = __fadd_rn(f1[fi], f2[fi]);
+        if (e3) v = __fadd_rn(v, e3[oi]);
+        out[oi] = v;
+    }
+}
+
 }  // namespace
 }  // namespace ep
 
@@ -488,7 +517,7 @@ int ep_patchify_gather(void* stream, const float* x, const int64_t* ids_keep, in
 }
 
 static int launch_patch_target(void* stream, bool loss, const float* frame, const float* pred, int batch,
-                               int channels, int height, int width, int patch, int norm_pix, float eps, float* out) {
+                               int channels, int height, int width, int patch, int norm_pix, float eps, const float* mask, float* out) {
     if (!frame || !out || (loss && !pred) || batch <= 0 || channels <= 0 || patch <= 0) return EP_EINVAL;
     if (height < patch || width < patch || height % patch || width % patch) return EP_EUNSUPPORTED;
     const int n = channels * patch * patch;
@@ -501,8 +530,8 @@ static int launch_patch_target(void* stream, bool loss, const float* frame, cons
     if (channels == 1 && (patch == 8 || patch == 16 || patch == 32) && width % 4 == 0 && ep::aligned16(frame) && ep::aligned16(out) &&
         (!loss || ep::aligned16(pred))) {
 #define EP_TARGET_C1(P)                                                                                                            \
-    if (loss) ep::k_patch_target_c1<P, true><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, out); \
-    else ep::k_patch_target_c1<P, false><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, out)
+    if (loss) ep::k_patch_target_c1<P, true><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, mask, out); \
+    else ep::k_patch_target_c1<P, false><<<blocks, warps * 32, 0, st>>>(frame, pred, patches, height, width, norm_pix, eps, mask, out)
         if (patch == 8) { EP_TARGET_C1(8); } else if (patch == 16) { EP_TARGET_C1(16); } else { EP_TARGET_C1(32); }
 #undef EP_TARGET_C1
         EP_LAUNCH_CHECK();
@@ -510,10 +539,10 @@ static int launch_patch_target(void* stream, bool loss, const float* frame, cons
     }
     if (loss) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(ep::k_patch_target<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ep::k_patch_target<true><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, out);
+        ep::k_patch_target<true><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, mask, out);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(ep::k_patch_target<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ep::k_patch_target<false><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, out);
+        ep::k_patch_target<false><<<blocks, warps * 32, smem, st>>>(frame, pred, patches, channels, height, width, patch, norm_pix, eps, mask, out);
     }
     EP_LAUNCH_CHECK();
     return EP_OK;
@@ -521,12 +550,18 @@ static int launch_patch_target(void* stream, bool loss, const float* frame, cons
 
 int ep_patchify_normpix(void* stream, const float* frame, int batch, int channels, int height, int width, int patch,
                         int norm_pix, float eps, float* out) {
-    return launch_patch_target(stream, false, frame, nullptr, batch, channels, height, width, patch, norm_pix, eps, out);
+    return launch_patch_target(stream, false, frame, nullptr, batch, channels, height, width, patch, norm_pix, eps, nullptr, out);
 }
 
 int ep_target_patch_loss(void* stream, const float* frame, const float* pred, int batch, int channels, int height,
                          int width, int patch, int norm_pix, float eps, float* patch_loss) {
-    return launch_patch_target(stream, true, frame, pred, batch, channels, height, width, patch, norm_pix, eps, patch_loss);
+    return launch_patch_target(stream, true, frame, pred, batch, channels, height, width, patch, norm_pix, eps, nullptr, patch_loss);
+}
+
+int ep_target_patch_loss_masked(void* stream, const float* frame, const float* pred, const float* mask, int batch, int channels,
+                                int height, int width, int patch, int norm_pix, float eps, float* patch_loss) {
+    if (!mask) return EP_EINVAL;
+    return launch_patch_target(stream, true, frame, pred, batch, channels, height, width, patch, norm_pix, eps, mask, patch_loss);
 }
 
 int ep_block_mask_expand(void* stream, const float* mask, int batch, int grid, int rep, int invert, float* out) {
@@ -569,6 +604,15 @@ int ep_gather_tokens_nchw(void* stream, const float* feat, const int64_t* ids_ke
     if (!feat || !ids_keep || !out || batch <= 0 || L <= 0 || K <= 0 || D <= 0) return EP_EINVAL;
     if (batch > 65535) return EP_EUNSUPPORTED;
     ep::k_gather_tokens_nchw<<<dim3((unsigned)K, (unsigned)batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, ids_keep, L, K, D, out);
+    EP_LAUNCH_CHECK();
+    return EP_OK;
+}
+
+int ep_gather_sum_nchw(void* stream, const float* feat1, const float* feat2, const float* emb3, const int64_t* ids_keep, int batch,
+                       int L, int K, int D, float* out) {
+    if (!feat1 || !feat2 || !ids_keep || !out || batch <= 0 || L <= 0 || K <= 0 || D <= 0) return EP_EINVAL;
+    if (batch > 65535) return EP_EUNSUPPORTED;
+    ep::k_gather_sum_nchw<<<dim3((unsigned)K, (unsigned)batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat1, feat2, emb3, ids_keep, L, K, D, out);
     EP_LAUNCH_CHECK();
     return EP_OK;
 }

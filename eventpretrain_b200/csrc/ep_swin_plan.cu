@@ -77,4 +77,28 @@ int ep_swin_group_windows_host(int group_size, const int* num_ele_win, int n_win
     return EP_OK;
 }
 
+int ep_swin_group_tables_host(const int64_t* group_id, const int64_t* coords, int n_groups, int group_size, int window, int mask_rel,
+                              float* attn_mask, int64_t* rel_pos_idx) {
+    if (!group_id || !coords || !attn_mask || !rel_pos_idx || n_groups <= 0 || group_size <= 0 || window <= 0) return EP_EINVAL;
+    const int64_t span = 2 * (int64_t)window - 1;
+    for (int g = 0; g < n_groups; ++g) {
+        const int64_t* gid = group_id + (size_t)g * group_size;
+        const int64_t* c = coords + (size_t)g * group_size * 2;
+        float* am = attn_mask + (size_t)g * group_size * group_size;
+        int64_t* rp = rel_pos_idx + (size_t)g * group_size * group_size;
+        for (int i = 0; i < group_size; ++i) {
+            const float gi = (float)gid[i];                       // the reference compares the ids as float32
+            for (int j = 0; j < group_size; ++j) {
+                // two slots attend to each other when they carry the same window id and are not both padding (id -1)
+                const bool blocked = (gi - (float)gid[j]) != 0.0f || (gid[i] == -1 && gid[j] == -1);
+                am[(size_t)i * group_size + j] = blocked ? -100.0f : 0.0f;
+                const int64_t rel = (c[2 * i] - c[2 * j] + window - 1) * span + (c[2 * i + 1] - c[2 * j + 1] + window - 1);
+                rp[(size_t)i * group_size + j] = (mask_rel && blocked) ? 0 : rel;
+            }
+        }
+    }
+    return EP_OK;
+}
+
+
 }  // extern "C"

@@ -299,9 +299,9 @@ def collate_events(samples, ticks_per_unit=1.0e6, pin=True, threads=0):
     B = len(samples)
     if B == 0:
         raise ValueError("empty batch")
-    dt = np.asarray(samples[0]).dtype
-    if dt not in (np.float64, np.float32):
-        dt = np.dtype(np.float64)
+    # float32 rows only when every sample is float32 (DDD17 / DVS128-Gesture); one float64 sample promotes the batch, so that
+    # stamps in seconds never lose their microseconds to a narrower neighbour's dtype
+    dt = np.dtype(np.float32) if all(np.asarray(s).dtype == np.float32 for s in samples) else np.dtype(np.float64)
     arrs = [np.ascontiguousarray(s, dt).reshape(-1, 4) for s in samples]
     counts = np.array([a.shape[0] for a in arrs], np.int64)
     n = int(counts.sum())

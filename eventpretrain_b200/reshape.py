@@ -49,9 +49,10 @@ def target_normpix(frame, patch_size, norm_pix_loss=True, eps=1.0e-6):
     return out
 
 
-def target_patch_loss(pred, frame, patch_size, norm_pix_loss=True, eps=1.0e-6):
+def target_patch_loss(pred, frame, patch_size, norm_pix_loss=True, eps=1.0e-6, mask=None):
     """Per-patch mean((pred - target)^2), target built on the fly and never written   (pr_hub_model.py:126-134).
-    No autograd: use for evaluation / monitoring; training keeps target_normpix + torch ops for the gradient."""
+    mask (B,L), 1 = removed patch: only those patches are read, normalised and compared (the loss discards the rest, :139);
+    the others get 0.  No autograd: use for evaluation / monitoring; training keeps target_normpix + torch ops for the gradient."""
     require_cuda(pred, frame)
     frame = contiguous_f32(frame, "frame")
     pred = contiguous_f32(pred, "pred")
@@ -61,8 +62,15 @@ def target_patch_loss(pred, frame, patch_size, norm_pix_loss=True, eps=1.0e-6):
         raise ValueError("pred must be (B, L, p*p*c)")
     out = torch.empty((B, L), dtype=torch.float32, device=frame.device)
     with torch.cuda.device(frame.device):
-        rc = lib().ep_target_patch_loss(stream_ptr(frame.device), frame.data_ptr(), pred.data_ptr(), B, C, H, W,
-                                        patch_size, int(bool(norm_pix_loss)), float(eps), out.data_ptr())
+        if mask is None:
+            rc = lib().ep_target_patch_loss(stream_ptr(frame.device), frame.data_ptr(), pred.data_ptr(), B, C, H, W,
+                                            patch_size, int(bool(norm_pix_loss)), float(eps), out.data_ptr())
+        else:
+            mask = contiguous_f32(mask, "mask")
+            if tuple(mask.shape) != (B, L):
+                raise ValueError("mask must be (B, L)")
+            rc = lib().ep_target_patch_loss_masked(stream_ptr(frame.device), frame.data_ptr(), pred.data_ptr(), mask.data_ptr(), B, C, H, W,
+                                                   patch_size, int(bool(norm_pix_loss)), float(eps), out.data_ptr())
     _lib.check(rc, "ep_target_patch_loss")
     return out
 

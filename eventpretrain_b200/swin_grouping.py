@@ -17,7 +17,6 @@ from collections import OrderedDict
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from ._runtime import lib
@@ -74,34 +73,31 @@ class GroupingModule:
         self.attn_mask = None
         self.rel_pos_idx = None
 
-    def _get_group_id(self, coords):
-        group_id = coords.clone()
-        group_id += (self.window_size - self.shift_size) % self.window_size
-        group_id = group_id // self.window_size
-        return group_id[0, :, 0] * group_id.shape[1] + group_id[0, :, 1]
+    def _window_ids(self, ch):
+        """Window id of every visible token: ch (n, 2) int64 numpy (h, w) -> (n,) int64   (swin_block.py:363-366; the row
+        multiplier is the token count, as in the reference)."""
+        g = (ch + (self.window_size - self.shift_size) % self.window_size) // self.window_size
+        return g[:, 0] * ch.shape[0] + g[:, 1]
 
-    def _get_attn_mask(self, group_id):
-        pos_mask = (group_id == -1)
-        pos_mask = torch.logical_and(pos_mask[:, :, None], pos_mask[:, None, :])
-        gid = group_id.float()
-        attn_mask_float = gid.unsqueeze(2) - gid.unsqueeze(1)
-        attn_mask = torch.logical_or(attn_mask_float != 0, pos_mask)
-        attn_mask_float.masked_fill_(attn_mask, -100.)
-        return attn_mask_float
-
-    def _get_rel_pos_idx(self, coords):
-        rel_pos_idx = coords[:, :, None, :] - coords[:, None, :, :]
-        rel_pos_idx += self.window_size - 1
-        rel_pos_idx[..., 0] *= 2 * self.window_size - 1
-        return rel_pos_idx.sum(dim=-1)
+    def _tables(self, gid, coords, mask_rel, dev):
+        """(attn_mask f32, rel_pos_idx i64), each (nG, GS, GS), from the slots' window ids and coordinates: native host code
+        (ep_swin_group_tables_host), a few hundred KB at most, shipped to the device once per cached plan."""
+        gid = np.ascontiguousarray(gid, np.int64)
+        coords = np.ascontiguousarray(coords, np.int64)
+        nG, GS = gid.shape
+        attn = np.empty((nG, GS, GS), np.float32)
+        rel = np.empty((nG, GS, GS), np.int64)
+        rc = lib().ep_swin_group_tables_host(gid.ctypes.data, coords.ctypes.data, nG, GS, int(self.window_size), int(mask_rel),
+                                             attn.ctypes.data, rel.ctypes.data)
+        _lib.check(rc, "ep_swin_group_tables_host")
+        return torch.from_numpy(attn).to(dev), torch.from_numpy(rel).to(dev)
 
     def _prepare_masking(self, coords):
-        group_id = self._get_group_id(coords)
-        attn_mask = self._get_attn_mask(group_id.unsqueeze(0))
-        rel_pos_idx = self._get_rel_pos_idx(coords[:1])
+        # few tokens: one group holding all of them, attention restricted to the windows by the mask alone (:393-399)
+        ch = coords[0].detach().cpu().numpy().astype(np.int64)
         self.idx_shuffle = None
         self.idx_unshuffle = None
-        return attn_mask, rel_pos_idx
+        return self._tables(self._window_ids(ch)[None], ch[None], False, coords.device)
 
     def _prepare_grouping(self, coords):
         # The index bookkeeping runs on the host in numpy (the coordinates are a few KB; one small D2H copy instead of a
@@ -109,8 +105,7 @@ class GroupingModule:
         # back to the device, where the two (nG, GS, GS) tables are built.
         dev = coords.device
         ch = coords[0].detach().cpu().numpy().astype(np.int64)                       # (N_vis, 2)
-        g = (ch + (self.window_size - self.shift_size) % self.window_size) // self.window_size
-        group_id = g[:, 0] * ch.shape[0] + g[:, 1]                                    # :366 (the multiplier is N_vis, as in the reference)
+        group_id = self._window_ids(ch)
         idx_merge = np.argsort(group_id, kind="stable")
         gid_sorted = group_id[idx_merge]
         change = np.flatnonzero(np.diff(gid_sorted)) + 1
@@ -133,11 +128,7 @@ class GroupingModule:
         idx_shuffle = np.where(pad, 0, idx_shuffle)           # index_select does not permit negative index
         self.idx_shuffle = torch.from_numpy(idx_shuffle).to(dev)
         self.idx_unshuffle = torch.from_numpy(np.ascontiguousarray(idx_unshuffle)).to(dev)
-        attn_mask = self._get_attn_mask(torch.from_numpy(amask).to(dev))
-        coords_shuffled = torch.from_numpy(ch[idx_shuffle].reshape(-1, GS, 2)).to(dev)
-        rel_pos_idx = self._get_rel_pos_idx(coords_shuffled)
-        rel_pos_mask = torch.ones_like(rel_pos_idx).masked_fill_(attn_mask.bool(), 0)
-        return attn_mask, rel_pos_idx * rel_pos_mask
+        return self._tables(amask, ch[idx_shuffle].reshape(nG, GS, 2), True, dev)
 
     def prepare(self, coords, num_tokens):
         key = (self.window_size, self.shift_size, int(num_tokens), str(coords.device), coords[:1].cpu().numpy().tobytes())
@@ -159,8 +150,7 @@ class GroupingModule:
 
     def _select(self, x, idx):
         from .masking import gather_tokens
-        ids = idx.unsqueeze(0).expand(x.shape[0], -1).contiguous()
-        return gather_tokens(x, ids)
+        return gather_tokens(x, idx)          # batch-shared indices; carries the gradient (padded slots accumulate)
 
     def group(self, x):
         if self._mode == 'grouping':

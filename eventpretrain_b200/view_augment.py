@@ -13,8 +13,6 @@ import torch
 from . import _lib
 from ._runtime import contiguous_f32, lib, require_cuda, stream_ptr
 
-MODES = {"nearest": _lib.EP_RESIZE_NEAREST if hasattr(_lib, "EP_RESIZE_NEAREST") else 0, "bilinear": 1, "bicubic": 2}
-
 
 @dataclass
 class ViewChoice:
@@ -71,8 +69,12 @@ def apply_views(x, choices, size, mode="nearest"):
     require_cuda(x)
     x = contiguous_f32(x, "x")
     B, C, H, W = x.shape
+    if len(choices) != B:
+        raise ValueError(f"apply_views: {len(choices)} view choices for a batch of {B}")
     arr = (_lib.ViewParams * B)()
     for i, c in enumerate(choices):
+        if not (c.crop_w > 0 and c.crop_h > 0 and 0 <= c.crop_x and c.crop_x + c.crop_w <= W and 0 <= c.crop_y and c.crop_y + c.crop_h <= H):
+            raise ValueError(f"apply_views: crop box {(c.crop_x, c.crop_y, c.crop_w, c.crop_h)} of sample {i} leaves the {H}x{W} frame")
         arr[i] = _lib.ViewParams(c.crop_x, c.crop_y, c.crop_w, c.crop_h, int(c.hflip), int(c.time_flip), int(c.negate), 0)
     prm = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(x.device, non_blocking=True)
     out = torch.empty((B, C, int(size[0]), int(size[1])), dtype=torch.float32, device=x.device)

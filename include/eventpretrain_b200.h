@@ -241,6 +241,11 @@ EP_API int ep_patchify_normpix(void* stream, const float* frame, int batch, int 
  * (mask*loss).sum()/mask.sum() is two tiny reductions left to the caller. */
 EP_API int ep_target_patch_loss(void* stream, const float* frame, const float* pred, int batch, int channels,
                          int height, int width, int patch, int norm_pix, float eps, float* patch_loss);
+/* Same, computed only where the loss keeps it (pr_hub_model.py:139: `(mask * loss).sum() / mask.sum()`): mask (B,L) f32,
+ * 1 = removed patch = counted.  Patches with mask == 0 are neither read nor normalised; their patch_loss entry is 0, so the
+ * caller's (mask * patch_loss).sum() / mask.sum() is unchanged while 1 - mask_ratio of the target work disappears. */
+EP_API int ep_target_patch_loss_masked(void* stream, const float* frame, const float* pred, const float* mask, int batch,
+                                int channels, int height, int width, int patch, int norm_pix, float eps, float* patch_loss);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3 — masking, patchify, visible-token gather
@@ -301,10 +306,35 @@ EP_API int ep_swin_scatter_dense(void* stream, const float* x, const int64_t* co
 EP_API int ep_gather_tokens_nchw(void* stream, const float* feat, const int64_t* ids_keep, int batch, int L, int K, int D,
                           float* out);
 
+/* ConvViT feature fusion   model/backbone/convvit.py:137-140, 151-154, 166-167
+ * out[b,k,:] = (feat1[b,:,ids[b,k]] + feat2[b,:,ids[b,k]]) + emb3[b,k,:]: the two stage decoders' outputs (B,D,L) as the
+ * convolutions leave them, gathered by ids_keep (B,K) and added to the transformer stage's tokens emb3 (B,K,D; NULL = omit)
+ * in one launch — no flatten/permute copies, no separate gathers and adds.  Same association as the reference's sum. */
+EP_API int ep_gather_sum_nchw(void* stream, const float* feat1, const float* feat2, const float* emb3, const int64_t* ids_keep,
+                       int batch, int L, int K, int D, float* out);
+
 /* decoder un-shuffle   model/pretrain/pr_rec_decoder.py:56-62
  * out[b,l,:] = (ids_restore[b,l] < K ? emb[b, ids_restore[b,l], :] : mask_token[:]) + pos_embed[l,:]. */
 EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask_token, const float* pos_embed,
                         const int64_t* ids_restore, int batch, int L, int K, int D, float* out);
+
+/* Backward passes of the token permutations — the reference trains through these index ops (pr_trainer.py:26-36), so the
+ * drop-ins carry a gradient (torch.autograd.Function wrappers in eventpretrain_b200/masking.py).  D % 4 == 0.
+ * ep_scatter_add_tokens: out (B,L,D) = 0; out[b, ids[b,k], :] += grad[b,k,:]; ids (B,K) i64, or (K) shared by the batch when
+ *   ids_shared != 0.  Backward of ep_gather_tokens (vit.py:113-115), of GroupingModule.group / merge (swin_block.py:446-464;
+ *   padded slots repeat token 0, hence the accumulation) and of ep_swin_apply_mask (swin.py:154-179).
+ * ep_sum_over_batch: out[n] = sum_b in[b,n], fixed order (pos_embed / mask_token gradients).  n % 4 == 0.
+ * ep_unshuffle_tokens_bwd: backward of ep_unshuffle_tokens (pr_rec_decoder.py:56-62): grad_emb (B,K,D), grad_mask_token (D);
+ *   scratch: B*D floats.  The pos_embed gradient is ep_sum_over_batch of grad.
+ * ep_scatter_add_tokens_nchw: out (B,D,L) = 0; out[b,d,ids[b,k]] += grad[b,k,d]: backward of ep_gather_tokens_nchw
+ *   (swin.py:226-228); the backward of ep_swin_scatter_dense is ep_gather_tokens_nchw itself with the cells as indices. */
+EP_API int ep_scatter_add_tokens(void* stream, const float* grad, const int64_t* ids, int ids_shared, int batch, int L, int K,
+                          int D, float* out);
+EP_API int ep_sum_over_batch(void* stream, const float* in, int batch, int64_t n, float* out);
+EP_API int ep_unshuffle_tokens_bwd(void* stream, const float* grad, const int64_t* ids_restore, int batch, int L, int K, int D,
+                            float* grad_emb, float* grad_mask_token, float* scratch);
+EP_API int ep_scatter_add_tokens_nchw(void* stream, const float* grad, const int64_t* ids_keep, int batch, int L, int K, int D,
+                               float* out);
 
 /* Swin sparse-token grouping, HOST function, no device work:
  *   knapsack / group_windows   model/sub_module/swin_block.py:280-352 (called from GroupingModule._prepare_grouping :387-431)
@@ -314,6 +344,15 @@ EP_API int ep_unshuffle_tokens(void* stream, const float* emb, const float* mask
  * in increasing order; *n_groups groups (<= n_win).  Arrays sized n_win (group_first: n_win + 1). */
 EP_API int ep_swin_group_windows_host(int group_size, const int* num_ele_win, int n_win, int* num_ele_group, int* group_first,
                                       int* grouped_idx, int* n_groups);
+
+/* Attention tables of a window grouping, HOST function   model/sub_module/swin_block.py:368-385 (+ :424-431)
+ * group_id (n_groups, group_size) i64 window id per slot (-1 = padding), coords (n_groups, group_size, 2) i64 (h,w) ->
+ *   attn_mask (n_groups, gs, gs) f32: 0 where two slots share a window id (compared as float32, like the reference) and are
+ *     not both padding, else -100;
+ *   rel_pos_idx (n_groups, gs, gs) i64 = (dh + window-1) * (2*window-1) + (dw + window-1), zeroed where attn_mask != 0 when
+ *     mask_rel != 0 (the grouping mode's `rel_pos_idx * rel_pos_mask`). */
+EP_API int ep_swin_group_tables_host(const int64_t* group_id, const int64_t* coords, int n_groups, int group_size, int window,
+                                     int mask_rel, float* attn_mask, int64_t* rel_pos_idx);
 
 /* Ragged collate, HOST functions, multi-threaded (threads <= 0: all hardware threads), no device work.
  * The reference's DataLoader workers hand over per-sample (N,4) arrays with columns x, y, t, p (float64, or float32 for

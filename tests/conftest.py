@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are skipped (not errored) where no CUDA device exists, e.g. a plain `pytest` in the build container."""
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); run with -m gpu on the GPU box")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def _load(name):
     z = np.load(os.path.join(ROOT, "tests", "golden", name))
     cases = {}
@@ -45,6 +60,11 @@ def golden_views():
 @pytest.fixture(scope="session")
 def golden_swin_grouping():
     return _load("swin_grouping.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_swin_consumers():
+    return _load("swin_consumers.npz")
 
 
 @pytest.fixture(scope="session")

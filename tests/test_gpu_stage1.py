@@ -56,6 +56,30 @@ def test_dropins_vs_golden(ep, golden_stage1, name):
                               equal_nan=True)
 
 
+def test_mem_guard_normaliser(ep):
+    """EP_NORM_MEM_GUARD against the statements of ft_mvsec_dataset.py:244-249 (3-channel MEM image; channels 0 and 2 are scaled
+    by 1 / max, by 1 / 0.001 when that max is 0), executed in torch on the same tensors: bit-exact, batch of mixed cases."""
+    g = torch.Generator().manual_seed(77)
+    frames = torch.randint(0, 40, (5, 3, 33, 47), generator=g).float()
+    frames[1] = 0                              # an all-zero frame: the guard
+    frames[2, 0::2] = 0                        # only the untouched middle channel is populated
+    frames[3, 0::2] *= -1                      # max of the scaled channels is 0 with negative entries elsewhere
+    frames[3, 0, 0, 0] = 0
+    frames[4] /= 7                             # non-integer values: the division result is not exact
+    want = frames.clone()
+    for b in range(frames.shape[0]):
+        v = want[b]
+        if v[0::2, :, :].max() != 0:
+            factor = 1.0 / v[0::2, :, :].max()
+        else:
+            factor = 1.0 / 0.001
+        v[0::2, :, :] = v[0::2, :, :] * factor
+    got = ep.normalise(frames.cuda(), "mem_guard").cpu()
+    assert torch.equal(got, want)
+    one = ep.normalise(frames[4].clone().cuda(), "mem_guard").cpu()          # the (C,H,W) form
+    assert torch.equal(one, want[4])
+
+
 def test_fused_reshape_scale(ep, golden_stage1):
     """events_reshape fused as scale=(sx, sy): x*sx in fp64 then truncation (the 640->224 trap)."""
     for name in ("reshape_trap", "reshape_mvsec"):

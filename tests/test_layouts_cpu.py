@@ -131,6 +131,19 @@ def test_native_collate_equals_pack_events(dtype):
         ep.collate_events([np.array([[70000, 1, 0, 1]], dtype)], scale, pin=False)
 
 
+def test_collate_mixed_dtypes_promote_to_float64():
+    """A float32 first sample must not narrow the float64 samples behind it: stamps in seconds keep their microseconds."""
+    rng = np.random.default_rng(22)
+    t_us = np.sort(rng.integers(200_000_000, 200_250_000, 500))              # 200 s into the recording: fp32 would lose the us
+    wide = np.stack([rng.integers(0, 640, 500), rng.integers(0, 480, 500), t_us / 1e6, rng.integers(0, 2, 500)], 1)
+    narrow = np.array([[3, 4, 0.25, 1], [5, 6, 0.5, 0]], np.float32)
+    ev = ep.collate_events([narrow, wide], 1e6, pin=False)
+    lo = int(ev.offsets_host[1])
+    assert np.array_equal(ev.t.numpy()[lo:], t_us) and np.array_equal(ev.t.numpy()[:lo], [250_000, 500_000])
+    both32 = ep.collate_events([narrow, narrow], 1e6, pin=False)
+    assert np.array_equal(both32.t.numpy(), [250_000, 500_000] * 2)
+
+
 def test_native_compact_equals_the_numpy_rule():
     rng = np.random.default_rng(31)
     ev = _batch(rng, [3000, 0, 1, 70000, 2], span=2_000_000_000)

@@ -82,6 +82,12 @@ def test_batched_views_and_shared_seed(native_lib):
     for i in range(4):
         ref = _torch_apply(grids[i].cpu(), choices[i], (224, 224), "bilinear")
         assert torch.allclose(out[i].cpu(), ref, rtol=1e-5, atol=2e-6)
+    # a crop box that leaves the frame, or a choice list that does not match the batch, is refused on the host
+    bad = ep.ViewChoice(100, 0, 100, 50, False, False, False)
+    with pytest.raises(ValueError):
+        ep.apply_views(grids, [bad] * 4, (224, 224))
+    with pytest.raises(ValueError):
+        ep.apply_views(grids, choices[:3], (224, 224))
 
 
 def test_event_stream_augmentation_rng_mirror(golden_stream_aug):
