@@ -6,7 +6,8 @@
 Workload at every N (weak scaling: the same per-GPU batch on each rank): BASELINE.json configs[1] —
 an N-ImageNet-shaped ragged batch of 256 samples, 640x480 sensor, ~1M events/sample (+-20 %), time-sorted microsecond stamps
 uniform in a 0.3 s window, binned at sensor resolution into a 5-bin voxel grid plus the event-side
-difference-map target voxel.sum(0), plus the per-channel batch statistics that feed the path's one collective.  The batch is
+difference-map target voxel.sum(0) (the variant that also emits the per-channel batch statistics feeding the path's one
+collective is timed under extra.with_batch_statistics).  The batch is
 resident in the layout the collate step ships over PCIe: the densest lossless transport layout the stream fits
 (RaggedEvents.transport(): here 4 B/event; results bit-identical to the 13 B/event canonical SoA, whose number is under "extra").
 A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on rank 0.
@@ -287,11 +288,15 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
 
     def step(comm=True):
-        # the hot path: events -> voxel grid + voxel.sum(0) + batch statistics, one C-ABI call
+        # the hot path: events -> voxel grid + voxel.sum(0), one C-ABI call (no collective: samples are independent)
+        ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method)
+
+    def stats_step(comm=True):
+        # the same call with the per-channel batch statistics as a by-product of the sweep's flush, and (N > 1) the path's only
+        # collective: the small all-reduce of those statistics (SUM of count / sum / sum of squares, MAX of max) on a side
+        # stream, so that it never gates the next binning call
         ep.bin_events(ev, (H, W), num_bins=BINS, voxel_sum=True, out=out, method=args.method, stats=True)
         if world > 1 and comm:
-            # the path's only collective: the small all-reduce of the normalisation statistics the kernels just produced
-            # (SUM of count / sum / sum of squares, MAX of max), on a side stream so that it never gates the next binning call
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 reduced.copy_(out["stats"])
@@ -332,11 +337,14 @@ def run_ours(args):
     value = total_events * args.steps / (ms_total * 1e-3) / 1e9
     ms_step = ms_total / args.steps
 
-    # all-reduce overlap: the same K steps without the collective (N > 1)
-    ms_no_comm = None
+    # the statistics variant of the step (+ its all-reduce at N > 1), timed the same way
+    barrier()
+    ms_stats = allmax(timed_ms(stats_step, args.steps, warm=2))
+    ms_stats_no_comm = None
     if world > 1:
         barrier()
-        ms_no_comm = allmax(timed_ms(lambda: step(comm=False), args.steps, warm=1))
+        ms_stats_no_comm = allmax(timed_ms(lambda: stats_step(comm=False), args.steps, warm=1))
+        torch.cuda.synchronize()
 
     # ---- roofline: the same quotient at every N: algorithmic bytes of one rank's step / device time of the step ----
     L.ep_profile_enable(1)
@@ -357,16 +365,19 @@ def run_ours(args):
                 "frac_actual_layout_bytes": actual / (ms_step * 1e-3) / 1e9 / peak,
                 "actual_layout_bytes_per_step": actual,
                 "denominator": "device time of the whole step (CUDA events around the K timed steps), the same rule at every N",
-                "kernels": {"k_route_ms_per_step": route_ms, "k_sweep_ms_per_step": sweep_ms, "setup_and_statistics_ms_per_step": other_ms,
+                "kernels": {"k_route_ms_per_step": route_ms, "k_sweep_ms_per_step": sweep_ms, "setup_ms_per_step": other_ms,
                             "note": "each kernel timed alone with CUDA events around its launch (library instrumentation, profiling run "
                                     "after the timed region); they run back to back, their sum is the step"},
                 "algorithmic_bytes_per_step": alg,
                 "algorithmic_bytes_rule": f"SURVEY.md 8(d): 13 B/event canonical record + 4 B per output element, whatever the resident layout ({bpe:.1f} B/event here)"}
 
     extra = {}
-    if ms_no_comm is not None:
-        extra["allreduce_overlap"] = {"ms_per_step_with_allreduce": ms_step, "ms_per_step_without": ms_no_comm,
-                                      "note": "(6,4) fp64 statistics table, NCCL all-reduce SUM + MAX on a side stream"}
+    extra["with_batch_statistics"] = {
+        "what": "ep_bin_events_stats: the same step plus per-channel (count, sum, sum of squares, max) of the six output channels as a "
+                "by-product of the sweep's flush (bit-reproducible), feeding the path's one collective: the (6,4) fp64 all-reduce "
+                "(NCCL SUM + MAX) on a side stream at N > 1",
+        "ms_per_step": ms_stats, "Gevents_per_s": total_events / (ms_stats * 1e-3) / 1e9,
+        "ms_per_step_without_the_allreduce": ms_stats_no_comm}
 
     def gev(evx, method, size=(H, W), scale=(1.0, 1.0), o=None):
         o = out if o is None else o
@@ -377,7 +388,7 @@ def run_ours(args):
     #      reference's own pre-training does it (events_reshape to 224x224 fused, pr_n_imagenet_dataset.py:85-87) ----
     if world == 1:
         lay = {}
-        lay["packed_4B_tiled_path_Gevents_per_s (headline, without the statistics)"] = gev(ev, args.method)[0]
+        lay["packed_4B_tiled_path_Gevents_per_s (the headline step again)"] = gev(ev, args.method)[0]
         lay["packed_4B_global_RED_path_Gevents_per_s"] = gev(ev, "global")[0]
         lay["canonical_13B_layout_Gevents_per_s (global-RED path)"] = gev(ev13, args.method)[0]
         ev8 = host13.compact(threads=host_threads).to(dev)
@@ -579,8 +590,9 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "events_per_gpu": n_events, "layout": layout_name,
                            "stamps": "time-sorted int64 microseconds, uniform in a 0.3 s window per sample (SURVEY.md 8d)",
                            "cache": f"inputs ({host_gb:.1f} GB/GPU) and outputs (1.9 GB/GPU) exceed the 126 MB L2; no flush needed",
-                           "parallelism": f"shard-by-sample x{world}, no data-path collective; one (6,4) fp64 statistics all-reduce per step on a side stream",
-                           "method": args.method, "step": "ep_bin_events_stats: voxel grid + voxel.sum(0) + per-channel batch statistics"},
+                           "parallelism": f"shard-by-sample x{world}, no collective in the step (samples are independent); the statistics variant with its "
+                                          "(6,4) fp64 all-reduce is timed under extra.with_batch_statistics",
+                           "method": args.method, "step": "ep_bin_events: voxel grid + voxel.sum(0), one C-ABI call"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         emit(line)
     if world > 1:
@@ -659,20 +671,25 @@ def run_configs(ep, torch, dev, rank, world, peak, allmax, allsum, timed_ms):
     par = bool(close(o["voxel"][1].cpu().numpy(), oe.voxel_grid(sample_aos(h4, 1), bins, (h, w)))) if rank == 0 else None
     entry("C4 DSEC-shaped B=32 per GPU, 640x440, 15 bins, ~2M events/sample: voxel grid", ms, 13 * e4.num_events + 4 * bins * h * w * Bc,
           e4.num_events, "events", par, layout=layout_name_of(h4t)[0])
-    del o, t4, h4t
-    keep = {}
+    del o
+    keep = {"ev": torch.empty((Bc, 3, h, w), dtype=torch.float64, device=dev)}
 
     def do_evrep():
-        keep["ev"] = ep.evrep(e4, (h, w))
-    ms = timed_ms(do_evrep, 3, warm=1)
+        ep.evrep(t4, (h, w), out=keep["ev"])       # the transport layout: routed shared-memory path
+    ms = timed_ms(do_evrep, 5, warm=2)
+    ms_canon = timed_ms(lambda: ep.evrep(e4, (h, w), out=keep["ev"]), 2, warm=1)
+    do_evrep()
     par = None
     if rank == 0:
         s = sample_aos(h4, 1)
         # stamp value = ticks / t_div on both sides (the same fp64 quotient)
         par = bool(np.array_equal(keep["ev"][1].cpu().numpy(), oe.evrep(s[:, 0], s[:, 1], s[:, 2], s[:, 3], (w, h)), equal_nan=True))
     entry("C4 EvRep (3,440,640) f64, the pinned stand-in for the time surface (events_to_image.py:77-125)", ms,
-          13 * e4.num_events + 12 * h * w * Bc, e4.num_events, "events", par)
+          13 * e4.num_events + 12 * h * w * Bc, e4.num_events, "events", par, layout=layout_name_of(h4t)[0],
+          canonical_layout_global_sort_ms=allmax(ms_canon),
+          bytes_rule="13 B/event + 12 B per pixel (three planes at 4 B, as in round 1; the kernel writes the reference's float64: 24 B)")
     keep.clear()
+    del t4, h4t
     ms = timed_ms(lambda: ep.time_surface(e4, (h, w), tau=0.03), 5)
     entry("C4 exponential time surface (2,440,640) [parity unpinned: no reference routine, SURVEY F5]", ms,
           13 * e4.num_events + 8 * h * w * Bc, e4.num_events, "events", None)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ep_mem_hotpixel_workspace_bytes": (c_size_t, [c_int]),
     "ep_mem_hotpixel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_size_t]),
     "ep_evrep_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int64]),
+    "ep_evrep_workspace_bytes_for": (c_size_t, [c_void_p, c_int, c_int]),
     "ep_evrep": (c_int, [c_void_p, P(EventsSoa), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ep_time_surface_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ep_time_surface": (c_int, [c_void_p, P(EventsSoa), c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -246,6 +246,10 @@ __device__ __forceinline__ void bases_finish(const TiledArgs& a, const TaskDesc&
 // the chunk's run table), and its event words as soon as this chunk's are consumed.
 constexpr int kRouteWarps = kRouteThreads / 32;
 constexpr int kOffStride = kMaxTiles + 4;
+// TR = transposed tiles for EvRep: the tile and the row base come from x (tiles are column ranges, cells run x-major inside
+// a tile: the reference's lexsort order, events_to_image.py:104), the minor coordinate is y and must lie inside the grid
+// on its own (numpy's index check), a.H / a.W are then the image's width / height.
+template <bool TR>
 __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* lut_y = reinterpret_cast<uint32_t*>(smem_raw);                    // tile << 16 | (row in tile) * W
@@ -312,17 +316,23 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const uint32_t word = wv[q * 4 + e];
-                const uint32_t ly = lut_y[(word >> 11) & 0x7ffu];
-                const uint32_t xx = a.scaled ? lut_x[word & 0x7ffu] : (word & 0x7ffu);
+                const uint32_t fa = TR ? (word & 0x7ffu) : ((word >> 11) & 0x7ffu);      // major coordinate: tile, row base
+                const uint32_t fb = TR ? ((word >> 11) & 0x7ffu) : (word & 0x7ffu);      // minor coordinate
+                const uint32_t ly = lut_y[fa];
+                const uint32_t xx = (!TR && a.scaled) ? lut_x[fb] : fb;
                 const uint32_t cell = (ly & 0xffffu) + xx;
-                // x + y * W has no bound on x alone in the reference (events_to_voxel_grid.py:46): an x >= W stays correct while
-                // the sum stays inside the tile; anything that leaves it is redone exactly below (rare)
-                fix |= cell >= tc;
-                rt[q * 4 + e] = ly >> 16;
+                if (TR) {
+                    rt[q * 4 + e] = (fb < (uint32_t)a.W) ? (ly >> 16) : (uint32_t)NT;
+                } else {
+                    // x + y * W has no bound on x alone in the reference (events_to_voxel_grid.py:46): an x >= W stays correct while
+                    // the sum stays inside the tile; anything that leaves it is redone exactly below (rare)
+                    fix |= cell >= tc;
+                    rt[q * 4 + e] = ly >> 16;
+                }
                 wv[q * 4 + e] = pol2(word) + (cell << 2) + ((word >> 23) << fmt) + add;
             }
         }
-        if (fix) {
+        if (!TR && fix) {
             // cold: redo the thread's 16 events from the source words with the reference's own index arithmetic
 #pragma unroll 1
             for (int i = 0; i < kRouteEv; ++i) {
@@ -1016,7 +1026,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
+        cudaFuncSetAttribute(k_route<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
         cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
         cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
         attr_done = true;
@@ -1024,7 +1034,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     if (pl.n_tasks > 0) {
         const int grid = pl.n_tasks < 2 * kNumSMs ? pl.n_tasks : 2 * kNumSMs;
         profile_begin(st, kProfScatter);
-        k_route<<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        k_route<false><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
         profile_end(st);
         EP_LAUNCH_CHECK();
     }
@@ -1048,6 +1058,478 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
         EP_LAUNCH_CHECK();
         k_stats_final<<<n_out, 32, 0, st>>>(part2, (double)B * p->height * p->width, out_stats);
         profile_end(st);
+        EP_LAUNCH_CHECK();
+    }
+    return EP_OK;
+}
+
+// =====================================================================================================================
+// EvRep over the routed records   events_to_EvRep, dataset/dataset_utils/events_to_image.py:77-125
+//
+// The reference sorts the events with np.lexsort((t, y, x)) and accumulates, per pixel and in that order, the differences
+// of consecutive sorted stamps into float32 sums (np.add.at); the first event of a pixel is differenced against the last
+// event of the previous non-empty pixel in x-major order.  Here, for a ragged batch in the 4 B packed transport layout:
+//   * k_route<true>: the same route as the voxel path with transposed tiles — a tile is a range of columns, its cells run
+//     x-major, so the concatenation (sample, tile, cell) IS the lexsort order;
+//   * k_evrep_sweep (persistent CTAs, task = (sample, tile), two CTAs per SM):
+//       A  count per cell with one shared-memory atomic per record (events | positives << 16);
+//       -  block scan of the counts -> segment starts; the tile's own offset inside the sample is the sum of the bucket starts
+//          the route wrote, so the stamps of a sample land in a scratch array in exactly the reference's sorted order;
+//       B  every record's stamp (ticks relative to the sample's first row, u32) goes to its pixel's segment (one returning
+//          shared-memory atomic for the slot, one 4-byte store into the L2-resident scratch);
+//       -  the tile publishes the last stamp of its last non-empty pixel (decoupled look-back: the first non-empty pixel of a
+//          tile needs it from the nearest non-empty tile before; tasks are drawn in order, so the chain always advances);
+//       C  a warp takes 32 consecutive cells: their segments are one contiguous piece of the scratch, loaded coalesced into
+//          a per-warp staging buffer, each lane sorts its own short segment there and replays numpy's accumulation exactly
+//          (fp32 accumulators updated as (float)((double)acc + d), fp64 statistics of :117-120): bit-exact;
+//       D  E_C, E_I, E_T leave through a shared-memory transpose as row pieces of the (3, H, W) float64 output.
+// Limits reported through bad_count: bit 31 = more than 65535 events on one pixel of one sample, bit 30 = a stamp more than
+// 2^32 ticks away from (or before) the sample's first row.
+// =====================================================================================================================
+namespace {
+
+constexpr int kEvThreads = 512;
+constexpr int kEvWarps = kEvThreads / 32;
+constexpr int kEvTileCells = 5800;            // 16 B per cell of shared memory -> two CTAs per SM
+constexpr int kEvTab = 256;                   // chunks per run-table round
+constexpr int kEvStage = 192;                 // stamps of a warp's staging buffer
+
+struct EvRepArgs {
+    TiledArgs t;                // t.H = image width (major), t.W = image height (minor), t.rows = columns per tile
+    const int64_t* t_base;      // B, or null
+    double t_div;
+    double* out;                // (B, 3, Himg, Wimg)
+    uint32_t* sorted;           // stamps in lexsort order, indexed like rec
+    uint32_t* sorted2;          // second copy for segments sorted outside the staging buffer
+    long long* lb_val;          // per task: last stamp of the last non-empty pixel
+    int* lb_flag;               // per task: 0 = not yet, 1 = empty tile, 2 = value valid
+};
+
+__host__ __device__ inline size_t evrep_smem_bytes(int tile_cells) {
+    return (size_t)tile_cells * 16 + (size_t)kEvWarps * kEvStage * 4 + (size_t)kEvTab * 16 + 64;
+}
+
+__device__ __forceinline__ void sort_u32(uint32_t* s, int n) {
+    if (n <= 48) {
+        for (int i = 1; i < n; ++i) {
+            const uint32_t v = s[i];
+            int j = i - 1;
+            while (j >= 0 && s[j] > v) { s[j + 1] = s[j]; --j; }
+            s[j + 1] = v;
+        }
+        return;
+    }
+    for (int root0 = n / 2 - 1; root0 >= 0; --root0) {              // heapsort for hot pixels
+        int root = root0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= n) break;
+            if (child + 1 < n && s[child] < s[child + 1]) ++child;
+            if (s[root] >= s[child]) break;
+            const uint32_t tmp = s[root]; s[root] = s[child]; s[child] = tmp;
+            root = child;
+        }
+    }
+    for (int end = n - 1; end > 0; --end) {
+        const uint32_t tmp = s[0]; s[0] = s[end]; s[end] = tmp;
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && s[child] < s[child + 1]) ++child;
+            if (s[root] >= s[child]) break;
+            const uint32_t t2 = s[root]; s[root] = s[child]; s[child] = t2;
+            root = child;
+        }
+    }
+}
+
+// stamp of a record in ticks relative to the sample's first row
+__device__ __forceinline__ bool rec_ticks(uint32_t r, long long cbase, bool narrow, const uint32_t* crel, uint32_t& out) {
+    long long dt = cbase;
+    if (narrow) dt += (long long)(r >> 16);
+    else dt += (long long)crel[(r >> 16) & 31u] + (long long)(r >> 21);
+    out = (uint32_t)dt;
+    return dt >= 0 && dt < (1ll << 32);
+}
+
+__global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TiledArgs& a = e.t;
+    const int tile_cells = a.rows * a.W;
+    double* s_et = reinterpret_cast<double*>(smem_raw);                          // E_T per cell
+    uint32_t* s_cp = reinterpret_cast<uint32_t*>(s_et + tile_cells);             // events | positives << 16
+    uint32_t* s_st = s_cp + tile_cells;                                          // segment start, then cursor / end
+    uint32_t* s_stage = s_st + tile_cells;
+    long long* t_cb = reinterpret_cast<long long*>(s_stage + kEvWarps * kEvStage);
+    uint32_t* t_pos = reinterpret_cast<uint32_t*>(t_cb + kEvTab);
+    uint16_t* t_len = reinterpret_cast<uint16_t*>(t_pos + kEvTab);
+    uint16_t* t_nar = t_len + kEvTab;
+    __shared__ int s_task, s_warp[kEvWarps], s_last_cell, s_first_cell;
+    __shared__ unsigned int s_lastmax, s_tile_base, s_bad;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Himg = a.W, Wimg = a.H;                       // the route ran on the transposed image
+    const int64_t HW = (int64_t)Himg * Wimg;
+    const int n_sweep = a.B * a.NT;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_task = (int)atomicAdd(a.counters, 1u); s_lastmax = 0u; s_tile_base = 0u; s_bad = 0u; s_last_cell = -1; s_first_cell = 0x7fffffff; }
+        for (int i = tid; i < tile_cells; i += kEvThreads) s_cp[i] = 0u;
+        __syncthreads();
+        const int task = s_task;
+        if (task >= n_sweep) break;
+        const int b = task / a.NT, tile = task - b * a.NT;
+        const int first = a.first_task[b], nch = a.first_task[b + 1] - first;
+        const int col0 = tile * a.rows;
+        const int ncols = (Wimg - col0 < a.rows) ? Wimg - col0 : a.rows;
+        const int ncell = ncols * Himg;
+        const int cell0 = tile_cells - ncell;               // a narrower last tile sits at the end (k_route's lut_y)
+        const uint32_t sample_pos0 = nch > 0 ? a.cmeta[first].pos0 : 0u;
+
+        // ---- the two passes over the tile's runs share this walker: a warp takes one run at a time ----
+        auto walk = [&](auto&& table_hook, auto&& body) {
+            for (int c_round = 0; c_round < nch; c_round += kEvTab) {
+                const int ci = c_round + tid;
+                uint32_t o0v = 0;
+                if (tid < kEvTab) {
+                    if (ci < nch) {
+                        const ChunkMeta cm = a.cmeta[first + ci];
+                        const uint16_t* co = a.coff + (size_t)(first + ci) * a.off_stride + tile;
+                        const uint32_t o0 = co[0], o1 = co[1];
+                        t_pos[tid] = cm.pos0 + o0;
+                        t_len[tid] = (uint16_t)(o1 - o0);
+                        t_nar[tid] = (uint16_t)((cm.flags & kChunkNarrow) ? 1 : 0);
+                        t_cb[tid] = cm.cbase;
+                        o0v = o0;
+                    } else {
+                        t_len[tid] = 0;
+                    }
+                }
+                table_hook(o0v);
+                __syncthreads();
+                const int n_run = (nch - c_round < kEvTab) ? nch - c_round : kEvTab;
+                for (int r = wid; r < n_run; r += kEvWarps) {
+                    const int len = t_len[r];
+                    const uint32_t* p = a.rec + t_pos[r];
+                    const long long cb = t_cb[r];
+                    const bool nar = t_nar[r] != 0;
+                    const uint32_t* crel = a.crel + (size_t)(first + c_round + r) * 32;
+                    for (int i0 = 0; i0 < len; i0 += 128) {
+                        uint32_t rv[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = i0 + 32 * j + lane;
+                            rv[j] = (i < len) ? __ldcg(p + i) : 0xffffffffu;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (i0 + 32 * j + lane < len) body(rv[j], cb, nar, crel);
+                    }
+                }
+                __syncthreads();
+            }
+        };
+
+        // ---- A: events and positive events per cell; the tile's offset inside the sample = sum of the bucket starts ----
+        walk([&](uint32_t o0v) {
+                 uint32_t v = o0v;
+#pragma unroll
+                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                 if (lane == 0 && v) atomicAdd(&s_tile_base, v);
+             },
+             [&](uint32_t r, long long, bool, const uint32_t*) {
+                 const uint32_t cell = (r >> 2) & 0x3fffu;
+                 const uint32_t old = atomicAdd(&s_cp[cell], 1u + ((r & 2u) ? 0u : 0x10000u));
+                 if ((old & 0xffffu) == 0xffffu) atomicOr(&s_bad, 0x80000000u);
+             });
+
+        // ---- exclusive scan of the counts in cell (= x-major) order; first / last non-empty cell ----
+        {
+            const int per = (tile_cells + kEvThreads - 1) / kEvThreads;
+            const int c_lo = tid * per, c_hi = (c_lo + per < tile_cells) ? c_lo + per : tile_cells;
+            int sum = 0, lastc = -1, firstc = 0x7fffffff;
+            for (int c = c_lo; c < c_hi; ++c) {
+                const int n = (int)(s_cp[c] & 0xffffu);
+                if (n) { lastc = c; if (firstc == 0x7fffffff) firstc = c; }
+                sum += n;
+            }
+            const int incl = warp_incl_scan(sum, lane);
+            if (lane == 31) s_warp[wid] = incl;
+            if (lastc >= 0) { atomicMax(&s_last_cell, lastc); atomicMin(&s_first_cell, firstc); }
+            __syncthreads();
+            int wbase = 0;
+            for (int w = 0; w < wid; ++w) wbase += s_warp[w];
+            int run = wbase + incl - sum;
+            for (int c = c_lo; c < c_hi; ++c) { const int n = (int)(s_cp[c] & 0xffffu); s_st[c] = (uint32_t)run; run += n; }
+            __syncthreads();
+        }
+        const int last_cell = s_last_cell, first_cell = s_first_cell;
+        uint32_t* seg = e.sorted + sample_pos0 + s_tile_base;       // this tile's stamps, cells in order
+        uint32_t* seg2 = e.sorted2 + sample_pos0 + s_tile_base;
+
+        // ---- B: every stamp to its pixel's segment ----
+        walk([&](uint32_t) {},
+             [&](uint32_t r, long long cb, bool nar, const uint32_t* crel) {
+                 const uint32_t cell = (r >> 2) & 0x3fffu;
+                 uint32_t tk;
+                 if (!rec_ticks(r, cb, nar, crel, tk)) { atomicOr(&s_bad, 0x40000000u); tk = 0u; }
+                 const uint32_t slot = atomicAdd(&s_st[cell], 1u);
+                 seg[slot] = tk;
+                 if ((int)cell == last_cell) atomicMax(&s_lastmax, tk);
+             });
+        // (walk ends with a barrier: s_st[c] is now the END of cell c's segment, the stamps are in the scratch)
+
+        // ---- publish for the tiles behind; errors ----
+        if (tid == 0) {
+            if (last_cell >= 0) {
+                e.lb_val[task] = (long long)s_lastmax;
+                __threadfence();
+                *reinterpret_cast<volatile int*>(e.lb_flag + task) = 2;
+            } else {
+                __threadfence();
+                *reinterpret_cast<volatile int*>(e.lb_flag + task) = 1;
+            }
+            if (s_bad && a.bad_count) atomicOr(a.bad_count, s_bad);
+        }
+        __threadfence_block();
+
+        // ---- C: sort + replay, 32 consecutive cells per warp ----
+        const SampleMeta* mp = a.meta + b;
+        const long long abs0 = (e.t_base ? e.t_base[b] : 0) + mp->t0_ticks;
+        const double tdiv = e.t_div;
+        auto stamp = [&](uint32_t tk) -> double {
+            const double v = (double)(abs0 + (long long)tk);
+            return (tdiv != 1.0) ? v / tdiv : v;
+        };
+        uint32_t* stg = s_stage + wid * kEvStage;
+        const int n_groups = (tile_cells + 31) / 32;
+        for (int g = wid; g < n_groups; g += kEvWarps) {
+            const int c = g * 32 + lane;
+            int n = 0, end = 0;
+            if (c < tile_cells) { n = (int)(s_cp[c] & 0xffffu); end = (int)s_st[c]; }
+            const int beg = end - n;
+            const unsigned nz = __ballot_sync(0xffffffffu, n > 0);
+            if (!nz) { if (c < tile_cells) s_et[c] = 0.0; continue; }
+            const int lo_lane = __ffs(nz) - 1, hi_lane = 31 - __clz(nz);
+            const int r0 = __shfl_sync(0xffffffffu, beg, lo_lane), r1 = __shfl_sync(0xffffffffu, end, hi_lane);
+            const bool staged = (r1 - r0) <= kEvStage;
+            const uint32_t* mine;                                   // this lane's sorted stamps
+            if (staged) {
+                for (int j = lane; j < r1 - r0; j += 32) stg[j] = __ldcg(seg + r0 + j);
+                __syncwarp();
+                if (n > 1) sort_u32(stg + (beg - r0), n);
+                __syncwarp();
+                mine = stg + (beg - r0);
+            } else {
+                // a hot group: the lanes sort their segments in a second copy (the first stays as written: other warps read
+                // the multiset of a predecessor's stamps from it)
+                for (int j = 0; j < n; ++j) seg2[beg + j] = __ldcg(seg + beg + j);
+                if (n > 1) sort_u32(seg2 + beg, n);
+                mine = seg2 + beg;
+            }
+            // the stamp this cell's first event is differenced against
+            double prev = 0.0;
+            bool has_prev = false;
+            if (n > 0) {
+                const unsigned lower = nz & ((1u << lane) - 1u);
+                if (lower) {
+                    // (placeholder: filled by the shuffle below)
+                } else if (beg > 0) {
+                    // the previous non-empty cell of the tile lies in an earlier group: its stamps end at `beg`
+                    int cprev = c - 1;
+                    while ((s_cp[cprev] & 0xffffu) == 0u) --cprev;
+                    const int np = (int)(s_cp[cprev] & 0xffffu);
+                    uint32_t mx = 0;
+                    for (int j = 0; j < np; ++j) mx = max(mx, __ldcg(seg + beg - np + j));
+                    prev = stamp(mx); has_prev = true;
+                } else if (tile > 0) {
+                    // first non-empty cell of the tile: the nearest non-empty tile before it (decoupled look-back)
+                    for (int tj = task - 1; tj >= b * a.NT; --tj) {
+                        int f;
+                        while ((f = *reinterpret_cast<volatile int*>(e.lb_flag + tj)) == 0) __nanosleep(64);
+                        if (f == 2) {
+                            __threadfence();
+                            prev = stamp((uint32_t)*reinterpret_cast<volatile long long*>(e.lb_val + tj));
+                            has_prev = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            // last (largest) stamp of every lane's segment, for the lanes behind it in the group
+            const uint32_t my_last = (n > 0) ? mine[n - 1] : 0u;
+            {
+                const unsigned lower = nz & ((1u << lane) - 1u);
+                const int src = lower ? 31 - __clz(lower) : lane;
+                const uint32_t pl = __shfl_sync(0xffffffffu, my_last, src);
+                if (n > 0 && lower) { prev = stamp(pl); has_prev = true; }
+            }
+            if (c < tile_cells) {
+                float tsum = 0.f, tsq = 0.f;
+                if (n > 0) {
+                    double pv = has_prev ? prev : stamp(mine[0]);          // np.diff(prepend=sorted[0]), :110
+                    for (int k = 0; k < n; ++k) {
+                        const double t = stamp(mine[k]);
+                        const double d = __dsub_rn(t, pv);
+                        pv = t;
+                        tsum = (float)__dadd_rn((double)tsum, d);                        // np.add.at into float32, :113
+                        tsq = (float)__dadd_rn((double)tsq, __dmul_rn(d, d));            // :114
+                    }
+                }
+                const double cnt = (double)(n < 1 ? 1 : n);                              // :117
+                const double mean = __ddiv_rn((double)tsum, cnt);                         // :118
+                double v = __dsub_rn(__ddiv_rn((double)tsq, cnt), __dmul_rn(mean, mean)); // :119
+                if (!(v > 0.0)) v = (v != v) ? v : 0.0;
+                double et = sqrt(v);
+                if (et > 1000.0) et = 1000.0;                                             // :120
+                s_et[c] = et;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- D: (3, H, W) float64 rows: pieces of ncols consecutive x per image row ----
+        double* o = e.out + (int64_t)b * 3 * HW + col0;
+        for (int i = tid; i < ncell; i += kEvThreads) {
+            const int y = i / ncols, xl = i - y * ncols;
+            const int c = cell0 + xl * Himg + y;
+            const uint32_t cp = s_cp[c];
+            const int n = (int)(cp & 0xffffu), pos = (int)(cp >> 16);
+            double* q = o + (int64_t)y * Wimg + xl;
+            q[0] = (double)n;
+            q[HW] = (double)(2 * pos - n);
+            q[2 * HW] = s_et[c];
+        }
+        (void)first_cell;
+    }
+}
+
+}  // namespace
+
+// layout of the workspace of the tiled EvRep
+struct EvRepPlan {
+    TiledPlan t;
+    size_t off_sorted, off_sorted2, off_lbval, off_lbflag, total;
+};
+
+static bool evrep_plan(const ep_events_soa* ev, int height, int width, EvRepPlan& pl) {
+    if (ev->xy_dtype != EP_U32 || ev->t_dtype != 0 || ev->t != nullptr) return false;      // 4 B packed layout only
+    if (!ev->offsets_host || ev->batch <= 0) return false;
+    if (height > kEvTileCells || height > 2048 || width > 2048) return false;
+    int cols = kEvTileCells / height;
+    if (cols > width) cols = width;
+    int NT = (width + cols - 1) / cols;
+    if (NT > kMaxTiles) return false;
+    cols = (width + NT - 1) / NT;
+    NT = (width + cols - 1) / cols;
+    const int B = ev->batch;
+    int64_t tasks = 0;
+    for (int b = 0; b < B; ++b) {
+        const int64_t lo = ev->offsets_host[b], hi = ev->offsets_host[b + 1];
+        if (hi > lo) tasks += ((hi - 1) >> kChunkShift) - (lo >> kChunkShift) + 1;
+    }
+    if (tasks > (1ll << 30) || (int64_t)B * NT > (1ll << 30)) return false;
+    TiledPlan& t = pl.t;
+    t.NT = NT; t.rows = cols; t.n_tasks = (int)tasks;
+    t.rec_pos0 = (ev->offsets_host[0] >> kChunkShift) << kChunkShift;
+    t.n_rec = ev->offsets_host[B] - t.rec_pos0;
+    if (t.n_rec >= (1ll << 32)) return false;
+    const size_t nt = (size_t)(tasks ? tasks : 1);
+    const size_t nrec = (size_t)(t.n_rec > 0 ? t.n_rec : 1);
+    size_t o = 0;
+    t.off_meta = o; o += align_up(sizeof(SampleMeta) * (size_t)B, 256);
+    t.off_first = o; o += align_up(sizeof(int) * ((size_t)B + 1), 256);
+    t.off_desc = o; o += align_up(sizeof(TaskDesc) * nt, 256);
+    t.off_cmeta = o; o += align_up(sizeof(ChunkMeta) * nt, 256);
+    t.off_coff = o; o += align_up(sizeof(uint16_t) * nt * (size_t)(NT + 2), 256);
+    t.off_crel = o; o += align_up(sizeof(uint32_t) * nt * 32, 256);
+    t.off_counters = o; o += 256;
+    pl.off_lbflag = o; o += align_up(sizeof(int) * (size_t)B * NT, 256);          // zeroed together with the counters
+    pl.off_lbval = o; o += align_up(sizeof(long long) * (size_t)B * NT, 256);
+    t.off_stats = t.off_stats2 = o;
+    t.off_rec = o; o += align_up(sizeof(uint32_t) * nrec, 256);
+    pl.off_sorted = o; o += align_up(sizeof(uint32_t) * nrec, 256);
+    pl.off_sorted2 = o; o += align_up(sizeof(uint32_t) * nrec, 256);
+    t.total = pl.total = o;
+    return true;
+}
+
+size_t evrep_packed4_workspace_bytes(const ep_events_soa* ev, int height, int width) {
+    EvRepPlan pl;
+    return evrep_plan(ev, height, width, pl) ? pl.total : 0;
+}
+
+int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int width, double* out, void* ws, size_t ws_bytes,
+                      unsigned int* bad) {
+    EvRepPlan pl;
+    if (!evrep_plan(ev, height, width, pl)) return EP_EUNSUPPORTED;
+    if (!ws || ws_bytes < pl.total) return EP_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(ws) & 255u) return EP_EALIGN;
+    if (!out || !aligned16(ev->x)) return EP_EALIGN;
+    const int B = ev->batch;
+    char* base = static_cast<char*>(ws);
+    EvRepArgs e;
+    TiledArgs& a = e.t;
+    a.w = static_cast<const uint32_t*>(ev->x);
+    a.blk_base = static_cast<const uint32_t*>(ev->p);
+    a.offsets = ev->offsets;
+    a.n_total = ev->offsets_host[B];
+    a.rec_pos0 = pl.t.rec_pos0;
+    a.B = B; a.H = width; a.W = height; a.num_bins = 2;              // transposed: tiles are column ranges
+    a.NT = pl.t.NT; a.rows = pl.t.rows; a.off_stride = pl.t.NT + 2;
+    a.sx = a.sy = 1.0; a.scaled = 0;
+    a.n_tasks = pl.t.n_tasks;
+    a.meta = reinterpret_cast<SampleMeta*>(base + pl.t.off_meta);
+    a.first_task = reinterpret_cast<int*>(base + pl.t.off_first);
+    a.desc = reinterpret_cast<TaskDesc*>(base + pl.t.off_desc);
+    a.cmeta = reinterpret_cast<ChunkMeta*>(base + pl.t.off_cmeta);
+    a.coff = reinterpret_cast<uint16_t*>(base + pl.t.off_coff);
+    a.crel = reinterpret_cast<uint32_t*>(base + pl.t.off_crel);
+    a.counters = reinterpret_cast<unsigned int*>(base + pl.t.off_counters);
+    a.rec = reinterpret_cast<uint32_t*>(base + pl.t.off_rec);
+    a.bad_count = bad;
+    a.out_voxel = nullptr; a.out_sum = nullptr; a.stats_part = nullptr;
+    e.t_base = ev->t_base; e.t_div = ev->t_div; e.out = out;
+    e.sorted = reinterpret_cast<uint32_t*>(base + pl.off_sorted);
+    e.sorted2 = reinterpret_cast<uint32_t*>(base + pl.off_sorted2);
+    e.lb_val = reinterpret_cast<long long*>(base + pl.off_lbval);
+    e.lb_flag = reinterpret_cast<int*>(base + pl.off_lbflag);
+
+    SoaPackedLoader<false> ld{a.w, nullptr, a.blk_base, ev->t_base, ev->t_div};
+    BinArgs ba = {};
+    ba.offsets = ev->offsets; ba.num_bins = 2; ba.meta = a.meta;
+    k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
+    EP_LAUNCH_CHECK();
+    k_tiled_setup<<<1, 1024, 0, st>>>(a);
+    EP_LAUNCH_CHECK();
+    cudaError_t ce = cudaMemsetAsync(a.counters, 0, pl.off_lbval - pl.t.off_counters, st);      // task counter + look-back flags
+    if (ce != cudaSuccess) return (int)ce;
+    static bool attr_done = false;
+    static int sweep_ctas_per_sm = 0;
+    const size_t smem = evrep_smem_bytes(kEvTileCells);
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_route<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
+        cudaFuncSetAttribute(k_evrep_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_ctas_per_sm, k_evrep_sweep, kEvThreads, smem);
+        attr_done = true;
+    }
+    if (sweep_ctas_per_sm < 1) return EP_EUNSUPPORTED;
+    if (pl.t.n_tasks > 0) {
+        const int grid = pl.t.n_tasks < 2 * kNumSMs ? pl.t.n_tasks : 2 * kNumSMs;
+        k_route<true><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        EP_LAUNCH_CHECK();
+    }
+    {
+        // every CTA must be resident: the look-back of a tile waits for tiles drawn earlier
+        int dev = 0, sms = kNumSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t n_sweep = (int64_t)B * pl.t.NT;
+        const int64_t cap = (int64_t)sms * sweep_ctas_per_sm;
+        const int grid = (int)(n_sweep < cap ? n_sweep : cap);
+        k_evrep_sweep<<<grid, kEvThreads, smem, st>>>(e);
         EP_LAUNCH_CHECK();
     }
     return EP_OK;

@@ -42,6 +42,12 @@ inline bool patch_tma_disabled() {
     return on == 0;
 }
 
+// csrc/ep_binning_tiled.cu: EvRep for the 4 B packed transport layout (transposed route + shared-memory sweep);
+// EP_EUNSUPPORTED = layout / shape does not qualify.  Workspace bytes 0 = does not qualify.
+size_t evrep_packed4_workspace_bytes(const ep_events_soa* ev, int height, int width);
+int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int width, double* out, void* ws, size_t ws_bytes,
+                      unsigned int* bad);
+
 // ---- streaming loads / stores (events and finished outputs are touched exactly once) ------------
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }

@@ -266,12 +266,21 @@ size_t ep_evrep_workspace_bytes(int batch, int height, int width, int64_t n_tota
     return ep::rep_layout(batch, height, width, n_total).total;
 }
 
+size_t ep_evrep_workspace_bytes_for(const ep_events_soa* ev, int height, int width) {
+    if (!ev || !ev->offsets_host || ev->batch <= 0 || height <= 0 || width <= 0) return 0;
+    const size_t tiled = ep::evrep_packed4_workspace_bytes(ev, height, width);
+    if (tiled) return tiled;
+    return ep_evrep_workspace_bytes(ev->batch, height, width, ev->offsets_host[ev->batch] - ev->offsets_host[0]);
+}
+
 int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, double* out, void* workspace,
              size_t workspace_bytes, unsigned int* bad_count) {
     using namespace ep;
     if (!ev || !out || !workspace || ev->batch <= 0 || height <= 0 || width <= 0) return EP_EINVAL;
     if (!ev->offsets || !ev->offsets_host) return EP_EINVAL;
-    if (ev->t_base || ev->xy_dtype == EP_U32 || ev->t_dtype == EP_U32) return EP_EUNSUPPORTED;   // transport layouts: ep_bin_events only
+    if (ev->xy_dtype == EP_U32 && ev->t_dtype == 0 && ev->t == nullptr)      // 4 B packed transport layout: route + shared-memory sweep
+        return run_evrep_packed4(static_cast<cudaStream_t>(stream), ev, height, width, out, workspace, workspace_bytes, bad_count);
+    if (ev->t_base || ev->xy_dtype == EP_U32 || ev->t_dtype == EP_U32) return EP_EUNSUPPORTED;   // the other transport layouts: ep_bin_events only
     if (!valid_dtype(ev->xy_dtype) || !valid_dtype(ev->t_dtype) || !valid_dtype(ev->p_dtype) || !(ev->t_div != 0.0))
         return EP_EINVAL;
     const int B = ev->batch;

@@ -494,21 +494,29 @@ def mem_hotpixel(hist, num_stds=10.0, divide_by=1.0):
     return hist
 
 
-def evrep(ev, size, check=False):
-    """Batched EvRep: (B,3,H,W) float64 = [E_C, E_I, E_T] (events_to_image.py:77-125)."""
+def evrep(ev, size, check=False, out=None):
+    """Batched EvRep: (B,3,H,W) float64 = [E_C, E_I, E_T] (events_to_image.py:77-125).  Canonical / generic layouts take the
+    global counting sort; the 4 B packed transport layout (`RaggedEvents.transport()` on dense streams) takes the routed
+    shared-memory path, bit-identical (stamp value = (t_base + ticks) / t_div in both)."""
     require_cuda(ev.x)
     dev = ev.device
     H, W = size
     B = ev.batch
-    out = torch.empty((B, 3, H, W), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((B, 3, H, W), dtype=torch.float64, device=dev)
     L = lib()
-    ws = workspace(L.ep_evrep_workspace_bytes(B, H, W, ev.num_events), dev, "evrep")
-    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
     desc = ev._desc()
+    ws = workspace(L.ep_evrep_workspace_bytes_for(ctypes.byref(desc), H, W), dev, "evrep")
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
     with torch.cuda.device(dev):
         rc = L.ep_evrep(stream_ptr(dev), ctypes.byref(desc), H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), ptr(bad))
     _lib.check(rc, "ep_evrep")
     if check:
+        v = int(bad.item())
+        if v & 0x80000000:
+            raise OverflowError("EvRep: more than 65535 events on one pixel of one sample (routed path)")
+        if v & 0x40000000:
+            raise BadEventsError("EvRep: a stamp lies before, or 2^32 ticks or more after, its sample's first row (routed path)")
         _raise_bad(bad)
     return out
 

@@ -189,6 +189,11 @@ EP_API int ep_mem_hotpixel(void* stream, float* hist, int batch, int height, int
  * counting-sorted by pixel in the reference's lexsort order and each pixel's deltas are accumulated
  * sequentially with numpy's add.at rounding. */
 EP_API size_t ep_evrep_workspace_bytes(int batch, int height, int width, int64_t n_total);
+/* Same, knowing the batch: the 4 B packed transport layout takes the routed path (events bucketed into column tiles, per-tile
+ * counting sort and replay in shared memory; timestamp value = (t_base[b] + ticks) / t_div), whose workspace also holds the
+ * routed records.  bad_count then also reports: bit 31 = more than 65535 events on one pixel of one sample, bit 30 = a stamp
+ * before, or 2^32 ticks or more after, the sample's first row. */
+EP_API size_t ep_evrep_workspace_bytes_for(const ep_events_soa* ev, int height, int width);
 EP_API int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, double* out,
              void* workspace, size_t workspace_bytes, unsigned int* bad_count);
 
