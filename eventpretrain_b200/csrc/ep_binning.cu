@@ -349,6 +349,7 @@ size_t l2_group_budget() {
     // accumulator bytes a group touches, kept L2-resident: measured on B200 with the bench workload (5 samples = 49 MB -> 97.2,
     // 6 = 59 MB -> 99.1, 7 = 69 MB -> 93.1, 8 = 79 MB -> 86.5 Gev/s; 64 rather than 60 lets two 15-bin 640x440 samples
     // (63 MB) share a group: C4 0.81-0.83 -> 0.77-0.83 ms, C5 1.33 -> 1.28 ms)
+    // (read per call, ~0.1 us: tests/test_gpu_stage1.py::test_group_chain_orderings changes it between calls to force one-sample groups)
     const char* e = getenv("EP_L2_GROUP_MB");
     long mb = e ? atol(e) : 64;
     if (mb < 1) mb = 1;
@@ -377,14 +378,13 @@ cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, b
 }
 
 bool persist_l2_enabled() {
-    const char* e = getenv("EP_PERSIST_L2");
-    return e ? atoi(e) != 0 : false;
+    static const bool on = [] { const char* e = getenv("EP_PERSIST_L2"); return e ? atoi(e) != 0 : false; }();
+    return on;
 }
 
 int scatter_ctas_per_sm() {
-    const char* e = getenv("EP_SCATTER_CTAS_PER_SM");
-    int v = e ? atoi(e) : 8;
-    return v < 1 ? 1 : v;
+    static const int v = [] { const char* e = getenv("EP_SCATTER_CTAS_PER_SM"); const int n = e ? atoi(e) : 8; return n < 1 ? 1 : n; }();
+    return v;
 }
 
 int check_params(const ep_bin_params* p) {

@@ -76,6 +76,7 @@ struct TiledArgs {
     int64_t rec_pos0;           // array position of rec[0] (multiple of kChunk)
     int B, H, W, num_bins;
     int NT, rows;               // row tiles per plane, rows per tile
+    int rep_shift;              // log2 of the rank-counter replicas per tile in the route (fewer same-address atomics)
     int off_stride;             // NT + 2 bucket offsets per task
     double sx, sy;
     int scaled;
@@ -98,7 +99,9 @@ __device__ __forceinline__ void pdl_wait_t() { asm volatile("griddepcontrol.wait
 __device__ __forceinline__ void pdl_trigger_t() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- setup: route tasks per sample ---------------------------------------------------------------------------------
-// task c of sample b covers the part of array chunk (offsets[b] >> 13) + c that belongs to the sample
+// task c of sample b covers the part of array chunk (offsets[b] >> 13) + c that belongs to the sample.
+// k_tiled_setup: first_task[b] = tasks of the samples before b (one CTA: a scan over the batch);
+// k_tiled_desc: one thread per task finds its sample by bisection and writes the descriptor.
 __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
@@ -108,9 +111,8 @@ __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
     for (int b0 = 0; b0 < a.B; b0 += 1024) {
         const int b = b0 + tid;
         int n = 0;
-        int64_t lo = 0, hi = 0;
         if (b < a.B) {
-            lo = a.offsets[b]; hi = a.offsets[b + 1];
+            const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
             if (hi > lo) n = (int)(((hi - 1) >> kChunkShift) - (lo >> kChunkShift)) + 1;
         }
         const int incl = warp_incl_scan(n, lane);
@@ -123,22 +125,29 @@ __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
         }
         __syncthreads();
         const int first = s_carry + s_warp[wid] + incl - n;
-        if (b < a.B) {
-            a.first_task[b] = first;
-            for (int c = 0; c < n; ++c) {
-                const int64_t c0 = ((lo >> kChunkShift) + c) << kChunkShift;
-                const uint32_t s_lo = (uint32_t)((lo > c0 ? lo : c0) - c0);
-                const uint32_t s_hi = (uint32_t)((hi < c0 + kChunk ? hi : c0 + kChunk) - c0);
-                TaskDesc d;
-                d.c0 = c0; d.b = b; d.lohi = s_lo | (s_hi << 16);
-                a.desc[first + c] = d;
-            }
-        }
+        if (b < a.B) a.first_task[b] = first;
         __syncthreads();
         if (tid == 1023) s_carry = first + n;
         __syncthreads();
     }
     if (tid == 0) a.first_task[a.B] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) k_tiled_desc(TiledArgs a) {
+    const int task = blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= a.n_tasks) return;
+    int lo_b = 0, hi_b = a.B;                          // largest b with first_task[b] <= task (empty samples share a value:
+    while (hi_b - lo_b > 1) {                          // the last of them is the one that owns tasks)
+        const int mid = (lo_b + hi_b) >> 1;
+        if (a.first_task[mid] <= task) lo_b = mid; else hi_b = mid;
+    }
+    const int b = lo_b, c = task - a.first_task[b];
+    const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
+    const int64_t c0 = ((lo >> kChunkShift) + c) << kChunkShift;
+    TaskDesc d;
+    d.c0 = c0; d.b = b;
+    d.lohi = (uint32_t)((lo > c0 ? lo : c0) - c0) | ((uint32_t)((hi < c0 + kChunk ? hi : c0 + kChunk) - c0) << 16);
+    a.desc[task] = d;
 }
 
 // ---- route ---------------------------------------------------------------------------------------------------------
@@ -262,6 +271,9 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NT = a.NT, NB = NT + 1;          // bucket NT = trash (coordinates outside the grid)
+    // every bucket has 2^rs rank counters, picked by the lane: with few tiles most lanes of a warp would hit the same word
+    const uint32_t rs = (uint32_t)a.rep_shift, rep = (uint32_t)lane & ((1u << rs) - 1u);
+    const int NBs = NB << rs;                   // sub-buckets (<= kMaxTiles + 1)
     uint32_t* s_off = s_off0 + wid * kOffStride;
     pdl_trigger_t();
     // events_reshape: x * (input_w / sensor_w) in fp64, truncated by the .long() of the binning call
@@ -322,12 +334,12 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
                 const uint32_t xx = (!TR && a.scaled) ? lut_x[fb] : fb;
                 const uint32_t cell = (ly & 0xffffu) + xx;
                 if (TR) {
-                    rt[q * 4 + e] = (fb < (uint32_t)a.W) ? (ly >> 16) : (uint32_t)NT;
+                    rt[q * 4 + e] = (((fb < (uint32_t)a.W) ? (ly >> 16) : (uint32_t)NT) << rs) + rep;
                 } else {
                     // x + y * W has no bound on x alone in the reference (events_to_voxel_grid.py:46): an x >= W stays correct while
                     // the sum stays inside the tile; anything that leaves it is redone exactly below (rare)
                     fix |= cell >= tc;
-                    rt[q * 4 + e] = ly >> 16;
+                    rt[q * 4 + e] = ((ly >> 16) << rs) + rep;
                 }
                 wv[q * 4 + e] = pol2(word) + (cell << 2) + ((word >> 23) << fmt) + add;
             }
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
                 const uint32_t rec = pol2(word) + (cell << 2) + ((word >> 23) << fmt) + addq;
                 // (static indexing: the arrays stay in registers)
 #pragma unroll
-                for (int j = 0; j < kRouteEv; ++j) if (j == i) { wv[j] = rec; rt[j] = tile; }
+                for (int j = 0; j < kRouteEv; ++j) if (j == i) { wv[j] = rec; rt[j] = (tile << rs) + rep; }
             }
         }
         if (full) {
@@ -374,7 +386,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
         {
             uint32_t c[3], sum = 0;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { const int t = lane * 3 + j; c[j] = (t < NB) ? (s_cnt[t] & 0xffffu) : 0u; sum += c[j]; }
+            for (int j = 0; j < 3; ++j) { const int t = lane * 3 + j; c[j] = (t < NBs) ? (s_cnt[t] & 0xffffu) : 0u; sum += c[j]; }
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
@@ -383,12 +395,21 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int t = lane * 3 + j;
-                if (t <= NB) { s_off[t] = run - ((uint32_t)t << 16); if (wid == 0) co[t] = (uint16_t)run; }
+                if (t <= NBs) {
+                    s_off[t] = run - ((uint32_t)t << 16);
+                    if (wid == 0 && (t & ((1 << rs) - 1)) == 0) co[t >> rs] = (uint16_t)run;      // a tile's records start at its first sub-bucket
+                }
                 run += c[j];
             }
-            if (tid == 0 && a.bad_count) {
-                const uint32_t nbad = s_cnt[NT] & 0xffffu;
-                if (nbad) atomicAdd(a.bad_count, nbad);
+            if (wid == 0 && a.bad_count) {
+                // events outside the grid: the sub-buckets of the trash bucket
+                const int t0 = NT << rs;
+                uint32_t nbad = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { const int t = lane * 3 + j; if (t >= t0 && t < NBs) nbad += c[j]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
+                if (lane == 0 && nbad) atomicAdd(a.bad_count, nbad);
             }
         }
         BasesRegs br;
@@ -884,6 +905,16 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
     }
 }
 
+// rank-counter replicas per bucket of the route: as many (a power of two, 4 or 8) as keep (tiles + trash) * replicas + 1
+// within the kMaxTiles + 2 counter words
+static int route_rep_shift(int NT) {
+    // measured on B200: 224x224 (4 tiles, 8 replicas) route 0.93 -> 0.76 ms per 255 M events; 640x480 (24 tiles, 2 replicas)
+    // 0.69 -> 0.74 (the lanes already spread over 25 words; two more scan entries per lane cost more): replicate from 4 up only
+    int rs = 0;
+    while (rs < 3 && (((NT + 1) << (rs + 1)) + 1) <= kMaxTiles + 2) ++rs;
+    return rs >= 2 ? rs : 0;
+}
+
 struct TiledPlan {
     int NT, rows, n_tasks;
     int64_t rec_pos0, n_rec;
@@ -996,6 +1027,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     a.rec_pos0 = pl.rec_pos0;
     a.B = B; a.H = p->height; a.W = p->width; a.num_bins = p->num_bins;
     a.NT = pl.NT; a.rows = pl.rows; a.off_stride = pl.NT + 2;
+    a.rep_shift = route_rep_shift(pl.NT);
     a.sx = p->scale_x; a.sy = p->scale_y; a.scaled = (p->scale_x != 1.0 || p->scale_y != 1.0);
     a.n_tasks = pl.n_tasks;
     a.meta = reinterpret_cast<SampleMeta*>(base + pl.off_meta);
@@ -1020,6 +1052,10 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     EP_LAUNCH_CHECK();
     k_tiled_setup<<<1, 1024, 0, st>>>(a);
     EP_LAUNCH_CHECK();
+    if (a.n_tasks > 0) {
+        k_tiled_desc<<<(a.n_tasks + 255) / 256, 256, 0, st>>>(a);
+        EP_LAUNCH_CHECK();
+    }
     cudaError_t ce = cudaMemsetAsync(a.counters, 0, 256, st);
     if (ce != cudaSuccess) return (int)ce;
     profile_end(st);
@@ -1090,9 +1126,9 @@ namespace {
 
 constexpr int kEvThreads = 512;
 constexpr int kEvWarps = kEvThreads / 32;
-constexpr int kEvTileCells = 5800;            // 16 B per cell of shared memory -> two CTAs per SM
+constexpr int kEvTileCells = 5400;            // 8 B per cell of shared memory + the staging buffers -> two CTAs per SM
 constexpr int kEvTab = 256;                   // chunks per run-table round
-constexpr int kEvStage = 192;                 // stamps of a warp's staging buffer
+constexpr int kEvStage = 960;                 // stamps of a warp's staging buffer
 
 struct EvRepArgs {
     TiledArgs t;                // t.H = image width (major), t.W = image height (minor), t.rows = columns per tile
@@ -1101,12 +1137,14 @@ struct EvRepArgs {
     double* out;                // (B, 3, Himg, Wimg)
     uint32_t* sorted;           // stamps in lexsort order, indexed like rec
     uint32_t* sorted2;          // second copy for segments sorted outside the staging buffer
+    double* et_scratch;         // per CTA: E_T of the tile's cells (L2-resident), read back transposed for the output rows
+    double t_rcp;               // 1 / t_div, correctly rounded
     long long* lb_val;          // per task: last stamp of the last non-empty pixel
     int* lb_flag;               // per task: 0 = not yet, 1 = empty tile, 2 = value valid
 };
 
 __host__ __device__ inline size_t evrep_smem_bytes(int tile_cells) {
-    return (size_t)tile_cells * 16 + (size_t)kEvWarps * kEvStage * 4 + (size_t)kEvTab * 16 + 64;
+    return (size_t)tile_cells * 8 + (size_t)kEvWarps * kEvStage * 4 + (size_t)kEvTab * 16 + 64;
 }
 
 __device__ __forceinline__ void sort_u32(uint32_t* s, int n) {
@@ -1157,12 +1195,12 @@ __global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TiledArgs& a = e.t;
     const int tile_cells = a.rows * a.W;
-    double* s_et = reinterpret_cast<double*>(smem_raw);                          // E_T per cell
-    uint32_t* s_cp = reinterpret_cast<uint32_t*>(s_et + tile_cells);             // events | positives << 16
+    long long* t_cb = reinterpret_cast<long long*>(smem_raw);
+    uint32_t* s_cp = reinterpret_cast<uint32_t*>(t_cb + kEvTab);                 // events | positives << 16
     uint32_t* s_st = s_cp + tile_cells;                                          // segment start, then cursor / end
     uint32_t* s_stage = s_st + tile_cells;
-    long long* t_cb = reinterpret_cast<long long*>(s_stage + kEvWarps * kEvStage);
-    uint32_t* t_pos = reinterpret_cast<uint32_t*>(t_cb + kEvTab);
+    double* s_et = e.et_scratch + (size_t)blockIdx.x * kEvTileCells;             // E_T per cell (global, stays in L2)
+    uint32_t* t_pos = s_stage + kEvWarps * kEvStage;
     uint16_t* t_len = reinterpret_cast<uint16_t*>(t_pos + kEvTab);
     uint16_t* t_nar = t_len + kEvTab;
     __shared__ int s_task, s_warp[kEvWarps], s_last_cell, s_first_cell;
@@ -1298,15 +1336,26 @@ __global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
         // ---- C: sort + replay, 32 consecutive cells per warp ----
         const SampleMeta* mp = a.meta + b;
         const long long abs0 = (e.t_base ? e.t_base[b] : 0) + mp->t0_ticks;
-        const double tdiv = e.t_div;
+        const double tdiv = e.t_div, trcp = e.t_rcp;
+        // stamp value = ticks / t_div, correctly rounded like the reference's fp64 division: with y = RN(1 / t_div), q = RN(x y)
+        // lies within one ulp of x / t_div, and RN(q + (x - t_div q) y) is then the correctly rounded quotient (Markstein)
         auto stamp = [&](uint32_t tk) -> double {
             const double v = (double)(abs0 + (long long)tk);
-            return (tdiv != 1.0) ? v / tdiv : v;
+            if (tdiv == 1.0) return v;
+            const double q = __dmul_rn(v, trcp);
+            const double r = __fma_rn(-q, tdiv, v);
+            return __fma_rn(r, trcp, q);
         };
         uint32_t* stg = s_stage + wid * kEvStage;
-        const int n_groups = (tile_cells + 31) / 32;
+        // cells per warp step: 32, or fewer on dense tiles so that their stamps (mean + margin) fit the staging buffer
+        int gs = 32;
+        {
+            const int total = (last_cell >= 0) ? (int)s_st[last_cell] : 0;        // events of the tile
+            while (gs > 1 && (int64_t)gs * total * 3 / 2 + 16LL * ncell > (int64_t)kEvStage * ncell) gs >>= 1;
+        }
+        const int n_groups = (tile_cells + gs - 1) / gs;
         for (int g = wid; g < n_groups; g += kEvWarps) {
-            const int c = g * 32 + lane;
+            const int c = (lane < gs) ? g * gs + lane : tile_cells;
             int n = 0, end = 0;
             if (c < tile_cells) { n = (int)(s_cp[c] & 0xffffu); end = (int)s_st[c]; }
             const int beg = end - n;
@@ -1400,7 +1449,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
             double* q = o + (int64_t)y * Wimg + xl;
             q[0] = (double)n;
             q[HW] = (double)(2 * pos - n);
-            q[2 * HW] = s_et[c];
+            q[2 * HW] = __ldcg(s_et + c);
         }
         (void)first_cell;
     }
@@ -1411,7 +1460,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
 // layout of the workspace of the tiled EvRep
 struct EvRepPlan {
     TiledPlan t;
-    size_t off_sorted, off_sorted2, off_lbval, off_lbflag, total;
+    size_t off_sorted, off_sorted2, off_lbval, off_lbflag, off_et, total;
 };
 
 static bool evrep_plan(const ep_events_soa* ev, int height, int width, EvRepPlan& pl) {
@@ -1448,6 +1497,7 @@ static bool evrep_plan(const ep_events_soa* ev, int height, int width, EvRepPlan
     t.off_counters = o; o += 256;
     pl.off_lbflag = o; o += align_up(sizeof(int) * (size_t)B * NT, 256);          // zeroed together with the counters
     pl.off_lbval = o; o += align_up(sizeof(long long) * (size_t)B * NT, 256);
+    pl.off_et = o; o += align_up(sizeof(double) * (size_t)kEvTileCells * 2 * 256, 256);      // up to 512 resident CTAs
     t.off_stats = t.off_stats2 = o;
     t.off_rec = o; o += align_up(sizeof(uint32_t) * nrec, 256);
     pl.off_sorted = o; o += align_up(sizeof(uint32_t) * nrec, 256);
@@ -1479,6 +1529,7 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     a.rec_pos0 = pl.t.rec_pos0;
     a.B = B; a.H = width; a.W = height; a.num_bins = 2;              // transposed: tiles are column ranges
     a.NT = pl.t.NT; a.rows = pl.t.rows; a.off_stride = pl.t.NT + 2;
+    a.rep_shift = route_rep_shift(pl.t.NT);
     a.sx = a.sy = 1.0; a.scaled = 0;
     a.n_tasks = pl.t.n_tasks;
     a.meta = reinterpret_cast<SampleMeta*>(base + pl.t.off_meta);
@@ -1491,7 +1542,8 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     a.rec = reinterpret_cast<uint32_t*>(base + pl.t.off_rec);
     a.bad_count = bad;
     a.out_voxel = nullptr; a.out_sum = nullptr; a.stats_part = nullptr;
-    e.t_base = ev->t_base; e.t_div = ev->t_div; e.out = out;
+    e.t_base = ev->t_base; e.t_div = ev->t_div; e.t_rcp = 1.0 / ev->t_div; e.out = out;
+    e.et_scratch = reinterpret_cast<double*>(base + pl.off_et);
     e.sorted = reinterpret_cast<uint32_t*>(base + pl.off_sorted);
     e.sorted2 = reinterpret_cast<uint32_t*>(base + pl.off_sorted2);
     e.lb_val = reinterpret_cast<long long*>(base + pl.off_lbval);
@@ -1504,6 +1556,10 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     EP_LAUNCH_CHECK();
     k_tiled_setup<<<1, 1024, 0, st>>>(a);
     EP_LAUNCH_CHECK();
+    if (a.n_tasks > 0) {
+        k_tiled_desc<<<(a.n_tasks + 255) / 256, 256, 0, st>>>(a);
+        EP_LAUNCH_CHECK();
+    }
     cudaError_t ce = cudaMemsetAsync(a.counters, 0, pl.off_lbval - pl.t.off_counters, st);      // task counter + look-back flags
     if (ce != cudaSuccess) return (int)ce;
     static bool attr_done = false;
@@ -1527,7 +1583,8 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int64_t n_sweep = (int64_t)B * pl.t.NT;
-        const int64_t cap = (int64_t)sms * sweep_ctas_per_sm;
+        int64_t cap = (int64_t)sms * sweep_ctas_per_sm;
+        if (cap > 512) cap = 512;                            // E_T scratch slots
         const int grid = (int)(n_sweep < cap ? n_sweep : cap);
         k_evrep_sweep<<<grid, kEvThreads, smem, st>>>(e);
         EP_LAUNCH_CHECK();

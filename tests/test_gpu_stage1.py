@@ -370,8 +370,9 @@ def test_packed_transport_layout(ep):
     b = ep.bin_events(p4.to("cuda"), (H, W), num_bins=5, count_channels=3, voxel_sum=True, check=True)
     for key in ("voxel", "voxel_sum", "count"):
         assert torch.equal(a[key], b[key]), key
+    assert torch.equal(ep.evrep(p4.to("cuda"), (H, W), check=True), ep.evrep(host.to("cuda"), (H, W), check=True))   # routed EvRep
     with pytest.raises(RuntimeError):
-        ep.evrep(p4.to("cuda"), (H, W))                 # transport layouts are for ep_bin_events only
+        ep.evrep(pk.to("cuda"), (H, W))                 # the 5 B and 8 B transport layouts are for ep_bin_events only
 
 
 def test_full_size_properties(ep):
