@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        cmd = [NVCC, *FLAGS, *os.environ.get("EP_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]      # e.g. -DEP_ITEM_RPL=2 (experiments)
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -48,7 +48,17 @@ constexpr int kRouteEv = kChunk / kRouteThreads;   // 16 events per thread, as 4
 constexpr int kSweepThreads = 512;
 constexpr int kTabCap = kSweepThreads;        // chunks of one sample whose run table is resident (one per thread)
 constexpr int kItemCap = 384;                 // items (<= 128 records each, 8-byte descriptors) listed per round of a phase
-constexpr int kItemRecs = 128;
+#ifndef EP_ITEM_RPL
+#define EP_ITEM_RPL 4
+#endif
+#ifndef EP_ITEM_DEPTH
+#define EP_ITEM_DEPTH 2
+#endif
+constexpr int kItemRPL = EP_ITEM_RPL;         // records per lane and item
+constexpr int kItemDepth = EP_ITEM_DEPTH;     // items whose records are in flight ahead of the current one (1 or 2)
+constexpr int kItemRecs = 32 * kItemRPL;
+static_assert(kItemRPL >= 1 && kItemRPL <= 4, "the item descriptor holds records - 1 in 7 bits");
+// measured on B200, sweep of the 256-sample batch: 64-record items 1.046 ms, 96 1.008, 128 0.953 (kept)
 constexpr int kSpillCap = 128;
 
 constexpr uint32_t kChunkFast = 1u;           // integer-tick sample, narrow records, every v of the chunk fits 32 bits
@@ -258,7 +268,9 @@ constexpr int kOffStride = kMaxTiles + 4;
 // TR = transposed tiles for EvRep: the tile and the row base come from x (tiles are column ranges, cells run x-major inside
 // a tile: the reference's lexsort order, events_to_image.py:104), the minor coordinate is y and must lie inside the grid
 // on its own (numpy's index check), a.H / a.W are then the image's width / height.
-template <bool TR>
+// REP: every bucket has 2^rep_shift rank counters, picked by the lane (grids with few tiles, where most lanes of a warp would
+// hit the same counter word).  (Tried and dropped: tile / row base by multiply-high instead of the y table, 0.728 -> 0.748 ms.)
+template <bool TR, bool REP = false>
 __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* lut_y = reinterpret_cast<uint32_t*>(smem_raw);                    // tile << 16 | (row in tile) * W
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NT = a.NT, NB = NT + 1;          // bucket NT = trash (coordinates outside the grid)
     // every bucket has 2^rs rank counters, picked by the lane: with few tiles most lanes of a warp would hit the same word
-    const uint32_t rs = (uint32_t)a.rep_shift, rep = (uint32_t)lane & ((1u << rs) - 1u);
+    const uint32_t rs = REP ? (uint32_t)a.rep_shift : 0u, rep = REP ? ((uint32_t)lane & ((1u << rs) - 1u)) : 0u;
     const int NBs = NB << rs;                   // sub-buckets (<= kMaxTiles + 1)
     uint32_t* s_off = s_off0 + wid * kOffStride;
     pdl_trigger_t();
@@ -682,14 +694,14 @@ __device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_b
 
 struct ItemRegs {
     uint2 d;             // .x = first record, .y = chunk slot | (records - 1) << 9 | slow << 16
-    uint32_t r0, r1, r2, r3;
+    uint32_t r[kItemRPL];
 };
 
-// The items (<= 128 records of one run) of a phase are dealt to the warps round-robin (they cost the same but for run
+// The items (<= kItemRecs records of one run) of a phase are dealt to the warps round-robin (they cost the same but for run
 // tails, and a shared counter would put an atomic and a shuffle on every item); the records of the next two items are in
 // flight while the current one is accumulated.
 // Fast path per record: v = (Q + ticks * tmul) >> tshift, two returning atomics, no branch (events of other intervals and
-// lanes past the end add zero); the returned values of the item's 8 atomics are screened together for words that came
+// lanes past the end add zero); the returned values of the item's atomics are screened together for words that came
 // near the int32 range (rare -> exact check, spill list).
 template <bool HAS_RIGHT>
 __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& c, const SampleMeta* mp, uint32_t tmul, uint32_t tshift,
@@ -701,52 +713,54 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
         const uint32_t cnt = ((g.d.y >> 9) & 127u) + 1u;
         const uint32_t* p = a.rec + g.d.x + lane;
         // lanes past the end of the item get a harmless record of their own (cell = lane): its weights are forced to 0 below
-        g.r0 = ((uint32_t)lane < cnt) ? ld_stream(p) : (uint32_t)lane << 2;
-        g.r1 = ((uint32_t)lane + 32u < cnt) ? ld_stream(p + 32) : (uint32_t)lane << 2;
-        g.r2 = ((uint32_t)lane + 64u < cnt) ? ld_stream(p + 64) : (uint32_t)lane << 2;
-        g.r3 = ((uint32_t)lane + 96u < cnt) ? ld_stream(p + 96) : (uint32_t)lane << 2;
+#pragma unroll
+        for (int j = 0; j < kItemRPL; ++j) g.r[j] = ((uint32_t)lane + 32u * j < cnt) ? ld_stream(p + 32 * j) : (uint32_t)lane << 2;
     };
     ItemRegs n1, n2;
     n1.d = n2.d = make_uint2(0u, 0u);
-    n1.r0 = n1.r1 = n1.r2 = n1.r3 = n2.r0 = n2.r1 = n2.r2 = n2.r3 = 0u;
+#pragma unroll
+    for (int j = 0; j < kItemRPL; ++j) n1.r[j] = n2.r[j] = 0u;
     int it = wid;
     if (it < n_items) load(it, n1);
-    if (it + kWarps < n_items) load(it + kWarps, n2);
+    if (kItemDepth > 1 && it + kWarps < n_items) load(it + kWarps, n2);
     for (; it < n_items; it += kWarps) {
         const ItemRegs cur = n1;
-        n1 = n2;
-        if (it + 2 * kWarps < n_items) load(it + 2 * kWarps, n2);
-        const uint32_t r[4] = {cur.r0, cur.r1, cur.r2, cur.r3};
+        if (kItemDepth > 1) {
+            n1 = n2;
+            if (it + 2 * kWarps < n_items) load(it + 2 * kWarps, n2);
+        } else {
+            if (it + kWarps < n_items) load(it + kWarps, n1);
+        }
         const uint32_t slot = cur.d.y & 511u;
         const uint32_t cnt = ((cur.d.y >> 9) & 127u) + 1u;
         if (!(cur.d.y >> 16)) {
             const uint64_t Q = t_q[slot];                                    // cbase * tmul + thalf
-            int o0[4], o1[4];
-            uint32_t u[4];
+            int o0[kItemRPL], o1[kItemRPL];
+            uint32_t u[kItemRPL];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint64_t q = (uint64_t)(r[j] >> 16) * tmul + Q;
+            for (int j = 0; j < kItemRPL; ++j) {
+                const uint64_t q = (uint64_t)(cur.r[j] >> 16) * tmul + Q;
                 const uint32_t v = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), tshift);
                 u[j] = v - c.kbase;
                 const bool ok = (uint32_t)lane + 32u * j < cnt && u[j] < (1u << kQ);
-                const int sgn = ok ? sgn2(r[j]) : 0;
-                const uint32_t boff = r[j] & 0xfffcu;                        // cell * 4
+                const int sgn = ok ? sgn2(cur.r[j]) : 0;
+                const uint32_t boff = cur.r[j] & 0xfffcu;                    // cell * 4
                 const int wr = (int)u[j] * sgn, wl = (sgn << kQ) - wr;
                 o0[j] = atoms_add(c.pl0s + boff, wl);
                 o1[j] = HAS_RIGHT ? atoms_add(c.pl1s + boff, wr) : 0;
             }
             uint32_t m = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kItemRPL; ++j) {
                 m = max(m, (uint32_t)o0[j] + 0x7f000000u);
                 if (HAS_RIGHT) m = max(m, (uint32_t)o1[j] + 0x7f000000u);
             }
             if (m >= 0xfe000000u) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kItemRPL; ++j) {
                     const bool ok = (uint32_t)lane + 32u * j < cnt && u[j] < (1u << kQ);
-                    const int sgn = ok ? sgn2(r[j]) : 0;
-                    const uint32_t cell = (r[j] & 0xfffcu) >> 2;
+                    const int sgn = ok ? sgn2(cur.r[j]) : 0;
+                    const uint32_t cell = (cur.r[j] & 0xfffcu) >> 2;
                     const int wr = (int)u[j] * sgn, wl = (sgn << kQ) - wr;
                     if (near_wrap(o0[j])) note_wrap(o0[j], wl, cell | ((uint32_t)c.k << 16), c.spill, c.n_spill, c.bad);
                     if (HAS_RIGHT && near_wrap(o1[j])) note_wrap(o1[j], wr, cell | ((uint32_t)(c.k + 1) << 16), c.spill, c.n_spill, c.bad);
@@ -754,9 +768,9 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < kItemRPL; ++j)
                 if ((uint32_t)lane + 32u * j < cnt)
-                    sweep_record_slow(a.cmeta + task0 + slot, a.crel + (size_t)(task0 + slot) * 32, a.num_bins, c, mp, r[j], HAS_RIGHT);
+                    sweep_record_slow(a.cmeta + task0 + slot, a.crel + (size_t)(task0 + slot) * 32, a.num_bins, c, mp, cur.r[j], HAS_RIGHT);
         }
     }
 }
@@ -1063,6 +1077,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_route<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
+        cudaFuncSetAttribute(k_route<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
         cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
         cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
         attr_done = true;
@@ -1070,7 +1085,8 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     if (pl.n_tasks > 0) {
         const int grid = pl.n_tasks < 2 * kNumSMs ? pl.n_tasks : 2 * kNumSMs;
         profile_begin(st, kProfScatter);
-        k_route<false><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        if (a.rep_shift) k_route<false, true><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        else k_route<false><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
         profile_end(st);
         EP_LAUNCH_CHECK();
     }
@@ -1567,6 +1583,7 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     const size_t smem = evrep_smem_bytes(kEvTileCells);
     if (!attr_done) {
         cudaFuncSetAttribute(k_route<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
+        cudaFuncSetAttribute(k_route<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
         cudaFuncSetAttribute(k_evrep_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweep_ctas_per_sm, k_evrep_sweep, kEvThreads, smem);
         attr_done = true;
@@ -1574,7 +1591,8 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     if (sweep_ctas_per_sm < 1) return EP_EUNSUPPORTED;
     if (pl.t.n_tasks > 0) {
         const int grid = pl.t.n_tasks < 2 * kNumSMs ? pl.t.n_tasks : 2 * kNumSMs;
-        k_route<true><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        if (a.rep_shift) k_route<true, true><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
+        else k_route<true><<<grid, kRouteThreads, kRouteSmem, st>>>(a);
         EP_LAUNCH_CHECK();
     }
     {
