@@ -42,10 +42,16 @@ constexpr int kChunkShift = 13;
 constexpr int kChunk = 1 << kChunkShift;      // events per route task = 32 tick blocks of the 4 B layout
 constexpr int kTickBlockShift = 8;            // 256-event tick blocks (SoaPackedLoader<false>)
 constexpr int kMaxTiles = 64;
-constexpr int kTileCells = 12800;             // cells of a plane tile: two live planes = 100 KB -> two sweep CTAs per SM
+#ifndef EP_SWEEP_THREADS
+#define EP_SWEEP_THREADS 512
+#define EP_SWEEP_CTAS 2
+#define EP_TILE_CELLS 12800
+#endif
+constexpr int kTileCells = EP_TILE_CELLS;     // cells of a plane tile: two live planes = 100 KB -> two sweep CTAs per SM
 constexpr int kRouteThreads = 512;
 constexpr int kRouteEv = kChunk / kRouteThreads;   // 16 events per thread, as 4 quads
-constexpr int kSweepThreads = 512;
+constexpr int kSweepThreads = EP_SWEEP_THREADS;
+constexpr int kSweepCtas = EP_SWEEP_CTAS;     // resident sweep CTAs per SM
 constexpr int kTabCap = kSweepThreads;        // chunks of one sample whose run table is resident (one per thread)
 constexpr int kItemCap = 384;                 // items (<= 128 records each, 8-byte descriptors) listed per round of a phase
 #ifndef EP_ITEM_RPL
@@ -778,7 +784,7 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <bool VEC>
-__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(TiledArgs a) {
+__global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_cells = a.rows * a.W;
     int* plane0 = reinterpret_cast<int*>(smem_raw);
@@ -1092,7 +1098,7 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     }
     {
         const int64_t n_sweep = (int64_t)B * pl.NT;
-        const int grid = n_sweep < 2 * kNumSMs ? (int)n_sweep : 2 * kNumSMs;
+        const int grid = n_sweep < kSweepCtas * kNumSMs ? (int)n_sweep : kSweepCtas * kNumSMs;
         const size_t smem = sweep_smem_bytes(pl.rows * p->width);
         const bool vec = (p->width % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
         profile_begin(st, kProfFinalize);
@@ -1140,11 +1146,17 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
 // =====================================================================================================================
 namespace {
 
-constexpr int kEvThreads = 512;
+#ifndef EP_EV_THREADS
+#define EP_EV_THREADS 512
+#define EP_EV_CTAS 2
+#define EP_EV_STAGE 960
+#endif
+constexpr int kEvThreads = EP_EV_THREADS;
+constexpr int kEvCtas = EP_EV_CTAS;           // CTAs per SM the shared-memory budget is sized for
 constexpr int kEvWarps = kEvThreads / 32;
 constexpr int kEvTileCells = 5400;            // 8 B per cell of shared memory + the staging buffers -> two CTAs per SM
 constexpr int kEvTab = 256;                   // chunks per run-table round
-constexpr int kEvStage = 960;                 // stamps of a warp's staging buffer
+constexpr int kEvStage = EP_EV_STAGE;         // stamps of a warp's staging buffer
 
 struct EvRepArgs {
     TiledArgs t;                // t.H = image width (major), t.W = image height (minor), t.rows = columns per tile
@@ -1207,7 +1219,7 @@ __device__ __forceinline__ bool rec_ticks(uint32_t r, long long cbase, bool narr
     return dt >= 0 && dt < (1ll << 32);
 }
 
-__global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
+__global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TiledArgs& a = e.t;
     const int tile_cells = a.rows * a.W;
@@ -1270,15 +1282,16 @@ __global__ void __launch_bounds__(kEvThreads, 2) k_evrep_sweep(EvRepArgs e) {
                     const long long cb = t_cb[r];
                     const bool nar = t_nar[r] != 0;
                     const uint32_t* crel = a.crel + (size_t)(first + c_round + r) * 32;
-                    for (int i0 = 0; i0 < len; i0 += 128) {
-                        uint32_t rv[4];
+                    // a run holds ~150 records at this tile size: all of its loads are issued before the first use
+                    for (int i0 = 0; i0 < len; i0 += 256) {
+                        uint32_t rv[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 8; ++j) {
                             const int i = i0 + 32 * j + lane;
                             rv[j] = (i < len) ? __ldcg(p + i) : 0xffffffffu;
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 8; ++j)
                             if (i0 + 32 * j + lane < len) body(rv[j], cb, nar, crel);
                     }
                 }
