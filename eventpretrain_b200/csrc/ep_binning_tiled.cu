@@ -893,21 +893,10 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a
                     for (int i = 0; i < len; i += 32) prefetch_l2(p + i);
                 }
             }
-            // Last phase: publish the next task and request its run-table sources (chunk headers, bucket offsets) into L2.
-            if (!has_right && tid == kSweepThreads - 1) {
-                const int nt = next_task;
-                s_task = nt;
-                if (nt < n_sweep) {
-                    const int nb = nt / a.NT, ntile = nt - nb * a.NT;
-                    const int nf = a.first_task[nb], nn = a.first_task[nb + 1] - nf;
-                    const char* cmp = reinterpret_cast<const char*>(a.cmeta + nf);
-                    for (int i = 0; i < nn * (int)sizeof(ChunkMeta); i += 128) prefetch_l2(cmp + i);
-                    const char* cop = reinterpret_cast<const char*>(a.coff + (size_t)nf * a.off_stride + ntile);
-                    const int span = nn * a.off_stride * 2;
-                    for (int i = 0; i < span; i += 128) prefetch_l2(cop + i);
-                    prefetch_l2(a.meta + nb);
-                }
-            }
+            // Last phase: publish the next task (drawn before the accumulation, so the atomic's latency is already paid).
+            // (Requesting the next task's chunk headers into L2 here was measured: no gain, and the dependent first_task
+            // loads make this warp late for the flush.)
+            if (!has_right && tid == kSweepThreads - 1) s_task = next_task;
             // plane k is complete: fp32 out (+ running voxel.sum(0)), buffer re-zeroed -> plane k + 2
             const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
             float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
