@@ -90,7 +90,7 @@ typedef struct ep_events_soa {
     double t_div;
     const int64_t* offsets;      /* device, B+1 entries, offsets[0] may be > 0 */
     const int64_t* offsets_host; /* host copy of the same B+1 entries (required: sizes the launches) */
-    const int64_t* t_base;       /* device, B entries, or NULL.  Transport layouts (ep_bin_events only), both bit-identical
+    const int64_t* t_base;       /* device, B entries, or NULL.  Transport layouts (ep_bin_events; the 4 B form also ep_evrep), bit-identical
                                     in results to the int64 canonical layout; timestamp value = (t_base[b] + ticks) / t_div:
                                     - compact, 8 B/event: t_dtype = EP_U32 holds ticks relative to t_base[b] in bits
                                       0..30 and the polarity in bit 31, p = NULL;

@@ -65,7 +65,8 @@ def test_gather_tokens_shared_ids_with_duplicates(ep):
     out = ep.gather_tokens(x, idx)
     ref = torch.index_select(x, 1, idx)
     assert torch.equal(out, ref)
-    torch.testing.assert_close(grads(out, (x,))[0], grads(ref, (x,))[0], rtol=1e-6, atol=1e-6)
+    # token 0 receives 29 gradient rows: fp32 atomics in either implementation, the order differs
+    torch.testing.assert_close(grads(out, (x,))[0], grads(ref, (x,))[0], rtol=1e-5, atol=1e-5)
 
 
 def test_grouping_module_carries_gradient(ep, golden_swin_grouping):
