@@ -583,27 +583,57 @@ struct StatAcc {
     __device__ __forceinline__ void add(float v) { s1 += v; s2 = fmaf(v, v, s2); mx = fmaxf(mx, v); }
 };
 
+// voxel.sum(0) is formed at the LAST plane only (EP_DEFERRED_SUM, default): the earlier planes of the same cells are read back
+// from the output tensor (written a few phases ago by this very thread with L2-resident stores), added in the reference's
+// order ((p0 + p1) + p2 ...) and the sum is written once.  The flushes of the other planes then consist of stores only —
+// nothing to wait for — where the running-sum form paid an L2 round trip per plane.  Same fp32 additions: bit-identical.
+#ifndef EP_DEFERRED_SUM
+#define EP_DEFERRED_SUM 1
+#endif
+
 template <bool VEC, bool FIRST, bool LAST, bool SUM, bool STATS>
-__device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so,
+__device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so, int64_t plane_stride,
                                               const int2* spill, int n_spill, int key0, StatAcc& sa, StatAcc& ss) {
     constexpr float kInv = 1.0f / 16777216.0f;
+    constexpr bool kDeferred = EP_DEFERRED_SUM != 0;
+    constexpr bool kReadBack = kDeferred && SUM && LAST && !FIRST;        // this flush adds planes 0 .. k-1 from the output
+    constexpr bool kRunning = !kDeferred && SUM;                         // the running-sum form
     if (VEC) {
         constexpr int kStep = kSweepThreads * 4;
-        for (int i0 = threadIdx.x * 4; i0 < ncell; i0 += kStep * kFlushUnroll) {
-            int4 q[kFlushUnroll];
-            float4 s[kFlushUnroll];
+        constexpr int kU = kReadBack ? 2 : kFlushUnroll;
+        for (int i0 = threadIdx.x * 4; i0 < ncell; i0 += kStep * kU) {
+            int4 q[kU];
+            float4 s[kU];
 #pragma unroll
-            for (int u = 0; u < kFlushUnroll; ++u) {
+            for (int u = 0; u < kU; ++u) {
                 const int i = i0 + u * kStep;
                 q[u] = make_int4(0, 0, 0, 0);
                 s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i < ncell) {
                     q[u] = *reinterpret_cast<const int4*>(pl + i);
-                    if (SUM && !FIRST) s[u] = __ldcg(reinterpret_cast<const float4*>(so + i));
+                    if (kRunning && !FIRST) s[u] = __ldcg(reinterpret_cast<const float4*>(so + i));
+                }
+            }
+            if (kReadBack) {
+                for (int j0 = 0; j0 < k; j0 += 4) {
+                    float4 v[kU][4];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int i = i0 + u * kStep;
+                            v[u][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (i < ncell && j0 + jj < k) v[u][jj] = __ldcg(reinterpret_cast<const float4*>(o + (int64_t)(j0 + jj - k) * plane_stride + i));
+                        }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (j0 + jj < k) { s[u].x += v[u][jj].x; s[u].y += v[u][jj].y; s[u].z += v[u][jj].z; s[u].w += v[u][jj].w; }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kFlushUnroll; ++u) {
+            for (int u = 0; u < kU; ++u) {
                 const int i = i0 + u * kStep;
                 if (i < ncell) {
                     *reinterpret_cast<int4*>(pl + i) = make_int4(0, 0, 0, 0);
@@ -619,9 +649,11 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
                             if (hi) fp[j] = __ll2float_rn((hi << 32) + (long long)qi[j]) * kInv;
                         }
                     }
-                    st_stream(reinterpret_cast<float4*>(o + i), f);
+                    // planes that the last flush reads back stay in L2 (plain store); everything else streams out
+                    if (kDeferred && SUM && !LAST) __stcg(reinterpret_cast<float4*>(o + i), f);
+                    else st_stream(reinterpret_cast<float4*>(o + i), f);
                     if (STATS) { sa.add(f.x); sa.add(f.y); sa.add(f.z); sa.add(f.w); }
-                    if (SUM) {
+                    if (kRunning || (kDeferred && SUM && LAST)) {
                         float4 t = s[u];
                         t.x += f.x; t.y += f.y; t.z += f.z; t.w += f.w;      // voxel.sum(dim=0): sequential fp32 over bins
                         if (LAST) st_stream(reinterpret_cast<float4*>(so + i), t);
@@ -641,7 +673,9 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
                 q[u] = 0; s[u] = 0.f;
                 if (i < ncell) {
                     q[u] = pl[i];
-                    if (SUM && !FIRST) s[u] = __ldcg(so + i);
+                    if (kRunning && !FIRST) s[u] = __ldcg(so + i);
+                    if (kReadBack)
+                        for (int j = 0; j < k; ++j) s[u] += __ldcg(o + (int64_t)(j - k) * plane_stride + i);
                 }
             }
 #pragma unroll
@@ -656,9 +690,10 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
                         for (int t = 0; t < n_spill; ++t) if (spill[t].x == key) hi += spill[t].y;
                         if (hi) f = __ll2float_rn((hi << 32) + (long long)q[u]) * kInv;
                     }
-                    st_stream(o + i, f);
+                    if (kDeferred && SUM && !LAST) __stcg(o + i, f);
+                    else st_stream(o + i, f);
                     if (STATS) sa.add(f);
-                    if (SUM) {
+                    if (kRunning || (kDeferred && SUM && LAST)) {
                         const float t = s[u] + f;
                         if (LAST) st_stream(so + i, t); else __stcg(so + i, t);
                         if (STATS && LAST) ss.add(t);
@@ -689,25 +724,25 @@ __device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part) {
 // pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys).
 // stats_part (or null): per-(task, channel, warp) partial statistics of the written values, channel num_bins = the sum plane.
 template <bool VEC>
-__device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, const int2* spill, int n_spill,
-                                            int key0, double* stats_part) {
+__device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, int64_t plane_stride,
+                                            const int2* spill, int n_spill, int key0, double* stats_part) {
     const bool first = k == 0, last = k == num_bins - 1;
     StatAcc sa, ss;
     sa.init(); ss.init();
     if (stats_part) {
-        if (!so) flush_plane_t<VEC, false, false, false, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (first && last) flush_plane_t<VEC, true, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (first) flush_plane_t<VEC, true, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (last) flush_plane_t<VEC, false, true, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else flush_plane_t<VEC, false, false, true, true>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        if (!so) flush_plane_t<VEC, false, false, false, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (first && last) flush_plane_t<VEC, true, true, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (first) flush_plane_t<VEC, true, false, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (last) flush_plane_t<VEC, false, true, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else flush_plane_t<VEC, false, false, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
         stat_reduce_store(sa, stats_part + (size_t)k * kStatSlot);
         if (so && last) stat_reduce_store(ss, stats_part + (size_t)num_bins * kStatSlot);
     } else {
-        if (!so) flush_plane_t<VEC, false, false, false, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (first && last) flush_plane_t<VEC, true, true, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (first) flush_plane_t<VEC, true, false, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else if (last) flush_plane_t<VEC, false, true, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
-        else flush_plane_t<VEC, false, false, true, false>(pl, ncell, k, o, so, spill, n_spill, key0, sa, ss);
+        if (!so) flush_plane_t<VEC, false, false, false, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (first && last) flush_plane_t<VEC, true, true, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (first) flush_plane_t<VEC, true, false, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else if (last) flush_plane_t<VEC, false, true, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        else flush_plane_t<VEC, false, false, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
     }
 }
 
@@ -921,7 +956,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a
             float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
             float* so = a.out_sum ? a.out_sum + (int64_t)b * HW + (int64_t)row0 * a.W : nullptr;
             double* sp = a.stats_part ? a.stats_part + (size_t)task * (a.num_bins + 1) * kStatSlot : nullptr;
-            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, s_spill, n_spill, cell0, sp);
+            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, HW, s_spill, n_spill, cell0, sp);
             if (!has_right && n_spill) {
                 // the spill list is per task
                 __syncthreads();
