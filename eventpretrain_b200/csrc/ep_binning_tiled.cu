@@ -103,6 +103,7 @@ struct TiledArgs {
     int task_lo, task_hi;       // route tasks of this launch (a group of samples; [0, n_tasks) for the whole batch)
     int sweep_lo, sweep_hi;     // sweep tasks (sample * NT + tile) of this launch
     int counter_idx;            // which of the sweep task counters this launch draws from
+    int deferred_sum;           // sweep: voxel.sum(0) at the last plane from the planes read back (else a running sum per plane)
     SampleMeta* meta;
     int* first_task;            // B+1
     TaskDesc* desc;             // n_tasks
@@ -587,15 +588,14 @@ struct StatAcc {
 // from the output tensor (written a few phases ago by this very thread with L2-resident stores), added in the reference's
 // order ((p0 + p1) + p2 ...) and the sum is written once.  The flushes of the other planes then consist of stores only —
 // nothing to wait for — where the running-sum form paid an L2 round trip per plane.  Same fp32 additions: bit-identical.
-#ifndef EP_DEFERRED_SUM
-#define EP_DEFERRED_SUM 1
-#endif
+// Chosen per call (TiledArgs::deferred_sum) when the planes waiting for the read-back fit L2; many-bin grids keep the
+// running sum (DEF = false), whose traffic per plane is one tile in and one out whatever the number of bins.
 
-template <bool VEC, bool FIRST, bool LAST, bool SUM, bool STATS>
+template <bool VEC, bool FIRST, bool LAST, bool SUM, bool STATS, bool DEF>
 __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* __restrict__ o, float* __restrict__ so, int64_t plane_stride,
                                               const int2* spill, int n_spill, int key0, StatAcc& sa, StatAcc& ss) {
     constexpr float kInv = 1.0f / 16777216.0f;
-    constexpr bool kDeferred = EP_DEFERRED_SUM != 0;
+    constexpr bool kDeferred = DEF;
     constexpr bool kReadBack = kDeferred && SUM && LAST && !FIRST;        // this flush adds planes 0 .. k-1 from the output
     constexpr bool kRunning = !kDeferred && SUM;                         // the running-sum form
     if (VEC) {
@@ -723,27 +723,29 @@ __device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part) {
 
 // pl points at the tile's first cell inside the plane buffer; key0 = that cell's index in the buffer (spill keys).
 // stats_part (or null): per-(task, channel, warp) partial statistics of the written values, channel num_bins = the sum plane.
-template <bool VEC>
-__device__ __forceinline__ void flush_plane(int* pl, int ncell, int k, int num_bins, float* o, float* so, int64_t plane_stride,
-                                            const int2* spill, int n_spill, int key0, double* stats_part) {
+template <bool VEC, bool DEF>
+__device__ __forceinline__ void flush_plane_d(int* pl, int ncell, int k, int num_bins, float* o, float* so, int64_t plane_stride,
+                                              const int2* spill, int n_spill, int key0, double* stats_part) {
     const bool first = k == 0, last = k == num_bins - 1;
     StatAcc sa, ss;
     sa.init(); ss.init();
+#define EP_FLUSH(F, L, S, T) flush_plane_t<VEC, F, L, S, T, DEF>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss)
     if (stats_part) {
-        if (!so) flush_plane_t<VEC, false, false, false, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (first && last) flush_plane_t<VEC, true, true, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (first) flush_plane_t<VEC, true, false, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (last) flush_plane_t<VEC, false, true, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else flush_plane_t<VEC, false, false, true, true>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        if (!so) EP_FLUSH(false, false, false, true);
+        else if (first && last) EP_FLUSH(true, true, true, true);
+        else if (first) EP_FLUSH(true, false, true, true);
+        else if (last) EP_FLUSH(false, true, true, true);
+        else EP_FLUSH(false, false, true, true);
         stat_reduce_store(sa, stats_part + (size_t)k * kStatSlot);
         if (so && last) stat_reduce_store(ss, stats_part + (size_t)num_bins * kStatSlot);
     } else {
-        if (!so) flush_plane_t<VEC, false, false, false, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (first && last) flush_plane_t<VEC, true, true, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (first) flush_plane_t<VEC, true, false, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else if (last) flush_plane_t<VEC, false, true, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
-        else flush_plane_t<VEC, false, false, true, false>(pl, ncell, k, o, so, plane_stride, spill, n_spill, key0, sa, ss);
+        if (!so) EP_FLUSH(false, false, false, false);
+        else if (first && last) EP_FLUSH(true, true, true, false);
+        else if (first) EP_FLUSH(true, false, true, false);
+        else if (last) EP_FLUSH(false, true, true, false);
+        else EP_FLUSH(false, false, true, false);
     }
+#undef EP_FLUSH
 }
 
 struct ItemRegs {
@@ -836,7 +838,7 @@ __device__ __forceinline__ void sweep_items(const TiledArgs& a, const SweepCtx& 
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <bool VEC>
+template <bool VEC, bool DEF>
 __global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_cells = a.rows * a.W;
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a
             float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + (int64_t)row0 * a.W;
             float* so = a.out_sum ? a.out_sum + (int64_t)b * HW + (int64_t)row0 * a.W : nullptr;
             double* sp = a.stats_part ? a.stats_part + (size_t)task * (a.num_bins + 1) * kStatSlot : nullptr;
-            flush_plane<VEC>(pl0 + cell0, ncell, k, a.num_bins, o, so, HW, s_spill, n_spill, cell0, sp);
+            flush_plane_d<VEC, DEF>(pl0 + cell0, ncell, k, a.num_bins, o, so, HW, s_spill, n_spill, cell0, sp);
             if (!has_right && n_spill) {
                 // the spill list is per task
                 __syncthreads();
@@ -1127,14 +1129,22 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     if (!attr_done) {
         cudaFuncSetAttribute(k_route<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
         cudaFuncSetAttribute(k_route<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRouteSmem);
-        cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
-        cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        cudaFuncSetAttribute(k_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        cudaFuncSetAttribute(k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        cudaFuncSetAttribute(k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
+        cudaFuncSetAttribute(k_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kTileCells));
         attr_done = true;
     }
     // (Measured and dropped: the batch cut into 4-32 sample groups with the routes on the caller's stream and the sweeps on a
     // side stream, one CTA of each kernel per SM, so that route(g + 1) runs under sweep(g): 1.74-2.1 ms against 1.65 ms in
     // plain order — both kernels live on the shared-memory pipe, and each loses its second CTA per SM.)
     a.task_lo = 0; a.task_hi = pl.n_tasks; a.sweep_lo = 0; a.sweep_hi = B * pl.NT; a.counter_idx = 0;
+    {
+        // planes waiting in L2 for the read-back: (bins - 1) tiles per resident sweep CTA.  EP_DEFERRED_SUM=0/1 overrides (per call).
+        const size_t waiting = (size_t)(p->num_bins > 1 ? p->num_bins - 1 : 0) * pl.rows * p->width * 4 * (size_t)(kSweepCtas * kNumSMs);
+        const char* e = getenv("EP_DEFERRED_SUM");
+        a.deferred_sum = e ? (e[0] != '0') : (waiting <= ((size_t)80 << 20));
+    }
     if (pl.n_tasks > 0) {
         const int grid = pl.n_tasks < 2 * kNumSMs ? pl.n_tasks : 2 * kNumSMs;
         profile_begin(st, kProfScatter);
@@ -1149,8 +1159,13 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
         const size_t smem = sweep_smem_bytes(pl.rows * p->width);
         const bool vec = (p->width % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
         profile_begin(st, kProfFinalize);
-        if (vec) k_sweep<true><<<grid, kSweepThreads, smem, st>>>(a);
-        else k_sweep<false><<<grid, kSweepThreads, smem, st>>>(a);
+        if (a.deferred_sum) {
+            if (vec) k_sweep<true, true><<<grid, kSweepThreads, smem, st>>>(a);
+            else k_sweep<false, true><<<grid, kSweepThreads, smem, st>>>(a);
+        } else {
+            if (vec) k_sweep<true, false><<<grid, kSweepThreads, smem, st>>>(a);
+            else k_sweep<false, false><<<grid, kSweepThreads, smem, st>>>(a);
+        }
         profile_end(st);
         EP_LAUNCH_CHECK();
     }
@@ -1608,7 +1623,7 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     a.rep_shift = route_rep_shift(pl.t.NT);
     a.sx = a.sy = 1.0; a.scaled = 0;
     a.n_tasks = pl.t.n_tasks;
-    a.task_lo = 0; a.task_hi = pl.t.n_tasks; a.sweep_lo = 0; a.sweep_hi = B * pl.t.NT; a.counter_idx = 0;
+    a.task_lo = 0; a.task_hi = pl.t.n_tasks; a.sweep_lo = 0; a.sweep_hi = B * pl.t.NT; a.counter_idx = 0; a.deferred_sum = 0;
     a.meta = reinterpret_cast<SampleMeta*>(base + pl.t.off_meta);
     a.first_task = reinterpret_cast<int*>(base + pl.t.off_first);
     a.desc = reinterpret_cast<TaskDesc*>(base + pl.t.off_desc);
