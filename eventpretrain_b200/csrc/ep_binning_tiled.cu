@@ -1437,28 +1437,59 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             const double r = __fma_rn(-q, tdiv, v);
             return __fma_rn(r, trcp, q);
         };
-        uint32_t* stg = s_stage + wid * kEvStage;
-        // cells per warp step: 32, or fewer on dense tiles so that their stamps (mean + margin) fit the staging buffer
+        // Every warp owns a contiguous range of cells, taken 32 (or fewer on dense tiles, so that mean + margin fit half the
+        // staging buffer) at a time.  The stamps of the next step are copied into the other half of the buffer (cp.async)
+        // while this step is sorted and replayed, and the last stamp seen is carried from step to step: the first cell of a
+        // step is differenced against it without another look into the scratch.
+        constexpr int kHalf = kEvStage / 2;
+        uint32_t* stg_base = s_stage + wid * kEvStage;
         int gs = 32;
         {
             const int total = (last_cell >= 0) ? (int)s_st[last_cell] : 0;        // events of the tile
-            while (gs > 1 && (int64_t)gs * total * 3 / 2 + 16LL * ncell > (int64_t)kEvStage * ncell) gs >>= 1;
+            while (gs > 1 && (int64_t)gs * total * 3 / 2 + 16LL * ncell > (int64_t)kHalf * ncell) gs >>= 1;
         }
         const int n_groups = (tile_cells + gs - 1) / gs;
-        for (int g = wid; g < n_groups; g += kEvWarps) {
-            const int c = (lane < gs) ? g * gs + lane : tile_cells;
-            int n = 0, end = 0;
+        const int per_warp = (n_groups + kEvWarps - 1) / kEvWarps;
+        const int g_lo = wid * per_warp, g_hi = (g_lo + per_warp < n_groups) ? g_lo + per_warp : n_groups;
+        // (n, begin, end) of this lane's cell in step g, the lanes holding events, the step's piece [r0, r1) of the scratch
+        auto describe = [&](int g, int& c, int& n, int& beg, int& end, unsigned& nz, int& r0, int& r1) {
+            c = (lane < gs) ? g * gs + lane : tile_cells;
+            n = 0; end = 0;
             if (c < tile_cells) { n = (int)(s_cp[c] & 0xffffu); end = (int)s_st[c]; }
-            const int beg = end - n;
-            const unsigned nz = __ballot_sync(0xffffffffu, n > 0);
+            beg = end - n;
+            nz = __ballot_sync(0xffffffffu, n > 0);
+            r0 = r1 = 0;
+            if (nz) {
+                r0 = __shfl_sync(0xffffffffu, beg, __ffs(nz) - 1);
+                r1 = __shfl_sync(0xffffffffu, end, 31 - __clz(nz));
+            }
+        };
+        auto stage_async = [&](int g, int half) {
+            int c, n, beg, end, r0, r1; unsigned nz;
+            describe(g, c, n, beg, end, nz, r0, r1);
+            if (nz && r1 - r0 <= kHalf) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stg_base + half * kHalf);
+                for (int j = lane; j < r1 - r0; j += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)j), "l"(seg + r0 + j) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        bool carry_valid = false;
+        uint32_t carry_tk = 0u;
+        if (g_lo < g_hi) stage_async(g_lo, 0);
+        for (int g = g_lo; g < g_hi; ++g) {
+            const int half = (g - g_lo) & 1;
+            if (g + 1 < g_hi) stage_async(g + 1, half ^ 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            int c, n, beg, end, r0, r1; unsigned nz;
+            describe(g, c, n, beg, end, nz, r0, r1);
             if (!nz) { if (c < tile_cells) s_et[c] = 0.0; continue; }
-            const int lo_lane = __ffs(nz) - 1, hi_lane = 31 - __clz(nz);
-            const int r0 = __shfl_sync(0xffffffffu, beg, lo_lane), r1 = __shfl_sync(0xffffffffu, end, hi_lane);
-            const bool staged = (r1 - r0) <= kEvStage;
+            const bool staged = (r1 - r0) <= kHalf;
+            uint32_t* stg = stg_base + half * kHalf;
             const uint32_t* mine;                                   // this lane's sorted stamps
             if (staged) {
-                for (int j = lane; j < r1 - r0; j += 32) stg[j] = __ldcg(seg + r0 + j);
-                __syncwarp();
                 if (n > 1) sort_u32(stg + (beg - r0), n);
                 __syncwarp();
                 mine = stg + (beg - r0);
@@ -1472,12 +1503,12 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             // the stamp this cell's first event is differenced against
             double prev = 0.0;
             bool has_prev = false;
-            if (n > 0) {
-                const unsigned lower = nz & ((1u << lane) - 1u);
-                if (lower) {
-                    // (placeholder: filled by the shuffle below)
+            const unsigned lower = nz & ((1u << lane) - 1u);
+            if (n > 0 && !lower) {
+                if (carry_valid) {
+                    prev = stamp(carry_tk); has_prev = true;        // the last non-empty cell of this warp's earlier steps
                 } else if (beg > 0) {
-                    // the previous non-empty cell of the tile lies in an earlier group: its stamps end at `beg`
+                    // the previous non-empty cell of the tile belongs to another warp: its stamps end at `beg`
                     int cprev = c - 1;
                     while ((s_cp[cprev] & 0xffffu) == 0u) --cprev;
                     const int np = (int)(s_cp[cprev] & 0xffffu);
@@ -1498,13 +1529,14 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
                     }
                 }
             }
-            // last (largest) stamp of every lane's segment, for the lanes behind it in the group
+            // last (largest) stamp of every lane's segment, for the lanes behind it in the step and for the next step
             const uint32_t my_last = (n > 0) ? mine[n - 1] : 0u;
             {
-                const unsigned lower = nz & ((1u << lane) - 1u);
                 const int src = lower ? 31 - __clz(lower) : lane;
                 const uint32_t pl = __shfl_sync(0xffffffffu, my_last, src);
                 if (n > 0 && lower) { prev = stamp(pl); has_prev = true; }
+                carry_tk = __shfl_sync(0xffffffffu, my_last, 31 - __clz(nz));
+                carry_valid = true;
             }
             if (c < tile_cells) {
                 float tsum = 0.f, tsq = 0.f;
@@ -1528,6 +1560,7 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             }
             __syncwarp();
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
         // ---- D: (3, H, W) float64 rows: pieces of ncols consecutive x per image row ----
