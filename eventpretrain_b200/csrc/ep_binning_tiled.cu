@@ -1191,42 +1191,39 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
 // event of the previous non-empty pixel in x-major order.  Here, for a ragged batch in the 4 B packed transport layout:
 //   * k_route<true>: the same route as the voxel path with transposed tiles — a tile is a range of columns, its cells run
 //     x-major, so the concatenation (sample, tile, cell) IS the lexsort order;
-//   * k_evrep_sweep (persistent CTAs, task = (sample, tile), two CTAs per SM):
+//   * k_evrep_sweep (persistent, one CTA of 1024 threads per SM, task = (sample, tile); the stamps of a whole tile live in
+//     shared memory — an earlier version placed them in an L2-resident scratch: the scattered 4-byte stores alone cost 0.30 of
+//     its 1.12 ms on the C4 shape):
 //       A  count per cell with one shared-memory atomic per record (events | positives << 16);
-//       -  block scan of the counts -> segment starts; the tile's own offset inside the sample is the sum of the bucket starts
-//          the route wrote, so the stamps of a sample land in a scratch array in exactly the reference's sorted order;
-//       B  every record's stamp (ticks relative to the sample's first row, u32) goes to its pixel's segment (one returning
-//          shared-memory atomic for the slot, one 4-byte store into the L2-resident scratch);
+//       -  block scan of the counts -> segment starts; windows = consecutive cell ranges whose stamps fit the 188 KB
+//          shared-memory window (one window for ordinary tiles, several for dense ones);
+//       B  per window: every record's stamp (ticks relative to the sample's first row, u32) goes to its pixel's segment of
+//          the window (one returning shared-memory atomic for the slot, one shared-memory store): the segments lie back to
+//          back in exactly the reference's sorted order;
 //       -  the tile publishes the last stamp of its last non-empty pixel (decoupled look-back: the first non-empty pixel of a
 //          tile needs it from the nearest non-empty tile before; tasks are drawn in order, so the chain always advances);
-//       C  a warp takes 32 consecutive cells: their segments are one contiguous piece of the scratch, loaded coalesced into
-//          a per-warp staging buffer, each lane sorts its own short segment there and replays numpy's accumulation exactly
-//          (fp32 accumulators updated as (float)((double)acc + d), fp64 statistics of :117-120): bit-exact;
-//       D  E_C, E_I, E_T leave through a shared-memory transpose as row pieces of the (3, H, W) float64 output.
+//       C  a lane per cell: the short segment is sorted in place, then numpy's accumulation is replayed exactly (fp32
+//          accumulators updated as (float)((double)acc + d), fp64 statistics of :117-120) — the stamp a pixel's first event is
+//          differenced against is simply the element in front of its segment: bit-exact;
+//       D  E_C, E_I, E_T leave as row pieces of the (3, H, W) float64 output (E_T through an L2-resident transpose buffer).
 // Limits reported through bad_count: bit 31 = more than 65535 events on one pixel of one sample, bit 30 = a stamp more than
-// 2^32 ticks away from (or before) the sample's first row.
+// 2^32 ticks away from (or before) the sample's first row, bit 29 = more than 47000 events on one pixel, or a tile whose
+// events need more than 16 windows (752 k events on ~10 columns).
 // =====================================================================================================================
 namespace {
 
-#ifndef EP_EV_THREADS
-#define EP_EV_THREADS 512
-#define EP_EV_CTAS 2
-#define EP_EV_STAGE 960
-#endif
-constexpr int kEvThreads = EP_EV_THREADS;
-constexpr int kEvCtas = EP_EV_CTAS;           // CTAs per SM the shared-memory budget is sized for
+constexpr int kEvThreads = 1024;              // one CTA per SM: the stamps of a whole tile live in its shared memory
 constexpr int kEvWarps = kEvThreads / 32;
-constexpr int kEvTileCells = 5400;            // 8 B per cell of shared memory + the staging buffers -> two CTAs per SM
+constexpr int kEvTileCells = 4400;            // 8 B per cell (count word + cursor)
 constexpr int kEvTab = 256;                   // chunks per run-table round
-constexpr int kEvStage = EP_EV_STAGE;         // stamps of a warp's staging buffer
+constexpr int kEvWin = 47000;                 // stamps of the shared-memory window (188 KB): a tile of the C4 shape holds ~34 k
+constexpr int kEvMaxWin = 16;                 // windows per tile (dense tiles are taken in several cell ranges)
 
 struct EvRepArgs {
     TiledArgs t;                // t.H = image width (major), t.W = image height (minor), t.rows = columns per tile
     const int64_t* t_base;      // B, or null
     double t_div;
     double* out;                // (B, 3, Himg, Wimg)
-    uint32_t* sorted;           // stamps in lexsort order, indexed like rec
-    uint32_t* sorted2;          // second copy for segments sorted outside the staging buffer
     double* et_scratch;         // per CTA: E_T of the tile's cells (L2-resident), read back transposed for the output rows
     double t_rcp;               // 1 / t_div, correctly rounded
     long long* lb_val;          // per task: last stamp of the last non-empty pixel
@@ -1234,7 +1231,7 @@ struct EvRepArgs {
 };
 
 __host__ __device__ inline size_t evrep_smem_bytes(int tile_cells) {
-    return (size_t)tile_cells * 8 + (size_t)kEvWarps * kEvStage * 4 + (size_t)kEvTab * 16 + 64;
+    return (size_t)tile_cells * 8 + (size_t)kEvWin * 4 + (size_t)kEvTab * 16 + 64;
 }
 
 __device__ __forceinline__ void sort_u32(uint32_t* s, int n) {
@@ -1281,20 +1278,21 @@ __device__ __forceinline__ bool rec_ticks(uint32_t r, long long cbase, bool narr
     return dt >= 0 && dt < (1ll << 32);
 }
 
-__global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e) {
+__global__ void __launch_bounds__(kEvThreads, 1) k_evrep_sweep(EvRepArgs e) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TiledArgs& a = e.t;
     const int tile_cells = a.rows * a.W;
     long long* t_cb = reinterpret_cast<long long*>(smem_raw);
     uint32_t* s_cp = reinterpret_cast<uint32_t*>(t_cb + kEvTab);                 // events | positives << 16
     uint32_t* s_st = s_cp + tile_cells;                                          // segment start, then cursor / end
-    uint32_t* s_stage = s_st + tile_cells;
+    uint32_t* s_win = s_st + tile_cells;                                         // the stamps of the window's cells, segment by segment
     double* s_et = e.et_scratch + (size_t)blockIdx.x * kEvTileCells;             // E_T per cell (global, stays in L2)
-    uint32_t* t_pos = s_stage + kEvWarps * kEvStage;
+    uint32_t* t_pos = s_win + kEvWin;
     uint16_t* t_len = reinterpret_cast<uint16_t*>(t_pos + kEvTab);
     uint16_t* t_nar = t_len + kEvTab;
-    __shared__ int s_task, s_warp[kEvWarps], s_last_cell, s_first_cell;
-    __shared__ unsigned int s_lastmax, s_tile_base, s_bad;
+    __shared__ int s_task, s_warp[kEvWarps], s_last_cell, s_nwin, s_winb[kEvMaxWin + 1], s_wlast_cell;
+    __shared__ unsigned int s_wlastmax, s_prevmax, s_bad;
+    __shared__ int s_prev_valid;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Himg = a.W, Wimg = a.H;                       // the route ran on the transposed image
@@ -1303,7 +1301,7 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_task = (int)atomicAdd(a.counters, 1u); s_lastmax = 0u; s_tile_base = 0u; s_bad = 0u; s_last_cell = -1; s_first_cell = 0x7fffffff; }
+        if (tid == 0) { s_task = (int)atomicAdd(a.counters, 1u); s_bad = 0u; s_last_cell = -1; s_prev_valid = 0; s_prevmax = 0u; }
         for (int i = tid; i < tile_cells; i += kEvThreads) s_cp[i] = 0u;
         __syncthreads();
         const int task = s_task;
@@ -1314,13 +1312,11 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
         const int ncols = (Wimg - col0 < a.rows) ? Wimg - col0 : a.rows;
         const int ncell = ncols * Himg;
         const int cell0 = tile_cells - ncell;               // a narrower last tile sits at the end (k_route's lut_y)
-        const uint32_t sample_pos0 = nch > 0 ? a.cmeta[first].pos0 : 0u;
 
-        // ---- the two passes over the tile's runs share this walker: a warp takes one run at a time ----
-        auto walk = [&](auto&& table_hook, auto&& body) {
+        // ---- the passes over the tile's runs share this walker: a warp takes one run at a time ----
+        auto walk = [&](auto&& body) {
             for (int c_round = 0; c_round < nch; c_round += kEvTab) {
                 const int ci = c_round + tid;
-                uint32_t o0v = 0;
                 if (tid < kEvTab) {
                     if (ci < nch) {
                         const ChunkMeta cm = a.cmeta[first + ci];
@@ -1330,12 +1326,10 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
                         t_len[tid] = (uint16_t)(o1 - o0);
                         t_nar[tid] = (uint16_t)((cm.flags & kChunkNarrow) ? 1 : 0);
                         t_cb[tid] = cm.cbase;
-                        o0v = o0;
                     } else {
                         t_len[tid] = 0;
                     }
                 }
-                table_hook(o0v);
                 __syncthreads();
                 const int n_run = (nch - c_round < kEvTab) ? nch - c_round : kEvTab;
                 for (int r = wid; r < n_run; r += kEvWarps) {
@@ -1344,7 +1338,7 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
                     const long long cb = t_cb[r];
                     const bool nar = t_nar[r] != 0;
                     const uint32_t* crel = a.crel + (size_t)(first + c_round + r) * 32;
-                    // a run holds ~150 records at this tile size: all of its loads are issued before the first use
+                    // a run holds ~130 records at this tile size: all of its loads are issued before the first use
                     for (int i0 = 0; i0 < len; i0 += 256) {
                         uint32_t rv[8];
 #pragma unroll
@@ -1361,32 +1355,26 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             }
         };
 
-        // ---- A: events and positive events per cell; the tile's offset inside the sample = sum of the bucket starts ----
-        walk([&](uint32_t o0v) {
-                 uint32_t v = o0v;
-#pragma unroll
-                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                 if (lane == 0 && v) atomicAdd(&s_tile_base, v);
-             },
-             [&](uint32_t r, long long, bool, const uint32_t*) {
-                 const uint32_t cell = (r >> 2) & 0x3fffu;
-                 const uint32_t old = atomicAdd(&s_cp[cell], 1u + ((r & 2u) ? 0u : 0x10000u));
-                 if ((old & 0xffffu) == 0xffffu) atomicOr(&s_bad, 0x80000000u);
-             });
+        // ---- A: events and positive events per cell ----
+        walk([&](uint32_t r, long long, bool, const uint32_t*) {
+            const uint32_t cell = (r >> 2) & 0x3fffu;
+            const uint32_t old = atomicAdd(&s_cp[cell], 1u + ((r & 2u) ? 0u : 0x10000u));
+            if ((old & 0xffffu) == 0xffffu) atomicOr(&s_bad, 0x80000000u);
+        });
 
-        // ---- exclusive scan of the counts in cell (= x-major) order; first / last non-empty cell ----
+        // ---- exclusive scan of the counts in cell (= x-major) order; last non-empty cell ----
         {
             const int per = (tile_cells + kEvThreads - 1) / kEvThreads;
             const int c_lo = tid * per, c_hi = (c_lo + per < tile_cells) ? c_lo + per : tile_cells;
-            int sum = 0, lastc = -1, firstc = 0x7fffffff;
+            int sum = 0, lastc = -1;
             for (int c = c_lo; c < c_hi; ++c) {
                 const int n = (int)(s_cp[c] & 0xffffu);
-                if (n) { lastc = c; if (firstc == 0x7fffffff) firstc = c; }
+                if (n) lastc = c;
                 sum += n;
             }
             const int incl = warp_incl_scan(sum, lane);
             if (lane == 31) s_warp[wid] = incl;
-            if (lastc >= 0) { atomicMax(&s_last_cell, lastc); atomicMin(&s_first_cell, firstc); }
+            if (lastc >= 0) atomicMax(&s_last_cell, lastc);
             __syncthreads();
             int wbase = 0;
             for (int w = 0; w < wid; ++w) wbase += s_warp[w];
@@ -1394,37 +1382,31 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             for (int c = c_lo; c < c_hi; ++c) { const int n = (int)(s_cp[c] & 0xffffu); s_st[c] = (uint32_t)run; run += n; }
             __syncthreads();
         }
-        const int last_cell = s_last_cell, first_cell = s_first_cell;
-        uint32_t* seg = e.sorted + sample_pos0 + s_tile_base;       // this tile's stamps, cells in order
-        uint32_t* seg2 = e.sorted2 + sample_pos0 + s_tile_base;
-
-        // ---- B: every stamp to its pixel's segment ----
-        walk([&](uint32_t) {},
-             [&](uint32_t r, long long cb, bool nar, const uint32_t* crel) {
-                 const uint32_t cell = (r >> 2) & 0x3fffu;
-                 uint32_t tk;
-                 if (!rec_ticks(r, cb, nar, crel, tk)) { atomicOr(&s_bad, 0x40000000u); tk = 0u; }
-                 const uint32_t slot = atomicAdd(&s_st[cell], 1u);
-                 seg[slot] = tk;
-                 if ((int)cell == last_cell) atomicMax(&s_lastmax, tk);
-             });
-        // (walk ends with a barrier: s_st[c] is now the END of cell c's segment, the stamps are in the scratch)
-
-        // ---- publish for the tiles behind; errors ----
+        const int last_cell = s_last_cell;
+        // ---- windows: consecutive cell ranges whose stamps fit the shared-memory window (one for ordinary tiles) ----
         if (tid == 0) {
-            if (last_cell >= 0) {
-                e.lb_val[task] = (long long)s_lastmax;
-                __threadfence();
-                *reinterpret_cast<volatile int*>(e.lb_flag + task) = 2;
-            } else {
-                __threadfence();
-                *reinterpret_cast<volatile int*>(e.lb_flag + task) = 1;
+            int nw = 0, c = 0;
+            s_winb[0] = 0;
+            const int total = (last_cell >= 0) ? (int)s_st[last_cell] + (int)(s_cp[last_cell] & 0xffffu) : 0;
+            while (c < tile_cells && nw < kEvMaxWin) {
+                const int base = (int)s_st[c];
+                if (total - base <= kEvWin) { c = tile_cells; }
+                else {
+                    // largest c2 with begin(c2) - base <= kEvWin: cells [c, c2) fit
+                    int lo = c, hi = tile_cells;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)s_st[mid] - base <= kEvWin) lo = mid; else hi = mid; }
+                    if (lo == c) { atomicOr(&s_bad, 0x20000000u); c = tile_cells; }        // one pixel alone overflows the window
+                    else c = lo;
+                }
+                s_winb[++nw] = c;
             }
-            if (s_bad && a.bad_count) atomicOr(a.bad_count, s_bad);
+            if (c < tile_cells) { atomicOr(&s_bad, 0x20000000u); s_winb[nw] = tile_cells; }
+            s_nwin = nw;
         }
-        __threadfence_block();
+        __syncthreads();
+        const int n_win = s_nwin;
+        const bool tile_ok = (s_bad & 0x20000000u) == 0u;
 
-        // ---- C: sort + replay, 32 consecutive cells per warp ----
         const SampleMeta* mp = a.meta + b;
         const long long abs0 = (e.t_base ? e.t_base[b] : 0) + mp->t0_ticks;
         const double tdiv = e.t_div, trcp = e.t_rcp;
@@ -1437,111 +1419,81 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             const double r = __fma_rn(-q, tdiv, v);
             return __fma_rn(r, trcp, q);
         };
-        // Every warp owns a contiguous range of cells, taken 32 (or fewer on dense tiles, so that mean + margin fit half the
-        // staging buffer) at a time.  The stamps of the next step are copied into the other half of the buffer (cp.async)
-        // while this step is sorted and replayed, and the last stamp seen is carried from step to step: the first cell of a
-        // step is differenced against it without another look into the scratch.
-        constexpr int kHalf = kEvStage / 2;
-        uint32_t* stg_base = s_stage + wid * kEvStage;
-        int gs = 32;
-        {
-            const int total = (last_cell >= 0) ? (int)s_st[last_cell] : 0;        // events of the tile
-            while (gs > 1 && (int64_t)gs * total * 3 / 2 + 16LL * ncell > (int64_t)kHalf * ncell) gs >>= 1;
-        }
-        const int n_groups = (tile_cells + gs - 1) / gs;
-        const int per_warp = (n_groups + kEvWarps - 1) / kEvWarps;
-        const int g_lo = wid * per_warp, g_hi = (g_lo + per_warp < n_groups) ? g_lo + per_warp : n_groups;
-        // (n, begin, end) of this lane's cell in step g, the lanes holding events, the step's piece [r0, r1) of the scratch
-        auto describe = [&](int g, int& c, int& n, int& beg, int& end, unsigned& nz, int& r0, int& r1) {
-            c = (lane < gs) ? g * gs + lane : tile_cells;
-            n = 0; end = 0;
-            if (c < tile_cells) { n = (int)(s_cp[c] & 0xffffu); end = (int)s_st[c]; }
-            beg = end - n;
-            nz = __ballot_sync(0xffffffffu, n > 0);
-            r0 = r1 = 0;
-            if (nz) {
-                r0 = __shfl_sync(0xffffffffu, beg, __ffs(nz) - 1);
-                r1 = __shfl_sync(0xffffffffu, end, 31 - __clz(nz));
+
+        for (int w = 0; w < n_win; ++w) {
+            const int wc_lo = s_winb[w], wc_hi = s_winb[w + 1];
+            const int base = (wc_lo < tile_cells) ? (int)s_st[wc_lo] : 0;        // (cursor not advanced yet for this window's cells)
+            if (tid == 0) {
+                int lc = wc_hi - 1;
+                while (lc >= wc_lo && (s_cp[lc] & 0xffffu) == 0u) --lc;
+                s_wlast_cell = lc >= wc_lo ? lc : -1;
+                s_wlastmax = 0u;
             }
-        };
-        auto stage_async = [&](int g, int half) {
-            int c, n, beg, end, r0, r1; unsigned nz;
-            describe(g, c, n, beg, end, nz, r0, r1);
-            if (nz && r1 - r0 <= kHalf) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stg_base + half * kHalf);
-                for (int j = lane; j < r1 - r0; j += 32)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)j), "l"(seg + r0 + j) : "memory");
+            __syncthreads();
+            const int wlast = s_wlast_cell;
+            // ---- B: every stamp of the window's cells to its pixel's segment, in shared memory ----
+            if (tile_ok) {
+                const bool all = n_win == 1;
+                walk([&](uint32_t r, long long cb, bool nar, const uint32_t* crel) {
+                    const uint32_t cell = (r >> 2) & 0x3fffu;
+                    if (!all && ((int)cell < wc_lo || (int)cell >= wc_hi)) return;
+                    uint32_t tk;
+                    if (!rec_ticks(r, cb, nar, crel, tk)) { atomicOr(&s_bad, 0x40000000u); tk = 0u; }
+                    const uint32_t slot = atomicAdd(&s_st[cell], 1u) - (uint32_t)base;
+                    s_win[slot] = tk;
+                    if ((int)cell == wlast) atomicMax(&s_wlastmax, tk);
+                });
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        bool carry_valid = false;
-        uint32_t carry_tk = 0u;
-        if (g_lo < g_hi) stage_async(g_lo, 0);
-        for (int g = g_lo; g < g_hi; ++g) {
-            const int half = (g - g_lo) & 1;
-            if (g + 1 < g_hi) stage_async(g + 1, half ^ 1);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            __syncwarp();
-            int c, n, beg, end, r0, r1; unsigned nz;
-            describe(g, c, n, beg, end, nz, r0, r1);
-            if (!nz) { if (c < tile_cells) s_et[c] = 0.0; continue; }
-            const bool staged = (r1 - r0) <= kHalf;
-            uint32_t* stg = stg_base + half * kHalf;
-            const uint32_t* mine;                                   // this lane's sorted stamps
-            if (staged) {
-                if (n > 1) sort_u32(stg + (beg - r0), n);
-                __syncwarp();
-                mine = stg + (beg - r0);
-            } else {
-                // a hot group: the lanes sort their segments in a second copy (the first stays as written: other warps read
-                // the multiset of a predecessor's stamps from it)
-                for (int j = 0; j < n; ++j) seg2[beg + j] = __ldcg(seg + beg + j);
-                if (n > 1) sort_u32(seg2 + beg, n);
-                mine = seg2 + beg;
+            // (walk ends with a barrier: s_st[c] is now the END of cell c's segment for the window's cells)
+            // ---- the tile's last stamp for the tiles behind (after the last window); errors ----
+            if (tid == 0 && w == n_win - 1) {
+                if (last_cell >= 0 && tile_ok) {
+                    e.lb_val[task] = (long long)s_wlastmax;
+                    __threadfence();
+                    *reinterpret_cast<volatile int*>(e.lb_flag + task) = 2;
+                } else {
+                    __threadfence();
+                    *reinterpret_cast<volatile int*>(e.lb_flag + task) = 1;
+                }
+                if (s_bad && a.bad_count) atomicOr(a.bad_count, s_bad);
             }
-            // the stamp this cell's first event is differenced against
-            double prev = 0.0;
-            bool has_prev = false;
-            const unsigned lower = nz & ((1u << lane) - 1u);
-            if (n > 0 && !lower) {
-                if (carry_valid) {
-                    prev = stamp(carry_tk); has_prev = true;        // the last non-empty cell of this warp's earlier steps
-                } else if (beg > 0) {
-                    // the previous non-empty cell of the tile belongs to another warp: its stamps end at `beg`
-                    int cprev = c - 1;
-                    while ((s_cp[cprev] & 0xffffu) == 0u) --cprev;
-                    const int np = (int)(s_cp[cprev] & 0xffffu);
-                    uint32_t mx = 0;
-                    for (int j = 0; j < np; ++j) mx = max(mx, __ldcg(seg + beg - np + j));
-                    prev = stamp(mx); has_prev = true;
-                } else if (tile > 0) {
-                    // first non-empty cell of the tile: the nearest non-empty tile before it (decoupled look-back)
-                    for (int tj = task - 1; tj >= b * a.NT; --tj) {
-                        int f;
-                        while ((f = *reinterpret_cast<volatile int*>(e.lb_flag + tj)) == 0) __nanosleep(64);
-                        if (f == 2) {
-                            __threadfence();
-                            prev = stamp((uint32_t)*reinterpret_cast<volatile long long*>(e.lb_val + tj));
-                            has_prev = true;
-                            break;
-                        }
-                    }
+
+            // ---- C1: every pixel's segment sorted in place (a lane per cell, 32 consecutive cells per warp step) ----
+            const int n_groups = (wc_hi - wc_lo + 31) / 32;
+            for (int g = wid; g < n_groups; g += kEvWarps) {
+                const int c = wc_lo + g * 32 + lane;
+                if (c < wc_hi && tile_ok) {
+                    const int n = (int)(s_cp[c] & 0xffffu);
+                    if (n > 1) sort_u32(s_win + ((int)s_st[c] - n - base), n);
                 }
             }
-            // last (largest) stamp of every lane's segment, for the lanes behind it in the step and for the next step
-            const uint32_t my_last = (n > 0) ? mine[n - 1] : 0u;
-            {
-                const int src = lower ? 31 - __clz(lower) : lane;
-                const uint32_t pl = __shfl_sync(0xffffffffu, my_last, src);
-                if (n > 0 && lower) { prev = stamp(pl); has_prev = true; }
-                carry_tk = __shfl_sync(0xffffffffu, my_last, 31 - __clz(nz));
-                carry_valid = true;
-            }
-            if (c < tile_cells) {
+            __syncthreads();
+            // ---- C2: replay.  The segments lie back to back in the reference's order, so the stamp a pixel's first event is
+            //          differenced against is simply the element in front of its segment ----
+            for (int g = wid; g < n_groups; g += kEvWarps) {
+                const int c = wc_lo + g * 32 + lane;
+                if (c >= wc_hi) continue;
+                const int n = tile_ok ? (int)(s_cp[c] & 0xffffu) : 0;
                 float tsum = 0.f, tsq = 0.f;
                 if (n > 0) {
-                    double pv = has_prev ? prev : stamp(mine[0]);          // np.diff(prepend=sorted[0]), :110
+                    const int beg = (int)s_st[c] - n - base;
+                    const uint32_t* mine = s_win + beg;
+                    double pv;
+                    if (beg > 0) pv = stamp(s_win[beg - 1]);                     // last stamp of the previous non-empty pixel
+                    else if (s_prev_valid) pv = stamp(s_prevmax);                // ... which lies in the window before
+                    else {
+                        pv = stamp(mine[0]);                                     // np.diff(prepend=sorted[0]), :110
+                        // first non-empty pixel of the tile: the nearest non-empty tile before it (decoupled look-back)
+                        for (int tj = task - 1; tj >= b * a.NT; --tj) {
+                            int f;
+                            while ((f = *reinterpret_cast<volatile int*>(e.lb_flag + tj)) == 0) __nanosleep(64);
+                            if (f == 2) {
+                                __threadfence();
+                                pv = stamp((uint32_t)*reinterpret_cast<volatile long long*>(e.lb_val + tj));
+                                break;
+                            }
+                        }
+                    }
                     for (int k = 0; k < n; ++k) {
                         const double t = stamp(mine[k]);
                         const double d = __dsub_rn(t, pv);
@@ -1558,10 +1510,11 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
                 if (et > 1000.0) et = 1000.0;                                             // :120
                 s_et[c] = et;
             }
-            __syncwarp();
+            __syncthreads();
+            if (tid == 0 && s_wlast_cell >= 0) { s_prevmax = s_wlastmax; s_prev_valid = 1; }
+            __syncthreads();
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+        if (n_win == 0) __syncthreads();
 
         // ---- D: (3, H, W) float64 rows: pieces of ncols consecutive x per image row ----
         double* o = e.out + (int64_t)b * 3 * HW + col0;
@@ -1575,7 +1528,6 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
             q[HW] = (double)(2 * pos - n);
             q[2 * HW] = __ldcg(s_et + c);
         }
-        (void)first_cell;
     }
 }
 
@@ -1584,7 +1536,7 @@ __global__ void __launch_bounds__(kEvThreads, kEvCtas) k_evrep_sweep(EvRepArgs e
 // layout of the workspace of the tiled EvRep
 struct EvRepPlan {
     TiledPlan t;
-    size_t off_sorted, off_sorted2, off_lbval, off_lbflag, off_et, total;
+    size_t off_lbval, off_lbflag, off_et, total;
 };
 
 static bool evrep_plan(const ep_events_soa* ev, int height, int width, EvRepPlan& pl) {
@@ -1624,8 +1576,6 @@ static bool evrep_plan(const ep_events_soa* ev, int height, int width, EvRepPlan
     pl.off_et = o; o += align_up(sizeof(double) * (size_t)kEvTileCells * 2 * 256, 256);      // up to 512 resident CTAs
     t.off_stats = t.off_stats2 = o;
     t.off_rec = o; o += align_up(sizeof(uint32_t) * nrec, 256);
-    pl.off_sorted = o; o += align_up(sizeof(uint32_t) * nrec, 256);
-    pl.off_sorted2 = o; o += align_up(sizeof(uint32_t) * nrec, 256);
     t.total = pl.total = o;
     return true;
 }
@@ -1669,8 +1619,6 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     a.out_voxel = nullptr; a.out_sum = nullptr; a.stats_part = nullptr;
     e.t_base = ev->t_base; e.t_div = ev->t_div; e.t_rcp = 1.0 / ev->t_div; e.out = out;
     e.et_scratch = reinterpret_cast<double*>(base + pl.off_et);
-    e.sorted = reinterpret_cast<uint32_t*>(base + pl.off_sorted);
-    e.sorted2 = reinterpret_cast<uint32_t*>(base + pl.off_sorted2);
     e.lb_val = reinterpret_cast<long long*>(base + pl.off_lbval);
     e.lb_flag = reinterpret_cast<int*>(base + pl.off_lbflag);
 

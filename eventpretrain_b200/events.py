@@ -517,6 +517,8 @@ def evrep(ev, size, check=False, out=None):
             raise OverflowError("EvRep: more than 65535 events on one pixel of one sample (routed path)")
         if v & 0x40000000:
             raise BadEventsError("EvRep: a stamp lies before, or 2^32 ticks or more after, its sample's first row (routed path)")
+        if v & 0x20000000:
+            raise OverflowError("EvRep: more than 47000 events on one pixel, or more than 752k events on one column tile (routed path)")
         _raise_bad(bad)
     return out
 

@@ -192,7 +192,8 @@ EP_API size_t ep_evrep_workspace_bytes(int batch, int height, int width, int64_t
 /* Same, knowing the batch: the 4 B packed transport layout takes the routed path (events bucketed into column tiles, per-tile
  * counting sort and replay in shared memory; timestamp value = (t_base[b] + ticks) / t_div), whose workspace also holds the
  * routed records.  bad_count then also reports: bit 31 = more than 65535 events on one pixel of one sample, bit 30 = a stamp
- * before, or 2^32 ticks or more after, the sample's first row. */
+ * before, or 2^32 ticks or more after, the sample's first row, bit 29 = more than 47000 events on one pixel or more than
+ * 752k events on one column tile (the per-tile shared-memory windows). */
 EP_API size_t ep_evrep_workspace_bytes_for(const ep_events_soa* ev, int height, int width);
 EP_API int ep_evrep(void* stream, const ep_events_soa* ev, int height, int width, double* out,
              void* workspace, size_t workspace_bytes, unsigned int* bad_count);
