@@ -99,3 +99,27 @@ def test_evrep_tiled_bad_events(ep):
     ev, _ = dense_batch(ep, rng, [5000], H, W, edit=edit)
     with pytest.raises(ep.BadEventsError):
         ep.evrep(ev.packed(4).to("cuda"), (H, W), check=True)
+
+
+def test_evrep_tiled_dense_tile_takes_several_windows(ep):
+    """More events on one column tile than the shared-memory window holds (47 000 stamps): the tile is swept in several
+    ranges of cells, each pixel still differenced against the previous non-empty one across the range boundary."""
+    rng = np.random.default_rng(12)
+    H, W = 7, 9                                    # 63 pixels, one tile
+    ev, samples = dense_batch(ep, rng, [200_000, 3, 120_000], H, W)
+    check(ep, ev, samples, H, W)
+    H, W = 40, 30                                  # several tiles? no: 30 columns x 40 rows = 1200 cells, one tile, ~250 events per pixel
+    ev, samples = dense_batch(ep, rng, [300_000], H, W)
+    check(ep, ev, samples, H, W)
+
+
+def test_evrep_tiled_pixel_beyond_the_window_is_reported(ep):
+    rng = np.random.default_rng(13)
+    H, W = 20, 20
+
+    def edit(xs, ys, ts, ps):
+        xs[0][:50_000] = 7
+        ys[0][:50_000] = 11                        # 50 000 events on one pixel: more than the window holds
+    ev, _ = dense_batch(ep, rng, [60_000], H, W, edit=edit)
+    with pytest.raises(OverflowError):
+        ep.evrep(ev.packed(4).to("cuda"), (H, W), check=True)
