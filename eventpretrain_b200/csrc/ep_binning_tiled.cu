@@ -20,8 +20,9 @@
 //     live in shared memory as int32 Q24 sums (100 KB).  The task walks the temporal intervals k = 0 .. bins-1: the events
 //     of interval k (found through the per-chunk interval range the route wrote; contiguous for time-sorted streams, any
 //     order is handled) add 2^24 - r to plane k and r to plane k + 1 with two shared-memory atomics, then plane k is
-//     converted to fp32 (one rounding), written to the output with 16-byte streaming stores, added into the voxel.sum(0)
-//     plane (sequential fp32 over bins, like the reference's sum), and its buffer is re-zeroed to become plane k + 2.
+//     converted to fp32 (one rounding), written to the output with 16-byte stores, and its buffer is re-zeroed to become
+//     plane k + 2.  voxel.sum(0) is formed at the last plane from the earlier planes read back out of L2 (sequential fp32
+//     over bins, like the reference's sum; grids with many bins keep a running sum instead).
 //     The runs (chunk, tile) of a phase are cut into items of at most 128 records that the warps draw from a shared
 //     counter, with the next item's records in flight while the current one is accumulated.
 //     Every record is read once; there are no global accumulators, no memset and no finalize pass.
@@ -519,6 +520,7 @@ __device__ __forceinline__ int atoms_add(uint32_t saddr, int w) {
     asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(w) : "memory");
     return old;
 }
+#if EP_SWEEP_PREDICATED
 // the same, predicated off (returning 0) where ok is false: lanes past the end of an item and records of another interval
 // then take no bank of the shared-memory pipe
 __device__ __forceinline__ int atoms_add_if(bool ok, uint32_t saddr, int w) {
@@ -527,6 +529,7 @@ __device__ __forceinline__ int atoms_add_if(bool ok, uint32_t saddr, int w) {
                  : "=&r"(old) : "r"(saddr), "r"(w), "r"((int)ok) : "memory");
     return old;
 }
+#endif
 __device__ __forceinline__ int sgn2(uint32_t rec) {              // signed 2-bit polarity field
     int r;
     asm("bfe.s32 %0, %1, 0, 2;" : "=r"(r) : "r"(rec));
