@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libeventpretrain_b200.so")
 EP_U8, EP_I8, EP_U16, EP_I16, EP_I32, EP_I64, EP_F32, EP_F64, EP_U32 = range(1, 10)
 EP_NORM_COUNT, EP_NORM_MEM, EP_NORM_MEM_GUARD = 1, 2, 3
 EP_ORDER_CPQ, EP_ORDER_PQC = 0, 1
-EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_TILED = 1, 4
+EP_BIN_FORCE_GLOBAL, EP_BIN_FORCE_TILED, EP_BIN_FORCE_PLANE = 1, 4, 8
 EP_EINVAL, EP_EWORKSPACE, EP_EUNSUPPORTED, EP_EALIGN = -1, -2, -3, -4
 EP_RESIZE_NEAREST, EP_RESIZE_BILINEAR, EP_RESIZE_BICUBIC = 0, 1, 2
 

@@ -586,8 +586,8 @@ static int bin_events_any(void* stream, const ep_events_soa* ev, const ep_bin_pa
             // outputs it does not take (count frames, > 64 row tiles) fall through to the global-RED kernels
             rc = run_tiled_packed4(st, ev, prm, out_voxel, out_voxel_sum, workspace, workspace_bytes, bad_count, out_stats);
             if (rc == EP_OK) *stats_done = true;
-            if (rc != EP_EUNSUPPORTED || (prm->flags & EP_BIN_FORCE_TILED)) return rc;
-        } else if (prm->flags & EP_BIN_FORCE_TILED) {
+            if (rc != EP_EUNSUPPORTED || (prm->flags & (EP_BIN_FORCE_TILED | EP_BIN_FORCE_PLANE))) return rc;
+        } else if (prm->flags & (EP_BIN_FORCE_TILED | EP_BIN_FORCE_PLANE)) {
             return EP_EUNSUPPORTED;
         }
         if (five) {
@@ -600,7 +600,7 @@ static int bin_events_any(void* stream, const ep_events_soa* ev, const ep_bin_pa
         return run_binning(st, ld, ev->offsets, ev->offsets_host, 0, B, prm, out_voxel, out_voxel_sum, out_count, workspace,
                            workspace_bytes, bad_count);
     }
-    if (prm->flags & EP_BIN_FORCE_TILED) return EP_EUNSUPPORTED;
+    if (prm->flags & (EP_BIN_FORCE_TILED | EP_BIN_FORCE_PLANE)) return EP_EUNSUPPORTED;
     const bool compact = ev->t_dtype == EP_U32;
     if (compact) {
         // compact transport layout: u16 x,y + u32 (relative ticks | polarity << 31) + per-sample int64 base

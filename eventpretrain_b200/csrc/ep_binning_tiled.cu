@@ -70,6 +70,7 @@ constexpr int kItemRecs = 32 * kItemRPL;
 static_assert(kItemRPL >= 1 && kItemRPL <= 4, "the item descriptor holds records - 1 in 7 bits");
 // measured on B200, sweep of the 256-sample batch: 64-record items 1.046 ms, 96 1.008, 128 0.953 (kept)
 constexpr int kSpillCap = 128;
+constexpr int kPlaneCellsMax = 54272;         // whole-plane kernels: 212 KB of int32 plane + 13 KB of tables and spill list
 
 constexpr uint32_t kChunkFast = 1u;           // integer-tick sample, narrow records, every v of the chunk fits 32 bits
 constexpr uint32_t kChunkNarrow = 2u;         // records carry chunk-relative ticks (else: tick block + block-relative ticks)
@@ -105,6 +106,9 @@ struct TiledArgs {
     int sweep_lo, sweep_hi;     // sweep tasks (sample * NT + tile) of this launch
     int counter_idx;            // which of the sweep task counters this launch draws from
     int deferred_sum;           // sweep: voxel.sum(0) at the last plane from the planes read back (else a running sum per plane)
+    int count_bad;              // route: out-of-grid events are added to bad_count (0 when another kernel already counted them)
+    const unsigned int* run_if; // null, or a device word: every kernel of the path returns at once while it is 0 (the path
+                                // then stands by as the fallback of the whole-plane kernels, run_plane_packed4)
     SampleMeta* meta;
     int* first_task;            // B+1
     TaskDesc* desc;             // n_tasks
@@ -129,6 +133,7 @@ __device__ __forceinline__ void pdl_trigger_t() { asm volatile("griddepcontrol.l
 __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
+    if (a.run_if && *a.run_if == 0u) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(1024) k_tiled_setup(TiledArgs a) {
 
 __global__ void __launch_bounds__(256) k_tiled_desc(TiledArgs a) {
     const int task = blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= a.n_tasks) return;
+    if (task >= a.n_tasks || (a.run_if && *a.run_if == 0u)) return;
     int lo_b = 0, hi_b = a.B;                          // largest b with first_task[b] <= task (empty samples share a value:
     while (hi_b - lo_b > 1) {                          // the last of them is the one that owns tasks)
         const int mid = (lo_b + hi_b) >> 1;
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
     __shared__ uint32_t s_fmt[2];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (a.run_if && *a.run_if == 0u) return;
     const int NT = a.NT, NB = NT + 1;          // bucket NT = trash (coordinates outside the grid)
     // every bucket has 2^rs rank counters, picked by the lane: with few tiles most lanes of a warp would hit the same word
     const uint32_t rs = REP ? (uint32_t)a.rep_shift : 0u, rep = REP ? ((uint32_t)lane & ((1u << rs) - 1u)) : 0u;
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) k_route(TiledArgs a) {
                 }
                 run += c[j];
             }
-            if (wid == 0 && a.bad_count) {
+            if (wid == 0 && a.bad_count && a.count_bad) {
                 // events outside the grid: the sub-buckets of the trash bucket
                 const int t0 = NT << rs;
                 uint32_t nbad = 0;
@@ -857,6 +863,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtas) k_sweep(TiledArgs a
     __shared__ SampleMeta s_meta;
 
     const int tid = threadIdx.x, lane = tid & 31;
+    if (a.run_if && *a.run_if == 0u) return;
     pdl_trigger_t();
     for (int i = tid; i < 2 * tile_cells; i += kSweepThreads) plane0[i] = 0;
     if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
@@ -987,6 +994,8 @@ struct TiledPlan {
     int NT, rows, n_tasks;
     int64_t rec_pos0, n_rec;
     size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_stats2, off_rec, total;
+    bool plane_ok;              // the grid's plane fits one SM's shared memory: whole-plane kernels (run_plane_packed4)
+    size_t off_plane, off_plane_bounds;
 };
 
 bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) {
@@ -1025,6 +1034,12 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_stats = o; o += align_up(sizeof(double) * kStatSlot * (size_t)B * NT * (size_t)(p->num_bins + 1), 256);
     pl.off_stats2 = o; o += align_up(sizeof(double) * 3 * kStatSlices * (size_t)(p->num_bins + 1), 256);
     pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
+    pl.plane_ok = (int64_t)H * W <= kPlaneCellsMax && (int64_t)B * p->num_bins < (1ll << 30);
+    pl.off_plane = pl.off_plane_bounds = 0;
+    if (pl.plane_ok) {
+        pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B, 256);          // counters | finished planes per sample
+        pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 1), 256);
+    }
     pl.total = o;
     return true;
 }
@@ -1076,9 +1091,15 @@ __global__ void __launch_bounds__(32) k_stats_final(const double* __restrict__ p
     if (lane == 0) { out[c * 4 + 0] = count; out[c * 4 + 1] = a1; out[c * 4 + 2] = a2; out[c * 4 + 3] = am; }
 }
 
-// Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
-int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
+namespace {
+int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                      void* ws, size_t ws_bytes, unsigned int* bad);
+}
+
+// standby = device word of the whole-plane path (run_plane_packed4): the kernels below return at once while it is 0, the
+// per-sample metadata is already in place and the out-of-grid events are already counted
+static int run_tiled_packed4_impl(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                                  void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats, const unsigned int* standby) {
     TiledPlan pl;
     if (!tiled_plan(ev, p, pl)) return EP_EUNSUPPORTED;
     if (!ws || ws_bytes < pl.total) return EP_EUNSUPPORTED;
@@ -1087,7 +1108,9 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     if (!aligned16(ev->x)) return EP_EALIGN;
     const int B = ev->batch;
     char* base = static_cast<char*>(ws);
-    TiledArgs a;
+    TiledArgs a = {};
+    a.run_if = standby;
+    a.count_bad = standby ? 0 : 1;
     a.w = static_cast<const uint32_t*>(ev->x);
     a.blk_base = static_cast<const uint32_t*>(ev->p);
     a.offsets = ev->offsets;
@@ -1116,8 +1139,10 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     BinArgs ba = {};
     ba.offsets = ev->offsets; ba.num_bins = p->num_bins; ba.meta = a.meta;
     profile_begin(st, kProfOther);
-    k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
-    EP_LAUNCH_CHECK();
+    if (!standby) {
+        k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
+        EP_LAUNCH_CHECK();
+    }
     k_tiled_setup<<<1, 1024, 0, st>>>(a);
     EP_LAUNCH_CHECK();
     if (a.n_tasks > 0) {
@@ -1184,6 +1209,570 @@ int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
         EP_LAUNCH_CHECK();
     }
     return EP_OK;
+}
+
+// =====================================================================================================================
+// Whole-plane path: grids whose plane fits the shared memory of one SM (224 x 224 of the reference's own pre-training
+// order — events_reshape to 224 x 224, then the voxel grid, dataset/pretrain/pr_n_imagenet_dataset.py:85-87 — 240 x 180,
+// anything up to kPlaneCells cells).  No route pass and no routed records:
+//   * k_plane_bounds: per sample, the array positions s_1 .. s_(bins-1) where the temporal intervals begin (bisection on the
+//     stamps, 128 probes per round; s_0 = first event, s_bins = end).  For a time-sorted sample the slice [s_j, s_(j+1)) holds
+//     exactly the events of interval j.
+//   * k_plane: persistent, one CTA of 1024 threads per SM, a task = (sample, output plane k).  The CTA streams the two slices
+//     that feed plane k — interval k-1 (right-node weights r) and interval k (left-node weights 2^24 - r) — straight from the
+//     packed words (coordinates through the shared-memory tables of the fused events_reshape, integer time arithmetic as in
+//     the sweep), adds them with one returning shared-memory atomic per event into the int32 Q24 plane (wraps go to the
+//     spill list as in the sweep), converts the plane to fp32 and writes it once.  Every event is read twice (the second
+//     time mostly from L2), every output element written once.  The CTA that finishes the last plane of a sample forms
+//     voxel.sum(0) from the planes in L2 (sequential fp32 over bins, the reference's order).
+//   * exactness for ANY input: every event a CTA reads is checked against the interval its slice stands for.  One mismatch
+//     (unsorted rows) raises a device flag, and the route + sweep kernels, which take any order and stand by behind the
+//     same stream (they return at once while the flag is 0), redo the whole batch.  Out-of-grid events are counted by
+//     position (every slice is some plane's left slice exactly once), so bad_count is right either way.
+// Same integers as the other two paths: bit-identical outputs.
+// =====================================================================================================================
+namespace {
+
+#ifndef EP_PLANE_THREADS
+#define EP_PLANE_THREADS 1024
+#endif
+constexpr int kPlaneThreads = EP_PLANE_THREADS;
+constexpr int kPlaneCells = kPlaneCellsMax;
+constexpr uint32_t kLutBad = 0x40000000u;     // row base of a y outside the grid: the cell test fails whatever x is
+
+// events_reshape of one axis without a table: trunc(fl(i * s)) == umulhi(i, mul) for every coordinate i < 2048 of the packed
+// layout, proven on the host by comparing all of them (plane_axis_mul).  fl() is the fp64 rounding of the product: for some
+// scales a few i whose exact product is an integer land just below it (0.35 * 180 = 62.99999999999999); such an axis keeps
+// its shared-memory table.
+constexpr int kCoordPlain = 0;       // no scale: y * W + x
+constexpr int kCoordLut = 1;         // both axes through the tables
+constexpr int kCoordMulY = 2;        // y by multiply-high, x through its table
+constexpr int kCoordMulX = 3;        // x by multiply-high, y through its table
+constexpr int kCoordMul = 4;         // both by multiply-high
+
+struct PlaneArgs {
+    const uint32_t* w;
+    const uint32_t* blk_base;
+    const int64_t* offsets;
+    int64_t n_total;
+    int B, H, W, num_bins;
+    double sx, sy;
+    int scaled;
+    int coord_mode;             // kCoord*
+    uint32_t mul_x, mul_y;      // multiply-high constants of the axes that have one
+    const SampleMeta* meta;
+    int64_t* bounds;            // B x (num_bins + 1): s_0 .. s_bins
+    unsigned int* counters;     // [0] task counter, [1] fallback flag (an event outside its slice's interval)
+    unsigned int* done;         // B: finished planes per sample
+    unsigned int* bad_count;
+    float* out_voxel;
+    float* out_sum;
+};
+
+__host__ __device__ inline size_t plane_smem_bytes(int hw) {
+    return (size_t)((hw + 3) & ~3) * 4 + 16 + 2048 * 4 + 2048 * 2 + kSpillCap * 8;      // plane | dump word | tables | spill list
+}
+
+// stamp of array position i of a sample that starts at lo, as ticks from the sample's first row
+__device__ __forceinline__ int64_t plane_dt(const PlaneArgs& a, int64_t i, int64_t lo, int64_t t0_ticks) {
+    const int64_t blk = i >> kTickBlockShift;
+    const int64_t base = (blk == (lo >> kTickBlockShift)) ? 0 : (int64_t)__ldg(a.blk_base + blk);
+    return base + (int64_t)(__ldg(a.w + i) >> 23) - t0_ticks;
+}
+
+__global__ void __launch_bounds__(128) k_plane_bounds(PlaneArgs a) {
+    __shared__ int s_min;
+    const int nb1 = a.num_bins > 1 ? a.num_bins - 1 : 1;
+    const int b = blockIdx.x / nb1, j = blockIdx.x % nb1 + 1;       // boundary j = first position of interval j
+    const int tid = threadIdx.x;
+    const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
+    int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 1);
+    if (j == 1 && tid == 0) { bd[0] = lo; bd[a.num_bins] = hi; }
+    if (a.num_bins < 2) return;
+    const SampleMeta m = a.meta[b];
+    const uint32_t T = (uint32_t)j << kQ;
+    // Every round probes 128 equidistant positions of [cl, ch) and keeps the gap in front of the first probe at or past the
+    // boundary.  The probe positions depend on (cl, ch) only, and "at or past T2" implies "at or past T1" for T1 < T2, so
+    // s_1 <= s_2 <= ... holds for any input: the slices always partition the sample.
+    int64_t cl = lo, ch = hi;
+    while (ch > cl) {
+        const int64_t stride = (ch - cl + 127) / 128;
+        if (tid == 0) s_min = 128;
+        __syncthreads();
+        const int64_t pos = cl + tid * stride;
+        bool past = true;                                  // positions from ch on are past the boundary
+        if (pos < ch) {
+            const int64_t dt = plane_dt(a, pos, lo, m.t0_ticks);
+            uint32_t v = 0;
+            past = v_general(dt, m, a.num_bins, v) ? (v >= T) : (dt > 0);
+        }
+        if (past) atomicMin(&s_min, tid);
+        __syncthreads();
+        const int t = s_min;
+        const int64_t pt = cl + t * stride;
+        const int64_t nl = t == 0 ? cl : cl + (t - 1) * stride + 1;
+        const int64_t nh = pt < ch ? pt : ch;
+        __syncthreads();
+        cl = nl; ch = nh;
+    }
+    if (tid == 0) bd[j] = cl;
+}
+
+struct PlaneCtx {
+    uint32_t plane_s;           // shared-memory address of the plane
+    uint32_t luty_s, lutx_s;    // shared-memory addresses of the coordinate tables
+    const uint32_t* lut_y;
+    const uint16_t* lut_x;
+    int2* spill;
+    int* n_spill;
+    unsigned int* bad;
+    uint32_t hw;                // cells of the plane
+    uint32_t dump;              // index of the word behind the plane: out-of-grid events add there (never read)
+    uint32_t W, mul_x, mul_y;
+};
+
+// Per-task constants of the time arithmetic
+struct PlaneTime {
+    uint32_t tmul, tshift, dT;  // FAST: v = (dt * tmul + thalf) >> tshift for 0 <= dt <= dT ticks (v(dT) = (bins - 1) << 24)
+    uint64_t thalf;
+};
+
+// Running maxima of a slice: every event of the slice must lie in the slice's interval (u < 2^24) at a stamp inside the
+// sample (dt <= dT); one event outside (unsorted rows) hands the batch to the route + sweep kernels.  ce = largest cell index
+// (left slices: events outside the grid are counted in a cold path when it leaves the plane).
+struct PlaneMax {
+    uint32_t u, dt, ce;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// cell of a packed word through the tables of the fused events_reshape: row base + column; anything >= hw is outside the grid
+__device__ __forceinline__ uint32_t plane_cell(const PlaneCtx& c, uint32_t word) {
+    const uint32_t ly = lds_u32(c.luty_s + ((word >> 9) & 0x1ffcu));
+    const uint32_t lx = lds_u16(c.lutx_s + ((word << 1) & 0xffeu));
+    return ly + lx;
+}
+
+// cells of the four words of a quad.  A table look-up costs ~3.5 shared-memory wavefronts for random coordinates (bank
+// conflicts), as much as the atomic itself: with both axes on tables the look-ups, not the atomics, bound the kernel; an
+// axis whose scale has a proven multiply-high form costs one IMAD.HI instead.
+template <int CM>
+__device__ __forceinline__ void plane_cells(const PlaneCtx& c, const uint32_t (&ws)[4], uint32_t (&ce)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t word = ws[e];
+        if (CM == kCoordPlain) {
+            ce[e] = ((word >> 11) & 0x7ffu) * c.W + (word & 0x7ffu);
+        } else {
+            const uint32_t row = (CM == kCoordMulY || CM == kCoordMul) ? __umulhi((word >> 11) & 0x7ffu, c.mul_y) * c.W
+                                                                       : lds_u32(c.luty_s + ((word >> 9) & 0x1ffcu));
+            const uint32_t col = (CM == kCoordMulX || CM == kCoordMul) ? __umulhi(word & 0x7ffu, c.mul_x)
+                                                                       : lds_u16(c.lutx_s + ((word << 1) & 0xffeu));
+            ce[e] = row + col;
+        }
+    }
+}
+
+// One quad (four packed words of one 16-byte load) of one slice.  LEFT: the slice is interval kexp = k and feeds the plane
+// with the left-node weights 2^24 - r, else it is interval kexp = k - 1 and feeds it with r.  EDGE: the quad lies in a tick
+// block that straddles an end of the slice, event e belongs to the slice when (rel0 + e) < len (unsigned).  FAST:
+// integer-tick sample whose dT leaves room for the wrap-around test: dtb = block base - first-row ticks (mod 2^32), a stamp
+// before the first row wraps to more than dT like one past the last row.  An event outside its interval adds a
+// meaningless weight — the batch is redone anyway.
+template <bool FAST, int CM, bool LEFT, bool EDGE>
+__device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int num_bins, uint4 wq,
+                                           int64_t dtb, uint32_t rel0, uint32_t len, uint32_t kbase, PlaneMax& mx, uint32_t& mismatch) {
+    const uint32_t ws[4] = {wq.x, wq.y, wq.z, wq.w};
+    int old[4], val[4];
+    uint32_t cell[4], cev[4];
+    plane_cells<CM>(c, ws, cev);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t word = ws[e];
+        const bool in = !EDGE || rel0 + (uint32_t)e < len;
+        uint32_t u;
+        if (FAST) {
+            const uint32_t dt = (uint32_t)dtb + (word >> 23);
+            const uint64_t q = (uint64_t)dt * tm.tmul + tm.thalf;
+            u = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), tm.tshift) - kbase;
+            if (!EDGE) { mx.dt = max(mx.dt, dt); mx.u = max(mx.u, u); }
+            else if (in) { mx.dt = max(mx.dt, dt); mx.u = max(mx.u, u); }
+        } else {
+            uint32_t v = 0;
+            const bool ok = v_general(dtb + (int64_t)(word >> 23), m, num_bins, v);
+            u = v - kbase;
+            if (in && !(ok && u < (1u << kQ))) { mismatch = 1u; u = 0u; }
+        }
+        const uint32_t ce = cev[e];
+        if (LEFT && in) mx.ce = max(mx.ce, ce);
+        const int wgt = LEFT ? (int)((1u << kQ) - u) : (int)u;
+        val[e] = ((word >> 22) & 1u) ? wgt : -wgt;
+        if (EDGE && !in) val[e] = 0;
+        cell[e] = min(ce, c.dump);
+        old[e] = atoms_add(c.plane_s + cell[e] * 4u, val[e]);
+    }
+    uint32_t near = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) near = max(near, (uint32_t)old[e] + 0x7f000000u);
+    if (near >= 0xfe000000u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (cell[e] < c.hw && near_wrap(old[e])) note_wrap(old[e], val[e], cell[e], c.spill, c.n_spill, c.bad);
+    }
+}
+
+#ifndef EP_PLANE_PIPE
+#define EP_PLANE_PIPE 2        // 0 = plain loop, 1 = the block after next is requested into L2, 2 = next block's words in registers
+#endif
+
+// The slice [s0, s1) of the sample that starts at lo: interval kexp (kbase = kexp << 24).  A warp takes one 256-event tick
+// block per step (two quads per lane, one block base for the warp); only the first and the last block of a slice can
+// straddle its ends.
+template <bool FAST, int CM, bool LEFT>
+__device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int64_t lo,
+                                            int64_t s0, int64_t s1, uint32_t kbase, uint32_t& mismatch, uint32_t& nbad) {
+    constexpr int kWarps = kPlaneThreads / 32;
+    constexpr int kBlk = 1 << kTickBlockShift;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t blk0 = s0 >> kTickBlockShift;
+    const uint32_t nblk = (uint32_t)(((s1 - 1) >> kTickBlockShift) - blk0) + 1u;
+    const uint32_t first_rel = (uint32_t)((lo >> kTickBlockShift) - blk0);       // the block where the sample starts has base 0
+    const bool head = (s0 & (kBlk - 1)) != 0, tail = (s1 & (kBlk - 1)) != 0;
+    const uint32_t* wp = a.w + (blk0 << kTickBlockShift) + lane * 4;
+    const uint32_t* bp = a.blk_base + blk0;
+    const uint32_t t0 = (uint32_t)m.t0_ticks;
+    const uint32_t len = (uint32_t)(s1 - s0);
+    PlaneMax mx;
+    mx.u = 0u; mx.dt = 0u; mx.ce = 0u;
+#if EP_PLANE_PIPE == 2
+    uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+    uint32_t nb = 0u;
+    auto fetch = [&](uint32_t i) {
+        const uint4* p = reinterpret_cast<const uint4*>(wp + ((size_t)i << kTickBlockShift));
+        const bool edge = (i == 0u && head) || (i == nblk - 1u && tail);
+        if (!edge) { n0 = ld_stream(p); n1 = ld_stream(p + 32); }
+        nb = (i == first_rel) ? 0u : __ldg(bp + i);
+    };
+    if ((uint32_t)wid < nblk) fetch((uint32_t)wid);
+#endif
+    for (uint32_t i = (uint32_t)wid; i < nblk; i += kWarps) {
+        const uint4* p = reinterpret_cast<const uint4*>(wp + ((size_t)i << kTickBlockShift));
+        const bool edge = (i == 0u && head) || (i == nblk - 1u && tail);
+#if EP_PLANE_PIPE == 2
+        const uint4 w0 = n0, w1 = n1;
+        const uint32_t base = nb;
+        if (i + kWarps < nblk) fetch(i + kWarps);
+#else
+        const uint32_t base = (i == first_rel) ? 0u : __ldg(bp + i);
+#if EP_PLANE_PIPE == 1
+        if (i + 2 * kWarps < nblk) {
+            prefetch_l2(p + 2 * kWarps * (kBlk / 4));
+            prefetch_l2(p + 2 * kWarps * (kBlk / 4) + 32);
+        }
+#endif
+#endif
+        if (FAST && base > 0xfffffdffu) { mismatch = 1u; continue; }       // (a block 2^32 ticks past the first row: unsorted input)
+        const int64_t dtb = FAST ? (int64_t)(base - t0) : (int64_t)base - m.t0_ticks;
+        if (!edge) {
+#if EP_PLANE_PIPE != 2
+            const uint4 w0 = ld_stream(p), w1 = ld_stream(p + 32);
+#endif
+            plane_quad<FAST, CM, LEFT, false>(c, m, tm, a.num_bins, w0, dtb, 0u, len, kbase, mx, mismatch);
+            plane_quad<FAST, CM, LEFT, false>(c, m, tm, a.num_bins, w1, dtb, 0u, len, kbase, mx, mismatch);
+        } else {
+            // first / last block of the slice: only the events inside [s0, s1) are loaded and added
+            const int64_t bs = (blk0 + (int64_t)i) << kTickBlockShift;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int64_t pos = bs + h * 128 + lane * 4;
+                uint32_t t4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (pos + e >= s0 && pos + e < s1) t4[e] = a.w[pos + e];
+                plane_quad<FAST, CM, LEFT, true>(c, m, tm, a.num_bins, make_uint4(t4[0], t4[1], t4[2], t4[3]), dtb,
+                                                     (uint32_t)(pos - s0), len, kbase, mx, mismatch);
+            }
+        }
+        if (LEFT && mx.ce >= c.hw) {
+            // cold: events outside the grid are counted where their slice is the left one (every position exactly once)
+            const int64_t bs = (blk0 + (int64_t)i) << kTickBlockShift;
+            for (int h = 0; h < 2; ++h)
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t pos = bs + h * 128 + lane * 4 + e;
+                    if (pos >= s0 && pos < s1 && plane_cell(c, a.w[pos]) >= c.hw) ++nbad;
+                }
+            mx.ce = 0u;
+        }
+    }
+    if (FAST && (mx.u >= (1u << kQ) || mx.dt > tm.dT)) mismatch = 1u;
+}
+
+// plane k of a sample: right-node weights of interval k - 1 = [a0, mid), left-node weights of interval k = [mid, a1)
+template <bool FAST, int CM>
+__device__ __forceinline__ void plane_accumulate(const PlaneArgs& a, const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int64_t lo,
+                                                 int64_t a0, int64_t mid, int64_t a1, uint32_t k, uint32_t& mismatch, uint32_t& nbad) {
+    // Slice j is read by the CTAs of planes j (left) and j + 1 (right), which are drawn one after the other and run side by
+    // side: even planes take their left slice first, odd planes their right one, so both read it at the same time and the
+    // second reader finds it in L2.
+    if (k & 1u) {
+        if (mid > a0) plane_slice<FAST, CM, false>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
+        if (a1 > mid) plane_slice<FAST, CM, true>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
+    } else {
+        if (a1 > mid) plane_slice<FAST, CM, true>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
+        if (mid > a0) plane_slice<FAST, CM, false>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int HW = a.H * a.W, HWp = (HW + 3) & ~3;
+    int* plane = reinterpret_cast<int*>(smem_raw);
+    uint32_t* lut_y = reinterpret_cast<uint32_t*>(plane + HWp + 4);
+    uint16_t* lut_x = reinterpret_cast<uint16_t*>(lut_y + 2048);
+    int2* s_spill = reinterpret_cast<int2*>(lut_x + 2048);
+    __shared__ int s_task[2], s_nspill, s_last;
+
+    const int tid = threadIdx.x;
+    const int n_tasks = a.B * a.num_bins;
+    if (tid == 0) { s_task[0] = (int)atomicAdd(&a.counters[0], 1u); s_nspill = 0; }
+    for (int i = tid; i < HWp; i += kPlaneThreads) plane[i] = 0;
+    if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
+    for (int i = tid; i < 2048; i += kPlaneThreads) {
+        const long long yy = a.scaled ? __double2ll_rz(__dmul_rn((double)i, a.sy)) : (long long)i;
+        const long long xx = a.scaled ? __double2ll_rz(__dmul_rn((double)i, a.sx)) : (long long)i;
+        lut_y[i] = (yy < a.H + 65536 && yy * a.W < (long long)HW) ? (uint32_t)(yy * a.W) : kLutBad;
+        lut_x[i] = (uint16_t)(xx < 65535 ? xx : 65535);            // x + y * W has no bound on x alone (events_to_voxel_grid.py:46)
+    }
+    __syncthreads();
+    PlaneCtx c;
+    c.plane_s = (uint32_t)__cvta_generic_to_shared(plane);
+    c.luty_s = (uint32_t)__cvta_generic_to_shared(lut_y); c.lutx_s = (uint32_t)__cvta_generic_to_shared(lut_x);
+    c.lut_y = lut_y; c.lut_x = lut_x; c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
+    c.hw = (uint32_t)HW; c.dump = (uint32_t)HWp; c.W = (uint32_t)a.W; c.mul_x = a.mul_x; c.mul_y = a.mul_y;
+    uint32_t mismatch = 0, nbad = 0;
+    int cur = 0;
+    for (;;) {
+        const int task = s_task[cur];
+        if (task >= n_tasks) break;
+        if (tid == 0) s_task[cur ^ 1] = (int)atomicAdd(&a.counters[0], 1u);       // read behind this task's barriers
+        const int b = task / a.num_bins, k = task - b * a.num_bins;       // the planes of a sample run side by side (L2 reuse)
+        const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 1);
+        const int64_t lo = bd[0];
+        const int64_t a0 = bd[k > 0 ? k - 1 : 0], mid = bd[k], a1 = bd[k + 1];
+        const SampleMeta m = a.meta[b];
+        if (mid < a0 || a1 < mid || a1 - a0 >= (1ll << 32)) {
+            mismatch = 1u;                                         // (never: the boundaries are monotone by construction)
+        } else if (a1 > a0) {
+            const int64_t hi = bd[a.num_bins];
+            PlaneTime tm;
+            tm.tmul = m.tmul; tm.tshift = m.tshift; tm.thalf = m.thalf;
+            const int64_t dT = plane_dt(a, hi - 1, lo, m.t0_ticks);               // > 0 and < 2^32 for an integer-time sample
+            tm.dT = (uint32_t)dT;
+            const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024;
+            if (fast) {
+#define EP_PLANE_ACC(CM) plane_accumulate<true, CM>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad)
+                switch (a.coord_mode) {
+                    case kCoordPlain: EP_PLANE_ACC(kCoordPlain); break;
+                    case kCoordMulY: EP_PLANE_ACC(kCoordMulY); break;
+                    case kCoordMulX: EP_PLANE_ACC(kCoordMulX); break;
+                    case kCoordMul: EP_PLANE_ACC(kCoordMul); break;
+                    default: EP_PLANE_ACC(kCoordLut); break;
+                }
+#undef EP_PLANE_ACC
+            } else {
+                plane_accumulate<false, kCoordLut>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad);
+            }
+        }
+        __syncthreads();
+        // ---- plane k complete: fp32 out (one rounding), plane re-zeroed ----
+        constexpr float kInv = 1.0f / 16777216.0f;
+        const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
+        float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW;
+        const bool keep = a.out_sum != nullptr;                    // the planes are read back for voxel.sum(0): leave them in L2
+        if (VEC) {
+            for (int i = tid * 4; i < HW; i += kPlaneThreads * 4) {
+                const int4 q = *reinterpret_cast<const int4*>(plane + i);
+                *reinterpret_cast<int4*>(plane + i) = make_int4(0, 0, 0, 0);
+                float4 f = make_float4(__int2float_rn(q.x) * kInv, __int2float_rn(q.y) * kInv, __int2float_rn(q.z) * kInv,
+                                       __int2float_rn(q.w) * kInv);
+                if (n_spill) {
+                    const int qi[4] = {q.x, q.y, q.z, q.w};
+                    float* fp = reinterpret_cast<float*>(&f);
+                    for (int j = 0; j < 4; ++j) {
+                        long long hi = 0;
+                        for (int t = 0; t < n_spill; ++t) if (s_spill[t].x == i + j) hi += s_spill[t].y;
+                        if (hi) fp[j] = __ll2float_rn((hi << 32) + (long long)qi[j]) * kInv;
+                    }
+                }
+                if (keep) __stcg(reinterpret_cast<float4*>(o + i), f);
+                else st_stream(reinterpret_cast<float4*>(o + i), f);
+            }
+        } else {
+            for (int i = tid; i < HW; i += kPlaneThreads) {
+                const int q = plane[i];
+                plane[i] = 0;
+                float f = __int2float_rn(q) * kInv;
+                if (n_spill) {
+                    long long hi = 0;
+                    for (int t = 0; t < n_spill; ++t) if (s_spill[t].x == i) hi += s_spill[t].y;
+                    if (hi) f = __ll2float_rn((hi << 32) + (long long)q) * kInv;
+                }
+                if (keep) __stcg(o + i, f);
+                else st_stream(o + i, f);
+            }
+        }
+        if (keep) {
+            // ---- the CTA that completes a sample's last plane forms voxel.sum(0) ----
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int old = atomicAdd(&a.done[b], 1u);
+                s_last = (old + 1u == (unsigned int)a.num_bins) ? 1 : 0;
+                if (s_last) __threadfence();
+            }
+            __syncthreads();
+            if (s_last) {
+                const float* p0 = a.out_voxel + (int64_t)b * a.num_bins * HW;
+                float* so = a.out_sum + (int64_t)b * HW;
+                if (VEC) {
+                    for (int i = tid * 4; i < HW; i += kPlaneThreads * 4) {
+                        float4 s = __ldcg(reinterpret_cast<const float4*>(p0 + i));
+                        for (int j0 = 1; j0 < a.num_bins; j0 += 4) {
+                            float4 v[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (j0 + jj < a.num_bins) v[jj] = __ldcg(reinterpret_cast<const float4*>(p0 + (int64_t)(j0 + jj) * HW + i));
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (j0 + jj < a.num_bins) { s.x += v[jj].x; s.y += v[jj].y; s.z += v[jj].z; s.w += v[jj].w; }
+                        }
+                        st_stream(reinterpret_cast<float4*>(so + i), s);
+                    }
+                } else {
+                    for (int i = tid; i < HW; i += kPlaneThreads) {
+                        float s = __ldcg(p0 + i);
+                        for (int j = 1; j < a.num_bins; ++j) s += __ldcg(p0 + (int64_t)j * HW + i);      // sequential fp32 over bins
+                        st_stream(so + i, s);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (n_spill) {
+            if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
+            if (tid == 0) s_nspill = 0;
+            __syncthreads();
+        }
+        cur ^= 1;
+    }
+    if (mismatch) atomicOr(&a.counters[1], 1u);
+    if (nbad && a.bad_count) atomicAdd(a.bad_count, nbad);
+}
+
+// Host: multiply-high form of one axis of events_reshape, proven against the reference's expression (fp64 product, truncation)
+// on all 2048 coordinates of the packed layout; false = the axis keeps its table.
+static bool plane_axis_mul(double s, uint32_t& mul_out) {
+    if (!(s > 0.0) || !(s < 1.0)) return false;
+    const uint64_t mul = (uint64_t)ceil(ldexp(s, 32));
+    if (mul == 0 || mul >= (1ull << 32)) return false;
+    for (uint32_t i = 0; i < 2048; ++i) {
+        const volatile double prod = (double)i * s;
+        if ((int64_t)prod != (int64_t)(((uint64_t)i * mul) >> 32)) return false;
+    }
+    mul_out = (uint32_t)mul;
+    return true;
+}
+
+int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                      void* ws, size_t ws_bytes, unsigned int* bad) {
+    TiledPlan pl;
+    if (!tiled_plan(ev, p, pl) || !pl.plane_ok) return EP_EUNSUPPORTED;
+    if (!ws || ws_bytes < pl.total) return EP_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(ws) & 255u) return EP_EALIGN;
+    if (!out_voxel) return EP_EINVAL;
+    if (!aligned16(ev->x)) return EP_EALIGN;
+    const int B = ev->batch;
+    char* base = static_cast<char*>(ws);
+    PlaneArgs a = {};
+    a.w = static_cast<const uint32_t*>(ev->x);
+    a.blk_base = static_cast<const uint32_t*>(ev->p);
+    a.offsets = ev->offsets;
+    a.n_total = ev->offsets_host[B];
+    a.B = B; a.H = p->height; a.W = p->width; a.num_bins = p->num_bins;
+    a.sx = p->scale_x; a.sy = p->scale_y; a.scaled = (p->scale_x != 1.0 || p->scale_y != 1.0);
+    SampleMeta* meta = reinterpret_cast<SampleMeta*>(base + pl.off_meta);
+    a.meta = meta;
+    a.counters = reinterpret_cast<unsigned int*>(base + pl.off_plane);
+    a.done = a.counters + 64;
+    a.bounds = reinterpret_cast<int64_t*>(base + pl.off_plane_bounds);
+    a.bad_count = bad;
+    a.out_voxel = out_voxel;
+    a.out_sum = out_sum;
+
+    SoaPackedLoader<false> ld{a.w, nullptr, a.blk_base, ev->t_base, ev->t_div};
+    BinArgs ba = {};
+    ba.offsets = ev->offsets; ba.num_bins = p->num_bins; ba.meta = meta;
+    profile_begin(st, kProfOther);
+    k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
+    EP_LAUNCH_CHECK();
+    cudaError_t ce = cudaMemsetAsync(a.counters, 0, 256 + sizeof(unsigned int) * (size_t)B, st);
+    if (ce != cudaSuccess) return (int)ce;
+    k_plane_bounds<<<B * (p->num_bins > 1 ? p->num_bins - 1 : 1), 128, 0, st>>>(a);
+    EP_LAUNCH_CHECK();
+    profile_end(st);
+
+    a.coord_mode = kCoordPlain;
+    if (a.scaled) {
+        // (per call: 4096 fp64 products on the host, while the two kernels above start; EP_PLANE_LUT=1 keeps both tables)
+        static const bool no_mul = [] { const char* e = getenv("EP_PLANE_LUT"); return e && e[0] == '1'; }();
+        const bool mx = !no_mul && plane_axis_mul(a.sx, a.mul_x), my = !no_mul && plane_axis_mul(a.sy, a.mul_y);
+        a.coord_mode = mx ? (my ? kCoordMul : kCoordMulX) : (my ? kCoordMulY : kCoordLut);
+    }
+    const int hw = p->height * p->width;
+    const size_t smem = plane_smem_bytes(hw);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_plane<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem_bytes(kPlaneCells));
+        cudaFuncSetAttribute(k_plane<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem_bytes(kPlaneCells));
+        attr_done = true;
+    }
+    const int64_t n_tasks = (int64_t)B * p->num_bins;
+    const int grid = n_tasks < kNumSMs ? (int)n_tasks : kNumSMs;
+    const bool vec = (hw % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
+    profile_begin(st, kProfFinalize);
+    if (vec) k_plane<true><<<grid, kPlaneThreads, smem, st>>>(a);
+    else k_plane<false><<<grid, kPlaneThreads, smem, st>>>(a);
+    profile_end(st);
+    EP_LAUNCH_CHECK();
+    // the route + sweep kernels stand by: they run only if k_plane met an event outside its slice's interval
+    return run_tiled_packed4_impl(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, nullptr, a.counters + 1);
+}
+
+}  // namespace
+
+// Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
+// Grids whose plane fits one SM's shared memory take the whole-plane kernels (unless the statistics by-product is asked
+// for, which lives in the sweep's flush), everything else route + sweep; EP_BIN_FORCE_TILED / EP_BIN_FORCE_PLANE pin one.
+int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
+                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
+    if (!out_stats && !(p->flags & EP_BIN_FORCE_TILED)) {
+        const int rc = run_plane_packed4(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad);
+        if (rc != EP_EUNSUPPORTED || (p->flags & EP_BIN_FORCE_PLANE)) return rc;
+    } else if (p->flags & EP_BIN_FORCE_PLANE) {
+        return EP_EUNSUPPORTED;
+    }
+    return run_tiled_packed4_impl(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, out_stats, nullptr);
 }
 
 // =====================================================================================================================
@@ -1597,8 +2186,9 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
     if (!out || !aligned16(ev->x)) return EP_EALIGN;
     const int B = ev->batch;
     char* base = static_cast<char*>(ws);
-    EvRepArgs e;
+    EvRepArgs e = {};
     TiledArgs& a = e.t;
+    a.count_bad = 1; a.run_if = nullptr;
     a.w = static_cast<const uint32_t*>(ev->x);
     a.blk_base = static_cast<const uint32_t*>(ev->p);
     a.offsets = ev->offsets;

@@ -359,7 +359,8 @@ def from_soa(x, y, t, p, offsets, t_div=1.0, pin=True):
     return RaggedEvents(*tens, offsets_host=off, t_div=t_div)
 
 
-_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "tiled": _lib.EP_BIN_FORCE_TILED}
+_METHOD = {None: 0, "auto": 0, "global": _lib.EP_BIN_FORCE_GLOBAL, "tiled": _lib.EP_BIN_FORCE_TILED,
+           "plane": _lib.EP_BIN_FORCE_PLANE}
 
 
 def _bin_params(size, num_bins, count_channels, scale, time_f32, method=None):
@@ -386,7 +387,7 @@ def _raise_bad(bad):
 
 
 def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_sum=False, time_f32=False,
-               check=False, out=None, method=None, stats=False):
+               check=False, out=None, method=None, stats=False, bad_out=None):
     """Batched events -> tensors: voxel grid (B,num_bins,H,W), optional voxel.sum(0) plane (B,1,H,W) and/or
     polarity count frame (B,count_channels,H,W); one C-ABI call (ep_bin_events).
 
@@ -395,8 +396,11 @@ def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_s
     the last row, of the sum plane (valid when voxel_sum) — the table dist.allreduce_statistics reduces over the ranks; on
     the tiled path it is a by-product of the kernel that writes the planes.
     check=True synchronises and raises for events the reference would have raised on.
-    method: None/"auto" (the tiled shared-memory kernels for the 4 B/event packed layout without count frames, else the
-    global-RED kernels), "global", "tiled" — same results bit for bit.
+    method: None/"auto" (for the 4 B/event packed layout without count frames: the whole-plane shared-memory kernels when the
+    grid's plane fits one SM — 224 x 224, 240 x 180 — else route + sweep; the global-RED kernels for everything else),
+    "global", "tiled", "plane" — same results bit for bit.
+    bad_out: optional zeroed int32 CUDA tensor that receives the number of events the reference would have raised on
+    (bit 31: accumulator overflow), without a synchronisation.
     """
     require_cuda(ev.x)
     dev = ev.device
@@ -413,7 +417,7 @@ def bin_events(ev, size, num_bins=0, count_channels=0, scale=(1.0, 1.0), voxel_s
     desc = ev._desc()
     nbytes = L.ep_bin_events_workspace_bytes_for(ctypes.byref(desc), ctypes.byref(prm))
     ws = workspace(nbytes, dev, "bin")
-    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    bad = bad_out if bad_out is not None else (torch.zeros(1, dtype=torch.int32, device=dev) if check else None)
     if stats:
         if not num_bins:
             raise ValueError("stats=True needs a voxel grid")

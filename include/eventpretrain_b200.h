@@ -119,11 +119,14 @@ typedef struct ep_bin_params {
     double scale_x, scale_y;     /* events_reshape fused (dataset/augmentation/events_augment.py:22-26):
                                     x*scale_x, y*scale_y in fp64, then truncation; 1.0 = none */
     int time_f32;                /* 1 = do the time arithmetic in fp32 (what torch does for float32 event arrays) */
-    int flags;                   /* 0 = choose; EP_BIN_FORCE_GLOBAL / EP_BIN_FORCE_TILED pin the kernel family */
+    int flags;                   /* 0 = choose; EP_BIN_FORCE_GLOBAL / EP_BIN_FORCE_TILED / EP_BIN_FORCE_PLANE pin the kernel family */
 } ep_bin_params;
 #define EP_BIN_FORCE_GLOBAL 1    /* packed-u64 global RED + finalize (any layout, any size) */
 #define EP_BIN_FORCE_TILED 4     /* route + two-plane shared-memory sweep, no global accumulators (4 B packed layout, voxel grid
                                     and sum plane only; EP_EUNSUPPORTED otherwise).  The default for what it takes. */
+#define EP_BIN_FORCE_PLANE 8     /* whole-plane kernels: grids of at most 54272 cells (224 x 224, 240 x 180), one output plane per
+                                    CTA in shared memory, no route pass (4 B packed layout; EP_EUNSUPPORTED otherwise).  The
+                                    default for what it takes; unsorted samples are redone by the tiled kernels in the same call. */
 
 /* Scratch for ep_bin_events*: per-sample accumulator slots.  Returns the recommended size (enough
  * slots to keep one group of samples L2-resident); any size >= the minimum (one slot + per-sample

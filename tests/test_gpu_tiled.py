@@ -8,6 +8,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+PLANE_CELLS = 54272     # EP_BIN_FORCE_PLANE: largest grid of the whole-plane kernels (include/eventpretrain_b200.h)
+
+
 def close(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return bool(np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-6))
@@ -58,10 +61,14 @@ def dense_batch(ep, rng, counts, H, W, Ws=None, Hs=None, ticks_per_event=0.25, h
 def both(ep, p4, size, **kw):
     a = ep.bin_events(p4, size, method="global", **kw)
     b = ep.bin_events(p4, size, method="tiled", **kw)
-    c = ep.bin_events(p4, size, **kw)                 # default = tiled for this layout
+    c = ep.bin_events(p4, size, **kw)                 # default = whole-plane kernels where the plane fits an SM, else tiled
     for key in a:
         assert torch.equal(a[key], b[key]), key
         assert torch.equal(a[key], c[key]), key
+    if size[0] * size[1] <= PLANE_CELLS and not kw.get("stats"):
+        d = ep.bin_events(p4, size, method="plane", **kw)
+        for key in a:
+            assert torch.equal(a[key], d[key]), key
     return b
 
 
@@ -184,20 +191,22 @@ def test_tiled_row_wrap_and_bad_events(ep):
             ep.bin_events(p4, (H, W), num_bins=5, method=method, check=True)
 
 
-def test_tiled_in_cuda_graph(ep):
-    """No allocation, no synchronisation, no host-side state: the call can be captured and replayed."""
+@pytest.mark.parametrize("method,shuffle", [("tiled", False), ("plane", False), ("plane", True)])
+def test_tiled_in_cuda_graph(ep, method, shuffle):
+    """No allocation, no synchronisation, no host-side state: the call can be captured and replayed (the whole-plane
+    kernels too, including their stand-by fallback for an unsorted sample)."""
     rng = np.random.default_rng(12)
     H, W = 96, 128
-    ev, _ = dense_batch(ep, rng, [20000, 30000], H, W)
+    ev, _ = dense_batch(ep, rng, [20000, 30000], H, W, block_shuffle=shuffle)
     p4 = ev.packed(4).to("cuda")
-    ref = ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method="tiled")
+    ref = ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method="global")
     out = {k: torch.empty_like(v) for k, v in ref.items()}
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
-        ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method="tiled", out=out)
+        ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method=method, out=out)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
-            ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method="tiled", out=out)
+            ep.bin_events(p4, (H, W), num_bins=5, voxel_sum=True, method=method, out=out)
         for v in out.values():
             v.zero_()
         g.replay()
@@ -248,3 +257,57 @@ def test_fused_statistics(ep):
     assert torch.allclose(epd.plane_statistics(x), table(x), rtol=1e-12, atol=1e-9)
     fin = epd.finalize_statistics(epd.plane_statistics(x))
     assert torch.allclose(fin["mean"], x.double().mean((0, 2, 3)), atol=1e-12)
+
+
+@pytest.mark.parametrize("bins", [1, 2, 3, 5, 9])
+def test_plane_path_mixed_batch(ep, bins):
+    """Whole-plane kernels (one output plane per CTA in shared memory, csrc/ep_binning_tiled.cu) on the reference's own
+    pre-training shape — events_reshape 640x480 -> 224x224 fused (pr_n_imagenet_dataset.py:85-87) — with samples that end on
+    repeated last stamps, many events on interval nodes, a sample of one tick block, and out-of-grid events counted once;
+    then the same batch with one unsorted sample: the stand-by route + sweep kernels redo it, same bits, same count."""
+    from oracle import events as oe
+    rng = np.random.default_rng(900 + bins)
+    sc = (224 / 640, 224 / 480)
+
+    def nodes(xs, ys, ts, ps):
+        ts[1][-50:] = ts[1][-1]                      # 50 events on the last stamp: interval bins - 1, weight 1 on the last plane
+        span = ts[2][-1] - ts[2][0]
+        for j in range(1, max(bins - 1, 1)):         # events exactly on the interior nodes
+            k = np.searchsorted(ts[2], ts[2][0] + span * j // max(bins - 1, 1))
+            ts[2][k:k + 3] = ts[2][k]
+    counts = [60000, 30011, 45000, 200, 0, 8191]
+    ev, samples = dense_batch(ep, rng, counts, 224, 224, Ws=640, Hs=480, edit=nodes, hot=700)
+    p4 = ev.packed(4).to("cuda")
+    out = both(ep, p4, (224, 224), num_bins=bins, voxel_sum=True, scale=sc, check=True)
+    for i, s in enumerate(samples):
+        if len(s) == 0:
+            continue
+        r = s.copy()
+        r[:, 0] *= sc[0]
+        r[:, 1] *= sc[1]
+        ref = oe.voxel_grid(r, bins, (224, 224))
+        got = out["voxel"][i].cpu().numpy()
+        hx, hy = int(3 * sc[0]), int(2 * sc[1])
+        got[:, hy, hx] = ref[:, hy, hx]               # the hot cell: the reference's sequential fp32 sum drifts (see above)
+        assert close(got, ref), i
+
+    def bad_and_unsorted(unsort):
+        def edit(xs, ys, ts, ps):
+            xs[0][100], ys[0][100] = 2047, 2047       # outside the 224 x 224 grid after the scale
+            xs[2][7], ys[2][7] = 2047, 2047
+            if unsort:
+                for i, j in ((1900, 2200), (4000, 4200)):      # across interval boundaries (2048, 4096), inside the 9-bit tick range
+                    ts[5][i], ts[5][j] = ts[5][j], ts[5][i]
+        return edit
+    counts = [30000, 256, 12000, 1, 0, 8191]
+    for unsort in (False, True):
+        ev, _ = dense_batch(ep, np.random.default_rng(77), counts, 224, 224, Ws=640, Hs=480, edit=bad_and_unsorted(unsort))
+        p4 = ev.packed(4).to("cuda")
+        res, bad = {}, {}
+        for m in ("global", "tiled", "plane"):
+            bad[m] = torch.zeros(1, dtype=torch.int32, device="cuda")
+            res[m] = ep.bin_events(p4, (224, 224), num_bins=bins, voxel_sum=True, scale=sc, method=m, bad_out=bad[m])
+        for m in ("tiled", "plane"):
+            assert torch.equal(res[m]["voxel"], res["global"]["voxel"]), (m, unsort)
+            assert torch.equal(res[m]["voxel_sum"], res["global"]["voxel_sum"]), (m, unsort)
+            assert int(bad[m]) == int(bad["global"]) == 2, (m, unsort)

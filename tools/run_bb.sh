@@ -1,0 +1,13 @@
+set -x
+mkdir -p gpurun_out
+T=r02bb
+cp eventpretrain_b200/libeventpretrain_b200.so /tmp/lib_default.so
+for V in t1024q1 t1024q2 t512q2 t512q1 nolut; do
+  cp build/variants/$V.so eventpretrain_b200/libeventpretrain_b200.so
+  echo "== $V" | tee -a gpurun_out/${T}_ab.log
+  timeout 200 python tools/quick_bin.py --batch 256 --packed4 --size 224x224 --methods plane --steps 10 2>&1 | tail -1 | tee -a gpurun_out/${T}_ab.log
+done
+cp build/variants/t1024q1.so eventpretrain_b200/libeventpretrain_b200.so
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_plane$' -c 1 -f -o gpurun_out/${T}_plane python tools/quick_bin.py --batch 256 --packed4 --size 224x224 --methods plane --steps 1 > gpurun_out/${T}_ncu.log 2>&1
+tail -3 gpurun_out/${T}_ncu.log
+cp /tmp/lib_default.so eventpretrain_b200/libeventpretrain_b200.so
