@@ -403,8 +403,16 @@ def run_ours(args):
                                               "+ voxel.sum(0) (dataset/pretrain/pr_n_imagenet_dataset.py:85-87)",
                                       "Gevents_per_s": g224, "ms_per_step": ms224, "algorithmic_bytes_per_step": alg224,
                                       "roofline_frac": alg224 / (ms224 * 1e-3) / 1e9 / peak,
-                                      "global_RED_path_Gevents_per_s": gev(ev, "global", (224, 224), (224 / W, 224 / H), o224)[0]}
-        del o224
+                                      "kernels": "whole-plane path (k_plane_bounds + k_plane): a 224x224 plane fits one SM's shared memory, so a "
+                                                 "CTA owns one output plane of one sample and streams the two time-contiguous event slices "
+                                                 "that feed it; no route pass, no routed records (DESIGN.md 3.0)"}
+        ref224 = {k: v.clone() for k, v in o224.items()}
+        r224 = extra["reference_res_224"]
+        r224["route_sweep_path_Gevents_per_s"] = gev(ev, "tiled", (224, 224), (224 / W, 224 / H), o224)[0]
+        same = all(torch.equal(ref224[k], o224[k]) for k in ref224)
+        r224["global_RED_path_Gevents_per_s"] = gev(ev, "global", (224, 224), (224 / W, 224 / H), o224)[0]
+        r224["bit_identical_across_the_three_paths"] = bool(same and all(torch.equal(ref224[k], o224[k]) for k in ref224))
+        del o224, ref224
     del ev13
     torch.cuda.empty_cache()
     if world == 1:

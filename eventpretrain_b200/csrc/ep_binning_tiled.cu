@@ -994,7 +994,8 @@ struct TiledPlan {
     int NT, rows, n_tasks;
     int64_t rec_pos0, n_rec;
     size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_stats2, off_rec, total;
-    bool plane_ok;              // the grid's plane fits one SM's shared memory: whole-plane kernels (run_plane_packed4)
+    bool plane_ok;              // the grid's plane fits one SM's shared memory in at most 3 row tiles: whole-plane kernels
+    int plane_T, plane_rows;    // (run_plane_packed4)
     size_t off_plane, off_plane_bounds;
 };
 
@@ -1034,10 +1035,21 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_stats = o; o += align_up(sizeof(double) * kStatSlot * (size_t)B * NT * (size_t)(p->num_bins + 1), 256);
     pl.off_stats2 = o; o += align_up(sizeof(double) * 3 * kStatSlices * (size_t)(p->num_bins + 1), 256);
     pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
-    pl.plane_ok = (int64_t)H * W <= kPlaneCellsMax && (int64_t)B * p->num_bins < (1ll << 30);
+    // Whole-plane kernels: every event is read 2 x (row tiles) times, so more than one tile only pays where the output
+    // outweighs the events (MVSEC-shaped batches: 346 x 260, 9 bins, ~100 k events): 2 tiles always, 3 when cells >= 2 x events
+    pl.plane_ok = false; pl.plane_T = 1; pl.plane_rows = H;
+    if (W <= kPlaneCellsMax && (int64_t)B * p->num_bins * 3 < (1ll << 30)) {
+        int prow = kPlaneCellsMax / W;
+        if (prow > H) prow = H;
+        int T = (H + prow - 1) / prow;
+        prow = (H + T - 1) / T;
+        T = (H + prow - 1) / prow;
+        const int64_t cells = (int64_t)B * p->num_bins * H * W, n_ev = ev->offsets_host[B] - ev->offsets_host[0];
+        if (T <= 2 || (T == 3 && cells >= 2 * n_ev)) { pl.plane_ok = true; pl.plane_T = T; pl.plane_rows = prow; }
+    }
     pl.off_plane = pl.off_plane_bounds = 0;
     if (pl.plane_ok) {
-        pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B, 256);          // counters | finished planes per sample
+        pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B * 3, 256);      // counters | finished planes per (sample, tile)
         pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 1), 256);
     }
     pl.total = o;
@@ -1256,6 +1268,7 @@ struct PlaneArgs {
     const int64_t* offsets;
     int64_t n_total;
     int B, H, W, num_bins;
+    int T, rows;                // row tiles per plane (1 = the whole plane in one CTA), rows per tile
     double sx, sy;
     int scaled;
     int coord_mode;             // kCoord*
@@ -1263,14 +1276,14 @@ struct PlaneArgs {
     const SampleMeta* meta;
     int64_t* bounds;            // B x (num_bins + 1): s_0 .. s_bins
     unsigned int* counters;     // [0] task counter, [1] fallback flag (an event outside its slice's interval)
-    unsigned int* done;         // B: finished planes per sample
+    unsigned int* done;         // B x T: finished planes per (sample, tile)
     unsigned int* bad_count;
     float* out_voxel;
     float* out_sum;
 };
 
-__host__ __device__ inline size_t plane_smem_bytes(int hw) {
-    return (size_t)((hw + 3) & ~3) * 4 + 16 + 2048 * 4 + 2048 * 2 + kSpillCap * 8;      // plane | dump word | tables | spill list
+__host__ __device__ inline size_t plane_smem_bytes(int tile_cells) {
+    return (size_t)((tile_cells + 3) & ~3) * 4 + 128 + 2048 * 4 + 2048 * 2 + kSpillCap * 8;      // plane | dump words | tables | spill list
 }
 
 // stamp of array position i of a sample that starts at lo, as ticks from the sample's first row
@@ -1326,9 +1339,13 @@ struct PlaneCtx {
     int2* spill;
     int* n_spill;
     unsigned int* bad;
-    uint32_t hw;                // cells of the plane
+    uint32_t hw;                // cells of the grid
     uint32_t dump;              // index of the word behind the plane: out-of-grid events add there (never read)
     uint32_t W, mul_x, mul_y;
+    // grids of 2 or 3 row tiles (MT): the CTA owns cells [tbase, tbase + tcells) of the flat index and drops the rest of the
+    // slice's events into 32 dump words (one per lane: no same-address serialisation); tile 0 counts the out-of-grid events
+    uint32_t tbase, tcells, dumpl;
+    bool count_bad;
 };
 
 // Per-task constants of the time arithmetic
@@ -1388,7 +1405,7 @@ __device__ __forceinline__ void plane_cells(const PlaneCtx& c, const uint32_t (&
 // integer-tick sample whose dT leaves room for the wrap-around test: dtb = block base - first-row ticks (mod 2^32), a stamp
 // before the first row wraps to more than dT like one past the last row.  An event outside its interval adds a
 // meaningless weight — the batch is redone anyway.
-template <bool FAST, int CM, bool LEFT, bool EDGE>
+template <bool FAST, int CM, bool LEFT, bool EDGE, bool MT>
 __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int num_bins, uint4 wq,
                                            int64_t dtb, uint32_t rel0, uint32_t len, uint32_t kbase, PlaneMax& mx, uint32_t& mismatch) {
     const uint32_t ws[4] = {wq.x, wq.y, wq.z, wq.w};
@@ -1417,7 +1434,8 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
         const int wgt = LEFT ? (int)((1u << kQ) - u) : (int)u;
         val[e] = ((word >> 22) & 1u) ? wgt : -wgt;
         if (EDGE && !in) val[e] = 0;
-        cell[e] = min(ce, c.dump);
+        if (MT) { const uint32_t cl = ce - c.tbase; cell[e] = cl < c.tcells ? cl : c.dumpl; }
+        else cell[e] = min(ce, c.dump);
         old[e] = atoms_add(c.plane_s + cell[e] * 4u, val[e]);
     }
     uint32_t near = 0;
@@ -1426,7 +1444,7 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
     if (near >= 0xfe000000u) {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (cell[e] < c.hw && near_wrap(old[e])) note_wrap(old[e], val[e], cell[e], c.spill, c.n_spill, c.bad);
+            if (cell[e] < c.tcells && near_wrap(old[e])) note_wrap(old[e], val[e], cell[e], c.spill, c.n_spill, c.bad);
     }
 }
 
@@ -1437,7 +1455,7 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
 // The slice [s0, s1) of the sample that starts at lo: interval kexp (kbase = kexp << 24).  A warp takes one 256-event tick
 // block per step (two quads per lane, one block base for the warp); only the first and the last block of a slice can
 // straddle its ends.
-template <bool FAST, int CM, bool LEFT>
+template <bool FAST, int CM, bool LEFT, bool MT>
 __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int64_t lo,
                                             int64_t s0, int64_t s1, uint32_t kbase, uint32_t& mismatch, uint32_t& nbad) {
     constexpr int kWarps = kPlaneThreads / 32;
@@ -1486,8 +1504,8 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
 #if EP_PLANE_PIPE != 2
             const uint4 w0 = ld_stream(p), w1 = ld_stream(p + 32);
 #endif
-            plane_quad<FAST, CM, LEFT, false>(c, m, tm, a.num_bins, w0, dtb, 0u, len, kbase, mx, mismatch);
-            plane_quad<FAST, CM, LEFT, false>(c, m, tm, a.num_bins, w1, dtb, 0u, len, kbase, mx, mismatch);
+            plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w0, dtb, 0u, len, kbase, mx, mismatch);
+            plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w1, dtb, 0u, len, kbase, mx, mismatch);
         } else {
             // first / last block of the slice: only the events inside [s0, s1) are loaded and added
             const int64_t bs = (blk0 + (int64_t)i) << kTickBlockShift;
@@ -1497,11 +1515,11 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
                 uint32_t t4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) if (pos + e >= s0 && pos + e < s1) t4[e] = a.w[pos + e];
-                plane_quad<FAST, CM, LEFT, true>(c, m, tm, a.num_bins, make_uint4(t4[0], t4[1], t4[2], t4[3]), dtb,
+                plane_quad<FAST, CM, LEFT, true, MT>(c, m, tm, a.num_bins, make_uint4(t4[0], t4[1], t4[2], t4[3]), dtb,
                                                      (uint32_t)(pos - s0), len, kbase, mx, mismatch);
             }
         }
-        if (LEFT && mx.ce >= c.hw) {
+        if (LEFT && mx.ce >= c.hw && c.count_bad) {
             // cold: events outside the grid are counted where their slice is the left one (every position exactly once)
             const int64_t bs = (blk0 + (int64_t)i) << kTickBlockShift;
             for (int h = 0; h < 2; ++h)
@@ -1516,35 +1534,35 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
 }
 
 // plane k of a sample: right-node weights of interval k - 1 = [a0, mid), left-node weights of interval k = [mid, a1)
-template <bool FAST, int CM>
+template <bool FAST, int CM, bool MT>
 __device__ __forceinline__ void plane_accumulate(const PlaneArgs& a, const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int64_t lo,
                                                  int64_t a0, int64_t mid, int64_t a1, uint32_t k, uint32_t& mismatch, uint32_t& nbad) {
     // Slice j is read by the CTAs of planes j (left) and j + 1 (right), which are drawn one after the other and run side by
     // side: even planes take their left slice first, odd planes their right one, so both read it at the same time and the
     // second reader finds it in L2.
     if (k & 1u) {
-        if (mid > a0) plane_slice<FAST, CM, false>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
-        if (a1 > mid) plane_slice<FAST, CM, true>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
+        if (mid > a0) plane_slice<FAST, CM, false, MT>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
+        if (a1 > mid) plane_slice<FAST, CM, true, MT>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
     } else {
-        if (a1 > mid) plane_slice<FAST, CM, true>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
-        if (mid > a0) plane_slice<FAST, CM, false>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
+        if (a1 > mid) plane_slice<FAST, CM, true, MT>(a, c, m, tm, lo, mid, a1, k << kQ, mismatch, nbad);
+        if (mid > a0) plane_slice<FAST, CM, false, MT>(a, c, m, tm, lo, a0, mid, (k - 1u) << kQ, mismatch, nbad);
     }
 }
 
 template <bool VEC>
 __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int HW = a.H * a.W, HWp = (HW + 3) & ~3;
+    const int HW = a.H * a.W, tile_full = a.rows * a.W, HWp = (tile_full + 3) & ~3;      // HWp: words of the plane buffer
     int* plane = reinterpret_cast<int*>(smem_raw);
-    uint32_t* lut_y = reinterpret_cast<uint32_t*>(plane + HWp + 4);
+    uint32_t* lut_y = reinterpret_cast<uint32_t*>(plane + HWp + 32);
     uint16_t* lut_x = reinterpret_cast<uint16_t*>(lut_y + 2048);
     int2* s_spill = reinterpret_cast<int2*>(lut_x + 2048);
     __shared__ int s_task[2], s_nspill, s_last;
 
     const int tid = threadIdx.x;
-    const int n_tasks = a.B * a.num_bins;
+    const int per_sample = a.num_bins * a.T, n_tasks = a.B * per_sample;
     if (tid == 0) { s_task[0] = (int)atomicAdd(&a.counters[0], 1u); s_nspill = 0; }
-    for (int i = tid; i < HWp; i += kPlaneThreads) plane[i] = 0;
+    for (int i = tid; i < HWp + 32; i += kPlaneThreads) plane[i] = 0;
     if (tid < kSpillCap) s_spill[tid] = make_int2(-1, 0);
     for (int i = tid; i < 2048; i += kPlaneThreads) {
         const long long yy = a.scaled ? __double2ll_rz(__dmul_rn((double)i, a.sy)) : (long long)i;
@@ -1558,13 +1576,17 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
     c.luty_s = (uint32_t)__cvta_generic_to_shared(lut_y); c.lutx_s = (uint32_t)__cvta_generic_to_shared(lut_x);
     c.lut_y = lut_y; c.lut_x = lut_x; c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
     c.hw = (uint32_t)HW; c.dump = (uint32_t)HWp; c.W = (uint32_t)a.W; c.mul_x = a.mul_x; c.mul_y = a.mul_y;
+    c.dumpl = (uint32_t)HWp + (uint32_t)(tid & 31);
     uint32_t mismatch = 0, nbad = 0;
     int cur = 0;
     for (;;) {
         const int task = s_task[cur];
         if (task >= n_tasks) break;
         if (tid == 0) s_task[cur ^ 1] = (int)atomicAdd(&a.counters[0], 1u);       // read behind this task's barriers
-        const int b = task / a.num_bins, k = task - b * a.num_bins;       // the planes of a sample run side by side (L2 reuse)
+        // the planes (and tiles) of a sample run side by side (L2 reuse of its events)
+        const int b = task / per_sample, k = (task - b * per_sample) / a.T, t = task - b * per_sample - k * a.T;
+        const int tbase = t * tile_full, ncell = (HW - tbase < tile_full) ? HW - tbase : tile_full;
+        c.tbase = (uint32_t)tbase; c.tcells = (uint32_t)ncell; c.count_bad = (t == 0);
         const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 1);
         const int64_t lo = bd[0];
         const int64_t a0 = bd[k > 0 ? k - 1 : 0], mid = bd[k], a1 = bd[k + 1];
@@ -1578,28 +1600,34 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
             const int64_t dT = plane_dt(a, hi - 1, lo, m.t0_ticks);               // > 0 and < 2^32 for an integer-time sample
             tm.dT = (uint32_t)dT;
             const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024;
-            if (fast) {
-#define EP_PLANE_ACC(CM) plane_accumulate<true, CM>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad)
+            if (fast && a.T == 1) {
+#define EP_PLANE_ACC(CM, MT) plane_accumulate<true, CM, MT>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad)
                 switch (a.coord_mode) {
-                    case kCoordPlain: EP_PLANE_ACC(kCoordPlain); break;
-                    case kCoordMulY: EP_PLANE_ACC(kCoordMulY); break;
-                    case kCoordMulX: EP_PLANE_ACC(kCoordMulX); break;
-                    case kCoordMul: EP_PLANE_ACC(kCoordMul); break;
-                    default: EP_PLANE_ACC(kCoordLut); break;
+                    case kCoordPlain: EP_PLANE_ACC(kCoordPlain, false); break;
+                    case kCoordMulY: EP_PLANE_ACC(kCoordMulY, false); break;
+                    case kCoordMulX: EP_PLANE_ACC(kCoordMulX, false); break;
+                    case kCoordMul: EP_PLANE_ACC(kCoordMul, false); break;
+                    default: EP_PLANE_ACC(kCoordLut, false); break;
+                }
+            } else if (fast) {
+                switch (a.coord_mode) {
+                    case kCoordPlain: EP_PLANE_ACC(kCoordPlain, true); break;
+                    case kCoordMul: EP_PLANE_ACC(kCoordMul, true); break;
+                    default: EP_PLANE_ACC(kCoordLut, true); break;
                 }
 #undef EP_PLANE_ACC
             } else {
-                plane_accumulate<false, kCoordLut>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad);
+                plane_accumulate<false, kCoordLut, true>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad);
             }
         }
         __syncthreads();
         // ---- plane k complete: fp32 out (one rounding), plane re-zeroed ----
         constexpr float kInv = 1.0f / 16777216.0f;
         const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
-        float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW;
+        float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + tbase;
         const bool keep = a.out_sum != nullptr;                    // the planes are read back for voxel.sum(0): leave them in L2
         if (VEC) {
-            for (int i = tid * 4; i < HW; i += kPlaneThreads * 4) {
+            for (int i = tid * 4; i < ncell; i += kPlaneThreads * 4) {
                 const int4 q = *reinterpret_cast<const int4*>(plane + i);
                 *reinterpret_cast<int4*>(plane + i) = make_int4(0, 0, 0, 0);
                 float4 f = make_float4(__int2float_rn(q.x) * kInv, __int2float_rn(q.y) * kInv, __int2float_rn(q.z) * kInv,
@@ -1617,7 +1645,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
                 else st_stream(reinterpret_cast<float4*>(o + i), f);
             }
         } else {
-            for (int i = tid; i < HW; i += kPlaneThreads) {
+            for (int i = tid; i < ncell; i += kPlaneThreads) {
                 const int q = plane[i];
                 plane[i] = 0;
                 float f = __int2float_rn(q) * kInv;
@@ -1635,16 +1663,16 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
             __threadfence();
             __syncthreads();
             if (tid == 0) {
-                const unsigned int old = atomicAdd(&a.done[b], 1u);
+                const unsigned int old = atomicAdd(&a.done[b * a.T + t], 1u);
                 s_last = (old + 1u == (unsigned int)a.num_bins) ? 1 : 0;
                 if (s_last) __threadfence();
             }
             __syncthreads();
             if (s_last) {
-                const float* p0 = a.out_voxel + (int64_t)b * a.num_bins * HW;
-                float* so = a.out_sum + (int64_t)b * HW;
+                const float* p0 = a.out_voxel + (int64_t)b * a.num_bins * HW + tbase;
+                float* so = a.out_sum + (int64_t)b * HW + tbase;
                 if (VEC) {
-                    for (int i = tid * 4; i < HW; i += kPlaneThreads * 4) {
+                    for (int i = tid * 4; i < ncell; i += kPlaneThreads * 4) {
                         float4 s = __ldcg(reinterpret_cast<const float4*>(p0 + i));
                         for (int j0 = 1; j0 < a.num_bins; j0 += 4) {
                             float4 v[4];
@@ -1660,7 +1688,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
                         st_stream(reinterpret_cast<float4*>(so + i), s);
                     }
                 } else {
-                    for (int i = tid; i < HW; i += kPlaneThreads) {
+                    for (int i = tid; i < ncell; i += kPlaneThreads) {
                         float s = __ldcg(p0 + i);
                         for (int j = 1; j < a.num_bins; ++j) s += __ldcg(p0 + (int64_t)j * HW + i);      // sequential fp32 over bins
                         st_stream(so + i, s);
@@ -1710,6 +1738,7 @@ int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     a.offsets = ev->offsets;
     a.n_total = ev->offsets_host[B];
     a.B = B; a.H = p->height; a.W = p->width; a.num_bins = p->num_bins;
+    a.T = pl.plane_T; a.rows = pl.plane_rows;
     a.sx = p->scale_x; a.sy = p->scale_y; a.scaled = (p->scale_x != 1.0 || p->scale_y != 1.0);
     SampleMeta* meta = reinterpret_cast<SampleMeta*>(base + pl.off_meta);
     a.meta = meta;
@@ -1726,7 +1755,7 @@ int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     profile_begin(st, kProfOther);
     k_sample_meta<SoaPackedLoader<false>><<<(B + 127) / 128, 128, 0, st>>>(ld, ba, B);
     EP_LAUNCH_CHECK();
-    cudaError_t ce = cudaMemsetAsync(a.counters, 0, 256 + sizeof(unsigned int) * (size_t)B, st);
+    cudaError_t ce = cudaMemsetAsync(a.counters, 0, 256 + sizeof(unsigned int) * (size_t)B * a.T, st);
     if (ce != cudaSuccess) return (int)ce;
     k_plane_bounds<<<B * (p->num_bins > 1 ? p->num_bins - 1 : 1), 128, 0, st>>>(a);
     EP_LAUNCH_CHECK();
@@ -1739,17 +1768,17 @@ int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
         const bool mx = !no_mul && plane_axis_mul(a.sx, a.mul_x), my = !no_mul && plane_axis_mul(a.sy, a.mul_y);
         a.coord_mode = mx ? (my ? kCoordMul : kCoordMulX) : (my ? kCoordMulY : kCoordLut);
     }
-    const int hw = p->height * p->width;
-    const size_t smem = plane_smem_bytes(hw);
+    const int hw = p->height * p->width, tile_cells = a.rows * a.W;
+    const size_t smem = plane_smem_bytes(tile_cells);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_plane<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem_bytes(kPlaneCells));
         cudaFuncSetAttribute(k_plane<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem_bytes(kPlaneCells));
         attr_done = true;
     }
-    const int64_t n_tasks = (int64_t)B * p->num_bins;
+    const int64_t n_tasks = (int64_t)B * p->num_bins * a.T;
     const int grid = n_tasks < kNumSMs ? (int)n_tasks : kNumSMs;
-    const bool vec = (hw % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
+    const bool vec = (hw % 4 == 0) && (a.T == 1 || tile_cells % 4 == 0) && aligned16(out_voxel) && aligned16(out_sum);
     profile_begin(st, kProfFinalize);
     if (vec) k_plane<true><<<grid, kPlaneThreads, smem, st>>>(a);
     else k_plane<false><<<grid, kPlaneThreads, smem, st>>>(a);

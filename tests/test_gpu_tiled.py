@@ -8,7 +8,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-PLANE_CELLS = 54272     # EP_BIN_FORCE_PLANE: largest grid of the whole-plane kernels (include/eventpretrain_b200.h)
+PLANE_CELLS = 54272     # EP_BIN_FORCE_PLANE: cells of one CTA's plane tile in the whole-plane kernels (include/eventpretrain_b200.h)
+
+
+def plane_tiles(H, W):
+    """Row tiles the whole-plane kernels cut an H x W grid into (1 = the plane fits one SM; taken up to 3)."""
+    if W > PLANE_CELLS:
+        return 1 << 30
+    rows = min(PLANE_CELLS // W, H)
+    T = -(-H // rows)
+    rows = -(-H // T)
+    return -(-H // rows)
 
 
 def close(a, b):
@@ -65,15 +75,19 @@ def both(ep, p4, size, **kw):
     for key in a:
         assert torch.equal(a[key], b[key]), key
         assert torch.equal(a[key], c[key]), key
-    if size[0] * size[1] <= PLANE_CELLS and not kw.get("stats"):
+    tiles = plane_tiles(*size)
+    if not kw.get("stats") and (tiles <= 2 or (tiles == 3 and p4.batch * kw.get("num_bins", 0) * size[0] * size[1] >= 2 * p4.num_events)):
         d = ep.bin_events(p4, size, method="plane", **kw)
         for key in a:
             assert torch.equal(a[key], d[key]), key
+    elif not kw.get("stats"):
+        with pytest.raises(RuntimeError):
+            ep.bin_events(p4, size, method="plane", **kw)
     return b
 
 
 @pytest.mark.parametrize("H,W,bins", [(224, 224, 5), (480, 640, 5), (44, 64, 15), (65, 87, 9), (180, 240, 2), (33, 50, 1),
-                                      (700, 36, 3)])
+                                      (700, 36, 3), (260, 346, 9), (261, 347, 4), (300, 500, 12)])
 def test_tiled_equals_global_and_oracle(ep, H, W, bins):
     """Ragged batch with an empty sample, a 1-event sample, samples that start and end inside tick blocks and route chunks,
     and a hot pixel of 2000 same-polarity events (int32 plane words wrap: exercises the spill list)."""
