@@ -712,7 +712,7 @@ def run_configs(ep, torch, dev, rank, world, peak, allmax, allsum, timed_ms):
     t5 = h5t.to(dev)
     o = {"voxel": torch.empty((Bc, bins, h, w), dtype=torch.float32, device=dev)}
     from eventpretrain_b200.view_augment import ViewChoice
-    full = [ViewChoice(0, 0, w, h, False, False, False)] * Bc
+    full = ep.prepare_views([ViewChoice(0, 0, w, h, False, False, False)] * Bc, h, w, dev)      # the pair's resize is the whole frame: prepared once
     paired = {}
 
     def do_paired():

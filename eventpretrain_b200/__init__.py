@@ -20,7 +20,7 @@ from .readers import pack_soa, read_ddd17_memmap, read_nimagenet_npz  # noqa: F4
 from .reshape import (diffmap_frames, frame2emb, patchify_gather, reconstruct_loss, target_normpix,  # noqa: F401
                       target_patch_loss)
 
-from .view_augment import (ViewChoice, apply_views, draw_crop, draw_evg_choice, draw_frame_choice,  # noqa: F401
+from .view_augment import (ViewChoice, apply_views, prepare_views, draw_crop, draw_evg_choice, draw_frame_choice,  # noqa: F401
                            evg_augment, frame_augment)
 
 __version__ = "0.1.0"

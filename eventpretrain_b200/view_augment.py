@@ -64,19 +64,32 @@ def draw_frame_choice(args, shape, seed=None, time_flip_flag=False):
     return ViewChoice(x0, y0, cw, ch, hflip, False, bool(time_flip_flag))
 
 
+def prepare_views(choices, height, width, device):
+    """One ViewChoice per sample -> the device array of ep_view_params that ep_view_augment reads (validated on the host:
+    the kernel indexes the crop box directly).  Reusable: a fixed set of views (e.g. the full-frame resize of the MVSEC
+    pair, ft_mvsec_dataset.py:229-239) is prepared once and passed to apply_views in place of the list."""
+    B = len(choices)
+    arr = np.zeros((B, 8), np.int32)
+    arr[:, :7] = [(c.crop_x, c.crop_y, c.crop_w, c.crop_h, c.hflip, c.time_flip, c.negate) for c in choices]
+    ok = ((arr[:, 2] > 0) & (arr[:, 3] > 0) & (arr[:, 0] >= 0) & (arr[:, 0] + arr[:, 2] <= width) & (arr[:, 1] >= 0)
+          & (arr[:, 1] + arr[:, 3] <= height))
+    if not ok.all():
+        i = int(np.flatnonzero(~ok)[0])
+        raise ValueError(f"apply_views: crop box {tuple(int(v) for v in arr[i, :4])} of sample {i} leaves the {height}x{width} frame")
+    return torch.from_numpy(arr).to(device, non_blocking=True)
+
+
 def apply_views(x, choices, size, mode="nearest"):
-    """x (B,C,H,W) CUDA f32 + one ViewChoice per sample -> (B,C,size[0],size[1]) in one launch (ep_view_augment)."""
+    """x (B,C,H,W) CUDA f32 + one ViewChoice per sample (or the array prepare_views made of them) ->
+    (B,C,size[0],size[1]) in one launch (ep_view_augment)."""
     require_cuda(x)
     x = contiguous_f32(x, "x")
     B, C, H, W = x.shape
     if len(choices) != B:
         raise ValueError(f"apply_views: {len(choices)} view choices for a batch of {B}")
-    arr = (_lib.ViewParams * B)()
-    for i, c in enumerate(choices):
-        if not (c.crop_w > 0 and c.crop_h > 0 and 0 <= c.crop_x and c.crop_x + c.crop_w <= W and 0 <= c.crop_y and c.crop_y + c.crop_h <= H):
-            raise ValueError(f"apply_views: crop box {(c.crop_x, c.crop_y, c.crop_w, c.crop_h)} of sample {i} leaves the {H}x{W} frame")
-        arr[i] = _lib.ViewParams(c.crop_x, c.crop_y, c.crop_w, c.crop_h, int(c.hflip), int(c.time_flip), int(c.negate), 0)
-    prm = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(x.device, non_blocking=True)
+    prm = choices if isinstance(choices, torch.Tensor) else prepare_views(choices, H, W, x.device)
+    if prm.dtype != torch.int32 or tuple(prm.shape) != (B, 8) or prm.device != x.device:
+        raise ValueError("apply_views: prepared views must come from prepare_views() for this batch and device")
     out = torch.empty((B, C, int(size[0]), int(size[1])), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         rc = lib().ep_view_augment(stream_ptr(x.device), x.data_ptr(), B, C, H, W, prm.data_ptr(), int(size[0]), int(size[1]),

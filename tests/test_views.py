@@ -90,6 +90,30 @@ def test_batched_views_and_shared_seed(native_lib):
         ep.apply_views(grids, choices[:3], (224, 224))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,size", [((3, 9, 260, 346), (224, 224)), ((2, 5, 480, 640), (224, 224)), ((2, 3, 37, 53), (64, 80)),
+                                        ((1, 2, 1200, 1600), (96, 96))])
+def test_bilinear_staged_rows(native_lib, shape, size):
+    """The bilinear kernel that stages a tile's source rows in shared memory (the MVSEC pair: org grid + 224x224 copy,
+    ft_mvsec_dataset.py:229-239): full frames, odd crop offsets, flips, down- and up-scaling, and a frame whose rows exceed
+    the staging buffer (direct loads inside the same kernel), against F.interpolate of the same crop."""
+    import eventpretrain_b200 as ep
+    B, C, H, W = shape
+    x = torch.from_numpy(hash_uniform(shape, 11)).cuda()
+    rng = np.random.default_rng(H)
+    choices = [ep.ViewChoice(0, 0, W, H, False, False, False)]
+    for i in range(1, B):
+        cw, ch = int(rng.integers(W // 3, W)), int(rng.integers(H // 3, H))
+        choices.append(ep.ViewChoice(int(rng.integers(0, W - cw + 1)) | 1 if W - cw > 1 else 0, int(rng.integers(0, H - ch + 1)), cw, ch,
+                                     bool(i & 1), bool(i & 2), bool(i & 1)))
+    choices = [c if c.crop_x + c.crop_w <= W else ep.ViewChoice(W - c.crop_w, c.crop_y, c.crop_w, c.crop_h, c.hflip, c.time_flip, c.negate)
+               for c in choices]
+    out = ep.apply_views(x, choices, size, "bilinear")
+    for i in range(B):
+        ref = _torch_apply(x[i].cpu(), choices[i], size, "bilinear")
+        assert torch.allclose(out[i].cpu(), ref, rtol=1e-5, atol=2e-6), i
+
+
 def test_event_stream_augmentation_rng_mirror(golden_stream_aug):
     """Row f2: erase_and_add_events / add_noise_events drop-ins reproduce the reference's seeded output bit for bit."""
     import eventpretrain_b200 as ep

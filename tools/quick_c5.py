@@ -48,7 +48,10 @@ def main():
             ref = o["voxel"].clone()
         print(f"bin {str(m):7s} {ms:.3f} ms  identical={torch.equal(ref, o['voxel'])}  ({t5.num_events} events, {o['voxel'].numel() * 4 / 1e9:.2f} GB out)", flush=True)
     ms = timed(lambda: ep.apply_views(o["voxel"], full, (224, 224), "bilinear"))
-    print(f"view bilinear 224x224: {ms:.3f} ms")
+    print(f"view bilinear 224x224 (list of choices converted per call): {ms:.3f} ms")
+    prep = ep.prepare_views(full, h, w, dev)
+    ms = timed(lambda: ep.apply_views(o["voxel"], prep, (224, 224), "bilinear"))
+    print(f"view bilinear 224x224 (prepared views): {ms:.3f} ms")
 
 
 if __name__ == "__main__":
