@@ -71,6 +71,7 @@ static_assert(kItemRPL >= 1 && kItemRPL <= 4, "the item descriptor holds records
 // measured on B200, sweep of the 256-sample batch: 64-record items 1.046 ms, 96 1.008, 128 0.953 (kept)
 constexpr int kSpillCap = 128;
 constexpr int kPlaneCellsMax = 54272;         // whole-plane kernels: 212 KB of int32 plane + 13 KB of tables and spill list
+constexpr int kPlaneMaxTiles = 3;
 
 constexpr uint32_t kChunkFast = 1u;           // integer-tick sample, narrow records, every v of the chunk fits 32 bits
 constexpr uint32_t kChunkNarrow = 2u;         // records carry chunk-relative ticks (else: tick block + block-relative ticks)
@@ -1036,9 +1037,11 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_stats2 = o; o += align_up(sizeof(double) * 3 * kStatSlices * (size_t)(p->num_bins + 1), 256);
     pl.off_rec = o; o += align_up(sizeof(uint32_t) * (size_t)(pl.n_rec > 0 ? pl.n_rec : 1), 256);
     // Whole-plane kernels: every event is read 2 x (row tiles) times, so more than one tile only pays where the output
-    // outweighs the events (MVSEC-shaped batches: 346 x 260, 9 bins, ~100 k events): 2 tiles always, 3 when cells >= 2 x events
+    // outweighs the events (MVSEC-shaped batches: 346 x 260, 9 bins, ~100 k events): 2 tiles always, 3 when cells >= 2 x events.
+    // (Measured and dropped: half-size tiles with two 512-thread CTAs per SM for output-heavy batches — 346 x 260 x 9 bins,
+    // B = 512: 0.94 ms against 0.67 ms with two whole tiles; 224 x 224 with 512 threads at 64 registers: 0.83 against 0.75 ms.)
     pl.plane_ok = false; pl.plane_T = 1; pl.plane_rows = H;
-    if (W <= kPlaneCellsMax && (int64_t)B * p->num_bins * 3 < (1ll << 30)) {
+    if (W <= kPlaneCellsMax && (int64_t)B * p->num_bins * kPlaneMaxTiles < (1ll << 30)) {
         int prow = kPlaneCellsMax / W;
         if (prow > H) prow = H;
         int T = (H + prow - 1) / prow;
@@ -1049,8 +1052,8 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     }
     pl.off_plane = pl.off_plane_bounds = 0;
     if (pl.plane_ok) {
-        pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B * 3, 256);      // counters | finished planes per (sample, tile)
-        pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 1), 256);
+        pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B * kPlaneMaxTiles, 256);      // counters | finished planes per (sample, tile)
+        pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 2), 256);
     }
     pl.total = o;
     return true;
@@ -1274,7 +1277,7 @@ struct PlaneArgs {
     int coord_mode;             // kCoord*
     uint32_t mul_x, mul_y;      // multiply-high constants of the axes that have one
     const SampleMeta* meta;
-    int64_t* bounds;            // B x (num_bins + 1): s_0 .. s_bins
+    int64_t* bounds;            // B x (num_bins + 2): s_0 .. s_bins, then the last row's stamp in ticks from the first
     unsigned int* counters;     // [0] task counter, [1] fallback flag (an event outside its slice's interval)
     unsigned int* done;         // B x T: finished planes per (sample, tile)
     unsigned int* bad_count;
@@ -1299,10 +1302,13 @@ __global__ void __launch_bounds__(128) k_plane_bounds(PlaneArgs a) {
     const int b = blockIdx.x / nb1, j = blockIdx.x % nb1 + 1;       // boundary j = first position of interval j
     const int tid = threadIdx.x;
     const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
-    int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 1);
-    if (j == 1 && tid == 0) { bd[0] = lo; bd[a.num_bins] = hi; }
-    if (a.num_bins < 2) return;
+    int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 2);
     const SampleMeta m = a.meta[b];
+    if (j == 1 && tid == 0) {
+        bd[0] = lo; bd[a.num_bins] = hi;
+        bd[a.num_bins + 1] = hi > lo ? plane_dt(a, hi - 1, lo, m.t0_ticks) : 0;      // last row's stamp: dT in ticks
+    }
+    if (a.num_bins < 2) return;
     const uint32_t T = (uint32_t)j << kQ;
     // Every round probes 128 equidistant positions of [cl, ch) and keeps the gap in front of the first probe at or past the
     // boundary.  The probe positions depend on (cl, ch) only, and "at or past T2" implies "at or past T1" for T1 < T2, so
@@ -1587,17 +1593,16 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
         const int b = task / per_sample, k = (task - b * per_sample) / a.T, t = task - b * per_sample - k * a.T;
         const int tbase = t * tile_full, ncell = (HW - tbase < tile_full) ? HW - tbase : tile_full;
         c.tbase = (uint32_t)tbase; c.tcells = (uint32_t)ncell; c.count_bad = (t == 0);
-        const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 1);
+        const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 2);
         const int64_t lo = bd[0];
         const int64_t a0 = bd[k > 0 ? k - 1 : 0], mid = bd[k], a1 = bd[k + 1];
         const SampleMeta m = a.meta[b];
         if (mid < a0 || a1 < mid || a1 - a0 >= (1ll << 32)) {
             mismatch = 1u;                                         // (never: the boundaries are monotone by construction)
         } else if (a1 > a0) {
-            const int64_t hi = bd[a.num_bins];
             PlaneTime tm;
             tm.tmul = m.tmul; tm.tshift = m.tshift; tm.thalf = m.thalf;
-            const int64_t dT = plane_dt(a, hi - 1, lo, m.t0_ticks);               // > 0 and < 2^32 for an integer-time sample
+            const int64_t dT = bd[a.num_bins + 1];                                // > 0 and < 2^32 for an integer-time sample
             tm.dT = (uint32_t)dT;
             const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024;
             if (fast && a.T == 1) {

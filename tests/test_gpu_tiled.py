@@ -8,17 +8,23 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-PLANE_CELLS = 54272     # EP_BIN_FORCE_PLANE: cells of one CTA's plane tile in the whole-plane kernels (include/eventpretrain_b200.h)
+PLANE_CELLS = 54272     # csrc/ep_binning_tiled.cu: cells of one CTA's plane tile in the whole-plane kernels
 
 
 def plane_tiles(H, W):
-    """Row tiles the whole-plane kernels cut an H x W grid into (1 = the plane fits one SM; taken up to 3)."""
+    """Row tiles the whole-plane kernels cut an H x W grid into (1 = the plane fits one SM)."""
     if W > PLANE_CELLS:
-        return 1 << 30
+        return 1 << 20
     rows = min(PLANE_CELLS // W, H)
     T = -(-H // rows)
     rows = -(-H // T)
     return -(-H // rows)
+
+
+def plane_takes(H, W, cells, n_events):
+    """The rule of tiled_plan(): up to 2 row tiles, 3 when the output outweighs the events (cells >= 2 x events)."""
+    t = plane_tiles(H, W)
+    return t <= 2 or (t == 3 and cells >= 2 * n_events)
 
 
 def close(a, b):
@@ -75,8 +81,7 @@ def both(ep, p4, size, **kw):
     for key in a:
         assert torch.equal(a[key], b[key]), key
         assert torch.equal(a[key], c[key]), key
-    tiles = plane_tiles(*size)
-    if not kw.get("stats") and (tiles <= 2 or (tiles == 3 and p4.batch * kw.get("num_bins", 0) * size[0] * size[1] >= 2 * p4.num_events)):
+    if not kw.get("stats") and plane_takes(size[0], size[1], p4.batch * kw.get("num_bins", 0) * size[0] * size[1], p4.num_events):
         d = ep.bin_events(p4, size, method="plane", **kw)
         for key in a:
             assert torch.equal(a[key], d[key]), key
@@ -325,3 +330,16 @@ def test_plane_path_mixed_batch(ep, bins):
             assert torch.equal(res[m]["voxel"], res["global"]["voxel"]), (m, unsort)
             assert torch.equal(res[m]["voxel_sum"], res["global"]["voxel_sum"]), (m, unsort)
             assert int(bad[m]) == int(bad["global"]) == 2, (m, unsort)
+
+
+@pytest.mark.parametrize("H,W,bins", [(224, 224, 9), (260, 346, 9), (300, 500, 3), (50, 1000, 2)])
+def test_plane_path_few_events(ep, H, W, bins):
+    """Batches whose output outweighs the events (short samples, many bins: the flush and the per-(sample, tile) voxel.sum(0)
+    dominate), on one, two and three row tiles: same bits as the other paths."""
+    rng = np.random.default_rng(H + bins)
+    counts = [3000, 0, 1, 5000, 257, 4096]
+    ev, _ = dense_batch(ep, rng, counts, H, W, hot=300)
+    p4 = ev.packed(4).to("cuda")
+    assert plane_takes(H, W, p4.batch * bins * H * W, p4.num_events)
+    both(ep, p4, (H, W), num_bins=bins, voxel_sum=True, check=True)
+    both(ep, p4, (H, W), num_bins=bins, check=True)
