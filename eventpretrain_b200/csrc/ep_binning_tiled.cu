@@ -1183,10 +1183,10 @@ static int run_tiled_packed4_impl(cudaStream_t st, const ep_events_soa* ev, cons
     // plain order — both kernels live on the shared-memory pipe, and each loses its second CTA per SM.)
     a.task_lo = 0; a.task_hi = pl.n_tasks; a.sweep_lo = 0; a.sweep_hi = B * pl.NT; a.counter_idx = 0;
     {
-        // planes waiting in L2 for the read-back: (bins - 1) tiles per resident sweep CTA.  EP_DEFERRED_SUM=0/1 overrides (per call).
+        // planes waiting in L2 for the read-back: (bins - 1) tiles per resident sweep CTA.  EP_DEFERRED_SUM=0/1 overrides.
         const size_t waiting = (size_t)(p->num_bins > 1 ? p->num_bins - 1 : 0) * pl.rows * p->width * 4 * (size_t)(kSweepCtas * kNumSMs);
-        const char* e = getenv("EP_DEFERRED_SUM");
-        a.deferred_sum = e ? (e[0] != '0') : (waiting <= ((size_t)80 << 20));
+        static const int forced = [] { const char* e = getenv("EP_DEFERRED_SUM"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();      // read once
+        a.deferred_sum = forced >= 0 ? forced : (waiting <= ((size_t)80 << 20));
     }
     if (pl.n_tasks > 0) {
         const int grid = pl.n_tasks < 2 * kNumSMs ? pl.n_tasks : 2 * kNumSMs;

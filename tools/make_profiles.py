@@ -74,9 +74,39 @@ open(f"{P}{out}_bench_launches.txt", "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[6:20]))
 
 # ---- full ncu captures ----
-for rep, name, filt in ((f"{G}{tag}_tiled.ncu-rep", f"{P}{out}_binning_tiled_ncu.txt", ""), (f"{G}{tag}_evrep.ncu-rep", f"{P}{out}_evrep_ncu.txt", "k_evrep")):
+import os
+caps = [(f"{G}{tag}_tiled.ncu-rep", f"{P}{out}_binning_tiled_ncu.txt", ""), (f"{G}{tag}_evrep.ncu-rep", f"{P}{out}_evrep_ncu.txt", "k_evrep"),
+        (f"{G}{tag}_plane.ncu-rep", f"{P}{out}_plane_ncu.txt", "k_plane")]
+for rep, name, filt in [c for c in caps if os.path.exists(c[0])]:
     txt = subprocess.run([sys.executable, "tools/ncu_summary.py", rep], capture_output=True, text=True).stdout
     txt += subprocess.run([sys.executable, "tools/ncu_lines.py", rep, filt, "30"], capture_output=True, text=True).stdout
     open(name, "w").write(txt)
 shutil.copy(f"{G}{tag}_bench_1gpu.json", f"{P}{out}_bench_1gpu.json")
 shutil.copy(f"{G}{tag}_bench_ref.json", f"{P}{out}_bench_reference_arm.json")
+
+# ---- DRAM traffic of the whole-plane path (reference-res 224x224 step) ----
+if os.path.exists(f"{G}{tag}_traffic_plane.csv"):
+    rows = [r for r in csv.reader(open(f"{G}{tag}_traffic_plane.csv")) if len(r) > 10 and r[0].isdigit()]
+    d = collections.OrderedDict()
+    for r in rows:
+        d.setdefault((int(r[0]), r[4]), {})[r[12]] = float(r[14].replace(",", ""))
+    steps, cur = [], []
+    for (i, name), v in d.items():
+        short = "k_sample_meta" if "k_sample_meta" in name else name.split("(")[0].split("::")[-1]
+        if "k_sample_meta" in name and cur:
+            steps.append(cur); cur = []
+        cur.append((short, v))
+    steps.append(cur)
+    last = [s_ for s_ in steps if len(s_) >= 5][-1]
+    lines = ["# DRAM traffic of one reference-res step (256 x ~1M events, 640x480 -> 224x224 fused, 5 bins + sum plane, 4 B packed layout), per launch:",
+             "# the whole-plane kernels and, behind them, the stand-by route + sweep launches that return at once (sorted input).",
+             "# ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct",
+             "# command: python tools/quick_bin.py --batch 256 --packed4 --size 224x224 --methods plane --steps 1   (tools/run_final.sh)",
+             "kernel,dram_read_bytes,dram_write_bytes,duration_ns,l2_hit_pct"]
+    tot = 0
+    for short, v in last:
+        lines.append(f"{short},{int(v['dram__bytes_read.sum'])},{int(v['dram__bytes_write.sum'])},{int(v['gpu__time_duration.sum'])},{v['lts__t_sector_hit_rate.pct']}")
+        tot += v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]
+    lines.append(f"# total DRAM bytes per step: {int(tot)}  (compulsory: events 1.02 GB once + outputs 0.31 GB; algorithmic, SURVEY 8(d): 3.62 GB)")
+    open(f"{P}{out}_traffic_plane.csv", "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
