@@ -412,6 +412,9 @@ def run_ours(args):
         same = all(torch.equal(ref224[k], o224[k]) for k in ref224)
         r224["global_RED_path_Gevents_per_s"] = gev(ev, "global", (224, 224), (224 / W, 224 / H), o224)[0]
         r224["bit_identical_across_the_three_paths"] = bool(same and all(torch.equal(ref224[k], o224[k]) for k in ref224))
+        ms224s = timed_ms(lambda: ep.bin_events(ev, (224, 224), num_bins=BINS, voxel_sum=True, out=o224, method=args.method,
+                                                scale=(224 / W, 224 / H), stats=True), args.steps)
+        r224["with_batch_statistics_ms_per_step"] = ms224s
         del o224, ref224
     del ev13
     torch.cuda.empty_cache()

@@ -72,6 +72,10 @@ static_assert(kItemRPL >= 1 && kItemRPL <= 4, "the item descriptor holds records
 constexpr int kSpillCap = 128;
 constexpr int kPlaneCellsMax = 54272;         // whole-plane kernels: 212 KB of int32 plane + 13 KB of tables and spill list
 constexpr int kPlaneMaxTiles = 3;
+#ifndef EP_PLANE_THREADS
+#define EP_PLANE_THREADS 1024
+#endif
+constexpr int kPlaneStatSlot = (EP_PLANE_THREADS / 32) * 3;      // doubles per (sample, tile, channel): (sum, sum of squares, max) per warp of k_plane
 
 constexpr uint32_t kChunkFast = 1u;           // integer-tick sample, narrow records, every v of the chunk fits 32 bits
 constexpr uint32_t kChunkNarrow = 2u;         // records carry chunk-relative ticks (else: tick block + block-relative ticks)
@@ -714,9 +718,18 @@ __device__ __forceinline__ void flush_plane_t(int* pl, int ncell, int k, float* 
     }
 }
 
+// the same in fp64 (whole-plane kernels: a thread owns up to ~50 values of a plane, hot cells included)
+struct StatAcc64 {
+    double s1, s2;
+    float mx;
+    __device__ __forceinline__ void init() { s1 = 0.0; s2 = 0.0; mx = -INFINITY; }
+    __device__ __forceinline__ void add(float v) { const double d = (double)v; s1 += d; s2 = fma(d, d, s2); mx = fmaxf(mx, v); }
+};
+
 // per-warp reduction of the per-thread statistics (fixed shuffle tree) -> part[warp][0..2] = (sum, sum of squares, max) as
 // fp64; no barrier: every (task, channel, warp) slot is written exactly once and k_stats_reduce adds them in a fixed order
-__device__ __forceinline__ void stat_reduce_store(StatAcc a, double* part) {
+template <class Acc>
+__device__ __forceinline__ void stat_reduce_store(Acc a, double* part) {
     double d1 = (double)a.s1, d2 = (double)a.s2;
     float mx = a.mx;
 #pragma unroll
@@ -997,7 +1010,7 @@ struct TiledPlan {
     size_t off_meta, off_first, off_desc, off_cmeta, off_coff, off_crel, off_counters, off_stats, off_stats2, off_rec, total;
     bool plane_ok;              // the grid's plane fits one SM's shared memory in at most 3 row tiles: whole-plane kernels
     int plane_T, plane_rows;    // (run_plane_packed4)
-    size_t off_plane, off_plane_bounds;
+    size_t off_plane, off_plane_bounds, off_plane_stats;
 };
 
 bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) {
@@ -1050,10 +1063,11 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
         const int64_t cells = (int64_t)B * p->num_bins * H * W, n_ev = ev->offsets_host[B] - ev->offsets_host[0];
         if (T <= 2 || (T == 3 && cells >= 2 * n_ev)) { pl.plane_ok = true; pl.plane_T = T; pl.plane_rows = prow; }
     }
-    pl.off_plane = pl.off_plane_bounds = 0;
+    pl.off_plane = pl.off_plane_bounds = pl.off_plane_stats = 0;
     if (pl.plane_ok) {
         pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B * kPlaneMaxTiles, 256);      // counters | finished planes per (sample, tile)
         pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 2), 256);
+        pl.off_plane_stats = o; o += align_up(sizeof(double) * kPlaneStatSlot * (size_t)B * pl.plane_T * (size_t)(p->num_bins + 1), 256);
     }
     pl.total = o;
     return true;
@@ -1069,9 +1083,13 @@ size_t tiled_workspace_bytes(const ep_events_soa* ev, const ep_bin_params* p) {
 // Channel statistics from the sweep's per-(task, channel, warp) partials, in a fixed order (bit-reproducible):
 // k_stats_slices: CTA (channel c, slice s) adds the partials of its contiguous share of the tasks -> part2[c][s][0..2];
 // k_stats_final: out[c] = (count, sum, sum of squares, max) from the kStatSlices slice sums.
-__global__ void __launch_bounds__(256) k_stats_slices(const double* __restrict__ part, int n_tasks, int n_ch, double* __restrict__ part2) {
+// kWarps = warps of the kernel that wrote the partials; guard (or null): the kernels run only while (*guard != 0) == want —
+// the whole-plane path and its stand-by route + sweep each bring their own reduction, one of the two runs.
+__global__ void __launch_bounds__(256) k_stats_slices(const double* __restrict__ part, int n_tasks, int n_ch, double* __restrict__ part2,
+                                                      int kWarps, const unsigned int* guard, int want) {
     __shared__ double s1[256], s2[256], sm[256];
-    constexpr int kWarps = kSweepThreads / 32;
+    if (guard && ((*guard != 0u) != (want != 0))) return;
+    const int kStatSlot = kWarps * 3;
     const int c = blockIdx.x, sl = blockIdx.y, tid = threadIdx.x;
     const int per = (n_tasks + kStatSlices - 1) / kStatSlices;
     const int t0 = sl * per, t1 = (t0 + per < n_tasks) ? t0 + per : n_tasks;
@@ -1093,7 +1111,9 @@ __global__ void __launch_bounds__(256) k_stats_slices(const double* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(32) k_stats_final(const double* __restrict__ part2, double count, double* __restrict__ out) {
+__global__ void __launch_bounds__(32) k_stats_final(const double* __restrict__ part2, double count, double* __restrict__ out,
+                                                    const unsigned int* guard, int want) {
+    if (guard && ((*guard != 0u) != (want != 0))) return;
     const int c = blockIdx.x, lane = threadIdx.x;
     const double* q = part2 + ((size_t)c * kStatSlices + lane) * 3;
     double a1 = q[0], a2 = q[1], am = q[2];
@@ -1108,7 +1128,7 @@ __global__ void __launch_bounds__(32) k_stats_final(const double* __restrict__ p
 
 namespace {
 int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                      void* ws, size_t ws_bytes, unsigned int* bad);
+                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats);
 }
 
 // standby = device word of the whole-plane path (run_plane_packed4): the kernels below return at once while it is 0, the
@@ -1217,9 +1237,9 @@ static int run_tiled_packed4_impl(cudaStream_t st, const ep_events_soa* ev, cons
         profile_begin(st, kProfOther);
         double* part2 = reinterpret_cast<double*>(base + pl.off_stats2);
         const int n_out = out_sum ? n_ch : p->num_bins;
-        k_stats_slices<<<dim3((unsigned)n_out, kStatSlices), 256, 0, st>>>(a.stats_part, B * pl.NT, n_ch, part2);
+        k_stats_slices<<<dim3((unsigned)n_out, kStatSlices), 256, 0, st>>>(a.stats_part, B * pl.NT, n_ch, part2, kSweepThreads / 32, standby, 1);
         EP_LAUNCH_CHECK();
-        k_stats_final<<<n_out, 32, 0, st>>>(part2, (double)B * p->height * p->width, out_stats);
+        k_stats_final<<<n_out, 32, 0, st>>>(part2, (double)B * p->height * p->width, out_stats, standby, 1);
         profile_end(st);
         EP_LAUNCH_CHECK();
     }
@@ -1283,6 +1303,7 @@ struct PlaneArgs {
     unsigned int* bad_count;
     float* out_voxel;
     float* out_sum;
+    double* stats_part;         // (B x T) x (num_bins + 1) x warps x 3 partial statistics of the written values, or null
 };
 
 __host__ __device__ inline size_t plane_smem_bytes(int tile_cells) {
@@ -1631,6 +1652,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
         const int n_spill = s_nspill < kSpillCap ? s_nspill : kSpillCap;
         float* o = a.out_voxel + ((int64_t)b * a.num_bins + k) * HW + tbase;
         const bool keep = a.out_sum != nullptr;                    // the planes are read back for voxel.sum(0): leave them in L2
+        const bool stats = a.stats_part != nullptr;
+        StatAcc64 sa, ss;
+        sa.init(); ss.init();
         if (VEC) {
             for (int i = tid * 4; i < ncell; i += kPlaneThreads * 4) {
                 const int4 q = *reinterpret_cast<const int4*>(plane + i);
@@ -1648,6 +1672,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
                 }
                 if (keep) __stcg(reinterpret_cast<float4*>(o + i), f);
                 else st_stream(reinterpret_cast<float4*>(o + i), f);
+                if (stats) { sa.add(f.x); sa.add(f.y); sa.add(f.z); sa.add(f.w); }
             }
         } else {
             for (int i = tid; i < ncell; i += kPlaneThreads) {
@@ -1661,8 +1686,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
                 }
                 if (keep) __stcg(o + i, f);
                 else st_stream(o + i, f);
+                if (stats) sa.add(f);
             }
         }
+        // statistics of the written values as a by-product (fixed element order per thread, fixed shuffle tree per warp, one
+        // slot per (sample, tile, channel, warp) => bit-reproducible), reduced by k_stats_slices / k_stats_final
+        double* sp = stats ? a.stats_part + ((size_t)(b * a.T + t) * (a.num_bins + 1)) * kPlaneStatSlot : nullptr;
+        if (stats) stat_reduce_store(sa, sp + (size_t)k * kPlaneStatSlot);
         if (keep) {
             // ---- the CTA that completes a sample's last plane forms voxel.sum(0) ----
             __threadfence();
@@ -1691,14 +1721,17 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
                                 if (j0 + jj < a.num_bins) { s.x += v[jj].x; s.y += v[jj].y; s.z += v[jj].z; s.w += v[jj].w; }
                         }
                         st_stream(reinterpret_cast<float4*>(so + i), s);
+                        if (stats) { ss.add(s.x); ss.add(s.y); ss.add(s.z); ss.add(s.w); }
                     }
                 } else {
                     for (int i = tid; i < ncell; i += kPlaneThreads) {
                         float s = __ldcg(p0 + i);
                         for (int j = 1; j < a.num_bins; ++j) s += __ldcg(p0 + (int64_t)j * HW + i);      // sequential fp32 over bins
                         st_stream(so + i, s);
+                        if (stats) ss.add(s);
                     }
                 }
+                if (stats) stat_reduce_store(ss, sp + (size_t)a.num_bins * kPlaneStatSlot);
             }
         }
         __syncthreads();
@@ -1728,7 +1761,7 @@ static bool plane_axis_mul(double s, uint32_t& mul_out) {
 }
 
 int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
-                      void* ws, size_t ws_bytes, unsigned int* bad) {
+                      void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
     TiledPlan pl;
     if (!tiled_plan(ev, p, pl) || !pl.plane_ok) return EP_EUNSUPPORTED;
     if (!ws || ws_bytes < pl.total) return EP_EUNSUPPORTED;
@@ -1753,6 +1786,7 @@ int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     a.bad_count = bad;
     a.out_voxel = out_voxel;
     a.out_sum = out_sum;
+    a.stats_part = out_stats ? reinterpret_cast<double*>(base + pl.off_plane_stats) : nullptr;
 
     SoaPackedLoader<false> ld{a.w, nullptr, a.blk_base, ev->t_base, ev->t_div};
     BinArgs ba = {};
@@ -1789,22 +1823,30 @@ int run_plane_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_par
     else k_plane<false><<<grid, kPlaneThreads, smem, st>>>(a);
     profile_end(st);
     EP_LAUNCH_CHECK();
+    if (out_stats) {
+        // (runs only if the planes stand: the stand-by path brings its own reduction)
+        const int n_ch = p->num_bins + 1, n_out = out_sum ? n_ch : p->num_bins;
+        double* part2 = reinterpret_cast<double*>(base + pl.off_stats2);
+        profile_begin(st, kProfOther);
+        k_stats_slices<<<dim3((unsigned)n_out, kStatSlices), 256, 0, st>>>(a.stats_part, B * a.T, n_ch, part2, kPlaneStatSlot / 3, a.counters + 1, 0);
+        EP_LAUNCH_CHECK();
+        k_stats_final<<<n_out, 32, 0, st>>>(part2, (double)B * p->height * p->width, out_stats, a.counters + 1, 0);
+        profile_end(st);
+        EP_LAUNCH_CHECK();
+    }
     // the route + sweep kernels stand by: they run only if k_plane met an event outside its slice's interval
-    return run_tiled_packed4_impl(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, nullptr, a.counters + 1);
+    return run_tiled_packed4_impl(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, out_stats, a.counters + 1);
 }
 
 }  // namespace
 
 // Returns EP_EUNSUPPORTED when the layout / shape / workspace does not qualify (the caller then takes the global path).
-// Grids whose plane fits one SM's shared memory take the whole-plane kernels (unless the statistics by-product is asked
-// for, which lives in the sweep's flush), everything else route + sweep; EP_BIN_FORCE_TILED / EP_BIN_FORCE_PLANE pin one.
+// Grids whose plane fits one SM's shared memory take the whole-plane kernels, everything else route + sweep; EP_BIN_FORCE_TILED / EP_BIN_FORCE_PLANE pin one.
 int run_tiled_packed4(cudaStream_t st, const ep_events_soa* ev, const ep_bin_params* p, float* out_voxel, float* out_sum,
                       void* ws, size_t ws_bytes, unsigned int* bad, double* out_stats) {
-    if (!out_stats && !(p->flags & EP_BIN_FORCE_TILED)) {
-        const int rc = run_plane_packed4(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad);
+    if (!(p->flags & EP_BIN_FORCE_TILED)) {
+        const int rc = run_plane_packed4(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, out_stats);
         if (rc != EP_EUNSUPPORTED || (p->flags & EP_BIN_FORCE_PLANE)) return rc;
-    } else if (p->flags & EP_BIN_FORCE_PLANE) {
-        return EP_EUNSUPPORTED;
     }
     return run_tiled_packed4_impl(st, ev, p, out_voxel, out_sum, ws, ws_bytes, bad, out_stats, nullptr);
 }

@@ -125,6 +125,8 @@ def test_tiled_equals_global_and_oracle(ep, H, W, bins):
     assert torch.equal(v["voxel"], out["voxel"])
     sh = ep.bin_events(p4.shard(1, 2), (H, W), num_bins=bins, method="tiled", check=True)
     assert torch.equal(sh["voxel"], out["voxel"][4:])
+    sh = ep.bin_events(p4.shard(1, 2), (H, W), num_bins=bins, voxel_sum=True, check=True)        # default path of this shape, offsets[0] > 0
+    assert torch.equal(sh["voxel"], out["voxel"][4:]) and torch.equal(sh["voxel_sum"], out["voxel_sum"][4:])
     # run-to-run bit identity
     again = ep.bin_events(p4, (H, W), num_bins=bins, voxel_sum=True, method="tiled")
     assert torch.equal(again["voxel"], out["voxel"]) and torch.equal(again["voxel_sum"], out["voxel_sum"])
@@ -265,13 +267,24 @@ def test_fused_statistics(ep):
         return torch.stack([torch.full((x.shape[1],), float(xd.shape[1]), dtype=torch.float64, device=x.device), xd.sum(1),
                             (xd * xd).sum(1), xd.amax(1)], 1)
 
-    for method in ("tiled", "global"):
+    for method in ("tiled", "global", "plane", None):
         o = ep.bin_events(p4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method=method)
         ref = torch.cat([table(o["voxel"]), table(o["voxel_sum"])], 0)
         assert torch.allclose(o["stats"], ref, rtol=1e-6, atol=1e-6), method
         assert torch.equal(o["stats"][:, 0], ref[:, 0]) and torch.equal(o["stats"][:, 3], ref[:, 3]), method
         again = ep.bin_events(p4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method=method)
         assert torch.equal(again["stats"], o["stats"]), method
+    # whole-plane kernels: two row tiles without the sum plane, and an unsorted batch (the stand-by route + sweep redo the
+    # planes and bring their own reduction: same table as the forced tiled path, bit for bit)
+    ev2, _ = dense_batch(ep, rng, [30000, 500, 12000], 260, 346, hot=300)
+    q4 = ev2.packed(4).to("cuda")
+    o = ep.bin_events(q4, (260, 346), num_bins=9, stats=True, method="plane")
+    assert torch.allclose(o["stats"][:9], table(o["voxel"]), rtol=1e-6, atol=1e-6), (o["stats"][:9] - table(o["voxel"])).abs().max(0)
+    ev3, _ = dense_batch(ep, rng, [20000, 9000], H, W, block_shuffle=True)
+    r4 = ev3.packed(4).to("cuda")
+    a = ep.bin_events(r4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method="plane")
+    b = ep.bin_events(r4, (H, W), num_bins=bins, voxel_sum=True, stats=True, method="tiled")
+    assert torch.equal(a["stats"], b["stats"]) and torch.equal(a["voxel"], b["voxel"])
     x = torch.randn(7, 3, 33, 50, device="cuda")
     assert torch.allclose(epd.plane_statistics(x), table(x), rtol=1e-12, atol=1e-9)
     fin = epd.finalize_statistics(epd.plane_statistics(x))
