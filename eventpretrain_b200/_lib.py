@@ -57,6 +57,7 @@ SIGNATURES = {
     "ep_profile_read": (c_int, [P(ProfileStats)]),
     "ep_bin_events_workspace_bytes": (c_size_t, [P(BinParams), c_int, P(c_size_t)]),
     "ep_bin_events_workspace_bytes_for": (c_size_t, [P(EventsSoa), P(BinParams)]),
+    "ep_reshape_axis_multiplier_host": (c_int, [c_double, c_void_p]),
     "ep_bin_events": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "ep_bin_events_stats": (c_int, [c_void_p, P(EventsSoa), P(BinParams), c_void_p, c_void_p, c_void_p, c_void_p,

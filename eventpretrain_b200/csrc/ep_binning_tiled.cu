@@ -2337,3 +2337,10 @@ int run_evrep_packed4(cudaStream_t st, const ep_events_soa* ev, int height, int 
 }
 
 }  // namespace ep
+
+extern "C" int ep_reshape_axis_multiplier_host(double scale, uint32_t* multiplier) {
+    uint32_t m = 0;
+    const bool ok = ep::plane_axis_mul(scale, m);
+    if (multiplier) *multiplier = ok ? m : 0u;
+    return ok ? 1 : 0;
+}

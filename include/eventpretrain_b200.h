@@ -136,6 +136,13 @@ EP_API size_t ep_bin_events_workspace_bytes(const ep_bin_params* prm, int batch,
  * path, which is taken when the layout is the 4 B packed one and the workspace is large enough. */
 EP_API size_t ep_bin_events_workspace_bytes_for(const ep_events_soa* ev, const ep_bin_params* prm);
 
+/* Host-only query (no GPU): does one axis of the fused events_reshape (dataset/augmentation/events_augment.py:22-26:
+ * x * scale in fp64, then truncation) have a proven multiply-high form, trunc(fl(i * scale)) == (i * multiplier) >> 32 for every
+ * coordinate i < 2048 of the packed layouts?  Returns 1 and the multiplier when it does — the whole-plane kernels then
+ * compute that axis with one multiply instead of a shared-memory table — 0 when some coordinate differs (e.g. 0.35 * 180 =
+ * 62.99999999999999 in fp64) or scale >= 1; the kernels decide per call with this very function. */
+EP_API int ep_reshape_axis_multiplier_host(double scale, uint32_t* multiplier);
+
 /* Replaces, for a whole ragged batch in one call:
  *   events_to_voxel_grid(args, events, size)   dataset/dataset_utils/events_to_voxel_grid.py:4-61
  *   events_to_image_ecdp / events_to_image_mem dataset/dataset_utils/events_to_image.py:6-62

@@ -211,3 +211,34 @@ def test_native_packers_fuzz_against_numpy():
                 assert np.array_equal(got.unpack_host()[2], t)
 
     run()
+
+
+def test_reshape_axis_multiplier_against_numpy(native_lib):
+    """The host decision the whole-plane binning kernels take per call: an axis of the fused events_reshape
+    (events_augment.py:22-26: x * scale in fp64, truncated by .long()) is computed as (x * multiplier) >> 32 only where that
+    equals the reference's expression for every coordinate of the packed layouts; 0.35 (640 -> 224) has traps and keeps its
+    table, 224 / 480 does not."""
+    import ctypes
+    x = np.arange(2048, dtype=np.float64)
+    rng = np.random.default_rng(3)
+    scales = [224 / 640, 224 / 480, 224 / 346, 224 / 260, 224 / 240, 224 / 180, 0.4, 0.5, 1.0, 1.5, 1e-6, 0.999999]
+    scales += list(rng.uniform(0.01, 0.999, 40))
+    seen = set()
+    for s in scales:
+        m = ctypes.c_uint32(0)
+        ok = native_lib.ep_reshape_axis_multiplier_host(ctypes.c_double(s), ctypes.byref(m))
+        exact = (x * np.float64(s)).astype(np.int64)                      # the reference's arithmetic
+        if ok:
+            got = (np.arange(2048, dtype=np.uint64) * np.uint64(m.value)) >> np.uint64(32)
+            assert np.array_equal(got.astype(np.int64), exact), s
+        else:
+            assert m.value == 0
+            if s < 1.0:
+                mul = int(np.ceil(np.ldexp(np.float64(s), 32)))
+                got = (np.arange(2048, dtype=np.uint64) * np.uint64(mul)) >> np.uint64(32)
+                assert not np.array_equal(got.astype(np.int64), exact), s      # refused only where it would differ
+        seen.add(bool(ok))
+    m = ctypes.c_uint32(0)
+    assert native_lib.ep_reshape_axis_multiplier_host(ctypes.c_double(224 / 640), ctypes.byref(m)) == 0      # 0.35 * 180 = 62.99999999999999
+    assert native_lib.ep_reshape_axis_multiplier_host(ctypes.c_double(224 / 480), ctypes.byref(m)) == 1
+    assert seen == {True, False}
