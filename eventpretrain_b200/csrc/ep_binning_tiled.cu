@@ -1306,8 +1306,12 @@ struct PlaneArgs {
     double* stats_part;         // (B x T) x (num_bins + 1) x warps x 3 partial statistics of the written values, or null
 };
 
+// dynamic shared memory of k_plane: lut_x u16[2048] | lut_y u32[2048] | spill int2[kSpillCap] | plane int32[tile cells] | dump int32[32]
+constexpr uint32_t kPlaneOffLutX = 0, kPlaneOffLutY = 4096, kPlaneOffSpill = 12288, kPlaneOffPlane = kPlaneOffSpill + kSpillCap * 8;
+static_assert(kPlaneOffPlane % 16 == 0, "the plane is read with 16-byte loads");
+
 __host__ __device__ inline size_t plane_smem_bytes(int tile_cells) {
-    return (size_t)((tile_cells + 3) & ~3) * 4 + 128 + 2048 * 4 + 2048 * 2 + kSpillCap * 8;      // plane | dump words | tables | spill list
+    return kPlaneOffPlane + (size_t)((tile_cells + 3) & ~3) * 4 + 128;
 }
 
 // stamp of array position i of a sample that starts at lo, as ticks from the sample's first row
@@ -1359,10 +1363,8 @@ __global__ void __launch_bounds__(128) k_plane_bounds(PlaneArgs a) {
 }
 
 struct PlaneCtx {
-    uint32_t plane_s;           // shared-memory address of the plane
-    uint32_t luty_s, lutx_s;    // shared-memory addresses of the coordinate tables
-    const uint32_t* lut_y;
-    const uint16_t* lut_x;
+    uint32_t base_s;            // shared-memory address of the CTA's dynamic buffer: tables, spill list and plane sit at the fixed
+                                // offsets kPlaneOff* behind it, so one register addresses them all (immediate offsets)
     int2* spill;
     int* n_spill;
     unsigned int* bad;
@@ -1378,6 +1380,8 @@ struct PlaneCtx {
 // Per-task constants of the time arithmetic
 struct PlaneTime {
     uint32_t tmul, tshift, dT;  // FAST: v = (dt * tmul + thalf) >> tshift for 0 <= dt <= dT ticks (v(dT) = (bins - 1) << 24)
+    uint32_t dt_lim;            // block bases (minus the first row's ticks) up to here keep dt + 511 below 2^32 and v below 2^32:
+                                // v is then monotone in dt and "v inside the slice's interval" is the whole test
     uint64_t thalf;
 };
 
@@ -1388,21 +1392,30 @@ struct PlaneMax {
     uint32_t u, dt, ce;
 };
 
+// shared-memory accesses at (register + immediate offset): the offset goes into the instruction
+template <uint32_t OFF>
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF));
     return v;
 }
+template <uint32_t OFF>
 __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
     uint32_t v;
-    asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(saddr));
+    asm volatile("{\n\t.reg .u16 h;\n\tld.shared.u16 h, [%1+%2];\n\tcvt.u32.u16 %0, h;\n\t}" : "=r"(v) : "r"(saddr), "n"(OFF));
     return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ int atoms_add_at(uint32_t saddr, int w) {
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1+%3], %2;" : "=r"(old) : "r"(saddr), "r"(w), "n"(OFF) : "memory");
+    return old;
 }
 
 // cell of a packed word through the tables of the fused events_reshape: row base + column; anything >= hw is outside the grid
 __device__ __forceinline__ uint32_t plane_cell(const PlaneCtx& c, uint32_t word) {
-    const uint32_t ly = lds_u32(c.luty_s + ((word >> 9) & 0x1ffcu));
-    const uint32_t lx = lds_u16(c.lutx_s + ((word << 1) & 0xffeu));
+    const uint32_t ly = lds_u32<kPlaneOffLutY>(c.base_s + ((word >> 9) & 0x1ffcu));
+    const uint32_t lx = lds_u16<kPlaneOffLutX>(c.base_s + ((word << 1) & 0xffeu));
     return ly + lx;
 }
 
@@ -1418,9 +1431,9 @@ __device__ __forceinline__ void plane_cells(const PlaneCtx& c, const uint32_t (&
             ce[e] = ((word >> 11) & 0x7ffu) * c.W + (word & 0x7ffu);
         } else {
             const uint32_t row = (CM == kCoordMulY || CM == kCoordMul) ? __umulhi((word >> 11) & 0x7ffu, c.mul_y) * c.W
-                                                                       : lds_u32(c.luty_s + ((word >> 9) & 0x1ffcu));
+                                                                       : lds_u32<kPlaneOffLutY>(c.base_s + ((word >> 9) & 0x1ffcu));
             const uint32_t col = (CM == kCoordMulX || CM == kCoordMul) ? __umulhi(word & 0x7ffu, c.mul_x)
-                                                                       : lds_u16(c.lutx_s + ((word << 1) & 0xffeu));
+                                                                       : lds_u16<kPlaneOffLutX>(c.base_s + ((word << 1) & 0xffeu));
             ce[e] = row + col;
         }
     }
@@ -1448,7 +1461,7 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
             const uint32_t dt = (uint32_t)dtb + (word >> 23);
             const uint64_t q = (uint64_t)dt * tm.tmul + tm.thalf;
             u = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), tm.tshift) - kbase;
-            if (!EDGE) { mx.dt = max(mx.dt, dt); mx.u = max(mx.u, u); }
+            if (!EDGE) mx.u = max(mx.u, u);                  // (dt cannot leave the arithmetic's range: block base <= dt_lim)
             else if (in) { mx.dt = max(mx.dt, dt); mx.u = max(mx.u, u); }
         } else {
             uint32_t v = 0;
@@ -1463,7 +1476,7 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
         if (EDGE && !in) val[e] = 0;
         if (MT) { const uint32_t cl = ce - c.tbase; cell[e] = cl < c.tcells ? cl : c.dumpl; }
         else cell[e] = min(ce, c.dump);
-        old[e] = atoms_add(c.plane_s + cell[e] * 4u, val[e]);
+        old[e] = atoms_add_at<kPlaneOffPlane>(c.base_s + cell[e] * 4u, val[e]);
     }
     uint32_t near = 0;
 #pragma unroll
@@ -1480,8 +1493,10 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
 #endif
 
 // The slice [s0, s1) of the sample that starts at lo: interval kexp (kbase = kexp << 24).  A warp takes one 256-event tick
-// block per step (two quads per lane, one block base for the warp); only the first and the last block of a slice can
-// straddle its ends.
+// block per step (two quads per lane, one block base for the warp).  Blocks that lie inside the slice and whose stamps cannot
+// leave the range of the 32-bit time arithmetic (block base <= dt_lim) take the quads without per-event range tests; the
+// first and the last block of a slice (they may straddle its ends), the block where the sample starts (its base is the
+// sample's own, the first row's ticks are subtracted mod 2^32) and blocks past dt_lim (unsorted input) take the checked quads.
 template <bool FAST, int CM, bool LEFT, bool MT>
 __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& c, const SampleMeta& m, const PlaneTime& tm, int64_t lo,
                                             int64_t s0, int64_t s1, uint32_t kbase, uint32_t& mismatch, uint32_t& nbad) {
@@ -1511,7 +1526,7 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
 #endif
     for (uint32_t i = (uint32_t)wid; i < nblk; i += kWarps) {
         const uint4* p = reinterpret_cast<const uint4*>(wp + ((size_t)i << kTickBlockShift));
-        const bool edge = (i == 0u && head) || (i == nblk - 1u && tail);
+        bool edge = (i == 0u && head) || (i == nblk - 1u && tail);
 #if EP_PLANE_PIPE == 2
         const uint4 w0 = n0, w1 = n1;
         const uint32_t base = nb;
@@ -1525,8 +1540,8 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
         }
 #endif
 #endif
-        if (FAST && base > 0xfffffdffu) { mismatch = 1u; continue; }       // (a block 2^32 ticks past the first row: unsorted input)
         const int64_t dtb = FAST ? (int64_t)(base - t0) : (int64_t)base - m.t0_ticks;
+        if (FAST) edge = edge || i == first_rel || (base - t0) > tm.dt_lim;
         if (!edge) {
 #if EP_PLANE_PIPE != 2
             const uint4 w0 = ld_stream(p), w1 = ld_stream(p + 32);
@@ -1534,7 +1549,8 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
             plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w0, dtb, 0u, len, kbase, mx, mismatch);
             plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w1, dtb, 0u, len, kbase, mx, mismatch);
         } else {
-            // first / last block of the slice: only the events inside [s0, s1) are loaded and added
+            // checked block: only the events inside [s0, s1) are loaded and added, every event is tested against the sample's time range
+            if (FAST && base > 0xfffffdffu) { mismatch = 1u; continue; }       // (a block 2^32 ticks past the first row: unsorted input)
             const int64_t bs = (blk0 + (int64_t)i) << kTickBlockShift;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -1580,10 +1596,10 @@ template <bool VEC>
 __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int HW = a.H * a.W, tile_full = a.rows * a.W, HWp = (tile_full + 3) & ~3;      // HWp: words of the plane buffer
-    int* plane = reinterpret_cast<int*>(smem_raw);
-    uint32_t* lut_y = reinterpret_cast<uint32_t*>(plane + HWp + 32);
-    uint16_t* lut_x = reinterpret_cast<uint16_t*>(lut_y + 2048);
-    int2* s_spill = reinterpret_cast<int2*>(lut_x + 2048);
+    int* plane = reinterpret_cast<int*>(smem_raw + kPlaneOffPlane);
+    uint16_t* lut_x = reinterpret_cast<uint16_t*>(smem_raw + kPlaneOffLutX);
+    uint32_t* lut_y = reinterpret_cast<uint32_t*>(smem_raw + kPlaneOffLutY);
+    int2* s_spill = reinterpret_cast<int2*>(smem_raw + kPlaneOffSpill);
     __shared__ int s_task[2], s_nspill, s_last;
 
     const int tid = threadIdx.x;
@@ -1599,9 +1615,8 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
     }
     __syncthreads();
     PlaneCtx c;
-    c.plane_s = (uint32_t)__cvta_generic_to_shared(plane);
-    c.luty_s = (uint32_t)__cvta_generic_to_shared(lut_y); c.lutx_s = (uint32_t)__cvta_generic_to_shared(lut_x);
-    c.lut_y = lut_y; c.lut_x = lut_x; c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
+    c.base_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
     c.hw = (uint32_t)HW; c.dump = (uint32_t)HWp; c.W = (uint32_t)a.W; c.mul_x = a.mul_x; c.mul_y = a.mul_y;
     c.dumpl = (uint32_t)HWp + (uint32_t)(tid & 31);
     uint32_t mismatch = 0, nbad = 0;
@@ -1625,7 +1640,11 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
             tm.tmul = m.tmul; tm.tshift = m.tshift; tm.thalf = m.thalf;
             const int64_t dT = bd[a.num_bins + 1];                                // > 0 and < 2^32 for an integer-time sample
             tm.dT = (uint32_t)dT;
-            const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024;
+            // largest dt whose v still fits 32 bits
+            uint64_t dt_safe = 0xffffffffull;
+            if (m.tmul) { const uint64_t q = ((((1ull << 32) << m.tshift) - m.thalf) - 1ull) / m.tmul; dt_safe = q < dt_safe ? q : dt_safe; }
+            tm.dt_lim = dt_safe >= 1023u ? (uint32_t)(dt_safe - 1023u) : 0u;
+            const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024 && dt_safe >= 1023u;
             if (fast && a.T == 1) {
 #define EP_PLANE_ACC(CM, MT) plane_accumulate<true, CM, MT>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad)
                 switch (a.coord_mode) {
