@@ -1066,7 +1066,7 @@ bool tiled_plan(const ep_events_soa* ev, const ep_bin_params* p, TiledPlan& pl) 
     pl.off_plane = pl.off_plane_bounds = pl.off_plane_stats = 0;
     if (pl.plane_ok) {
         pl.off_plane = o; o += align_up(256 + sizeof(unsigned int) * (size_t)B * kPlaneMaxTiles, 256);      // counters | finished planes per (sample, tile)
-        pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 2), 256);
+        pl.off_plane_bounds = o; o += align_up(sizeof(int64_t) * (size_t)B * (size_t)(p->num_bins + 3), 256);
         pl.off_plane_stats = o; o += align_up(sizeof(double) * kPlaneStatSlot * (size_t)B * pl.plane_T * (size_t)(p->num_bins + 1), 256);
     }
     pl.total = o;
@@ -1297,7 +1297,7 @@ struct PlaneArgs {
     int coord_mode;             // kCoord*
     uint32_t mul_x, mul_y;      // multiply-high constants of the axes that have one
     const SampleMeta* meta;
-    int64_t* bounds;            // B x (num_bins + 2): s_0 .. s_bins, then the last row's stamp in ticks from the first
+    int64_t* bounds;            // B x (num_bins + 3): s_0 .. s_bins, the last row's stamp in ticks from the first, dt_lim
     unsigned int* counters;     // [0] task counter, [1] fallback flag (an event outside its slice's interval)
     unsigned int* done;         // B x T: finished planes per (sample, tile)
     unsigned int* bad_count;
@@ -1327,11 +1327,15 @@ __global__ void __launch_bounds__(128) k_plane_bounds(PlaneArgs a) {
     const int b = blockIdx.x / nb1, j = blockIdx.x % nb1 + 1;       // boundary j = first position of interval j
     const int tid = threadIdx.x;
     const int64_t lo = a.offsets[b], hi = a.offsets[b + 1];
-    int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 2);
+    int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 3);
     const SampleMeta m = a.meta[b];
     if (j == 1 && tid == 0) {
         bd[0] = lo; bd[a.num_bins] = hi;
         bd[a.num_bins + 1] = hi > lo ? plane_dt(a, hi - 1, lo, m.t0_ticks) : 0;      // last row's stamp: dT in ticks
+        // largest dt whose v = (dt * tmul + thalf) >> tshift still fits 32 bits (PlaneTime::dt_lim), -1 = the fast quads do not apply
+        uint64_t dt_safe = 0xffffffffull;
+        if (m.tmul) { const uint64_t q = ((((1ull << 32) << m.tshift) - m.thalf) - 1ull) / m.tmul; dt_safe = q < dt_safe ? q : dt_safe; }
+        bd[a.num_bins + 2] = dt_safe >= 1023u ? (int64_t)(dt_safe - 1023u) : -1;
     }
     if (a.num_bins < 2) return;
     const uint32_t T = (uint32_t)j << kQ;
@@ -1615,10 +1619,13 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
     }
     __syncthreads();
     PlaneCtx c;
+    // (laundered through an empty asm: otherwise the address and the dump index are recomputed for every quad, 6 of ~92 instructions)
     c.base_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    asm volatile("" : "+r"(c.base_s));
     c.spill = s_spill; c.n_spill = &s_nspill; c.bad = a.bad_count;
     c.hw = (uint32_t)HW; c.dump = (uint32_t)HWp; c.W = (uint32_t)a.W; c.mul_x = a.mul_x; c.mul_y = a.mul_y;
     c.dumpl = (uint32_t)HWp + (uint32_t)(tid & 31);
+    asm volatile("" : "+r"(c.dump));
     uint32_t mismatch = 0, nbad = 0;
     int cur = 0;
     for (;;) {
@@ -1629,7 +1636,7 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
         const int b = task / per_sample, k = (task - b * per_sample) / a.T, t = task - b * per_sample - k * a.T;
         const int tbase = t * tile_full, ncell = (HW - tbase < tile_full) ? HW - tbase : tile_full;
         c.tbase = (uint32_t)tbase; c.tcells = (uint32_t)ncell; c.count_bad = (t == 0);
-        const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 2);
+        const int64_t* bd = a.bounds + (size_t)b * (a.num_bins + 3);
         const int64_t lo = bd[0];
         const int64_t a0 = bd[k > 0 ? k - 1 : 0], mid = bd[k], a1 = bd[k + 1];
         const SampleMeta m = a.meta[b];
@@ -1640,11 +1647,9 @@ __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs a) {
             tm.tmul = m.tmul; tm.tshift = m.tshift; tm.thalf = m.thalf;
             const int64_t dT = bd[a.num_bins + 1];                                // > 0 and < 2^32 for an integer-time sample
             tm.dT = (uint32_t)dT;
-            // largest dt whose v still fits 32 bits
-            uint64_t dt_safe = 0xffffffffull;
-            if (m.tmul) { const uint64_t q = ((((1ull << 32) << m.tshift) - m.thalf) - 1ull) / m.tmul; dt_safe = q < dt_safe ? q : dt_safe; }
-            tm.dt_lim = dt_safe >= 1023u ? (uint32_t)(dt_safe - 1023u) : 0u;
-            const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024 && dt_safe >= 1023u;
+            const int64_t dt_lim = bd[a.num_bins + 2];
+            tm.dt_lim = (uint32_t)dt_lim;
+            const bool fast = (m.flags & kFlagIntTime) && dT > 0 && dT < (1ll << 32) - 1024 && dt_lim >= 0;
             if (fast && a.T == 1) {
 #define EP_PLANE_ACC(CM, MT) plane_accumulate<true, CM, MT>(a, c, m, tm, lo, a0, mid, a1, (uint32_t)k, mismatch, nbad)
                 switch (a.coord_mode) {
