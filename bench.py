@@ -522,8 +522,11 @@ def run_ours(args):
     n_ref_slices = len(ref_bounds) - 1
 
     def host_side(i):
-        hb = ep.collate_events(aos[ref_bounds[i]:ref_bounds[i + 1]], 1e6, pin=True, threads=host_threads)
-        return hb.transport(threads=host_threads)
+        # one pass over the rows straight into the 4 B layout (ep_collate_transport4_host; the two-step form is its fallback)
+        return ep.collate_transport(aos[ref_bounds[i]:ref_bounds[i + 1]], 1e6, pin=True, threads=host_threads)
+
+    def host_side_two_steps(i):
+        return ep.collate_events(aos[ref_bounds[i]:ref_bounds[i + 1]], 1e6, pin=True, threads=host_threads).transport(threads=host_threads)
 
     pool = ThreadPoolExecutor(max_workers=2)
 
@@ -546,13 +549,18 @@ def run_ours(args):
         for i in range(n_ref_slices):
             host_side(i)
         host_only_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for i in range(n_ref_slices):
+            host_side_two_steps(i)
+        host_two_s = time.perf_counter() - t0
         e2e["from_reference_format"] = {
             "Gevents_per_s": world * n_ref / ref_s / 1e9, "ms_per_sample_step": 1e3 * ref_s,
-            "what": "per-sample (N,4) float64 x,y,t,p arrays (the reference's event format, 32 B/event) -> ep.collate_events -> "
-                    "RaggedEvents.transport() -> H2D -> ep.bin_events; host work of slice i+1 / i+2 on worker threads while slice i is "
-                    "copied and binned",
+            "what": "per-sample (N,4) float64 x,y,t,p arrays (the reference's event format, 32 B/event) -> ep.collate_transport (one "
+                    "pass over the rows into the 4 B layout) -> H2D -> ep.bin_events; host work of slice i+1 / i+2 on worker threads "
+                    "while slice i is copied and binned",
             "sample": f"first {REF_SAMPLES} of {BATCH} samples per rank ({n_ref} events), slices of {REF_SLICE}, rate-normalised",
             "host_threads_per_rank": host_threads, "host_side_alone_Gevents_per_s": world * n_ref / host_only_s / 1e9,
+            "host_side_alone_two_step_form_Gevents_per_s (ep.collate_events + transport(), round 2's earlier figure)": world * n_ref / host_two_s / 1e9,
             "note": "bounded by the host: 32 B/event of float64 rows have to be read from host memory before anything is shipped"}
     except Exception as e:      # a side measurement: never at the expense of the result line
         e2e["from_reference_format"] = {"error": repr(e)}

@@ -11,7 +11,7 @@ from .augmentation import (add_noise_events, erase_and_add_events, events_augmen
 from .dataset_utils import (events_to_EvRep, events_to_image_ecdp, events_to_image_mem,  # noqa: F401
                             events_to_voxel_grid, remove_hot_pixel_mem)
 from .events import (BadEventsError, EventCollator, RaggedEvents, bin_events, bin_events_aos, evrep, from_soa,  # noqa: F401
-                     collate_events, mem_hotpixel, normalise, pack_events, time_surface)
+                     collate_events, collate_transport, mem_hotpixel, normalise, pack_events, time_surface)
 from .masking import (block_mask_expand, convvit_fuse_stages, convvit_keep_masks, gather_tokens, gather_tokens_nchw, len_keep_of,  # noqa: F401
                       mask_from_noise, patch_density, random_masking, swin_apply_mask, swin_scatter_dense, unshuffle_tokens)
 from .pipeline import MaskedInputPipeline  # noqa: F401

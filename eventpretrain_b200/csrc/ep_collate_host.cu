@@ -132,6 +132,60 @@ __attribute__((target("avx2"))) bool collate_f64_avx2(const double* s, int64_t n
 
 // rint() above is the 1.5 * 2^52 trick (round-to-nearest-even, exact for |v| < 2^51): no libm call in the loop.
 
+// Rows of one sample -> what the 4 B packed word needs: integer ticks and x | y << 11 | polarity << 22 (the collate rules of
+// EP_DEFINE_COLLATE above, with the packed layout's 11-bit coordinates).  Scalar form; the float64 form below takes four rows per step.
+template <typename T>
+EP_HOST_CLONES bool rows_to_partial(const T* s, int64_t n, double t_scale, int64_t* ticks, uint32_t* part) {
+    bool ok = true;
+    for (int64_t i = 0; i < n; ++i) {
+        const double fx = (double)s[4 * i], fy = (double)s[4 * i + 1], ft = (double)s[4 * i + 2], fp = (double)s[4 * i + 3];
+        const bool in_range = fx >= 0.0 && fx <= 2047.0 && fy >= 0.0 && fy <= 2047.0;
+        const uint32_t ux = in_range ? (uint32_t)fx : 0u, uy = in_range ? (uint32_t)fy : 0u;
+        ok &= in_range && (double)ux == fx && (double)uy == fy && (fp == 0.0 || fp == 1.0);
+        const double v = ft * t_scale;
+        const double tk = (v + 6755399441055744.0) - 6755399441055744.0;
+        ok &= std::fabs(v) < 2251799813685248.0;
+        ticks[i] = (int64_t)tk;
+        part[i] = ux | (uy << 11) | ((uint32_t)(fp != 0.0) << 22);
+    }
+    return ok;
+}
+
+#ifdef EP_HOST_AVX2
+__attribute__((target("avx2"))) bool rows_to_partial_f64_avx2(const double* s, int64_t n, double t_scale, int64_t* ticks, uint32_t* part) {
+    const __m256d zero = _mm256_setzero_pd(), one = _mm256_set1_pd(1.0), top = _mm256_set1_pd(2047.0);
+    const __m256d scale = _mm256_set1_pd(t_scale), magic = _mm256_set1_pd(6755399441055744.0), lim = _mm256_set1_pd(2251799813685248.0);
+    const __m256d absmask = _mm256_castsi256_pd(_mm256_set1_epi64x(0x7fffffffffffffffLL));
+    const __m256i magic_bits = _mm256_castpd_si256(magic);
+    __m256d ok = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m256d r0 = _mm256_loadu_pd(s + 4 * i), r1 = _mm256_loadu_pd(s + 4 * i + 4);
+        const __m256d r2 = _mm256_loadu_pd(s + 4 * i + 8), r3 = _mm256_loadu_pd(s + 4 * i + 12);
+        const __m256d a = _mm256_unpacklo_pd(r0, r1), b = _mm256_unpackhi_pd(r0, r1);      // [x0 x1 t0 t1], [y0 y1 p0 p1]
+        const __m256d c = _mm256_unpacklo_pd(r2, r3), d = _mm256_unpackhi_pd(r2, r3);
+        const __m256d X = _mm256_permute2f128_pd(a, c, 0x20), T = _mm256_permute2f128_pd(a, c, 0x31);
+        const __m256d Y = _mm256_permute2f128_pd(b, d, 0x20), P = _mm256_permute2f128_pd(b, d, 0x31);
+        const __m128i xi = _mm256_cvttpd_epi32(X), yi = _mm256_cvttpd_epi32(Y), pi = _mm256_cvttpd_epi32(P);
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(X, zero, _CMP_GE_OQ), _mm256_cmp_pd(X, top, _CMP_LE_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(Y, zero, _CMP_GE_OQ), _mm256_cmp_pd(Y, top, _CMP_LE_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtepi32_pd(xi), X, _CMP_EQ_OQ), _mm256_cmp_pd(_mm256_cvtepi32_pd(yi), Y, _CMP_EQ_OQ)));
+        ok = _mm256_and_pd(ok, _mm256_or_pd(_mm256_cmp_pd(P, zero, _CMP_EQ_OQ), _mm256_cmp_pd(P, one, _CMP_EQ_OQ)));
+        const __m256d v = _mm256_mul_pd(T, scale);
+        ok = _mm256_and_pd(ok, _mm256_cmp_pd(_mm256_and_pd(v, absmask), lim, _CMP_LT_OQ));
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(ticks + i), _mm256_sub_epi64(_mm256_castpd_si256(_mm256_add_pd(v, magic)), magic_bits));
+        const __m128i word = _mm_or_si128(_mm_and_si128(xi, _mm_set1_epi32(0x7ff)),
+                                          _mm_or_si128(_mm_slli_epi32(_mm_and_si128(yi, _mm_set1_epi32(0x7ff)), 11),
+                                                       _mm_slli_epi32(_mm_and_si128(pi, _mm_set1_epi32(1)), 22)));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(part + i), word);
+    }
+    bool all = _mm256_movemask_pd(ok) == 0xf;
+    if (i < n) all &= rows_to_partial<double>(s + 4 * i, n - i, t_scale, ticks + i, part + i);
+    return all;
+}
+#endif
+
+
 EP_HOST_CLONES int64_t min_run(const int64_t* t, int64_t i0, int64_t i1) {
     int64_t m = t[i0];
     for (int64_t i = i0 + 1; i < i1; ++i) m = t[i] < m ? t[i] : m;
@@ -295,6 +349,86 @@ int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const int64_t* 
             const int64_t hi = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
             const int64_t sub = t_base[b] + (offsets[b] / K == g ? 0 : add_own);
             viol |= nbytes == 5 ? pack_run5(x, y, t, p, lo, hi, sub, w, tick_low) : pack_run4(x, y, t, p, lo, hi, sub, w);
+            lo = hi;
+        }
+        if (!ok || viol) bad.store(1, std::memory_order_relaxed);
+    });
+    return bad.load() ? EP_EUNSUPPORTED : EP_OK;
+}
+
+
+int ep_collate_transport4_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale, uint32_t* w,
+                               uint32_t* blk_base, int64_t* t_base, int64_t* offsets, int threads) {
+    using namespace ep;
+    if (!samples || !counts || !offsets || !t_base || batch <= 0) return EP_EINVAL;
+    if (dtype != EP_F64 && dtype != EP_F32) return EP_EINVAL;
+    if (!(t_scale > 0.0)) return EP_EINVAL;
+    offsets[0] = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (counts[b] < 0 || (counts[b] > 0 && !samples[b])) return EP_EINVAL;
+        offsets[b + 1] = offsets[b] + counts[b];
+    }
+    const int64_t n = offsets[batch];
+    // the sample's base is its first row's stamp: the smallest one for a time-sorted sample (an earlier stamp further down
+    // shows up as a negative tick below and sends the batch to the two-step path, which takes the true minimum)
+    std::atomic<int> bad(0);
+    for (int b = 0; b < batch; ++b) {
+        t_base[b] = 0;
+        if (counts[b] > 0) {
+            const double ft = dtype == EP_F64 ? static_cast<const double*>(samples[b])[2] : (double)static_cast<const float*>(samples[b])[2];
+            const double v = ft * t_scale;
+            if (!(std::fabs(v) < 2251799813685248.0)) return EP_EUNSUPPORTED;
+            t_base[b] = (int64_t)((v + 6755399441055744.0) - 6755399441055744.0);
+        }
+    }
+    if (n == 0) return EP_OK;
+    if (!w || !blk_base) return EP_EINVAL;
+    constexpr int64_t K = 256;
+    const int64_t n_blocks = (n + K - 1) / K;
+#ifdef EP_HOST_AVX2
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+#endif
+    parallel_for(n_blocks, 64, threads, [&](int64_t g) {
+        const int64_t i0 = g * K, i1 = i0 + K < n ? i0 + K : n;
+        int64_t ticks[K];
+        uint32_t part[K];
+        int b0 = owner_of(offsets, batch, i0);
+        while (offsets[b0 + 1] <= i0) ++b0;
+        bool ok = true;
+        // rows of every sample inside the block -> ticks and partial words (one pass over the 32 B/event rows)
+        int b = b0;
+        for (int64_t lo = i0; lo < i1;) {
+            while (lo >= offsets[b + 1]) ++b;
+            const int64_t hi = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
+            const int64_t r0 = lo - offsets[b], cnt = hi - lo;
+#ifdef EP_HOST_AVX2
+            if (dtype == EP_F64 && have_avx2)
+                ok &= rows_to_partial_f64_avx2(static_cast<const double*>(samples[b]) + 4 * r0, cnt, t_scale, ticks + (lo - i0), part + (lo - i0));
+            else
+#endif
+            ok &= dtype == EP_F64 ? rows_to_partial<double>(static_cast<const double*>(samples[b]) + 4 * r0, cnt, t_scale, ticks + (lo - i0), part + (lo - i0))
+                                  : rows_to_partial<float>(static_cast<const float*>(samples[b]) + 4 * r0, cnt, t_scale, ticks + (lo - i0), part + (lo - i0));
+            lo = hi;
+        }
+        // tick offset of the block: smallest relative stamp among the events of the sample that owns the block's first slot
+        const int64_t own_end = offsets[b0 + 1] < i1 ? offsets[b0 + 1] : i1;
+        int64_t m = ticks[0];
+        for (int64_t i = 1; i < own_end - i0; ++i) m = ticks[i] < m ? ticks[i] : m;
+        m -= t_base[b0];
+        ok &= m >= 0 && m < ((int64_t)1 << 32);
+        const int64_t add_own = ok ? m : 0;
+        blk_base[g] = (uint32_t)add_own;
+        uint64_t viol = 0;
+        b = b0;
+        for (int64_t lo = i0; lo < i1;) {
+            while (lo >= offsets[b + 1]) ++b;
+            const int64_t hi = offsets[b + 1] < i1 ? offsets[b + 1] : i1;
+            const int64_t sub = t_base[b] + (offsets[b] / K == g ? 0 : add_own);
+            for (int64_t i = lo; i < hi; ++i) {
+                const uint64_t rel = (uint64_t)(ticks[i - i0] - sub);
+                viol |= rel >> 9;
+                w[i] = part[i - i0] | ((uint32_t)rel << 23);
+            }
             lo = hi;
         }
         if (!ok || viol) bad.store(1, std::memory_order_relaxed);

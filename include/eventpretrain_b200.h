@@ -389,6 +389,14 @@ EP_API int ep_pack_transport_host(const uint16_t* x, const uint16_t* y, const in
                                   const int64_t* offsets, int batch, int nbytes, uint32_t* w, uint8_t* tick_low,
                                   uint32_t* blk_base, int64_t* t_base, int threads);
 
+/* The two steps above in one pass for the 4 B packed layout: per-sample (N,4) x,y,t,p rows -> packed words, per-block tick
+ * offsets, per-sample bases and offsets, reading the 32 B/event rows once and writing 4 B/event (the two-step form moves 62 B
+ * of host memory per event, this one 36).  The sample's base is taken from its first row, so it covers time-sorted samples
+ * whose coordinates are < 2048, polarity in {0,1} and whose 256-event blocks span < 512 ticks: same arrays, bit for bit, as
+ * ep_collate_aos_host + ep_pack_transport_host(nbytes = 4).  EP_EUNSUPPORTED for anything else (take the two-step form). */
+EP_API int ep_collate_transport4_host(const void* const* samples, const int64_t* counts, int batch, int dtype, double t_scale,
+                               uint32_t* w, uint32_t* blk_base, int64_t* t_base, int64_t* offsets, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -242,3 +242,38 @@ def test_reshape_axis_multiplier_against_numpy(native_lib):
     assert native_lib.ep_reshape_axis_multiplier_host(ctypes.c_double(224 / 640), ctypes.byref(m)) == 0      # 0.35 * 180 = 62.99999999999999
     assert native_lib.ep_reshape_axis_multiplier_host(ctypes.c_double(224 / 480), ctypes.byref(m)) == 1
     assert seen == {True, False}
+
+
+def test_collate_transport_one_pass_equals_two_steps(native_lib):
+    """ep_collate_transport4_host (rows -> 4 B packed layout in one pass) against ep_collate_aos_host + ep_pack_transport_host:
+    the same words, block offsets, bases and offsets bit for bit on time-sorted samples (float64 and float32 rows, empty and
+    one-event samples, samples that start and end inside a tick block); batches the one-pass form does not take (unsorted
+    rows, sparse stamps, wide coordinates) fall back to the two-step form and its choice of layout."""
+    rng = np.random.default_rng(21)
+
+    def sample(n, dtype=np.float64, rate=4.0, W=640, H=480):
+        t = np.sort(rng.integers(0, max(int(n / rate), 1), n)).astype(np.float64) / 1e6 + 0.25
+        return np.stack([rng.integers(0, W, n), rng.integers(0, H, n), t, rng.integers(0, 2, n)], 1).astype(dtype)
+
+    batch = [sample(n) for n in (5000, 0, 1, 257, 70001, 255, 4096)]
+    one = ep.collate_transport(batch, pin=False, threads=3)
+    two = ep.collate_events(batch, pin=False, threads=3).packed(4, threads=3)
+    assert one.t is None and one.y is None and one.t_base is not None          # the 4 B layout
+    for a, b in ((one.x, two.x), (one.p, two.p), (one.t_base, two.t_base), (one.offsets, two.offsets)):
+        assert torch.equal(a, b)
+    assert np.array_equal(one.offsets_host, two.offsets_host) and one.t_div == two.t_div
+    # float32 rows (stamps with few digits so that float32 holds them)
+    b32 = [np.stack([rng.integers(0, 346, n), rng.integers(0, 260, n), np.sort(rng.integers(0, n // 3 + 1, n)) / 1e3,
+                     rng.integers(0, 2, n)], 1).astype(np.float32) for n in (3000, 700)]
+    one, two = ep.collate_transport(b32, ticks_per_unit=1e3, pin=False), ep.collate_events(b32, ticks_per_unit=1e3, pin=False).packed(4)
+    assert torch.equal(one.x, two.x) and torch.equal(one.p, two.p) and torch.equal(one.t_base, two.t_base)
+    # fallbacks: an unsorted sample (its first row is not its smallest stamp), sparse stamps (5 B layout), x >= 2048 (8 B layout)
+    uns = [sample(3000), sample(2000)[::-1].copy()]
+    for bad in (uns, [sample(4000, rate=0.01)], [sample(3000, W=4000)]):
+        got, ref = ep.collate_transport(bad, pin=False), ep.collate_events(bad, pin=False).transport()
+        assert (got.t is None) == (ref.t is None) and (got.y is None) == (ref.y is None)
+        assert torch.equal(got.x, ref.x) and torch.equal(got.offsets, ref.offsets)
+        x1, y1, t1, p1 = got.unpack_host() if got.y is None else (None,) * 4
+        if x1 is not None:
+            x2, y2, t2, p2 = ref.unpack_host()
+            assert np.array_equal(t1, t2) and np.array_equal(x1, x2) and np.array_equal(p1, p2)
