@@ -20,9 +20,12 @@ A "step" is one pass of the hot path over the batch.  Prints ONE JSON line on ra
             slices (copy of slice i+1 overlaps the binning of slice i) and a D2H read of a per-sample checksum inside the
             timed region; the tensors themselves stay on the device, where the encoder consumes them.  Sub-entries:
             from_reference_format = the whole host side too, starting from the reference's own per-sample (N,4) float64 arrays
-            (threaded collate + pack of slice i+1 overlapping H2D + binning of slice i; bounded sample, rate-normalised);
+            (threaded one-pass collate into the transport layout of slice i+1 overlapping H2D + binning of slice i; bounded
+            sample, rate-normalised);
             h2d_only = the same buffers copied with no kernels (the ceiling the interconnect sets at this N)
   cpu_baseline  the oracle C port of the reference routine on the host cores, bounded sample, rank 0 / N=1 only
+  extra.reference_res_224  the reference's own pre-training order (events rescaled to 224x224, then binned) on the three kernel
+            families (whole-plane kernels by default), with a bit-identity check
   extra.configs  BASELINE.json configs[0], [2], [3], [4] at their own sizes (per-GPU share at N > 1), each with
             throughput, SURVEY 8(d) bytes, roofline fraction and a parity check against the oracle
 
