@@ -1492,6 +1492,13 @@ __device__ __forceinline__ void plane_quad(const PlaneCtx& c, const SampleMeta& 
     }
 }
 
+// the words of a slice are read by two CTAs (planes k and k + 1) at about the same time: EP_PLANE_LDG = 1 loads them with the
+// default cache policy instead of evict-first, so that the second reader finds them in L2
+#ifndef EP_PLANE_LDG
+#define EP_PLANE_LDG 0
+#endif
+__device__ __forceinline__ uint4 plane_ld(const uint4* p) { return EP_PLANE_LDG ? __ldg(p) : ld_stream(p); }
+
 #ifndef EP_PLANE_PIPE
 #define EP_PLANE_PIPE 2        // 0 = plain loop, 1 = the block after next is requested into L2, 2 = next block's words in registers
 #endif
@@ -1523,7 +1530,7 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
     auto fetch = [&](uint32_t i) {
         const uint4* p = reinterpret_cast<const uint4*>(wp + ((size_t)i << kTickBlockShift));
         const bool edge = (i == 0u && head) || (i == nblk - 1u && tail);
-        if (!edge) { n0 = ld_stream(p); n1 = ld_stream(p + 32); }
+        if (!edge) { n0 = plane_ld(p); n1 = plane_ld(p + 32); }
         nb = (i == first_rel) ? 0u : __ldg(bp + i);
     };
     if ((uint32_t)wid < nblk) fetch((uint32_t)wid);
@@ -1548,7 +1555,7 @@ __device__ __forceinline__ void plane_slice(const PlaneArgs& a, const PlaneCtx& 
         if (FAST) edge = edge || i == first_rel || (base - t0) > tm.dt_lim;
         if (!edge) {
 #if EP_PLANE_PIPE != 2
-            const uint4 w0 = ld_stream(p), w1 = ld_stream(p + 32);
+            const uint4 w0 = plane_ld(p), w1 = plane_ld(p + 32);
 #endif
             plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w0, dtb, 0u, len, kbase, mx, mismatch);
             plane_quad<FAST, CM, LEFT, false, MT>(c, m, tm, a.num_bins, w1, dtb, 0u, len, kbase, mx, mismatch);
